@@ -1,0 +1,172 @@
+/* pmk.h -- C ABI of libpmk_b200.so: the B200-native (sm_100a) local-GP fit + mixture-query
+ * hot path of RoyCCWang/PatchMixtureKriging.
+ *
+ * The reference is pure Julia and has no FFI of its own; the drop-in boundary is its Julia
+ * function surface (src/PatchMixtureKriging.jl:54-71).  Each entry point below names the
+ * reference function whose BODY it replaces (paths relative to the reference repo);
+ * julia/PatchMixtureKrigingB200.jl and INTEGRATION.md show the `ccall` a maintainer adds.
+ *
+ * Conventions
+ *  - plain C types only; all matrices column-major (Julia layout); points are "point-major":
+ *    X is D x n column-major, i.e. exactly src/misc/utilities.jl:25-36 `array2matrix(X)`.
+ *  - every index RETURNED is 1-based (leaf ids, hyperplane ids) so it compares bit-for-bit
+ *    with the reference; offsets/CSR pointers PASSED IN are 0-based prefix sums.
+ *  - the caller owns every host buffer for the duration of the (blocking) call; the library
+ *    owns all device memory behind the opaque handle and retains no host pointer.
+ *  - return value: PMK_OK or a negative pmk_status; pmk_last_error() gives the text.
+ *    No C++ exception crosses this boundary.  There is NO CPU fallback: without a CUDA
+ *    device pmk_create fails with PMK_ERR_CUDA.
+ *  - one handle = one fitted model on one GPU; calls on one handle must be serialised.
+ *  - *_dev variants take DEVICE pointers (same layouts) and run on the handle's stream
+ *    without host synchronisation beyond what is documented.
+ */
+#ifndef PMK_H
+#define PMK_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pmk_handle pmk_handle;
+
+typedef enum {
+  PMK_OK = 0,
+  PMK_ERR_CUDA = -1,         /* CUDA runtime error (text in pmk_last_error)                    */
+  PMK_ERR_ARG = -2,          /* bad argument / size mismatch  (-> AssertionError/DimensionMismatch,
+                                mixtureGP.jl:298, RKHS.jl:18,199-203,225-227)                  */
+  PMK_ERR_NOT_POSDEF = -3,   /* a leaf's K+sigma2*I is not PD (-> PosDefException(info),
+                                mixtureGP.jl:109); bad_leaf (1-based) and LAPACK-style info set */
+  PMK_ERR_STATE = -4,        /* call order: query before fit / set_tree                        */
+  PMK_ERR_UNSUPPORTED = -5   /* D > 3, leaf larger than PMK_MAX_LEAF_POINTS, unknown kernel id */
+} pmk_status;
+
+/* kernel ids: src/misc/declarations.jl:25-100, evaluated as in src/RKHS/kernel.jl */
+typedef enum {
+  PMK_KERNEL_SQEXP = 0,     /* GaussianKernel1DType{eps_sq}: exp(-eps_sq*tau^2)      kernel.jl:350-357 */
+  PMK_KERNEL_SPLINE34 = 1,  /* Spline34KernelType{a}                                 kernel.jl:299-313 */
+  PMK_KERNEL_BB10 = 2,      /* BrownianBridge10: prod_d min(p,q)-p*q                 kernel.jl:156-158,196-198 */
+  PMK_KERNEL_BB20 = 3,      /* BrownianBridge20 (iterated, beta=2)                   kernel.jl:218-225 */
+  PMK_KERNEL_BB1EPS = 4,    /* BrownianBridge1eps{eps}                               kernel.jl:168-174 */
+  PMK_KERNEL_BB2EPS = 5,    /* BrownianBridge2eps{eps}                               kernel.jl:176-193 */
+  PMK_KERNEL_SPLINE12 = 6,  /* Spline12KernelType{a}                                 kernel.jl:316-330 */
+  PMK_KERNEL_SPLINE32 = 7,  /* Spline32KernelType{a}                                 kernel.jl:333-347 */
+  PMK_KERNEL_RQ = 8         /* RationalQuadraticKernelType{a}                        kernel.jl:360-366 */
+} pmk_kernel_id;
+
+#define PMK_MAX_DIM 3
+#define PMK_MAX_LEAF_POINTS 2048
+
+/* timing slots of pmk_get_timings (milliseconds, CUDA events on the handle's stream) */
+enum {
+  PMK_T_FIT_PACK = 0,      /* AoS -> padded SoA leaf packing                                   */
+  PMK_T_FIT_CHOL = 1,      /* fused Gram + blocked Cholesky (K1+K2)                            */
+  PMK_T_FIT_SOLVE = 2,     /* forward/back solves for alpha                                    */
+  PMK_T_Q_TREE = 3,        /* home leaf + neighbour search + pair build + binning              */
+  PMK_T_Q_PAIRS = 4,       /* fused cross-covariance / mean / TRSM-variance kernel (K3)        */
+  PMK_T_Q_COMBINE = 5,     /* convex mixture combine                                           */
+  PMK_T_GRAM = 6,          /* standalone Gram kernel                                           */
+  PMK_T_COUNT = 8
+};
+
+/* ---- lifetime ---------------------------------------------------------------------------- */
+int pmk_create(pmk_handle** out, int device);
+void pmk_destroy(pmk_handle* h);
+const char* pmk_last_error(const pmk_handle* h);   /* h may be NULL: error of a failed pmk_create */
+int pmk_version(void);
+
+/* ---- Gram matrices ----------------------------------------------------------------------- */
+/* constructkernelmatrix(X, theta) (src/RKHS/RKHS.jl:4-34): K_out[i + n*j] = k(X[i], X[j]) (+ sigma2
+ * on the diagonal; pass 0 for the plain Gram matrix).  Full symmetric n x n, column-major. */
+int pmk_gram(pmk_handle* h, int D, int64_t n, const double* X, int kernel_id, const double* kparams,
+             int nparams, double sigma2, double* K_out);
+/* constructkernelmatrix(X, Z, theta) (RKHS.jl:95-110): K_out[i + n*j] = k(X[i], Z[j]), n x m. */
+int pmk_cross_gram(pmk_handle* h, int D, int64_t n, const double* X, int64_t m, const double* Z,
+                   int kernel_id, const double* kparams, int nparams, double* K_out);
+
+/* ---- fit --------------------------------------------------------------------------------- */
+/* fitmixtureGP!(eta, y_parts, theta, sigma2) (src/RKHS/mixtureGP.jl:70-118) for all leaves at once;
+ * with n_leaves == 1 it is fitRKHS!(eta, y) (RKHS.jl:182-217).
+ *   leaf_off : n_leaves+1 prefix offsets (0-based, in points) into X_packed / y_packed
+ *   X_packed : D x sum(n_p), the leaves' training inputs back to back (array2matrix of each X_set[p])
+ *   y_packed : sum(n_p)
+ * On PMK_ERR_NOT_POSDEF, *bad_leaf = first (lowest) failing leaf, 1-based, *info = order of the
+ * first non-positive leading minor (LAPACK dpotrf convention).  Either may be NULL. */
+int pmk_fit(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X_packed,
+            const double* y_packed, int kernel_id, const double* kparams, int nparams, double sigma2,
+            int64_t* bad_leaf, int* info);
+/* same with device pointers for X_packed / y_packed (leaf_off stays a host array) */
+int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* dX_packed,
+                const double* dy_packed, int kernel_id, const double* kparams, int nparams, double sigma2,
+                int64_t* bad_leaf, int* info);
+
+/* per-leaf state of MixtureGPType (mixtureGP.jl:38-66); leaf is 1-based.
+ *   alpha: c_set[leaf] (n_p);  L: L_set[leaf] as dense n_p x n_p column-major, upper triangle zero;
+ *   K: U_set[leaf] = Gram WITHOUT sigma2 (mixtureGP.jl:99), recomputed on demand. */
+int pmk_leaf_size(pmk_handle* h, int64_t leaf, int64_t* n_out);
+int pmk_get_alpha(pmk_handle* h, int64_t leaf, double* out);
+int pmk_get_L(pmk_handle* h, int64_t leaf, double* out);
+int pmk_get_K(pmk_handle* h, int64_t leaf, double* out);
+
+/* ---- tree -------------------------------------------------------------------------------- */
+/* the BSP built by setuppartition (src/patchwork/partition.jl:106-129), flattened by the host wrapper:
+ * hyperplanes of the 2^(levels-1)-1 internal nodes in fetchhyperplanes order = PreOrderDFS
+ * (mixtureGP.jl:322-334): hp_v is D x n_hp column-major, hp_c has n_hp entries.  levels == 1 means
+ * "no tree" (a single GP: every query's home leaf is 1). */
+int pmk_set_tree(pmk_handle* h, int D, int levels, const double* hp_v, const double* hp_c);
+
+/* findpartition (partition.jl:248-262) for many points: leaf_out[j] 1-based. */
+int pmk_find_partition(pmk_handle* h, int64_t Nq, const double* Xq, int32_t* leaf_out);
+
+/* ---- query ------------------------------------------------------------------------------- */
+/* querymixtureGP!(Yq, Vq, Xq, eta, root, levels, radius, delta, theta, sigma2, weight_theta, ...)
+ * (mixtureGP.jl:159-294; inner: queryinner! :296-316, findneighbourpartitions :339-405,
+ * findpartition partition.jl:248-262).  Xq is D x Nq.  wkernel_id/wparams = weight_theta (a stationary
+ * kernel evaluated at abs(t)).  theta and sigma2 are those given to pmk_fit.
+ * flags: bit0 = mean only (Vq untouched; this is query!(Yq,Xq,eta), RKHS.jl:220-247, when levels==1). */
+int pmk_query(pmk_handle* h, int64_t Nq, const double* Xq, double radius, double delta, int wkernel_id,
+              const double* wparams, int nw, int flags, double* Yq, double* Vq);
+int pmk_query_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radius, double delta, int wkernel_id,
+                  const double* wparams, int nw, int flags, double* dYq, double* dVq);
+
+/* debug_flag=true outputs (MixtureGPDebugType, mixtureGP.jl:5-35,242-260) of the LAST query:
+ *   home[Nq]           p_region_ind_set (1-based)
+ *   pair_off[Nq+1]     CSR offsets: query j owns slots pair_off[j] .. pair_off[j+1]-1; the last slot is
+ *                      the home leaf (w_tilde = 1), the others the kept neighbours in hyperplane order
+ *   pair_leaf          region_inds_set (+ home last), 1-based
+ *   pair_hp            1-based index into hps of the hyperplane that produced the slot (0 for home)
+ *   pair_t             ts[hps_keep_flags]  (0 for home)
+ *   pair_w, pair_u, pair_v   w_tilde_set, u_set, v_set
+ * Call pmk_last_query_pairs first to size the pair arrays.  Any output pointer may be NULL. */
+int pmk_last_query_pairs(pmk_handle* h, int64_t* n_pairs);
+int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_t* pair_leaf, int32_t* pair_hp,
+                         double* pair_t, double* pair_w, double* pair_u, double* pair_v);
+
+/* ---- multi-GPU (leaf -> rank map) --------------------------------------------------------- */
+/* A rank that owns leaves [leaf_base+1, leaf_base+n_leaves] of a larger tree fits only those
+ * (pmk_fit with its slice) and declares the offset here BEFORE pmk_fit.  The query is then split:
+ *   pmk_query_plan_dev   : tree stage for ALL queries (replicated, cheap); returns n_pairs
+ *   pmk_query_pairs_dev  : fused pair kernel for the pairs whose leaf this rank owns; writes u,v into
+ *                          caller-provided DEVICE arrays of n_pairs doubles (0 for pairs owned elsewhere)
+ *   (caller sums pair_u / pair_v across ranks: one NCCL all-reduce over NVLink, exact because every
+ *    slot is non-zero on exactly one rank)
+ *   pmk_query_combine_dev: convex combination -> Yq, Vq. */
+int pmk_set_leaf_base(pmk_handle* h, int64_t leaf_base, int64_t total_leaves);
+int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radius, double delta,
+                       int wkernel_id, const double* wparams, int nw, int64_t* n_pairs);
+int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pair_v);
+int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d_pair_v, double* dYq, double* dVq);
+
+/* ---- instrumentation --------------------------------------------------------------------- */
+int pmk_get_timings(pmk_handle* h, double* ms /* PMK_T_COUNT entries */);
+/* number of kernel launches issued by this handle since creation */
+int64_t pmk_launch_count(const pmk_handle* h);
+/* stream the handle launches on, as a cudaStream_t cast to void* (for event timing by the caller) */
+void* pmk_stream(pmk_handle* h);
+int pmk_synchronize(pmk_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PMK_H */

@@ -1,0 +1,139 @@
+"""ctypes binding of libpmk_b200.so (C ABI in include/pmk.h).  There is no fallback: if the
+library is missing or no B200 is visible, the calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpmk_b200.so")
+
+PMK_OK, PMK_ERR_CUDA, PMK_ERR_ARG, PMK_ERR_NOT_POSDEF, PMK_ERR_STATE, PMK_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+T_FIT_PACK, T_FIT_CHOL, T_FIT_SOLVE, T_Q_TREE, T_Q_PAIRS, T_Q_COMBINE, T_GRAM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 8
+
+# every symbol include/pmk.h declares
+SYMBOLS = [
+    "pmk_create", "pmk_destroy", "pmk_last_error", "pmk_version", "pmk_gram", "pmk_cross_gram", "pmk_fit", "pmk_fit_dev",
+    "pmk_leaf_size", "pmk_get_alpha", "pmk_get_L", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_query",
+    "pmk_query_dev", "pmk_last_query_pairs", "pmk_last_query_debug", "pmk_set_leaf_base", "pmk_query_plan_dev",
+    "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_get_timings", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
+]
+
+_lib = None
+
+
+class PMKError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libpmk_b200 error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+class PosDefException(PMKError):
+    """Mirror of LinearAlgebra.PosDefException thrown by cholesky(U) (reference mixtureGP.jl:109)."""
+
+    def __init__(self, info: int, leaf: int, msg: str):
+        PMKError.__init__(self, PMK_ERR_NOT_POSDEF, msg)
+        self.info = info
+        self.leaf = leaf
+
+
+def lib() -> C.CDLL:
+    """Load the CUDA library; raises if it was not built (python -m patchmixturekriging_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(f"{LIB_PATH} not found: build it with `python -m patchmixturekriging_b200.build` "
+                           "(nvcc, sm_100a).  There is no CPU fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, i64, dbl = C.c_void_p, C.c_int, C.c_int64, C.c_double
+    dp = C.c_void_p  # raw pointers (host numpy or device addresses)
+    L.pmk_create.argtypes = [C.POINTER(vp), i32]
+    L.pmk_destroy.argtypes = [vp]
+    L.pmk_destroy.restype = None
+    L.pmk_last_error.argtypes = [vp]
+    L.pmk_last_error.restype = C.c_char_p
+    L.pmk_version.argtypes = []
+    L.pmk_gram.argtypes = [vp, i32, i64, dp, i32, dp, i32, dbl, dp]
+    L.pmk_cross_gram.argtypes = [vp, i32, i64, dp, i64, dp, i32, dp, i32, dp]
+    L.pmk_fit.argtypes = [vp, i32, i64, dp, dp, dp, i32, dp, i32, dbl, C.POINTER(i64), C.POINTER(i32)]
+    L.pmk_fit_dev.argtypes = L.pmk_fit.argtypes
+    L.pmk_leaf_size.argtypes = [vp, i64, C.POINTER(i64)]
+    L.pmk_get_alpha.argtypes = [vp, i64, dp]
+    L.pmk_get_L.argtypes = [vp, i64, dp]
+    L.pmk_get_K.argtypes = [vp, i64, dp]
+    L.pmk_set_tree.argtypes = [vp, i32, i32, dp, dp]
+    L.pmk_find_partition.argtypes = [vp, i64, dp, dp]
+    L.pmk_query.argtypes = [vp, i64, dp, dbl, dbl, i32, dp, i32, i32, dp, dp]
+    L.pmk_query_dev.argtypes = L.pmk_query.argtypes
+    L.pmk_last_query_pairs.argtypes = [vp, C.POINTER(i64)]
+    L.pmk_last_query_debug.argtypes = [vp, dp, dp, dp, dp, dp, dp, dp, dp]
+    L.pmk_set_leaf_base.argtypes = [vp, i64, i64]
+    L.pmk_query_plan_dev.argtypes = [vp, i64, dp, dbl, dbl, i32, dp, i32, C.POINTER(i64)]
+    L.pmk_query_pairs_dev.argtypes = [vp, i32, dp, dp]
+    L.pmk_query_combine_dev.argtypes = [vp, dp, dp, dp, dp]
+    L.pmk_get_timings.argtypes = [vp, dp]
+    L.pmk_launch_count.argtypes = [vp]
+    L.pmk_launch_count.restype = i64
+    L.pmk_stream.argtypes = [vp]
+    L.pmk_stream.restype = vp
+    L.pmk_synchronize.argtypes = [vp]
+    _lib = L
+    return L
+
+
+def ptr(a) -> int | None:
+    """Raw address of a C-contiguous numpy array (or an int device address, passed through)."""
+    if a is None:
+        return None
+    if isinstance(a, (int, np.integer)):
+        return int(a)
+    assert a.flags["C_CONTIGUOUS"] or a.flags["F_CONTIGUOUS"]
+    return a.ctypes.data
+
+
+class Handle:
+    """One fitted model on one GPU (pmk_handle)."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        L = lib()
+        rc = L.pmk_create(C.byref(self._h), int(device))
+        if rc != PMK_OK:
+            msg = L.pmk_last_error(None).decode()
+            self._h = C.c_void_p()
+            raise PMKError(rc, msg)
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().pmk_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != PMK_OK:
+            raise PMKError(rc, lib().pmk_last_error(self._h).decode())
+
+    @property
+    def raw(self):
+        return self._h
+
+    def timings(self) -> np.ndarray:
+        ms = np.zeros(T_COUNT)
+        self.check(lib().pmk_get_timings(self._h, ptr(ms)))
+        return ms
+
+    def launch_count(self) -> int:
+        return int(lib().pmk_launch_count(self._h))
+
+    def synchronize(self):
+        self.check(lib().pmk_synchronize(self._h))

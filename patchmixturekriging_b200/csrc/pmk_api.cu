@@ -1,0 +1,775 @@
+// C-ABI layer of libpmk_b200.so (see include/pmk.h).  Owns the device state of one fitted
+// mixture-GP model, validates arguments, orders the kernels on the handle's stream and maps
+// failures to status codes.  No CPU compute path exists here: every numerical result comes
+// from the sm_100a kernels in pmk_fit.cu / pmk_tree.cu / pmk_query.cu / pmk_gram.cu.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "pmk_internal.cuh"
+
+namespace pmk {
+// launchers defined in the kernel translation units
+void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const double* dX, const double* dy, cudaStream_t s);
+void launch_chol(int D, const LeafTable& lt, const int* d_order, KParams kp, double sigma2, cudaStream_t s);
+void launch_solve(const LeafTable& lt, const int* d_order, int max_npad, cudaStream_t s);
+void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
+void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, cudaStream_t s);
+void launch_neighbours(int D, bool fill, const TreeDev& tr, const QueryPlan& q, double radius, double delta, int wkind,
+                       double wparam, int32_t* d_leaf_count, cudaStream_t s);
+void launch_combine(int64_t Nq, const int64_t* pair_off, const double* pw, const double* pu, const double* pv, double* dYq,
+                    double* dVq, int mean_only, cudaStream_t s);
+void launch_scan_small(const int32_t* in, int64_t* out, int n, cudaStream_t s);
+void launch_aos_to_soa(int D, const double* dX, int64_t n, int64_t stride, double* xs, cudaStream_t s);
+void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double* xc, int64_t xc_stride, int m, KParams kp,
+                 double sigma2, int symmetric, double* dK, cudaStream_t s);
+int query_class_of(int npad);
+int query_class_mq(int cls);
+void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
+                        int mean_only, double* pu, double* pv, cudaStream_t s);
+void launch_class_tiles(const PairWork& w, int mq, int32_t* tiles, cudaStream_t s);
+}  // namespace pmk
+
+using namespace pmk;
+
+namespace {
+
+struct DBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+thread_local std::string g_create_error;
+
+}  // namespace
+
+struct pmk_handle {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  int64_t launches = 0;
+
+  // model
+  bool fitted = false;
+  int D = 0;
+  int64_t n_leaves = 0, leaf_base = 0, total_leaves = 0;
+  KParams kp{0, 1.0};
+  double sigma2 = 0.0;
+  int max_npad = 0;
+  std::vector<int> h_n, h_npad;
+  std::vector<int64_t> h_xoff, h_loff, h_ioff;
+  int64_t xstride = 0;
+  DBuf d_n, d_npad, d_xoff, d_loff, d_ioff, d_xs, d_y, d_alpha, d_L, d_Linv, d_info, d_order, d_leafoff, d_Xin, d_yin;
+  DBuf d_class_leaves[3], d_class_tiles[3], d_tile_off[3];
+  int n_class[3] = {0, 0, 0};
+  LeafTable lt{};
+
+  // tree
+  bool tree_set = false;
+  int tree_D = 0, levels = 1, n_hp = 0;
+  DBuf d_hv, d_hc;
+  TreeDev tree{};
+
+  // query
+  DBuf d_Xq, d_home, d_npairs, d_pair_off, d_Yq, d_Vq;
+  DBuf d_pair_leaf, d_pair_q, d_pair_hp, d_pair_t, d_pair_w, d_pair_u, d_pair_v, d_sorted_pair, d_keys_out, d_iota;
+  DBuf d_leaf_count, d_leaf_pair_start, d_cub;
+  DBuf d_scratch;   // Gram scratch
+  QueryPlan plan{};
+  bool plan_valid = false;
+  int last_flags = 0;
+
+  // timings
+  cudaEvent_t ev[2 * PMK_T_COUNT] = {};
+  bool ev_used[PMK_T_COUNT] = {};
+  double ms[PMK_T_COUNT] = {};
+};
+
+namespace {
+
+int fail(pmk_handle* h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU(h, expr)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess)                                                                            \
+      return fail(h, PMK_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__); \
+  } while (0)
+
+#define KCHECK(h, what)                                                                               \
+  do {                                                                                                \
+    cudaError_t e_ = cudaGetLastError();                                                              \
+    if (e_ != cudaSuccess) return fail(h, PMK_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e_)); \
+    ++(h)->launches;                                                                                  \
+  } while (0)
+
+struct Timer {
+  pmk_handle* h;
+  int slot;
+  Timer(pmk_handle* h_, int slot_) : h(h_), slot(slot_) {
+    cudaEventRecord(h->ev[2 * slot], h->stream);
+  }
+  ~Timer() {
+    cudaEventRecord(h->ev[2 * slot + 1], h->stream);
+    h->ev_used[slot] = true;
+  }
+};
+
+int parse_kernel(pmk_handle* h, int kernel_id, const double* kparams, int nparams, KParams* out) {
+  if (kernel_id < PMK_KERNEL_SQEXP || kernel_id > PMK_KERNEL_RQ) return fail(h, PMK_ERR_UNSUPPORTED, "unknown kernel id %d", kernel_id);
+  out->kind = kernel_id;
+  out->p = (nparams >= 1 && kparams) ? kparams[0] : 1.0;
+  return PMK_OK;
+}
+
+bool is_stationary_host(int kind) {
+  return kind == PMK_KERNEL_SQEXP || kind == PMK_KERNEL_SPLINE34 || kind == PMK_KERNEL_SPLINE12 ||
+         kind == PMK_KERNEL_SPLINE32 || kind == PMK_KERNEL_RQ;
+}
+
+int set_device(pmk_handle* h) {
+  CU(h, cudaSetDevice(h->device));
+  return PMK_OK;
+}
+
+}  // namespace
+
+// =============================================================================================
+extern "C" {
+
+int pmk_version(void) { return 100; }
+
+const char* pmk_last_error(const pmk_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int pmk_create(pmk_handle** out, int device) {
+  if (!out) return fail(nullptr, PMK_ERR_ARG, "pmk_create: out is NULL");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0)
+    return fail(nullptr, PMK_ERR_CUDA, "pmk_create: no CUDA device (%s); libpmk_b200 has no CPU fallback",
+                e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  if (device < 0 || device >= ndev) return fail(nullptr, PMK_ERR_ARG, "pmk_create: device %d out of range [0,%d)", device, ndev);
+  e = cudaSetDevice(device);
+  if (e != cudaSuccess) return fail(nullptr, PMK_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  cudaDeviceProp prop;
+  e = cudaGetDeviceProperties(&prop, device);
+  if (e != cudaSuccess) return fail(nullptr, PMK_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major < 10)
+    return fail(nullptr, PMK_ERR_CUDA, "pmk_create: device %s is sm_%d%d; this library is built for sm_100a only", prop.name,
+                prop.major, prop.minor);
+  pmk_handle* h = new (std::nothrow) pmk_handle();
+  if (!h) return fail(nullptr, PMK_ERR_CUDA, "out of host memory");
+  h->device = device;
+  e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+  if (e != cudaSuccess) {
+    delete h;
+    return fail(nullptr, PMK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  for (int i = 0; i < 2 * PMK_T_COUNT; ++i) cudaEventCreate(&h->ev[i]);
+  *out = h;
+  return PMK_OK;
+}
+
+void pmk_destroy(pmk_handle* h) {
+  if (!h) return;
+  cudaSetDevice(h->device);
+  cudaStreamSynchronize(h->stream);
+  DBuf* bufs[] = {&h->d_n, &h->d_npad, &h->d_xoff, &h->d_loff, &h->d_ioff, &h->d_xs, &h->d_y, &h->d_alpha, &h->d_L, &h->d_Linv,
+                  &h->d_info, &h->d_order, &h->d_leafoff, &h->d_Xin, &h->d_yin, &h->d_hv, &h->d_hc, &h->d_Xq, &h->d_home,
+                  &h->d_npairs, &h->d_pair_off, &h->d_Yq, &h->d_Vq, &h->d_pair_leaf, &h->d_pair_q, &h->d_pair_hp, &h->d_pair_t,
+                  &h->d_pair_w, &h->d_pair_u, &h->d_pair_v, &h->d_sorted_pair, &h->d_keys_out, &h->d_iota, &h->d_leaf_count,
+                  &h->d_leaf_pair_start, &h->d_cub, &h->d_scratch};
+  for (DBuf* b : bufs) b->release();
+  for (int c = 0; c < 3; ++c) {
+    h->d_class_leaves[c].release();
+    h->d_class_tiles[c].release();
+    h->d_tile_off[c].release();
+  }
+  for (int i = 0; i < 2 * PMK_T_COUNT; ++i)
+    if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+  cudaStreamDestroy(h->stream);
+  delete h;
+}
+
+void* pmk_stream(pmk_handle* h) { return h ? (void*)h->stream : nullptr; }
+
+int pmk_synchronize(pmk_handle* h) {
+  if (!h) return PMK_ERR_ARG;
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int64_t pmk_launch_count(const pmk_handle* h) { return h ? h->launches : 0; }
+
+int pmk_get_timings(pmk_handle* h, double* ms) {
+  if (!h || !ms) return PMK_ERR_ARG;
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int s = 0; s < PMK_T_COUNT; ++s) {
+    if (h->ev_used[s]) {
+      float t = 0.f;
+      if (cudaEventElapsedTime(&t, h->ev[2 * s], h->ev[2 * s + 1]) == cudaSuccess) h->ms[s] = t;
+    }
+    ms[s] = h->ms[s];
+  }
+  return PMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Gram
+static int gram_impl(pmk_handle* h, int D, int64_t n, const double* X, int64_t m, const double* Z, int kernel_id,
+                     const double* kparams, int nparams, double sigma2, double* K_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (D < 1 || D > PMK_MAX_DIM) return fail(h, PMK_ERR_UNSUPPORTED, "D=%d unsupported (1..%d)", D, PMK_MAX_DIM);
+  if (n < 0 || m < 0 || n > INT32_MAX || m > INT32_MAX) return fail(h, PMK_ERR_ARG, "bad sizes n=%lld m=%lld", (long long)n, (long long)m);
+  if (n == 0 || m == 0) return PMK_OK;
+  if (!X || !K_out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  KParams kp;
+  if (int rc = parse_kernel(h, kernel_id, kparams, nparams, &kp)) return rc;
+  const bool sym = (Z == nullptr);
+  const int64_t sx = (n + 127) / 128 * 128, sz = (m + 127) / 128 * 128;
+  const size_t need = (size_t)(D * (n + (sym ? 0 : m)) + D * (sx + (sym ? 0 : sz)) + n * m) * sizeof(double);
+  CU(h, h->d_scratch.ensure(need));
+  double* dXa = h->d_scratch.as<double>();
+  double* dZa = dXa + D * n;
+  double* xs = dZa + (sym ? 0 : D * m);
+  double* zs = xs + D * sx;
+  double* dK = zs + (sym ? 0 : D * sz);
+  CU(h, cudaMemcpyAsync(dXa, X, sizeof(double) * D * n, cudaMemcpyHostToDevice, h->stream));
+  launch_aos_to_soa(D, dXa, n, sx, xs, h->stream);
+  KCHECK(h, "k_aos_to_soa");
+  if (!sym) {
+    CU(h, cudaMemcpyAsync(dZa, Z, sizeof(double) * D * m, cudaMemcpyHostToDevice, h->stream));
+    launch_aos_to_soa(D, dZa, m, sz, zs, h->stream);
+    KCHECK(h, "k_aos_to_soa");
+  }
+  {
+    Timer t(h, PMK_T_GRAM);
+    launch_gram(D, xs, sx, (int)n, sym ? xs : zs, sym ? sx : sz, (int)m, kp, sigma2, sym ? 1 : 0, dK, h->stream);
+  }
+  KCHECK(h, "k_gram");
+  CU(h, cudaMemcpyAsync(K_out, dK, sizeof(double) * n * m, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_gram(pmk_handle* h, int D, int64_t n, const double* X, int kernel_id, const double* kparams, int nparams,
+             double sigma2, double* K_out) {
+  return gram_impl(h, D, n, X, n, nullptr, kernel_id, kparams, nparams, sigma2, K_out);
+}
+
+int pmk_cross_gram(pmk_handle* h, int D, int64_t n, const double* X, int64_t m, const double* Z, int kernel_id,
+                   const double* kparams, int nparams, double* K_out) {
+  if (!Z && m > 0) return fail(h, PMK_ERR_ARG, "Z is NULL");
+  return gram_impl(h, D, n, X, m, Z, kernel_id, kparams, nparams, 0.0, K_out);
+}
+
+// ---------------------------------------------------------------------------------------------
+// fit
+int pmk_set_leaf_base(pmk_handle* h, int64_t leaf_base, int64_t total_leaves) {
+  if (!h) return PMK_ERR_ARG;
+  if (leaf_base < 0 || total_leaves < 1 || leaf_base >= total_leaves) return fail(h, PMK_ERR_ARG, "bad leaf_base/total_leaves");
+  h->leaf_base = leaf_base;
+  h->total_leaves = total_leaves;
+  return PMK_OK;
+}
+
+int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* dX, const double* dy,
+                int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  h->fitted = false;
+  if (bad_leaf) *bad_leaf = 0;
+  if (info) *info = 0;
+  if (D < 1 || D > PMK_MAX_DIM) return fail(h, PMK_ERR_UNSUPPORTED, "D=%d unsupported (1..%d)", D, PMK_MAX_DIM);
+  if (n_leaves < 1 || n_leaves > (1 << 24)) return fail(h, PMK_ERR_ARG, "n_leaves=%lld out of range", (long long)n_leaves);
+  if (!leaf_off || !dX || !dy) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  KParams kp;
+  if (int rc = parse_kernel(h, kernel_id, kparams, nparams, &kp)) return rc;
+  if (leaf_off[0] != 0) return fail(h, PMK_ERR_ARG, "leaf_off[0] must be 0");
+  // host-side layout of the padded leaves
+  h->h_n.assign(n_leaves, 0);
+  h->h_npad.assign(n_leaves, 0);
+  h->h_xoff.assign(n_leaves, 0);
+  h->h_loff.assign(n_leaves, 0);
+  h->h_ioff.assign(n_leaves, 0);
+  int64_t xo = 0, lo = 0, io = 0;
+  int max_npad = 0;
+  for (int64_t p = 0; p < n_leaves; ++p) {
+    const int64_t np = leaf_off[p + 1] - leaf_off[p];
+    if (np < 1) return fail(h, PMK_ERR_ARG, "leaf %lld is empty (the reference asserts !isempty(X), RKHS.jl:199)", (long long)(p + 1));
+    if (np > PMK_MAX_LEAF_POINTS)
+      return fail(h, PMK_ERR_UNSUPPORTED, "leaf %lld has %lld points (> %d)", (long long)(p + 1), (long long)np, PMK_MAX_LEAF_POINTS);
+    const int npad = (int)((np + 31) / 32 * 32);
+    h->h_n[p] = (int)np;
+    h->h_npad[p] = npad;
+    h->h_xoff[p] = xo;
+    h->h_loff[p] = lo;
+    h->h_ioff[p] = io;
+    xo += npad;
+    lo += (int64_t)ltile_doubles(npad);
+    io += (int64_t)(npad / 32) * kInvDoublesPerBlock;
+    max_npad = std::max(max_npad, npad);
+  }
+  const int64_t total_pts = leaf_off[n_leaves];
+  h->xstride = xo + 256;   // slack: the Gram kernel's TMA tiles may read past the last leaf
+  h->max_npad = max_npad;
+  h->D = D;
+  h->n_leaves = n_leaves;
+  if (h->total_leaves == 0 || h->leaf_base + n_leaves > h->total_leaves) {
+    h->total_leaves = h->leaf_base + n_leaves;
+  }
+  h->kp = kp;
+  h->sigma2 = sigma2;
+
+  CU(h, h->d_n.ensure(sizeof(int) * n_leaves));
+  CU(h, h->d_npad.ensure(sizeof(int) * n_leaves));
+  CU(h, h->d_xoff.ensure(sizeof(int64_t) * n_leaves));
+  CU(h, h->d_loff.ensure(sizeof(int64_t) * n_leaves));
+  CU(h, h->d_ioff.ensure(sizeof(int64_t) * n_leaves));
+  CU(h, h->d_info.ensure(sizeof(int) * n_leaves));
+  CU(h, h->d_order.ensure(sizeof(int) * n_leaves));
+  CU(h, h->d_leafoff.ensure(sizeof(int64_t) * (n_leaves + 1)));
+  CU(h, h->d_xs.ensure(sizeof(double) * h->xstride * D));
+  CU(h, h->d_y.ensure(sizeof(double) * h->xstride));
+  CU(h, h->d_alpha.ensure(sizeof(double) * h->xstride));
+  CU(h, h->d_L.ensure(sizeof(double) * (size_t)lo));
+  CU(h, h->d_Linv.ensure(sizeof(double) * (size_t)io));
+  (void)total_pts;
+
+  // LPT order: largest leaves first
+  std::vector<int> order(n_leaves);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->h_npad[a] > h->h_npad[b]; });
+  // query size classes
+  std::vector<int> cls[3];
+  for (int64_t p = 0; p < n_leaves; ++p) cls[query_class_of(h->h_npad[p])].push_back((int)p);
+  for (int c = 0; c < 3; ++c) {
+    h->n_class[c] = (int)cls[c].size();
+    if (!cls[c].empty()) {
+      CU(h, h->d_class_leaves[c].ensure(sizeof(int) * cls[c].size()));
+      CU(h, h->d_class_tiles[c].ensure(sizeof(int32_t) * cls[c].size()));
+      CU(h, h->d_tile_off[c].ensure(sizeof(int64_t) * (cls[c].size() + 1)));
+      CU(h, cudaMemcpyAsync(h->d_class_leaves[c].p, cls[c].data(), sizeof(int) * cls[c].size(), cudaMemcpyHostToDevice, h->stream));
+    }
+  }
+  CU(h, cudaMemcpyAsync(h->d_n.p, h->h_n.data(), sizeof(int) * n_leaves, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_npad.p, h->h_npad.data(), sizeof(int) * n_leaves, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_xoff.p, h->h_xoff.data(), sizeof(int64_t) * n_leaves, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_loff.p, h->h_loff.data(), sizeof(int64_t) * n_leaves, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_ioff.p, h->h_ioff.data(), sizeof(int64_t) * n_leaves, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_order.p, order.data(), sizeof(int) * n_leaves, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_leafoff.p, leaf_off, sizeof(int64_t) * (n_leaves + 1), cudaMemcpyHostToDevice, h->stream));
+  // the host vectors above are pageable: the async copies have completed staging on return, but
+  // `order`/`cls` die at scope exit, so drain the stream before that.
+  CU(h, cudaStreamSynchronize(h->stream));
+
+  LeafTable& lt = h->lt;
+  lt.n_leaves = (int)n_leaves;
+  lt.n = h->d_n.as<int>();
+  lt.npad = h->d_npad.as<int>();
+  lt.xoff = h->d_xoff.as<int64_t>();
+  lt.loff = h->d_loff.as<int64_t>();
+  lt.ioff = h->d_ioff.as<int64_t>();
+  lt.xs = h->d_xs.as<double>();
+  lt.xstride = h->xstride;
+  lt.y = h->d_y.as<double>();
+  lt.alpha = h->d_alpha.as<double>();
+  lt.L = h->d_L.as<double>();
+  lt.Linv = h->d_Linv.as<double>();
+  lt.info = h->d_info.as<int>();
+
+  {
+    Timer t(h, PMK_T_FIT_PACK);
+    launch_pack(D, lt, h->d_leafoff.as<int64_t>(), dX, dy, h->stream);
+  }
+  KCHECK(h, "k_pack_leaves");
+  {
+    Timer t(h, PMK_T_FIT_CHOL);
+    launch_chol(D, lt, h->d_order.as<int>(), kp, sigma2, h->stream);
+  }
+  KCHECK(h, "k_chol");
+  {
+    Timer t(h, PMK_T_FIT_SOLVE);
+    launch_solve(lt, h->d_order.as<int>(), max_npad, h->stream);
+  }
+  KCHECK(h, "k_solve_alpha");
+  // status: first failing leaf
+  std::vector<int> h_info(n_leaves);
+  CU(h, cudaMemcpyAsync(h_info.data(), h->d_info.p, sizeof(int) * n_leaves, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int64_t p = 0; p < n_leaves; ++p) {
+    if (h_info[p] != 0) {
+      if (bad_leaf) *bad_leaf = h->leaf_base + p + 1;
+      if (info) *info = h_info[p];
+      return fail(h, PMK_ERR_NOT_POSDEF, "leaf %lld: K + sigma2*I is not positive definite (info=%d)",
+                  (long long)(h->leaf_base + p + 1), h_info[p]);
+    }
+  }
+  h->fitted = true;
+  h->plan_valid = false;
+  return PMK_OK;
+}
+
+int pmk_fit(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X, const double* y, int kernel_id,
+            const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!leaf_off || !X || !y || n_leaves < 1) return fail(h, PMK_ERR_ARG, "NULL pointer or n_leaves < 1");
+  if (D < 1 || D > PMK_MAX_DIM) return fail(h, PMK_ERR_UNSUPPORTED, "D=%d unsupported (1..%d)", D, PMK_MAX_DIM);
+  const int64_t total = leaf_off[n_leaves];
+  if (total < 1) return fail(h, PMK_ERR_ARG, "no training points");
+  CU(h, h->d_Xin.ensure(sizeof(double) * total * D));
+  CU(h, h->d_yin.ensure(sizeof(double) * total));
+  CU(h, cudaMemcpyAsync(h->d_Xin.p, X, sizeof(double) * total * D, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->d_yin.p, y, sizeof(double) * total, cudaMemcpyHostToDevice, h->stream));
+  return pmk_fit_dev(h, D, n_leaves, leaf_off, h->d_Xin.as<double>(), h->d_yin.as<double>(), kernel_id, kparams, nparams, sigma2,
+                     bad_leaf, info);
+}
+
+static int check_leaf(pmk_handle* h, int64_t leaf, int64_t* local) {
+  if (!h) return PMK_ERR_ARG;
+  if (!h->fitted) return fail(h, PMK_ERR_STATE, "model is not fitted");
+  const int64_t p = leaf - 1 - h->leaf_base;
+  if (p < 0 || p >= h->n_leaves) return fail(h, PMK_ERR_ARG, "leaf %lld not owned by this handle", (long long)leaf);
+  *local = p;
+  return PMK_OK;
+}
+
+int pmk_leaf_size(pmk_handle* h, int64_t leaf, int64_t* n_out) {
+  int64_t p;
+  if (int rc = check_leaf(h, leaf, &p)) return rc;
+  if (n_out) *n_out = h->h_n[p];
+  return PMK_OK;
+}
+
+int pmk_get_alpha(pmk_handle* h, int64_t leaf, double* out) {
+  int64_t p;
+  if (int rc = check_leaf(h, leaf, &p)) return rc;
+  if (!out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (int rc = set_device(h)) return rc;
+  CU(h, cudaMemcpyAsync(out, h->d_alpha.as<double>() + h->h_xoff[p], sizeof(double) * h->h_n[p], cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_get_L(pmk_handle* h, int64_t leaf, double* out) {
+  int64_t p;
+  if (int rc = check_leaf(h, leaf, &p)) return rc;
+  if (!out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (int rc = set_device(h)) return rc;
+  const int n = h->h_n[p];
+  CU(h, h->d_scratch.ensure(sizeof(double) * (size_t)n * n));
+  launch_unpack_L(h->lt, (int)p, n, h->d_scratch.as<double>(), h->stream);
+  KCHECK(h, "k_unpack_L");
+  CU(h, cudaMemcpyAsync(out, h->d_scratch.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_get_K(pmk_handle* h, int64_t leaf, double* out) {
+  int64_t p;
+  if (int rc = check_leaf(h, leaf, &p)) return rc;
+  if (!out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (int rc = set_device(h)) return rc;
+  const int n = h->h_n[p];
+  CU(h, h->d_scratch.ensure(sizeof(double) * (size_t)n * n));
+  const double* xs = h->d_xs.as<double>() + h->h_xoff[p];
+  {
+    Timer t(h, PMK_T_GRAM);
+    launch_gram(h->D, xs, h->xstride, n, xs, h->xstride, n, h->kp, 0.0, 1, h->d_scratch.as<double>(), h->stream);
+  }
+  KCHECK(h, "k_gram");
+  CU(h, cudaMemcpyAsync(out, h->d_scratch.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// tree
+int pmk_set_tree(pmk_handle* h, int D, int levels, const double* hp_v, const double* hp_c) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (D < 1 || D > PMK_MAX_DIM) return fail(h, PMK_ERR_UNSUPPORTED, "D=%d unsupported", D);
+  if (levels < 1 || levels > 25) return fail(h, PMK_ERR_ARG, "levels=%d out of range [1,25]", levels);
+  const int n_hp = (1 << (levels - 1)) - 1;
+  if (n_hp > 0 && (!hp_v || !hp_c)) return fail(h, PMK_ERR_ARG, "NULL hyperplane arrays");
+  h->tree_D = D;
+  h->levels = levels;
+  h->n_hp = n_hp;
+  if (n_hp > 0) {
+    std::vector<double> soa((size_t)D * n_hp);
+    for (int k = 0; k < n_hp; ++k)
+      for (int d = 0; d < D; ++d) soa[(size_t)d * n_hp + k] = hp_v[(size_t)k * D + d];
+    CU(h, h->d_hv.ensure(sizeof(double) * soa.size()));
+    CU(h, h->d_hc.ensure(sizeof(double) * n_hp));
+    CU(h, cudaMemcpyAsync(h->d_hv.p, soa.data(), sizeof(double) * soa.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_hc.p, hp_c, sizeof(double) * n_hp, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  h->tree.levels = levels;
+  h->tree.n_hp = n_hp;
+  h->tree.hv = h->d_hv.as<double>();
+  h->tree.hc = h->d_hc.as<double>();
+  h->tree_set = true;
+  h->plan_valid = false;
+  return PMK_OK;
+}
+
+int pmk_find_partition(pmk_handle* h, int64_t Nq, const double* Xq, int32_t* leaf_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->tree_set) return fail(h, PMK_ERR_STATE, "pmk_set_tree has not been called");
+  if (Nq < 0) return fail(h, PMK_ERR_ARG, "Nq < 0");
+  if (Nq == 0) return PMK_OK;
+  if (!Xq || !leaf_out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const int D = h->tree_D;
+  CU(h, h->d_Xq.ensure(sizeof(double) * Nq * D));
+  CU(h, h->d_home.ensure(sizeof(int32_t) * Nq));
+  CU(h, cudaMemcpyAsync(h->d_Xq.p, Xq, sizeof(double) * Nq * D, cudaMemcpyHostToDevice, h->stream));
+  launch_home(D, h->tree, Nq, h->d_Xq.as<double>(), h->d_home.as<int32_t>(), h->stream);
+  KCHECK(h, "k_home");
+  CU(h, cudaMemcpyAsync(leaf_out, h->d_home.p, sizeof(int32_t) * Nq, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->plan_valid = false;
+  return PMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// query
+int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radius, double delta, int wkernel_id,
+                       const double* wparams, int nw, int64_t* n_pairs_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  h->plan_valid = false;
+  if (!h->fitted) return fail(h, PMK_ERR_STATE, "query before fit");
+  if (!h->tree_set) return fail(h, PMK_ERR_STATE, "query before pmk_set_tree");
+  if (h->tree_D != h->D) return fail(h, PMK_ERR_ARG, "tree dimension %d != model dimension %d", h->tree_D, h->D);
+  if ((int64_t)(h->n_hp + 1) != h->total_leaves)
+    return fail(h, PMK_ERR_ARG, "tree has %d leaves but the model has %lld (length(hps) == length(X_parts)-1)", h->n_hp + 1,
+                (long long)h->total_leaves);
+  if (Nq < 1 || Nq > INT32_MAX) return fail(h, PMK_ERR_ARG, "Nq=%lld out of range (the reference asserts !isempty(Xq))", (long long)Nq);
+  if (!dXq) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  KParams wk;
+  if (int rc = parse_kernel(h, wkernel_id, wparams, nw, &wk)) return rc;
+  if (h->n_hp > 0 && !is_stationary_host(wk.kind))
+    return fail(h, PMK_ERR_ARG, "weight kernel must be stationary (evalkernel(abs(t), weight_theta), mixtureGP.jl:231)");
+  const int D = h->D;
+  const int64_t TL = h->total_leaves;
+  CU(h, h->d_home.ensure(sizeof(int32_t) * Nq));
+  CU(h, h->d_npairs.ensure(sizeof(int32_t) * (Nq + 1)));
+  CU(h, h->d_pair_off.ensure(sizeof(int64_t) * (Nq + 1)));
+  CU(h, h->d_leaf_count.ensure(sizeof(int32_t) * TL));
+  CU(h, h->d_leaf_pair_start.ensure(sizeof(int64_t) * (TL + 1)));
+
+  QueryPlan& q = h->plan;
+  q.Nq = Nq;
+  q.Xq = dXq;
+  q.home = h->d_home.as<int32_t>();
+  q.npairs = h->d_npairs.as<int32_t>();
+  q.pair_off = h->d_pair_off.as<int64_t>();
+
+  Timer tt(h, PMK_T_Q_TREE);
+  launch_home(D, h->tree, Nq, dXq, q.home, h->stream);
+  KCHECK(h, "k_home");
+  CU(h, cudaMemsetAsync(h->d_npairs.as<int32_t>() + Nq, 0, sizeof(int32_t), h->stream));
+  CU(h, cudaMemsetAsync(h->d_leaf_count.p, 0, sizeof(int32_t) * TL, h->stream));
+  launch_neighbours(D, false, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(), h->stream);
+  KCHECK(h, "k_neighbours<count>");
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveScan((void*)nullptr, tb, q.npairs, q.pair_off, cub::Sum(), (int64_t)0, (int)(Nq + 1), h->stream);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceScan::ExclusiveScan(h->d_cub.p, tb, q.npairs, q.pair_off, cub::Sum(), (int64_t)0, (int)(Nq + 1), h->stream));
+  }
+  int64_t n_pairs = 0;
+  CU(h, cudaMemcpyAsync(&n_pairs, q.pair_off + Nq, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (n_pairs < Nq || n_pairs > INT32_MAX) return fail(h, PMK_ERR_UNSUPPORTED, "pair count %lld out of range", (long long)n_pairs);
+  q.n_pairs = n_pairs;
+  CU(h, h->d_pair_leaf.ensure(sizeof(int32_t) * n_pairs));
+  CU(h, h->d_pair_q.ensure(sizeof(int32_t) * n_pairs));
+  CU(h, h->d_pair_hp.ensure(sizeof(int32_t) * n_pairs));
+  CU(h, h->d_pair_t.ensure(sizeof(double) * n_pairs));
+  CU(h, h->d_pair_w.ensure(sizeof(double) * n_pairs));
+  CU(h, h->d_sorted_pair.ensure(sizeof(int32_t) * n_pairs));
+  CU(h, h->d_keys_out.ensure(sizeof(int32_t) * n_pairs));
+  q.pair_leaf = h->d_pair_leaf.as<int32_t>();
+  q.pair_q = h->d_pair_q.as<int32_t>();
+  q.pair_hp = h->d_pair_hp.as<int32_t>();
+  q.pair_t = h->d_pair_t.as<double>();
+  q.pair_w = h->d_pair_w.as<double>();
+  launch_neighbours(D, true, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(), h->stream);
+  KCHECK(h, "k_neighbours<fill>");
+  launch_scan_small(h->d_leaf_count.as<int32_t>(), h->d_leaf_pair_start.as<int64_t>(), (int)TL, h->stream);
+  KCHECK(h, "k_scan_small");
+  // stable sort of pair ids by leaf
+  {
+    if (h->d_iota.cap < sizeof(int32_t) * (size_t)n_pairs) {
+      CU(h, h->d_iota.ensure(sizeof(int32_t) * n_pairs));
+      std::vector<int32_t> iota((size_t)(h->d_iota.cap / sizeof(int32_t)));
+      std::iota(iota.begin(), iota.end(), 0);
+      CU(h, cudaMemcpyAsync(h->d_iota.p, iota.data(), sizeof(int32_t) * iota.size(), cudaMemcpyHostToDevice, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+    }
+    int end_bit = 1;
+    while ((1ll << end_bit) <= TL) ++end_bit;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, q.pair_leaf, h->d_keys_out.as<int32_t>(), h->d_iota.as<int32_t>(),
+                                    h->d_sorted_pair.as<int32_t>(), (int)n_pairs, 0, end_bit, h->stream);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, q.pair_leaf, h->d_keys_out.as<int32_t>(), h->d_iota.as<int32_t>(),
+                                          h->d_sorted_pair.as<int32_t>(), (int)n_pairs, 0, end_bit, h->stream));
+  }
+  if (n_pairs_out) *n_pairs_out = n_pairs;
+  h->plan_valid = true;
+  return PMK_OK;
+}
+
+int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pair_v) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
+  if (!d_pair_u || !d_pair_v) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const QueryPlan& q = h->plan;
+  const int mean_only = flags & 1;
+  h->last_flags = flags;
+  Timer tt(h, PMK_T_Q_PAIRS);
+  if (h->n_leaves != h->total_leaves) {
+    CU(h, cudaMemsetAsync(d_pair_u, 0, sizeof(double) * q.n_pairs, h->stream));
+    CU(h, cudaMemsetAsync(d_pair_v, 0, sizeof(double) * q.n_pairs, h->stream));
+  }
+  for (int c = 0; c < 3; ++c) {
+    if (h->n_class[c] == 0) continue;
+    PairWork w;
+    w.class_leaves = h->d_class_leaves[c].as<int>();
+    w.n_class_leaves = h->n_class[c];
+    w.tile_off = h->d_tile_off[c].as<int64_t>();
+    w.leaf_pair_start = h->d_leaf_pair_start.as<int64_t>();
+    w.sorted_pair = h->d_sorted_pair.as<int32_t>();
+    w.leaf_base = h->leaf_base;
+    const int mq = query_class_mq(c);
+    launch_class_tiles(w, mq, h->d_class_tiles[c].as<int32_t>(), h->stream);
+    KCHECK(h, "k_class_tiles");
+    launch_scan_small(h->d_class_tiles[c].as<int32_t>(), h->d_tile_off[c].as<int64_t>(), h->n_class[c], h->stream);
+    KCHECK(h, "k_scan_small");
+    // upper bound on the tile count without a host round trip: excess CTAs exit at once
+    const int64_t ub = q.n_pairs / mq + h->n_class[c];
+    launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
+    KCHECK(h, "k_query_pairs");
+  }
+  return PMK_OK;
+}
+
+int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d_pair_v, double* dYq, double* dVq) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
+  const int mean_only = h->last_flags & 1;
+  if (!d_pair_u || !dYq || (!mean_only && (!d_pair_v || !dVq))) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const QueryPlan& q = h->plan;
+  Timer tt(h, PMK_T_Q_COMBINE);
+  launch_combine(q.Nq, q.pair_off, q.pair_w, d_pair_u, d_pair_v, dYq, dVq, mean_only, h->stream);
+  KCHECK(h, "k_combine");
+  return PMK_OK;
+}
+
+int pmk_query_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radius, double delta, int wkernel_id,
+                  const double* wparams, int nw, int flags, double* dYq, double* dVq) {
+  if (!h) return PMK_ERR_ARG;
+  int64_t np = 0;
+  if (int rc = pmk_query_plan_dev(h, Nq, dXq, radius, delta, wkernel_id, wparams, nw, &np)) return rc;
+  CU(h, h->d_pair_u.ensure(sizeof(double) * np));
+  CU(h, h->d_pair_v.ensure(sizeof(double) * np));
+  if (int rc = pmk_query_pairs_dev(h, flags, h->d_pair_u.as<double>(), h->d_pair_v.as<double>())) return rc;
+  return pmk_query_combine_dev(h, h->d_pair_u.as<double>(), h->d_pair_v.as<double>(), dYq, dVq);
+}
+
+int pmk_query(pmk_handle* h, int64_t Nq, const double* Xq, double radius, double delta, int wkernel_id, const double* wparams,
+              int nw, int flags, double* Yq, double* Vq) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->fitted) return fail(h, PMK_ERR_STATE, "query before fit");
+  if (Nq < 1) return fail(h, PMK_ERR_ARG, "Nq < 1 (the reference asserts !isempty(Xq))");
+  const int mean_only = flags & 1;
+  if (!Xq || !Yq || (!mean_only && !Vq)) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const int D = h->D;
+  CU(h, h->d_Xq.ensure(sizeof(double) * Nq * D));
+  CU(h, h->d_Yq.ensure(sizeof(double) * Nq));
+  CU(h, h->d_Vq.ensure(sizeof(double) * Nq));
+  CU(h, cudaMemcpyAsync(h->d_Xq.p, Xq, sizeof(double) * Nq * D, cudaMemcpyHostToDevice, h->stream));
+  if (int rc = pmk_query_dev(h, Nq, h->d_Xq.as<double>(), radius, delta, wkernel_id, wparams, nw, flags, h->d_Yq.as<double>(),
+                             h->d_Vq.as<double>()))
+    return rc;
+  CU(h, cudaMemcpyAsync(Yq, h->d_Yq.p, sizeof(double) * Nq, cudaMemcpyDeviceToHost, h->stream));
+  if (!mean_only) CU(h, cudaMemcpyAsync(Vq, h->d_Vq.p, sizeof(double) * Nq, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_last_query_pairs(pmk_handle* h, int64_t* n_pairs) {
+  if (!h) return PMK_ERR_ARG;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "no query plan");
+  if (n_pairs) *n_pairs = h->plan.n_pairs;
+  return PMK_OK;
+}
+
+int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_t* pair_leaf, int32_t* pair_hp, double* pair_t,
+                         double* pair_w, double* pair_u, double* pair_v) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "no query plan");
+  const QueryPlan& q = h->plan;
+  const int64_t np = q.n_pairs;
+  cudaStream_t s = h->stream;
+  if (home) CU(h, cudaMemcpyAsync(home, q.home, sizeof(int32_t) * q.Nq, cudaMemcpyDeviceToHost, s));
+  if (pair_off) CU(h, cudaMemcpyAsync(pair_off, q.pair_off, sizeof(int64_t) * (q.Nq + 1), cudaMemcpyDeviceToHost, s));
+  if (pair_leaf) CU(h, cudaMemcpyAsync(pair_leaf, q.pair_leaf, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, s));
+  if (pair_hp) CU(h, cudaMemcpyAsync(pair_hp, q.pair_hp, sizeof(int32_t) * np, cudaMemcpyDeviceToHost, s));
+  if (pair_t) CU(h, cudaMemcpyAsync(pair_t, q.pair_t, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+  if (pair_w) CU(h, cudaMemcpyAsync(pair_w, q.pair_w, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+  if (pair_u) {
+    if (!h->d_pair_u.p) return fail(h, PMK_ERR_STATE, "pair_u is caller-owned in the split (multi-GPU) query");
+    CU(h, cudaMemcpyAsync(pair_u, h->d_pair_u.p, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+  }
+  if (pair_v) {
+    if (!h->d_pair_v.p) return fail(h, PMK_ERR_STATE, "pair_v is caller-owned in the split (multi-GPU) query");
+    CU(h, cudaMemcpyAsync(pair_v, h->d_pair_v.p, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
+  }
+  CU(h, cudaStreamSynchronize(s));
+  return PMK_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,185 @@
+// Shared device helpers of libpmk_b200: kernel-function evaluation (bit-faithful to the
+// reference's operation order wherever a comparison or a parity check depends on it),
+// the FP64 tensor-core wrapper (mma.sync.m8n8k4.f64 -> SASS DMMA.8x8x4; tcgen05 has no f64
+// kind, so this is the FP64 MMA path sm_100a exposes) and the packed-tile layout of L.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "../../include/pmk.h"
+
+namespace pmk {
+
+struct KParams {
+  int kind;     // pmk_kernel_id
+  double p;     // eps_sq / a / eps
+};
+
+// ---------------------------------------------------------------------------------------
+// DMMA 8x8x4: D(8x8) += A(8x4) * B(4x8), FP64.  Fragment layout (verified on B200 by
+// tools/fp64_peak.cu):  A: lane holds A[lane>>2][lane&3];  B: lane holds B[lane&3][lane>>2];
+// C/D: lane holds C[lane>>2][2*(lane&3)+{0,1}].
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------
+// Packed storage of a leaf's lower-triangular factor L (n_pad x n_pad, n_pad % 32 == 0).
+// 8x8 tiles, row-tile-major, lower tiles only: tile (t, c), c <= t, sits at tile index
+// t(t+1)/2 + c.  Inside a tile the 64 doubles are stored "fragment-major": lane l of a warp
+// owns the double2 {M[l>>2][l&3], M[l>>2][4+(l&3)]} = its A-fragment for two consecutive
+// DMMA k-steps (and, because the SYRK/TRSM second operand is a transposed row block of L,
+// also its B-fragment).  One LDG.128 per lane = one fully coalesced 512-byte tile.
+// ---------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ size_t tri(int t) { return (size_t)t * (size_t)(t + 1) / 2; }
+// index in DOUBLES of element (r, c), r >= c (or same diagonal tile), within the leaf's storage
+__host__ __device__ __forceinline__ size_t ltile_elem(int r, int c) {
+  int t = r >> 3, ct = c >> 3, ri = r & 7, ci = c & 7;
+  return ((tri(t) + ct) * 32 + ri * 4 + (ci & 3)) * 2 + (ci >> 2);
+}
+// doubles needed for an n_pad x n_pad packed lower factor
+__host__ __device__ __forceinline__ size_t ltile_doubles(int npad) { return tri(npad >> 3) * 64; }
+// inverse diagonal blocks: per 32-row block, 10 lower tiles (a >= b) at a(a+1)/2 + b
+static constexpr int kInvTilesPerBlock = 10;
+static constexpr int kInvDoublesPerBlock = kInvTilesPerBlock * 64;
+
+// ---------------------------------------------------------------------------------------
+// kernel functions.  Products/sums that the oracle performs as separate IEEE operations
+// are written with __dmul_rn/__dadd_rn so nvcc cannot contract them into FMAs.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double k_tau(int kind, double a, double tau) {
+  switch (kind) {
+    case PMK_KERNEL_SQEXP:                                   // kernel.jl:350-357
+      return exp(__dmul_rn(-a, __dmul_rn(tau, tau)));
+    case PMK_KERNEL_SPLINE34: {                              // kernel.jl:299-313
+      double r = __dmul_rn(tau, a);
+      double t = __dsub_rn(1.0, r);
+      if (t < 0.0) return 0.0;
+      double t2 = __dmul_rn(t, t), t4 = __dmul_rn(t2, t2), t6 = __dmul_rn(t4, t2);
+      double poly = __dadd_rn(__dadd_rn(__dmul_rn(35.0, __dmul_rn(r, r)), __dmul_rn(18.0, r)), 3.0);
+      return __ddiv_rn(__dmul_rn(poly, t6), 3.0);
+    }
+    case PMK_KERNEL_SPLINE12: {                              // kernel.jl:316-330
+      double r = __dmul_rn(tau, a);
+      double t = __dsub_rn(1.0, r);
+      if (t < 0.0) return 0.0;
+      double t3 = __dmul_rn(__dmul_rn(t, t), t);
+      return __dmul_rn(__dadd_rn(__dmul_rn(3.0, r), 1.0), t3);
+    }
+    case PMK_KERNEL_SPLINE32: {                              // kernel.jl:333-347
+      double r = __dmul_rn(tau, a);
+      double t = __dsub_rn(1.0, r);
+      if (t < 0.0) return 0.0;
+      double t2 = __dmul_rn(t, t), t4 = __dmul_rn(t2, t2);
+      return __dmul_rn(__dadd_rn(__dmul_rn(4.0, r), 1.0), t4);
+    }
+    case PMK_KERNEL_RQ: {                                    // kernel.jl:360-366
+      double sa = __dsqrt_rn(a);
+      double sd = __dsqrt_rn(__dadd_rn(a, __dmul_rn(tau, tau)));
+      double num = __dmul_rn(__dmul_rn(sa, sa), sa);
+      double den = __dmul_rn(__dmul_rn(sd, sd), sd);
+      return __ddiv_rn(num, den);
+    }
+    default:
+      return 0.0;
+  }
+}
+
+__device__ __forceinline__ double k_bb_1d(int kind, double e, double x, double z) {
+  switch (kind) {
+    case PMK_KERNEL_BB10:                                    // kernel.jl:156-158
+      return __dsub_rn(fmin(x, z), __dmul_rn(x, z));
+    case PMK_KERNEL_BB20: {                                  // kernel.jl:218-225
+      double s = __dadd_rn(__dmul_rn(x, x), __dmul_rn(z, z));
+      if (z < x)
+        return __dmul_rn(__dmul_rn(__dmul_rn(-1.0 / 6.0, z), __dsub_rn(1.0, x)), __dsub_rn(s, __dmul_rn(2.0, x)));
+      return __dmul_rn(__dmul_rn(__dmul_rn(-1.0 / 6.0, x), __dsub_rn(1.0, z)), __dsub_rn(s, __dmul_rn(2.0, z)));
+    }
+    case PMK_KERNEL_BB1EPS: {                                // kernel.jl:168-174
+      double den = e * sinh(e);
+      double num = sinh(e * fmin(x, z)) * sinh(e * (1.0 - fmax(x, z)));
+      return num / den;
+    }
+    case PMK_KERNEL_BB2EPS: {                                // kernel.jl:176-193
+      double mn = fmin(x, z), mx = fmax(x, z), ad = fabs(x - z), s = x + z;
+      double em1 = exp(2.0 * e) - 1.0;
+      double mult = exp(-e * s) / (4.0 * (e * e * e) * (em1 * em1));
+      double t1 = exp(2.0 * e) * (2.0 * e - e * s - 1.0);
+      double t2 = exp(4.0 * e) * (e * s + 1.0);
+      double t3 = exp(2.0 * e * (1.0 + s)) * (2.0 * e - e * s + 1.0);
+      double t4 = exp(2.0 * e * s) * (e * s - 1.0);
+      double t5 = exp(2.0 * e * (2.0 + mn)) * (-e * ad - 1.0);
+      double t6 = exp(2.0 * e * mx) * (-e * ad + 1.0);
+      double t7 = exp(2.0 * e * (1.0 + mn)) * (1.0 - 2.0 * e + e * ad);
+      double t8 = exp(2.0 * e * (1.0 + mx)) * (1.0 + 2.0 * e - e * ad);
+      return mult * (((((((t1 + t2) + t3) + t4) + t5) + t6) + t7) + t8);
+    }
+    default:
+      return 0.0;
+  }
+}
+
+__device__ __forceinline__ bool kernel_is_stationary(int kind) {
+  return kind == PMK_KERNEL_SQEXP || kind == PMK_KERNEL_SPLINE34 || kind == PMK_KERNEL_SPLINE12 ||
+         kind == PMK_KERNEL_SPLINE32 || kind == PMK_KERNEL_RQ;
+}
+
+// evalkernel(x, z, theta) for two D-vectors: kernel.jl:277-287 (tau = norm(x1-x2): sequential sum of
+// squares, then sqrt; tau^2 re-squared from the rounded tau), kernel.jl:196-198 (tensor product).
+template <int D>
+__device__ __forceinline__ double stationary_tau(const double* x, const double* z) {
+  const double d0 = __dsub_rn(x[0], z[0]);
+  if (D == 1) return fabs(d0);
+  double s = __dmul_rn(d0, d0);
+#pragma unroll
+  for (int d = 1; d < D; ++d) {
+    const double dd = __dsub_rn(x[d], z[d]);
+    s = __dadd_rn(s, __dmul_rn(dd, dd));
+  }
+  return __dsqrt_rn(s);
+}
+
+// every kernel except the squared exponential: out of line, so the hot kernels inline only the
+// SqExp fast path (keeps code size and register pressure of the DMMA kernels down).  Points are
+// passed by value so they travel in registers, not through local memory.
+template <int D>
+struct Pt {
+  double v[D];
+};
+
+template <int D>
+__device__ __noinline__ double eval_kernel_generic(int kind, double p, Pt<D> x, Pt<D> z) {
+  if (kernel_is_stationary(kind)) return k_tau(kind, p, stationary_tau<D>(x.v, z.v));
+  double out = k_bb_1d(kind, p, x.v[0], z.v[0]);
+#pragma unroll
+  for (int d = 1; d < D; ++d) out = __dmul_rn(out, k_bb_1d(kind, p, x.v[d], z.v[d]));
+  return out;
+}
+
+template <int D>
+__device__ __forceinline__ double eval_kernel(const KParams& kp, const double* x, const double* z) {
+  if (kp.kind == PMK_KERNEL_SQEXP) {
+    const double tau = stationary_tau<D>(x, z);
+    return exp(__dmul_rn(-kp.p, __dmul_rn(tau, tau)));       // kernel.jl:350-357
+  }
+  Pt<D> xx, zz;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    xx.v[d] = x[d];
+    zz.v[d] = z[d];
+  }
+  return eval_kernel_generic<D>(kp.kind, kp.p, xx, zz);
+}
+
+// sequential dot product, no contraction (contract of partition.jl:69,254,285 and mixtureGP.jl:361)
+template <int D>
+__device__ __forceinline__ double dot_seq(const double* v, const double* x) {
+  double s = __dmul_rn(v[0], x[0]);
+#pragma unroll
+  for (int d = 1; d < D; ++d) s = __dadd_rn(s, __dmul_rn(v[d], x[d]));
+  return s;
+}
+
+}  // namespace pmk

@@ -1,0 +1,129 @@
+// K1: standalone Gram / cross-Gram kernel.  Replaces constructkernelmatrix(X, θ)
+// (reference src/RKHS/RKHS.jl:4-34: lower triangle by evalkernel(X[i],X[j]), then mirrored) and
+// constructkernelmatrix(X, Z, θ) (RKHS.jl:95-110).  HBM-write-bound: 8 n m bytes out, points in.
+// A CTA owns a 128 x 64 tile; the tile's row/column points are staged into shared memory with
+// 1-D TMA bulk copies (cp.async.bulk -> SASS UBLKCP) completing on an mbarrier; output is written
+// column-major with 16-byte stores, 1 KB contiguous per column segment.
+// (The fit path does NOT use this kernel: k_chol evaluates the Gram entries straight into its
+//  accumulators; this one serves the public constructkernelmatrix / U_set surface.)
+#include "pmk_internal.cuh"
+
+namespace pmk {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <int D>
+__global__ void k_aos_to_soa(const double* __restrict__ X, int64_t n, int64_t stride, double* __restrict__ xs) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i >= stride) return;
+#pragma unroll
+  for (int d = 0; d < D; ++d) xs[d * stride + i] = i < n ? X[i * D + d] : 0.0;
+}
+
+static constexpr int TM = 128, TN = 64;
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_gram(const double* __restrict__ xr, int64_t xr_stride, int n, const double* __restrict__ xc, int64_t xc_stride, int m,
+       KParams kp, double sigma2, int symmetric, double* __restrict__ K) {
+  __shared__ __align__(16) double s_r[D][TM];
+  __shared__ __align__(16) double s_c[D][TN];
+  __shared__ __align__(8) uint64_t bar;
+  const int tid = threadIdx.x;
+  const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+  if (tid == 0) mbar_init(&bar, 1);
+  __syncthreads();
+  if (tid == 0) {
+    mbar_expect_tx(&bar, (uint32_t)(D * (TM + TN) * sizeof(double)));
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      tma_load_1d(&s_r[d][0], xr + d * xr_stride + i0, TM * sizeof(double), &bar);
+      tma_load_1d(&s_c[d][0], xc + d * xc_stride + j0, TN * sizeof(double), &bar);
+    }
+  }
+  mbar_wait(&bar, 0);
+
+  const int r2 = (tid & 63) * 2;
+  const int i = i0 + r2;
+  if (i >= n) return;
+  double xa[D], xb[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    xa[d] = s_r[d][r2];
+    xb[d] = s_r[d][r2 + 1];
+  }
+  const bool two = (i + 1 < n);
+  const bool vec = two && ((n & 1) == 0);
+  for (int jj = tid >> 6; jj < TN; jj += 4) {
+    const int j = j0 + jj;
+    if (j >= m) break;
+    double xz[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) xz[d] = s_c[d][jj];
+    // reference evaluates the lower triangle as evalkernel(X[i], X[j]) (i >= j) and mirrors it
+    double k0 = (symmetric && i < j) ? eval_kernel<D>(kp, xz, xa) : eval_kernel<D>(kp, xa, xz);
+    if (symmetric && i == j) k0 = __dadd_rn(k0, sigma2);
+    double k1 = 0.0;
+    if (two) {
+      k1 = (symmetric && i + 1 < j) ? eval_kernel<D>(kp, xz, xb) : eval_kernel<D>(kp, xb, xz);
+      if (symmetric && i + 1 == j) k1 = __dadd_rn(k1, sigma2);
+    }
+    double* dst = K + (int64_t)j * n + i;
+    if (vec) {
+      *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
+    } else {
+      dst[0] = k0;
+      if (two) dst[1] = k1;
+    }
+  }
+}
+
+void launch_aos_to_soa(int D, const double* dX, int64_t n, int64_t stride, double* xs, cudaStream_t s) {
+  const unsigned B = (unsigned)((stride + 255) / 256);
+  switch (D) {
+    case 1: k_aos_to_soa<1><<<B, 256, 0, s>>>(dX, n, stride, xs); break;
+    case 2: k_aos_to_soa<2><<<B, 256, 0, s>>>(dX, n, stride, xs); break;
+    case 3: k_aos_to_soa<3><<<B, 256, 0, s>>>(dX, n, stride, xs); break;
+    default: break;
+  }
+}
+
+// xr/xc must be readable up to the next multiple of TM / TN points (callers pad).
+void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double* xc, int64_t xc_stride, int m, KParams kp,
+                 double sigma2, int symmetric, double* dK, cudaStream_t s) {
+  if (n <= 0 || m <= 0) return;
+  dim3 grid((n + TM - 1) / TM, (m + TN - 1) / TN);
+  switch (D) {
+    case 1: k_gram<1><<<grid, 256, 0, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, symmetric, dK); break;
+    case 2: k_gram<2><<<grid, 256, 0, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, symmetric, dK); break;
+    case 3: k_gram<3><<<grid, 256, 0, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, symmetric, dK); break;
+    default: break;
+  }
+}
+
+}  // namespace pmk

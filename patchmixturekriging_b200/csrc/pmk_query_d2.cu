@@ -1,0 +1,8 @@
+// K3 instantiations for D = 2 (see pmk_query_impl.cuh)
+#include "pmk_query_impl.cuh"
+namespace pmk {
+void launch_pairs_d2(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
+                      int mean_only, double* pu, double* pv, cudaStream_t s) {
+  launch_pairs_d<2>(cls, grid, lt, w, q, kp, mean_only, pu, pv, s);
+}
+}  // namespace pmk

@@ -1,0 +1,238 @@
+// K3: fused per-(query, leaf) kernel -- cross-covariance k(x*, X_p), predictive mean
+// dot(k, alpha), and latent variance k(x*,x*) - ||L^-1 k||^2 -- in one pass, so k(x*, X_p) never
+// touches HBM.  Replaces queryinner! (reference src/RKHS/mixtureGP.jl:296-316) for all pairs
+// of a leaf at once (the reference does one dtrsv per pair).
+//
+// One CTA = (leaf p, tile of MQ = 8*NQT pairs binned to p).  The n_pad x MQ cross-covariance tile
+// lives in REGISTERS as DMMA accumulators for the whole kernel (row tiles dealt cyclically to the
+// warps so the shrinking triangular work stays balanced); a right-looking blocked TRSM walks the
+// 32-row blocks J:
+//     S_J = inv(L_JJ) * C_J                    (stored 32x32 inverse, DMMA; C_J via shared memory)
+//     C_I -= L_IJ * S_J   for all I > J        (DMMA; L_IJ streamed from L2/HBM as packed fragment
+//                                               tiles, one LDG.128 per lane; S_J from shared memory)
+// Only S_J (32 x MQ) ever sits in shared memory; ||s||^2 and dot(k, alpha) are reduced on the fly.
+#pragma once
+#include "pmk_internal.cuh"
+
+namespace pmk {
+
+static constexpr unsigned kFullQ = 0xffffffffu;
+
+
+template <int D, int NW, int NT, int NQT>
+__global__ void __launch_bounds__(NW * 32, 1)
+k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, double* __restrict__ pair_u,
+              double* __restrict__ pair_v) {
+  constexpr int MQ = 8 * NQT;
+  constexpr int LDQ = MQ + 4;                 // == 4 (mod 16) for MQ in {8,16,32}: conflict-free fragment loads
+  constexpr int OT = (4 * NQT + NW - 1) / NW; // diagonal-solve output tiles per warp
+  __shared__ __align__(16) double Cbuf[32 * LDQ];
+  __shared__ __align__(16) double Sbuf[32 * LDQ];
+  __shared__ double s_xq[D * MQ];
+  __shared__ int64_t s_pair[MQ];
+  __shared__ double ured[NW * MQ];
+  __shared__ double vred[4 * NQT * 8];
+
+  const int64_t tile = blockIdx.x;
+  if (tile >= w.tile_off[w.n_class_leaves]) return;
+  int lo = 0, hi = w.n_class_leaves;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (w.tile_off[mid] <= tile) lo = mid; else hi = mid;
+  }
+  const int p = w.class_leaves[lo];
+  const int64_t gleaf = w.leaf_base + p;
+  const int64_t pstart = w.leaf_pair_start[gleaf] + (tile - w.tile_off[lo]) * MQ;
+  const int64_t pend = w.leaf_pair_start[gleaf + 1];
+  const int cnt = (int)((pend - pstart) < (int64_t)MQ ? (pend - pstart) : (int64_t)MQ);
+
+  const int n = lt.n[p], npad = lt.npad[p];
+  const int nblk = npad >> 5, ntl = npad >> 3;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int g = lane >> 2, l = lane & 3;
+  const double* __restrict__ xs = lt.xs + lt.xoff[p];
+  const double* __restrict__ al = lt.alpha + lt.xoff[p];
+  const int64_t xstride = lt.xstride;
+  const double2* __restrict__ Lp = reinterpret_cast<const double2*>(lt.L + lt.loff[p]);
+  const double2* __restrict__ Ip = reinterpret_cast<const double2*>(lt.Linv + lt.ioff[p]);
+
+  if (tid < MQ) {
+    const int qi = tid < cnt ? tid : cnt - 1;
+    const int64_t gp = w.sorted_pair[pstart + qi];
+    s_pair[tid] = tid < cnt ? gp : (int64_t)-1;
+    const int64_t j = q.pair_q[gp];
+#pragma unroll
+    for (int d = 0; d < D; ++d) s_xq[d * MQ + tid] = q.Xq[j * D + d];
+  }
+  __syncthreads();
+
+  // ---- cross-covariance tile straight into the accumulators (acc = -k), mean partials ---------
+  // (query n-tile outermost so that only two query points are live at a time)
+  double acc[NT][NQT][2];
+#pragma unroll
+  for (int nt = 0; nt < NQT; ++nt) {
+    double xq0[D], xq1[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      xq0[d] = s_xq[d * MQ + nt * 8 + 2 * l];
+      xq1[d] = s_xq[d * MQ + nt * 8 + 2 * l + 1];
+    }
+    double up0 = 0.0, up1 = 0.0;
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int t = warp + NW * i;
+      const int row = 8 * t + g;
+      double k0 = 0.0, k1 = 0.0;
+      if ((t < ntl) && (row < n)) {
+        double xr[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xr[d] = xs[d * xstride + row];
+        const double a_row = al[row];
+        k0 = eval_kernel<D>(kp, xq0, xr);        // evalkernel(xq, X[i])   mixtureGP.jl:304
+        k1 = eval_kernel<D>(kp, xq1, xr);
+        up0 = fma(k0, a_row, up0);               // dot(kq, c)             mixtureGP.jl:308
+        up1 = fma(k1, a_row, up1);
+      }
+      acc[i][nt][0] = -k0;
+      acc[i][nt][1] = -k1;
+    }
+    up0 += __shfl_xor_sync(kFullQ, up0, 4);
+    up0 += __shfl_xor_sync(kFullQ, up0, 8);
+    up0 += __shfl_xor_sync(kFullQ, up0, 16);
+    up1 += __shfl_xor_sync(kFullQ, up1, 4);
+    up1 += __shfl_xor_sync(kFullQ, up1, 8);
+    up1 += __shfl_xor_sync(kFullQ, up1, 16);
+    if (g == 0) {
+      ured[warp * MQ + nt * 8 + 2 * l] = up0;
+      ured[warp * MQ + nt * 8 + 2 * l + 1] = up1;
+    }
+  }
+
+  if (mean_only) {
+    __syncthreads();
+    if (tid < cnt) {
+      double u = 0.0;
+      for (int ww = 0; ww < NW; ++ww) u += ured[ww * MQ + tid];
+      pair_u[s_pair[tid]] = u;
+    }
+    return;
+  }
+
+  // ---- right-looking blocked TRSM:  s = L^-1 k  (mixtureGP.jl:311), ||s||^2 on the fly ----------
+  double vacc[OT][2];
+#pragma unroll
+  for (int k = 0; k < OT; ++k) vacc[k][0] = vacc[k][1] = 0.0;
+
+  for (int J = 0; J < nblk; ++J) {
+    // 1. owners of block J's four row tiles publish C_J = -acc
+#pragma unroll
+    for (int i = 0; i < NT; ++i) {
+      const int t = warp + NW * i;
+      if ((t >> 2) == J) {
+        const int a = t & 3;
+#pragma unroll
+        for (int nt = 0; nt < NQT; ++nt)
+          *reinterpret_cast<double2*>(&Cbuf[(8 * a + g) * LDQ + nt * 8 + 2 * l]) =
+              make_double2(-acc[i][nt][0], -acc[i][nt][1]);
+      }
+    }
+    __syncthreads();
+    // 2. S_J = inv(L_JJ) * C_J : 4 x NQT output tiles spread over the warps
+#pragma unroll
+    for (int k = 0; k < OT; ++k) {
+      const int ot = warp + NW * k;
+      if (ot < 4 * NQT) {
+        const int a = ot / NQT, nt = ot % NQT;
+        double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
+        const double2* It = Ip + (size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          if (b <= a) {
+            const double2 f = It[b * 32];
+            const double b0 = Cbuf[(8 * b + l) * LDQ + nt * 8 + g];
+            const double b1 = Cbuf[(8 * b + 4 + l) * LDQ + nt * 8 + g];
+            dmma884(s0, s1, f.x, b0);
+            dmma884(r0, r1, f.y, b1);
+          }
+        }
+        s0 += r0;
+        s1 += r1;
+        *reinterpret_cast<double2*>(&Sbuf[(8 * a + g) * LDQ + nt * 8 + 2 * l]) = make_double2(s0, s1);
+        vacc[k][0] = fma(s0, s0, vacc[k][0]);
+        vacc[k][1] = fma(s1, s1, vacc[k][1]);
+      }
+    }
+    __syncthreads();
+    // 3. acc[I] += L_IJ * S_J for the row tiles below block J
+    if (J + 1 < nblk) {
+#pragma unroll
+      for (int ct = 0; ct < 4; ++ct) {
+        double bf[2][NQT];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks)
+#pragma unroll
+          for (int nt = 0; nt < NQT; ++nt) bf[ks][nt] = Sbuf[(8 * ct + 4 * ks + l) * LDQ + nt * 8 + g];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) {
+          const int t = warp + NW * i;
+          if (t >= 4 * J + 4 && t < ntl) {
+            const double2 af = Lp[(tri(t) + 4 * J + ct) * 32 + lane];
+#pragma unroll
+            for (int nt = 0; nt < NQT; ++nt) {
+              dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[0][nt]);
+              dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[1][nt]);
+            }
+          }
+        }
+      }
+    }
+  }
+
+  // ---- reduce ||s||^2 and finish --------------------------------------------------------------
+#pragma unroll
+  for (int k = 0; k < OT; ++k) {
+    const int ot = warp + NW * k;
+    if (ot < 4 * NQT) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        double v = vacc[k][e];
+        v += __shfl_xor_sync(kFullQ, v, 4);
+        v += __shfl_xor_sync(kFullQ, v, 8);
+        v += __shfl_xor_sync(kFullQ, v, 16);
+        if (g == 0) vred[ot * 8 + 2 * l + e] = v;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid < cnt) {
+    const int nt = tid >> 3, qi = tid & 7;
+    double vs = 0.0;
+#pragma unroll
+    for (int a = 0; a < 4; ++a) vs += vred[(a * NQT + nt) * 8 + qi];
+    double u = 0.0;
+    for (int ww = 0; ww < NW; ++ww) u += ured[ww * MQ + tid];
+    double xq[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) xq[d] = s_xq[d * MQ + tid];
+    const double kxx = eval_kernel<D>(kp, xq, xq);
+    double v = kxx - vs;                               // mixtureGP.jl:312, clamp(., 1e-12, Inf)
+    if (v < 1e-12) v = 1e-12;
+    const int64_t gp = s_pair[tid];
+    pair_u[gp] = u;
+    pair_v[gp] = v;
+  }
+}
+
+
+// one translation unit per D (pmk_query_d{1,2,3}.cu) instantiates the three size classes
+//   class 0: n_pad <=  512, MQ = 32     class 1: n_pad <= 1024, MQ = 16     class 2: n_pad <= 2048, MQ = 8
+template <int D>
+void launch_pairs_d(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
+                    int mean_only, double* pu, double* pv, cudaStream_t s) {
+  constexpr int NW = 16;
+  if (cls == 0) k_query_pairs<D, NW, 4, 4><<<grid, NW * 32, 0, s>>>(lt, w, q, kp, mean_only, pu, pv);
+  else if (cls == 1) k_query_pairs<D, NW, 8, 2><<<grid, NW * 32, 0, s>>>(lt, w, q, kp, mean_only, pu, pv);
+  else k_query_pairs<D, NW, 16, 1><<<grid, NW * 32, 0, s>>>(lt, w, q, kp, mean_only, pu, pv);
+}
+
+}  // namespace pmk

@@ -1,0 +1,211 @@
+"""Host mirror of the reference's mixture-GP layer (src/RKHS/mixtureGP.jl): same names, argument
+order and return values; the bodies call the CUDA library through the C ABI.
+
+  MixtureGPType(X_set, hps)                                 mixtureGP.jl:54-66
+  fitmixtureGP_(η, y_parts, θ, σ²) -> η                     fitmixtureGP!          :70-118
+  querymixtureGP_(Yq, Vq, Xq, η, root, levels, radius, δ, θ, σ², weight_θ, debug_vars; debug_flag)
+                                                            querymixtureGP!        :159-294
+  querymixtureGP(Xq | xq, η, root, levels, radius, δ, θ, σ², weight_θ; debug_flag) -> Yq, Vq, debug_vars
+                                                            :120-157
+  fetchhyperplanes(root)                                    :322-334 (in partition.py)
+Julia's `!` suffix is spelled `_` here.  Vector{Vector{Float64}} inputs are (n, D) arrays (or lists
+of them): a C-contiguous (n, D) array IS array2matrix(X) (utilities.jl:25-36) in column-major terms.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import Handle, PMKError, PosDefException, lib, ptr
+from .partition import BSPTree
+
+
+def _as_points(X) -> np.ndarray:
+    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+    if X.ndim == 1:
+        X = X[:, None]
+    return X
+
+
+@dataclass
+class MixtureGPDebugType:
+    """mixtureGP.jl:5-35: per-query debug outputs (filled when debug_flag=True)."""
+    w_tilde_set: List[np.ndarray] = field(default_factory=list)
+    u_set: List[np.ndarray] = field(default_factory=list)
+    v_set: List[np.ndarray] = field(default_factory=list)
+    region_inds_set: List[np.ndarray] = field(default_factory=list)
+    p_region_ind_set: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
+    # hyperplane bookkeeping: instead of Nq x n_hp dense ts/zs/keep_flags arrays (4095 per query in
+    # the 1M-point configuration) the kept hyperplane ids and their t are returned per query
+    kept_hp_set: List[np.ndarray] = field(default_factory=list)
+    t_kept_set: List[np.ndarray] = field(default_factory=list)
+    # flat CSR form of the same data
+    pair_off: Optional[np.ndarray] = None
+
+
+class _LazyLeafList:
+    """c_set / L_set / U_set of MixtureGPType: fetched from the GPU on indexing (0-based Python index)."""
+
+    def __init__(self, eta: "MixtureGPType", what: str):
+        self._eta, self._what = eta, what
+
+    def __len__(self):
+        return len(self._eta.X_parts)
+
+    def __getitem__(self, i: int) -> np.ndarray:
+        eta = self._eta
+        if not eta._fitted:
+            raise PMKError(_lib.PMK_ERR_STATE, "MixtureGPType is not fitted (Julia: UndefRefError on c_set[n])")
+        n = eta.X_parts[i].shape[0]
+        leaf = eta._leaf_base + i + 1
+        L = lib()
+        if self._what == "c":
+            out = np.empty(n)
+            eta._h.check(L.pmk_get_alpha(eta._h.raw, leaf, ptr(out)))
+            return out
+        out = np.empty((n, n), order="F")
+        fn = L.pmk_get_L if self._what == "L" else L.pmk_get_K
+        eta._h.check(fn(eta._h.raw, leaf, ptr(out)))
+        return out
+
+
+class MixtureGPType:
+    """MixtureGPType{T} (mixtureGP.jl:38-66).  Fields: X_parts, c_set, σ²_set, U_set, L_set, hps.
+    The fitted state lives in HBM; c_set / L_set / U_set materialise a leaf on the host on demand
+    (U_set is the Gram matrix WITHOUT σ², mixtureGP.jl:99)."""
+
+    def __init__(self, X_parts: Sequence[np.ndarray], hps, device: int = 0, leaf_base: int = 0,
+                 total_leaves: Optional[int] = None):
+        self.X_parts = [_as_points(X) for X in X_parts]
+        self.hps = hps                     # (hps_v, hps_c) as returned by fetchhyperplanes
+        self.σ2_set: List[float] = []
+        self.c_set = _LazyLeafList(self, "c")
+        self.L_set = _LazyLeafList(self, "L")
+        self.U_set = _LazyLeafList(self, "K")
+        self._h = Handle(device)
+        self._fitted = False
+        self._leaf_base = leaf_base
+        self._total_leaves = total_leaves
+        self._tree_key = None
+        self.θ = None
+
+    # -- convenience
+    @property
+    def handle(self) -> Handle:
+        return self._h
+
+    def close(self):
+        self._h.close()
+
+
+def fitmixtureGP_(η: MixtureGPType, y_parts: Sequence[np.ndarray], θ, σ2: float) -> MixtureGPType:
+    """fitmixtureGP!(η, y_parts, θ, σ²) (mixtureGP.jl:70-118): per leaf, Gram + σ²I, weights c and the
+    Cholesky factor L -- all leaves in one batched launch sequence on the GPU."""
+    N_parts = len(η.X_parts)
+    if len(y_parts) != N_parts:
+        raise PMKError(_lib.PMK_ERR_ARG, "length(y_parts) != length(η.X_parts)")
+    sizes = np.array([X.shape[0] for X in η.X_parts], dtype=np.int64)
+    for n, y in zip(sizes, y_parts):
+        if np.shape(y)[0] != n:
+            raise PMKError(_lib.PMK_ERR_ARG, "DimensionMismatch: length(y) != length(X) in a leaf")
+    D = η.X_parts[0].shape[1]
+    leaf_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    X_packed = np.ascontiguousarray(np.concatenate(η.X_parts, axis=0))
+    y_packed = np.ascontiguousarray(np.concatenate([np.asarray(y, dtype=np.float64) for y in y_parts]))
+    L = lib()
+    if η._total_leaves is not None:
+        η._h.check(L.pmk_set_leaf_base(η._h.raw, η._leaf_base, η._total_leaves))
+    bad, info = C.c_int64(0), C.c_int(0)
+    kp = θ.params
+    η._fitted = False
+    rc = L.pmk_fit(η._h.raw, D, N_parts, ptr(leaf_off), ptr(X_packed), ptr(y_packed), θ.kernel_id, ptr(kp), kp.shape[0],
+                   float(σ2), C.byref(bad), C.byref(info))
+    if rc == _lib.PMK_ERR_NOT_POSDEF:
+        raise PosDefException(info.value, bad.value, L.pmk_last_error(η._h.raw).decode())
+    η._h.check(rc)
+    η._fitted = True
+    η.θ = θ
+    η.σ2_set = [float(σ2)] * N_parts
+    return η
+
+
+def _set_tree(η: MixtureGPType, root: Optional[BSPTree], levels: int):
+    L = lib()
+    D = η.X_parts[0].shape[1]
+    if root is None or levels == 1:
+        key = ("none",)
+        if η._tree_key != key:
+            η._h.check(L.pmk_set_tree(η._h.raw, D, 1, None, None))
+            η._tree_key = key
+        return
+    if levels != root.levels:
+        raise PMKError(_lib.PMK_ERR_ARG, "levels does not match the tree")
+    key = (id(root), levels)
+    if η._tree_key != key:
+        hv = np.ascontiguousarray(root.hps_v, dtype=np.float64)
+        hc = np.ascontiguousarray(root.hps_c, dtype=np.float64)
+        η._h.check(L.pmk_set_tree(η._h.raw, D, levels, ptr(hv), ptr(hc)))
+        η._tree_key = key
+
+
+def _fetch_debug(η: MixtureGPType, Nq: int, debug_vars: MixtureGPDebugType):
+    L = lib()
+    npairs = C.c_int64(0)
+    η._h.check(L.pmk_last_query_pairs(η._h.raw, C.byref(npairs)))
+    P = npairs.value
+    home = np.empty(Nq, dtype=np.int32)
+    off = np.empty(Nq + 1, dtype=np.int64)
+    leaf = np.empty(P, dtype=np.int32)
+    hp = np.empty(P, dtype=np.int32)
+    t, w, u, v = (np.empty(P) for _ in range(4))
+    η._h.check(L.pmk_last_query_debug(η._h.raw, ptr(home), ptr(off), ptr(leaf), ptr(hp), ptr(t), ptr(w), ptr(u), ptr(v)))
+    debug_vars.p_region_ind_set = home
+    debug_vars.pair_off = off
+    debug_vars.w_tilde_set = [w[off[j]:off[j + 1]] for j in range(Nq)]
+    debug_vars.u_set = [u[off[j]:off[j + 1]] for j in range(Nq)]
+    debug_vars.v_set = [v[off[j]:off[j + 1]] for j in range(Nq)]
+    debug_vars.region_inds_set = [leaf[off[j]:off[j + 1] - 1] for j in range(Nq)]
+    debug_vars.kept_hp_set = [hp[off[j]:off[j + 1] - 1] for j in range(Nq)]
+    debug_vars.t_kept_set = [t[off[j]:off[j + 1] - 1] for j in range(Nq)]
+    debug_vars._flat = dict(home=home, pair_off=off, pair_leaf=leaf, pair_hp=hp, pair_t=t, pair_w=w, pair_u=u, pair_v=v)
+
+
+def querymixtureGP_(Yq: np.ndarray, Vq: np.ndarray, Xq, η: MixtureGPType, root: Optional[BSPTree], levels: int,
+                    radius: float, δ: float, θ, σ2, weight_θ, debug_vars: Optional[MixtureGPDebugType] = None, *,
+                    debug_flag: bool = False) -> None:
+    """querymixtureGP!(Yq, Vq, Xq, η, root, levels, radius, δ, θ, σ², weight_θ, debug_vars; debug_flag)
+    (mixtureGP.jl:159-294).  Yq, Vq must be float64 arrays of length(Xq) (Julia resizes them in place;
+    numpy arrays cannot be resized, so the caller allocates).  Returns None."""
+    Xq = _as_points(Xq)
+    Nq = Xq.shape[0]
+    if Yq.shape != (Nq,) or Vq.shape != (Nq,) or Yq.dtype != np.float64 or Vq.dtype != np.float64:
+        raise PMKError(_lib.PMK_ERR_ARG, "Yq / Vq must be float64 arrays of length(Xq)")
+    if not η._fitted:
+        raise PMKError(_lib.PMK_ERR_STATE, "query before fitmixtureGP_")
+    if θ is not η.θ and (θ.kernel_id != η.θ.kernel_id or not np.array_equal(θ.params, η.θ.params)):
+        raise PMKError(_lib.PMK_ERR_ARG, "θ differs from the kernel the model was fitted with")
+    _set_tree(η, root, levels)
+    wp = weight_θ.params
+    η._h.check(lib().pmk_query(η._h.raw, Nq, ptr(Xq), float(radius), float(δ), weight_θ.kernel_id, ptr(wp), wp.shape[0], 0,
+                               ptr(Yq), ptr(Vq)))
+    if debug_flag and debug_vars is not None:
+        _fetch_debug(η, Nq, debug_vars)
+    return None
+
+
+def querymixtureGP(Xq, η: MixtureGPType, root, levels, radius, δ, θ, σ2, weight_θ, *, debug_flag: bool = False):
+    """querymixtureGP(xq or Xq, ...) -> (Yq, Vq, debug_vars)  (mixtureGP.jl:120-157)."""
+    Xq = np.asarray(Xq, dtype=np.float64)
+    D = η.X_parts[0].shape[1]
+    if Xq.ndim == 1 and Xq.shape[0] == D and D > 1:
+        Xq = Xq[None, :]                       # single query point
+    Xq = _as_points(Xq)
+    Yq = np.empty(Xq.shape[0])
+    Vq = np.empty(Xq.shape[0])
+    dv = MixtureGPDebugType()
+    querymixtureGP_(Yq, Vq, Xq, η, root, levels, radius, δ, θ, σ2, weight_θ, dv, debug_flag=debug_flag)
+    return Yq, Vq, dv

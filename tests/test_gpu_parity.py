@@ -1,0 +1,244 @@
+"""GPU parity tests: the CUDA path, called through the C ABI (ctypes), against the CPU oracle on the
+same seeded inputs.  Bit-exact for leaf assignment / point indexing / neighbour lists; floating point
+within the tolerances written next to each assert (north star: 1e-9 relative on mean and variance)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import cases
+import helpers
+import patchmixturekriging_b200 as P
+from oracle import pmk_oracle as O
+from patchmixturekriging_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+
+# tolerance on posterior mean / variance: |gpu - oracle| <= TOL * max(|oracle|, rms(oracle))
+TOL = 1e-9
+
+
+def assert_close(name, a, b, tol=TOL):
+    st = helpers.err_stats(a, b)
+    print(f"{name}: {st}")
+    scale = np.sqrt(np.mean(np.asarray(b) ** 2))
+    bound = tol * np.maximum(np.abs(b), scale)
+    bad = np.abs(np.asarray(a) - np.asarray(b)) > bound
+    assert not bad.any(), f"{name}: {int(bad.sum())} of {bad.size} exceed {tol}: {st}"
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kname,param", [("SQEXP", 3.0), ("SPLINE34", 0.4), ("SPLINE12", 0.4), ("SPLINE32", 0.4), ("RQ", 1.7)])
+@pytest.mark.parametrize("D,n", [(1, 77), (2, 130), (3, 257), (2, 1)])
+def test_gram_stationary(built_lib, kname, param, D, n):
+    X = P.synth.uniform_points(3 + D + n, n, [-1.0] * D, [1.0] * D) if hasattr(P, "synth") else None
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(3 + D + n, n, [-1.0] * D, [1.0] * D)
+    ok, pk = helpers.kernels((kname, param))
+    K = P.constructkernelmatrix(X, pk)
+    Kref = O.constructkernelmatrix(X, ok)
+    assert K.shape == (n, n)
+    assert np.array_equal(K, K.T)                       # mirrored, exactly symmetric (RKHS.jl:27-31)
+    np.testing.assert_allclose(K, Kref, rtol=5e-15, atol=1e-300)   # a few ulp: exp / t^6 implementations differ
+    Ks = P.constructkernelmatrix(X, pk, σ2=0.25)
+    np.testing.assert_allclose(np.diag(Ks), np.diag(Kref) + 0.25, rtol=5e-15)
+
+
+@pytest.mark.parametrize("kname,param", [("BB10", 1.0), ("BB20", 1.0), ("BB1EPS", 4.5), ("BB2EPS", 2.5)])
+@pytest.mark.parametrize("D,n", [(1, 15), (2, 100)])
+def test_gram_brownian_bridge(built_lib, kname, param, D, n):
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(17 + n, n, [1e-3] * D, [1.0 - 1e-3] * D)
+    ok, pk = helpers.kernels((kname, param))
+    K = P.constructkernelmatrix(X, pk)
+    Kref = O.constructkernelmatrix(X, ok)
+    rtol = 5e-15 if kname in ("BB10", "BB20") else 1e-11    # eps-kernels: cancellation-prone exponent sums (kernel.jl:176-193)
+    np.testing.assert_allclose(K, Kref, rtol=rtol, atol=1e-18 if rtol > 1e-14 else 0)
+
+
+def test_cross_gram_and_evalkernel(built_lib):
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(1, 70, [-1.0, -1.0], [1.0, 1.0])
+    Z = synth.uniform_points(2, 45, [-1.0, -1.0], [1.0, 1.0])
+    ok, pk = helpers.kernels(("SQEXP", 2.0))
+    K = P.constructkernelmatrix(X, pk, Z)
+    np.testing.assert_allclose(K, O.kernel_cross(X, Z, ok), rtol=5e-15)
+    assert P.evalkernel(X[0], Z[0], pk) == K[0, 0]
+    # known answers: BB10(0.3,0.7) = 0.09, Spline34(0) = 1, Spline34(r>=1) = 0
+    assert abs(P.evalkernel([0.3], [0.7], P.BrownianBridge10()) - 0.09) < 1e-16
+    assert P.evalkernel([0.0, 0.0], [0.0, 0.0], P.Spline34KernelType(2.0)) == 1.0
+    assert P.evalkernel([0.0, 0.0], [0.6, 0.0], P.Spline34KernelType(2.0)) == 0.0
+
+
+# ---------------------------------------------------------------------------------------------
+def _fit_product(case, m):
+    _, pk = helpers.kernels(case["kernel"])
+    X, y = case["X"], case["y"]
+    root, X_parts, X_parts_inds = P.setuppartition(X, case["levels"])
+    X_set, X_set_inds, _, _ = P.organizetrainingsets(root, case["levels"], X, case["eps"])
+    for a, b in zip(X_set_inds, m["X_set_inds"]):
+        assert np.array_equal(a, b)                      # bit-exact point indexing
+    eta = P.MixtureGPType(X_set, P.fetchhyperplanes(root))
+    P.fitmixtureGP_(eta, [y[i - 1] for i in X_set_inds], pk, case["sigma2"])
+    return root, eta, pk
+
+
+CASES = {"mixgp_file": cases.mixgp_file, "c3_mini": cases.c3_mini, "c4_mini": cases.c4_mini, "mixgp_driver": cases.mixgp_driver}
+_cache = {}
+
+
+def _setup(name):
+    if name not in _cache:
+        case = CASES[name]()
+        m = helpers.oracle_model(case)
+        root, eta, pk = _fit_product(case, m)
+        _cache[name] = (case, m, root, eta, pk)
+    return _cache[name]
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fit_factor_and_weights(built_lib, name):
+    case, m, root, eta, pk = _setup(name)
+    oeta = m["eta"]
+    worst_L, worst_res = 0.0, 0.0
+    for leaf in sorted({0, 1, len(oeta.L_set) // 2, len(oeta.L_set) - 1}):
+        L = eta.L_set[leaf]
+        Lref = oeta.L_set[leaf]
+        assert np.array_equal(np.triu(L, 1), np.zeros_like(L))
+        worst_L = max(worst_L, np.abs(L - Lref).max() / np.abs(Lref).max())
+        # U_set = Gram without sigma2 (mixtureGP.jl:99)
+        K = eta.U_set[leaf]
+        np.testing.assert_allclose(K, O.constructkernelmatrix(oeta.X_parts[leaf], m["th"]), rtol=5e-15, atol=1e-300)
+        # alpha: residual of (K + s2 I) alpha = y, and agreement with the oracle's LU solution
+        c = eta.c_set[leaf]
+        U = K + case["sigma2"] * np.eye(K.shape[0])
+        y = case["y"][m["X_set_inds"][leaf] - 1]
+        worst_res = max(worst_res, np.abs(U @ c - y).max() / (np.abs(U).sum(1).max() * np.abs(c).max()))
+    print(f"{name}: L max rel err {worst_L:.3e}, alpha scaled residual {worst_res:.3e}")
+    assert worst_L < 1e-9       # blocked DMMA Cholesky vs LAPACK dpotrf, relative to max|L|
+    assert worst_res < 1e-14    # backward-stable solve
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_query_structure_bit_exact(built_lib, name):
+    case, m, root, eta, pk = _setup(name)
+    _, wk = helpers.kernels(case["wkernel"])
+    Xq = case["Xq"]
+    Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk,
+                                  debug_flag=True)
+    home, pq, ph, pl, pt = O.query_structure_vec(Xq, m["hv"], m["hc"], case["levels"], case["radius"], case["delta"])
+    f = dv._flat
+    assert np.array_equal(f["home"], home)                                   # p_region_ind: bit-exact
+    counts = np.bincount(pq, minlength=Xq.shape[0]) + 1
+    assert np.array_equal(np.diff(f["pair_off"]), counts)
+    nb = f["pair_hp"] != 0
+    assert np.array_equal(f["pair_leaf"][nb], pl)                            # region_inds, in hyperplane order
+    assert np.array_equal(f["pair_hp"][nb], ph + 1)
+    assert np.array_equal(f["pair_t"][nb], pt)                               # ts[keep]: same operations, same bits
+    assert np.array_equal(f["pair_leaf"][~nb], home)
+    wth, _ = helpers.kernels(case["wkernel"])
+    np.testing.assert_allclose(f["pair_w"][nb], O.evalkernel_tau(np.abs(pt), wth), rtol=5e-15, atol=1e-300)
+    assert np.all(f["pair_w"][~nb] == 1.0)
+    # device findpartition entry point
+    out = np.empty(Xq.shape[0], dtype=np.int32)
+    eta.handle.check(_lib.lib().pmk_find_partition(eta.handle.raw, Xq.shape[0], _lib.ptr(np.ascontiguousarray(Xq)), _lib.ptr(out)))
+    assert np.array_equal(out, home)
+    assert np.array_equal(P.findpartition(Xq, root), home)
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_query_mean_variance(built_lib, name):
+    case, m, root, eta, pk = _setup(name)
+    wth, wk = helpers.kernels(case["wkernel"])
+    Xq = case["Xq"]
+    Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk,
+                                  debug_flag=True)
+    Yo, Vo, od = O.querymixtureGP_vec(Xq, m["eta"], case["levels"], case["radius"], case["delta"], m["th"], wth)
+    f = dv._flat
+    assert np.array_equal(f["pair_leaf"], od["pair_leaf"])
+    tol = TOL if case["sigma2"] >= 1e-4 else 2e-8      # sigma2 = 1e-5: cond ~1e6-1e7, two CPU algorithms differ by ~1e-9 too
+    assert_close(f"{name} pair_u", f["pair_u"], od["pair_u"], tol)
+    assert_close(f"{name} pair_v", f["pair_v"], od["pair_v"], tol)
+    assert_close(f"{name} Yq", Yq, Yo, tol)
+    assert_close(f"{name} Vq", Vq, Vo, tol)
+    assert np.all(Vq >= 1e-12 * 0.999)
+
+
+def test_single_query_and_scalar_oracle(built_lib):
+    """querymixtureGP(xq::Vector, ...) wrapper (mixtureGP.jl:120-135) and the scalar-loop oracle."""
+    case, m, root, eta, pk = _setup("mixgp_file")
+    wth, wk = helpers.kernels(case["wkernel"])
+    Xq = case["Xq"][::97][:60]
+    Yo, Vo, dbg = O.querymixtureGP(Xq, m["eta"], m["root"], case["levels"], case["radius"], case["delta"], m["th"],
+                                   case["sigma2"], wth, debug=True)
+    Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk, debug_flag=True)
+    assert list(dv.p_region_ind_set) == dbg["p_region_ind"]
+    for a, b in zip(dv.region_inds_set, dbg["region_inds"]):
+        assert list(a) == list(b)
+    assert_close("scalar Yq", Yq, Yo, 2e-8)
+    assert_close("scalar Vq", Vq, Vo, 2e-8)
+    y1, v1, _ = P.querymixtureGP(Xq[3], eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
+    assert y1.shape == (1,) and y1[0] == Yq[3] and v1[0] == Vq[3]
+
+
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("kind", ["BB10", "BB20"])
+@pytest.mark.parametrize("N,Nq", [(15, 100), (1000, 100)])
+def test_single_gp_ibb1d(built_lib, kind, N, Nq):
+    """examples/IBB1D.jl: fitRKHS! + query! (mean only)."""
+    case = cases.ibb1d(N, Nq, kind)
+    ok, pk = helpers.kernels(case["kernel"])
+    eta = P.RKHSProblemType(np.zeros(N), case["X"], pk, case["sigma2"])
+    P.fitRKHS_(eta, case["y"])
+    c_ref = O.fitRKHS(case["X"], case["y"], ok, case["sigma2"])
+    yq = np.empty(Nq)
+    P.query_(yq, case["Xq"], eta)
+    yref = O.query_rkhs(case["Xq"], case["X"], c_ref, ok)
+    # N=1000 Brownian-bridge Gram with sigma2=1e-5 is ill-conditioned (cond ~1e7): compare predictions, not weights
+    assert_close(f"ibb1d {kind} N={N} yq", yq, yref, 1e-9 if N == 15 else 1e-7)
+    if N == 15:
+        np.testing.assert_allclose(eta.c, c_ref, rtol=1e-8)
+
+
+def test_not_positive_definite(built_lib):
+    """cholesky(U) throws PosDefException(info) (mixtureGP.jl:109): duplicated point, sigma2 = 0."""
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(4, 40, [-1.0, -1.0], [1.0, 1.0])
+    X[29] = X[7]
+    ok, pk = helpers.kernels(("SQEXP", 1.0))
+    eta = P.MixtureGPType([X[:20], X], (np.zeros((1, 2)), np.zeros(1)))
+    with pytest.raises(P.PosDefException) as ei:
+        P.fitmixtureGP_(eta, [np.zeros(20), np.zeros(40)], pk, 0.0)
+    with pytest.raises(O.PosDefException) as eo:
+        U = O.constructkernelmatrix(X, ok)
+        O.cholesky_L(U, 2)
+    print("gpu info", ei.value.info, "leaf", ei.value.leaf, "| lapack info", eo.value.info)
+    assert ei.value.leaf == 2
+    assert ei.value.info == eo.value.info == 30
+
+
+def test_argument_errors(built_lib):
+    eta = P.MixtureGPType([np.zeros((4, 2))], (np.zeros((0, 2)), np.zeros(0)))
+    with pytest.raises(P.PMKError):
+        P.fitmixtureGP_(eta, [np.zeros(3)], P.GaussianKernel1DType(1.0), 1e-3)       # length(y) != length(X)
+    with pytest.raises(P.PMKError):
+        P.querymixtureGP(np.zeros((1, 2)), eta, None, 1, 0.1, 1e-5, P.GaussianKernel1DType(1.0), 1e-3, P.Spline34KernelType(1.0))
+
+
+def test_leaf_size_edges(built_lib):
+    """ragged leaves around the padding / size-class boundaries: 1, 31, 32, 33, 512, 513 points."""
+    from patchmixturekriging_b200 import synth
+    sizes = [1, 31, 32, 33, 512, 513]
+    ok, pk = helpers.kernels(("SQEXP", 30.0))
+    Xs = [synth.uniform_points(100 + s, s, [0.0, 0.0], [1.0, 1.0]) for s in sizes]
+    ys = [np.sin(4 * X[:, 0]) + X[:, 1] for X in Xs]
+    eta = P.MixtureGPType(Xs, (np.zeros((0, 2)), np.zeros(0)))
+    P.fitmixtureGP_(eta, ys, pk, 1e-3)
+    for i, (X, y) in enumerate(zip(Xs, ys)):
+        U = O.constructkernelmatrix(X, ok) + 1e-3 * np.eye(len(X))
+        Lref = O.cholesky_L(U)
+        assert np.abs(eta.L_set[i] - Lref).max() < 1e-11
+        cref = O.backslash(U, y)
+        assert np.abs(U @ eta.c_set[i] - y).max() < 1e-12 * max(1.0, np.abs(cref).max())

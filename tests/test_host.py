@@ -1,0 +1,103 @@
+"""CPU tests of the host layer: BSP mirror vs oracle (bit-exact), the C-ABI library loads and exports
+every symbol include/pmk.h declares, and the product fails loudly without a GPU (no fallback)."""
+from __future__ import annotations
+
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import cases
+import patchmixturekriging_b200 as P
+from oracle import pmk_oracle as O
+from patchmixturekriging_b200 import _lib
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("N,levels,D", [(850, 3, 2), (5000, 6, 2), (4097, 4, 3), (3000, 2, 1)])
+def test_setuppartition_bit_exact(N, levels, D):
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(25, N, [-5.0, -10.0, -5.0][:D], [5.0, 10.0, 5.0][:D])
+    root, X_parts, X_parts_inds = P.setuppartition(X, levels)
+    oroot, oX_parts, oinds = O.setuppartition(X, levels)
+    hv, hc = O.fetchhyperplanes(oroot)
+    assert np.array_equal(root.hps_v, hv) and np.array_equal(root.hps_c, hc)
+    assert len(X_parts_inds) == len(oinds) == 2 ** (levels - 1)
+    for a, b, Xa in zip(X_parts_inds, oinds, X_parts):
+        assert np.array_equal(a, b) and np.array_equal(Xa, X[b - 1])
+    v2, c2 = P.fetchhyperplanes(root)
+    assert len(c2) == len(X_parts) - 1
+    q = synth.uniform_points(9, 700, [-6.0, -11.0, -6.0][:D], [6.0, 11.0, 6.0][:D])
+    assert np.array_equal(P.findpartition(q, root), O._descend_vec(q, hv, hc, levels))
+    assert P.findpartition(q[5], root) == O.findpartition(q[5], oroot, levels)
+
+
+@pytest.mark.parametrize("eps", [0.0, 0.3, 1.5])
+def test_organizetrainingsets_bit_exact(eps):
+    case = cases.mixgp_driver(N=4000, levels=5)
+    X = case["X"]
+    root, _, _ = P.setuppartition(X, 5)
+    oroot, _, _ = O.setuppartition(X, 5)
+    X_set, X_set_inds, rl, prob = P.organizetrainingsets(root, 5, X, eps)
+    oX_set, oinds, orl, _ = O.organizetrainingsets(oroot, 5, X, eps)
+    assert prob == []
+    for a, b, Xa in zip(X_set_inds, oinds, X_set):
+        assert np.array_equal(a, b) and np.array_equal(Xa, X[b - 1])
+    for i in range(0, 4000, 37):
+        assert list(rl[i]) == orl[i]
+    if eps == 0.0:
+        assert sum(len(a) for a in X_set_inds) == 4000
+
+
+def test_svd_row_form_switch():
+    X = cases.mixgp_file()["X"]
+    r1, _, _ = P.setuppartition(X, 3, svd_form="row")
+    o1, _, _ = O.setuppartition(X, 3, svd_form="row")
+    assert np.array_equal(r1.hps_v, O.fetchhyperplanes(o1)[0])
+
+
+def test_library_exports_every_declared_symbol(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "pmk.h")).read()
+    declared = set(re.findall(r"\b(pmk_[a-z_A-Z0-9]+)\s*\(", hdr))
+    declared -= {"pmk_handle"}
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    L = ctypes.CDLL(built_lib)
+    for s in declared:
+        assert hasattr(L, s), s
+    assert L.pmk_version() >= 100
+
+
+def test_no_cpu_fallback(built_lib):
+    """Without a CUDA device the product refuses to run (it never routes through the oracle)."""
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    with pytest.raises(P.PMKError) as e:
+        P.Handle(0)
+    assert e.value.code == _lib.PMK_ERR_CUDA and "no CPU fallback" in str(e.value)
+    with pytest.raises(P.PMKError):
+        P.constructkernelmatrix(np.zeros((3, 2)), P.GaussianKernel1DType(1.0))
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "patchmixturekriging_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f), encoding="utf-8").read()
+                assert "pmk_oracle" not in src and "from oracle" not in src and "import oracle" not in src, f
+                assert "dlopen" not in src and "libpmk_oracle" not in src, f
+
+
+def test_kernel_descriptors():
+    assert P.Spline34KernelType(0.5).kernel_id == 1 and P.Spline34KernelType(0.5).params[0] == 0.5
+    assert P.GaussianKernel1DType(400.0).kernel_id == 0 and P.GaussianKernel1DType(400.0).stationary
+    assert P.BrownianBridge10().kernel_id == 2 and not P.BrownianBridge10().stationary
+    assert P.BrownianBridge2ϵ(2.5).params[0] == 2.5
