@@ -260,13 +260,16 @@ static int gram_impl(pmk_handle* h, int D, int64_t n, const double* X, int64_t m
   if (int rc = parse_kernel(h, kernel_id, kparams, nparams, &kp)) return rc;
   const bool sym = (Z == nullptr);
   const int64_t sx = (n + 127) / 128 * 128, sz = (m + 127) / 128 * 128;
-  const size_t need = (size_t)(D * (n + (sym ? 0 : m)) + D * (sx + (sym ? 0 : sz)) + n * m) * sizeof(double);
+  auto up16 = [](int64_t v) { return (v + 15) / 16 * 16; };   // keep every sub-buffer 128-byte aligned (TMA, 16-B stores)
+  const int64_t nXa = up16((int64_t)D * n), nZa = sym ? 0 : up16((int64_t)D * m);
+  const int64_t nxs = (int64_t)D * sx, nzs = sym ? 0 : (int64_t)D * sz;
+  const size_t need = (size_t)(nXa + nZa + nxs + nzs + n * m) * sizeof(double);
   CU(h, h->d_scratch.ensure(need));
   double* dXa = h->d_scratch.as<double>();
-  double* dZa = dXa + D * n;
-  double* xs = dZa + (sym ? 0 : D * m);
-  double* zs = xs + D * sx;
-  double* dK = zs + (sym ? 0 : D * sz);
+  double* dZa = dXa + nXa;
+  double* xs = dZa + nZa;
+  double* zs = xs + nxs;
+  double* dK = zs + nzs;
   CU(h, cudaMemcpyAsync(dXa, X, sizeof(double) * D * n, cudaMemcpyHostToDevice, h->stream));
   launch_aos_to_soa(D, dXa, n, sx, xs, h->stream);
   KCHECK(h, "k_aos_to_soa");
