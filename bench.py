@@ -1,0 +1,433 @@
+#!/usr/bin/env python
+"""bench.py -- local-GP fit + mixture query on B200 (BASELINE.json: "GP fit leaves/s and query pts/s").
+
+One STEP = one full pass of the hot path over the synthetic workload: fit every BSP leaf
+(fused Gram + Cholesky + alpha), then answer every query (home leaf, neighbours, fused
+cross-covariance / mean / variance, convex mixture).  `value` = query points per second (the
+10M-point mixture query dominates the step); the fit throughput is reported beside it as
+`fit_leaves_per_s`.  Inputs are resident in HBM for `value`; `e2e` repeats the step through the
+public host API (patchmixturekriging_b200.fitmixtureGP_ / querymixtureGP_) with pinned host buffers,
+host<->device copies inside the timed region.
+
+    python bench.py --gpus N --steps K --warmup W [--workload c3|c3_mini|c2] [--impl reference]
+
+N > 1 is launched by torchrun, one rank per GPU: leaves are dealt to ranks by a contiguous
+leaf->rank map (fit), the factors are exchanged with NCCL broadcasts over NVLink, queries are sliced
+across ranks with no data-path collective and gathered once at the end (strong scaling of the named
+workload).  `--impl reference` times the CPU restatement of the reference's algorithm (oracle/pmk_oracle.c,
+all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FP64_PEAK_FALLBACK_TFLOPS = 37.1   # tools/fp64_peak.cu on this pool's B200 (profiles/fp64_peaks_r01.json)
+EVAL_FLOPS_2D = 3 * 2 + 2 + 20     # one SqExp evaluation: differences/squares/sum + sqrt + exp (DESIGN.md "flop counts")
+
+
+# --------------------------------------------------------------------------------------------
+def workload(name: str, nq_override: int | None = None):
+    from patchmixturekriging_b200 import synth
+    if name == "c3":          # BASELINE configs[2]: 2-D, N = 1M, 4096 leaves of ~512 points with overlap, 10M queries
+        N, levels, eps, nq = 1_000_000, 13, 0.043, 10_000_000
+    elif name == "c3_mini":   # same shape, 1/16 size (for quick runs)
+        N, levels, eps, nq = 62_500, 9, 0.043, 625_000
+    elif name == "c2":        # BASELINE configs[1]: examples/mixGP.jl, SqExp, N = 20k, 64 leaves
+        N, levels, eps, nq = 20_000, 7, 0.5, 20_000
+    else:
+        raise SystemExit(f"unknown workload {name}")
+    lo, hi = [-5.0, -10.0], [5.0, 10.0]
+    if name == "c3_mini":     # keep the point density of c3
+        lo, hi = [-1.25, -2.5], [1.25, 2.5]
+    nq = nq_override or nq
+    X = synth.uniform_points(25, N, lo, hi)
+    y = synth.f_mixgp(X)
+    spacing = np.sqrt((hi[0] - lo[0]) * (hi[1] - lo[1]) / N)
+    eps_sq = 8.0 if name == "c2" else round(1.0 / (3.5 * spacing) ** 2)      # c3: 408 ~ SURVEY's "eps_sq ~ 400"
+    radius = 0.3 if name == "c2" else eps
+    return dict(name=name, X=X, y=y, levels=levels, eps=eps, radius=radius, delta=1e-5, sigma2=1e-3, eps_sq=float(eps_sq),
+                nq=nq, lo=lo, hi=hi)
+
+
+def gen_queries(w, first: int, count: int) -> np.ndarray:
+    """queries [first, first+count) of the workload's stream (uniform on the domain)."""
+    from patchmixturekriging_b200 import synth
+    lo, hi = np.asarray(w["lo"]), np.asarray(w["hi"])
+    Xq = np.empty((count, 2))
+    for d in range(2):
+        u = synth.uniform01(1234567, count, d * w["nq"] + first)
+        Xq[:, d] = u * (hi[d] - lo[d]) + lo[d]
+    return Xq
+
+
+def partition(w):
+    import patchmixturekriging_b200 as P
+    root, X_parts, X_parts_inds = P.setuppartition(w["X"], w["levels"])
+    X_set, X_set_inds, _, _ = P.organizetrainingsets(root, w["levels"], w["X"], w["eps"])
+    sizes = np.array([len(i) for i in X_set_inds], dtype=np.int64)
+    leaf_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    idx = np.concatenate(X_set_inds) - 1
+    return root, sizes, leaf_off, np.ascontiguousarray(w["X"][idx]), np.ascontiguousarray(w["y"][idx])
+
+
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.device)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, pw = [], [], set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2])); pw.append(float(f[3]))
+            except ValueError:
+                continue
+            for nm, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        busy = [s for s, p in zip(sm, pw) if p > 0.5 * max(pw)] or sm
+        return {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "power_w_max": float(max(pw)),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def fp64_peak():
+    p = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
+    try:
+        d = json.load(open(p))
+        return float(d["dmma_tflops"]), "measured: tools/fp64_peak.cu DMMA.8x8x4 loop on this pool's B200 (profiles/fp64_peaks_r01.json); MEASURED_PEAKS.json has no FP64 entry"
+    except Exception:
+        return FP64_PEAK_FALLBACK_TFLOPS, "fallback constant (profiles/fp64_peaks_r01.json missing)"
+
+
+# --------------------------------------------------------------------------------------------
+def cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=1, warmup=0, sample_leaves=512, sample_queries=200000, threads=0):
+    """The reference's algorithm (C restatement, oracle/pmk_oracle.c) on the host cores, bounded sample:
+    the first `sample_leaves` leaves of the REAL tree are fitted; sample queries are drawn from the workload's own
+    query stream among those whose home and neighbour leaves are all in that set (the all-hyperplanes scan of
+    findneighbourpartitions runs over the full tree, as in the reference)."""
+    from oracle import c_oracle
+    SQEXP, SPLINE34 = 0, 1
+    threads = threads or c_oracle.max_threads()
+    nl = min(sample_leaves, len(sizes))
+    off_s = leaf_off.copy()
+    off_s[nl + 1:] = off_s[nl]                      # leaves >= nl absent
+    Xs, ys = Xp[:leaf_off[nl]], yp[:leaf_off[nl]]
+    X_set = [Xs[leaf_off[p]:leaf_off[p + 1]] for p in range(nl)]
+    y_set = [ys[leaf_off[p]:leaf_off[p + 1]] for p in range(nl)]
+    hv, hc = np.ascontiguousarray(root.hps_v), np.ascontiguousarray(root.hps_c)
+    # candidate queries: those of the stream whose home leaf is in the sample (host findpartition), then the
+    # structure-only pass of the oracle keeps the ones that touch no absent leaf
+    import patchmixturekriging_b200 as P
+    cand = []
+    first, chunk = 0, 400_000
+    while sum(len(c) for c in cand) < 3 * sample_queries and first < w["nq"]:
+        cnt = min(chunk, w["nq"] - first)
+        Xq = gen_queries(w, first, cnt)
+        home = P.findpartition(Xq, root)
+        cand.append(Xq[home <= nl])
+        first += cnt
+    cand = np.concatenate(cand) if cand else np.zeros((0, 2))
+    _, _, _, _, absent = c_oracle.query(hv, hc, w["levels"], off_s, Xs, np.zeros(len(Xs)), np.zeros(1), SQEXP, w["eps_sq"], cand,
+                                        w["radius"], w["delta"], SPLINE34, 1.0 / w["radius"], threads, structure_only=True)
+    Xq_s = np.ascontiguousarray(cand[absent == 0][:sample_queries])
+    fit_t, q_t = [], []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        alpha, L, off2, Xpk = c_oracle.fit(X_set, y_set, SQEXP, w["eps_sq"], w["sigma2"], threads)
+        t1 = time.perf_counter()
+        Yq, Vq, _, npairs, ab = c_oracle.query(hv, hc, w["levels"], off_s, Xpk, alpha, L, SQEXP, w["eps_sq"], Xq_s, w["radius"],
+                                               w["delta"], SPLINE34, 1.0 / w["radius"], threads)
+        t2 = time.perf_counter()
+        if it >= warmup:
+            fit_t.append(t1 - t0); q_t.append(t2 - t1)
+    assert np.isfinite(Yq).all()
+    return dict(fit_leaves_per_s=nl / np.mean(fit_t), query_pts_per_s=len(Xq_s) / np.mean(q_t), cores=threads,
+                sample=f"first {nl} leaves of the real {len(sizes)}-leaf tree fitted ({np.mean(fit_t):.2f} s); {len(Xq_s)} queries of the "
+                       f"workload's stream whose leaves are all in that set ({np.mean(q_t):.2f} s); full-tree hyperplane scan per query",
+                fit_s=float(np.mean(fit_t)), query_s=float(np.mean(q_t)), sample_xq=Xq_s, sample_y=Yq, sample_v=Vq,
+                pairs_per_query=float(npairs.mean()))
+
+
+# --------------------------------------------------------------------------------------------
+class _CudaSpan:
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200")
+    ap.add_argument("--workload", default="c3")
+    ap.add_argument("--nq", type=int, default=None)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    w = workload(args.workload, args.nq)
+    cfg = {"workload": f"{w['name']}: 2-D mixture-GP, N={len(w['X'])}, {1 << (w['levels'] - 1)} BSP leaves, eps={w['eps']}, "
+                       f"radius={w['radius']}, delta={w['delta']}, SqExp eps_sq={w['eps_sq']}, sigma2={w['sigma2']}, Nq={w['nq']}",
+           "l2": "inputs larger than L2 (packed factors + queries + pair arrays are GBs per step vs 126 MB L2)"}
+
+    # ---------------- reference arm: CPU restatement on the host cores -----------------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        root, sizes, leaf_off, Xp, yp = partition(w)
+        cb = cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=args.steps, warmup=min(args.warmup, 1))
+        line = {"impl": "reference", "metric": "query_pts_per_s (mixture-GP query; fit throughput in fit_leaves_per_s)",
+                "value": cb["query_pts_per_s"], "unit": "pts/s", "fit_leaves_per_s": cb["fit_leaves_per_s"], "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * (cb["fit_s"] + cb["query_s"]),
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "config": cfg,
+                "cpu_baseline": {"value": cb["query_pts_per_s"], "unit": "pts/s", "fit_leaves_per_s": cb["fit_leaves_per_s"],
+                                 "cores": cb["cores"], "kind": "port", "sample": cb["sample"]},
+                "e2e": {"value": cb["query_pts_per_s"], "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ---------------- B200 arm ---------------------------------------------------------------
+    import torch
+    import torch.distributed as dist
+    import patchmixturekriging_b200 as P
+    from patchmixturekriging_b200 import _lib, mixturegp
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
+    dev = local_rank if world > 1 else 0
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
+
+    root, sizes, leaf_off, Xp, yp = partition(w)
+    n_leaves = len(sizes)
+    Nq = w["nq"]
+    q0, q1 = (Nq * rank) // world, (Nq * (rank + 1)) // world
+    Xq_h = gen_queries(w, q0, q1 - q0)
+    nq_loc = q1 - q0
+    l0, l1 = (n_leaves * rank) // world, (n_leaves * (rank + 1)) // world
+
+    θ = P.GaussianKernel1DType(w["eps_sq"])
+    wθ = P.Spline34KernelType(1.0 / w["radius"])
+    X_set = [Xp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
+    y_set = [yp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
+    η = P.MixtureGPType(X_set, P.fetchhyperplanes(root), device=dev, fit_range=(l0, l1 - l0) if world > 1 else None)
+    h = η.handle
+    L = _lib.lib()
+    hv = np.ascontiguousarray(root.hps_v); hc = np.ascontiguousarray(root.hps_c)
+    h.check(L.pmk_set_tree(h.raw, 2, w["levels"], _lib.ptr(hv), _lib.ptr(hc)))
+    if world > 1:
+        h.check(L.pmk_set_fit_range(h.raw, l0, l1 - l0))
+
+    dX = torch.from_numpy(Xp).cuda(); dy = torch.from_numpy(yp).cuda(); dXq = torch.from_numpy(Xq_h).cuda()
+    dYq = torch.empty(nq_loc, dtype=torch.float64, device="cuda"); dVq = torch.empty_like(dYq)
+    dY_all = torch.empty(Nq, dtype=torch.float64, device="cuda") if world > 1 else None
+    dV_all = torch.empty(Nq, dtype=torch.float64, device="cuda") if world > 1 else None
+    kp = θ.params; wp = wθ.params
+    stream = torch.cuda.ExternalStream(int(L.pmk_stream(h.raw)), device=dev)
+    bad, info = C.c_int64(0), C.c_int(0)
+
+    def exchange_factors():
+        """leaf -> rank map: every rank broadcasts the spans it factorised (NCCL over NVLink)."""
+        for which in (_lib.BUF_L, _lib.BUF_LINV, _lib.BUF_ALPHA):
+            for r in range(world):
+                a, b = (n_leaves * r) // world, (n_leaves * (r + 1)) // world
+                ptr, nb = mixturegp.model_buffer(η, which, a, b - a)
+                if nb:
+                    dist.broadcast(torch.as_tensor(_CudaSpan(ptr, nb), device=f"cuda:{dev}"), src=r)
+        torch.cuda.current_stream().synchronize()
+        mixturegp.mark_fitted(η)
+
+    def step_device():
+        """fit + query with inputs resident in HBM; returns (fit_ms, query_ms) from CUDA events on the handle's stream."""
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        e[0].record(stream)
+        h.check(L.pmk_fit_dev(h.raw, 2, n_leaves, _lib.ptr(leaf_off), dX.data_ptr(), dy.data_ptr(), θ.kernel_id, _lib.ptr(kp), 1,
+                              w["sigma2"], C.byref(bad), C.byref(info)))
+        if world > 1:
+            h.synchronize()
+            exchange_factors()
+        e[1].record(stream)
+        h.check(L.pmk_query_dev(h.raw, nq_loc, dXq.data_ptr(), w["radius"], w["delta"], wθ.kernel_id, _lib.ptr(wp), 1, 0,
+                                dYq.data_ptr(), dVq.data_ptr()))
+        if world > 1:
+            h.synchronize()
+            dist.all_gather_into_tensor(dY_all, dYq) if Nq % world == 0 else None
+            dist.all_gather_into_tensor(dV_all, dVq) if Nq % world == 0 else None
+            torch.cuda.current_stream().synchronize()
+        e[2].record(stream)
+        e[2].synchronize()
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    barrier()
+    launches0 = h.launch_count()
+    sampler = ClockSampler(dev)
+    if rank == 0:
+        sampler.start()
+    t_wall0 = time.perf_counter()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    fit_ms, query_ms, kt = [], [], []
+    for _ in range(args.steps):
+        f, q = step_device()
+        fit_ms.append(f); query_ms.append(q)
+        kt.append(h.timings().copy())
+    ev1.record(stream)
+    barrier()
+    ev1.synchronize()
+    total_ms = ev0.elapsed_time(ev1)
+    wall_ms = 1e3 * (time.perf_counter() - t_wall0)
+    clocks = sampler.stop() if rank == 0 else None
+    launches = h.launch_count() - launches0
+
+    t = torch.tensor([total_ms, float(np.mean(fit_ms)), float(np.mean(query_ms))], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, fit_ms_m, query_ms_m = (float(x) for x in t.cpu())
+    kt = np.mean(np.array(kt), axis=0)
+
+    # ---------------- e2e through the public host API, pinned host buffers --------------------
+    e2e = None
+    if not args.no_e2e:
+        hXq = torch.from_numpy(Xq_h).pin_memory().numpy()
+        hYq = torch.empty(nq_loc, dtype=torch.float64).pin_memory().numpy()
+        hVq = torch.empty(nq_loc, dtype=torch.float64).pin_memory().numpy()
+        hXp = torch.from_numpy(Xp).pin_memory().numpy()
+        hyp = torch.from_numpy(yp).pin_memory().numpy()
+        η.X_parts = [hXp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
+        y_set_p = [hyp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
+
+        def step_host():
+            t0 = time.perf_counter()
+            # fitmixtureGP_ packs the leaf list; the packed arrays are what crosses the ABI
+            h.check(L.pmk_fit(h.raw, 2, n_leaves, _lib.ptr(leaf_off), _lib.ptr(hXp), _lib.ptr(hyp), θ.kernel_id, _lib.ptr(kp), 1,
+                              w["sigma2"], C.byref(bad), C.byref(info)))
+            if world > 1:
+                exchange_factors()
+            η._fitted, η.θ = True, θ
+            t1 = time.perf_counter()
+            P.querymixtureGP_(hYq, hVq, hXq, η, root, w["levels"], w["radius"], w["delta"], θ, w["sigma2"], wθ)
+            if world > 1:
+                dist.all_gather_into_tensor(dY_all, torch.from_numpy(hYq).cuda()) if Nq % world == 0 else None
+                torch.cuda.synchronize()
+            t2 = time.perf_counter()
+            return 1e3 * (t1 - t0), 1e3 * (t2 - t1)
+
+        step_host()
+        barrier()
+        ef, eq = [], []
+        for _ in range(max(1, min(args.steps, 3))):
+            a, b = step_host()
+            ef.append(a); eq.append(b)
+        te = torch.tensor([float(np.mean(ef)), float(np.mean(eq))], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        ef_m, eq_m = (float(x) for x in te.cpu())
+        e2e = {"value": Nq / (eq_m * 1e-3), "unit": "pts/s", "fit_leaves_per_s": n_leaves / (ef_m * 1e-3),
+               "h2d_bytes_per_step": int(Xq_h.nbytes + Xp.nbytes + yp.nbytes), "d2h_bytes_per_step": int(2 * 8 * nq_loc),
+               "ms_fit": ef_m, "ms_query": eq_m,
+               "api": "pmk_fit(host X,y) + patchmixturekriging_b200.querymixtureGP_(Yq, Vq, Xq, ...) with pinned host arrays"}
+
+    # ---------------- roofline of the dominant kernel (K3, k_query_pairs) ---------------------
+    if rank == 0:
+        npairs = C.c_int64(0)
+        h.check(L.pmk_last_query_pairs(h.raw, C.byref(npairs)))
+        pl = np.empty(npairs.value, dtype=np.int32)
+        h.check(L.pmk_last_query_debug(h.raw, None, None, _lib.ptr(pl), None, None, None, None, None))
+        per_leaf = np.bincount(pl - 1, minlength=n_leaves).astype(np.float64)
+        nn = sizes.astype(np.float64)
+        flops_pairs = float((per_leaf * (nn * nn + nn * (EVAL_FLOPS_2D + 4))).sum())      # TRSM n^2 + n*(eval + mean 2 + ||s||^2 2)
+        flops_fit = float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * EVAL_FLOPS_2D).sum()) * (l1 - l0) / n_leaves if world > 1 else \
+            float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * EVAL_FLOPS_2D).sum())
+        peak, peak_src = fp64_peak()
+        ach = flops_pairs / (kt[_lib.T_Q_PAIRS] * 1e-3) / 1e12
+        roofline = {"kernel": "k_query_pairs (fused cross-covariance + mean + DMMA TRSM variance)", "bound": "tensor",
+                    "pipe": "FP64 DMMA.8x8x4 (mma.sync.m8n8k4.f64); tcgen05 has no f64 kind", "achieved": ach, "peak": peak,
+                    "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                    "algorithmic_flops_per_launch": flops_pairs, "ms_per_launch": float(kt[_lib.T_Q_PAIRS]),
+                    "pairs_per_launch": int(npairs.value)}
+        fit_ach = flops_fit / (kt[_lib.T_FIT_CHOL] * 1e-3) / 1e12
+        phases = {"fit_pack_ms": float(kt[_lib.T_FIT_PACK]), "fit_chol_ms": float(kt[_lib.T_FIT_CHOL]),
+                  "fit_solve_ms": float(kt[_lib.T_FIT_SOLVE]), "query_tree_ms": float(kt[_lib.T_Q_TREE]),
+                  "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]), "query_combine_ms": float(kt[_lib.T_Q_COMBINE]),
+                  "fit_chol_tflops": fit_ach, "fit_chol_frac_of_fp64_peak": fit_ach / peak}
+
+        line = {"metric": "query_pts_per_s (mixture-GP query; fit throughput in fit_leaves_per_s)", "value": Nq / (query_ms_m * 1e-3),
+                "unit": "pts/s", "fit_leaves_per_s": n_leaves / (fit_ms_m * 1e-3), "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "ms_fit": fit_ms_m, "ms_query": query_ms_m,
+                "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
+                "roofline": roofline, "phases": phases}
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(w, root, sizes, leaf_off, Xp, yp)
+            # parity spot check of the sample against the GPU through the public API
+            Yg, Vg, _ = P.querymixtureGP(cb["sample_xq"], η, root, w["levels"], w["radius"], w["delta"], θ, w["sigma2"], wθ)
+            sc_y, sc_v = np.sqrt(np.mean(cb["sample_y"] ** 2)), np.sqrt(np.mean(cb["sample_v"] ** 2))
+            line["cpu_baseline"] = {"value": cb["query_pts_per_s"], "unit": "pts/s", "fit_leaves_per_s": cb["fit_leaves_per_s"],
+                                    "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
+                                    "parity_vs_gpu": {"mean_max_err_over_rms": float(np.abs(Yg - cb["sample_y"]).max() / sc_y),
+                                                      "var_max_err_over_rms": float(np.abs(Vg - cb["sample_v"]).max() / sc_v)}}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -144,15 +144,21 @@ int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_
                          double* pair_t, double* pair_w, double* pair_u, double* pair_v);
 
 /* ---- multi-GPU (leaf -> rank map) --------------------------------------------------------- */
-/* A rank that owns leaves [leaf_base+1, leaf_base+n_leaves] of a larger tree fits only those
- * (pmk_fit with its slice) and declares the offset here BEFORE pmk_fit.  The query is then split:
- *   pmk_query_plan_dev   : tree stage for ALL queries (replicated, cheap); returns n_pairs
- *   pmk_query_pairs_dev  : fused pair kernel for the pairs whose leaf this rank owns; writes u,v into
- *                          caller-provided DEVICE arrays of n_pairs doubles (0 for pairs owned elsewhere)
- *   (caller sums pair_u / pair_v across ranks: one NCCL all-reduce over NVLink, exact because every
- *    slot is non-zero on exactly one rank)
+/* Leaves are independent (reference: one GP per leaf, mixtureGP.jl:92-115), so a rank factorises only
+ * the leaves the leaf->rank map gives it: pmk_set_fit_range(first_leaf 0-based, n) BEFORE pmk_fit (which
+ * still receives ALL leaves' inputs, so every rank lays the model out identically).  After the fit each
+ * rank's L / inv-diagonal-block / alpha ranges are contiguous device spans (pmk_model_buffer) that the
+ * host layer exchanges with NCCL over NVLink; pmk_mark_fitted then declares the replicated model
+ * complete.  Queries are sliced across ranks with no data-path collective; results are gathered once. */
+enum { PMK_BUF_L = 0, PMK_BUF_LINV = 1, PMK_BUF_ALPHA = 2 };
+int pmk_set_fit_range(pmk_handle* h, int64_t first_leaf, int64_t n_leaves /* -1 = to the end */);
+int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_leaves, void** dptr, int64_t* bytes);
+int pmk_mark_fitted(pmk_handle* h);
+
+/* The query in three stages on DEVICE buffers (pmk_query_dev = the three in sequence):
+ *   pmk_query_plan_dev   : home leaves, neighbours, weights, pair list binned by leaf; returns n_pairs
+ *   pmk_query_pairs_dev  : fused pair kernel; writes u,v of every pair into n_pairs-long device arrays
  *   pmk_query_combine_dev: convex combination -> Yq, Vq. */
-int pmk_set_leaf_base(pmk_handle* h, int64_t leaf_base, int64_t total_leaves);
 int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radius, double delta,
                        int wkernel_id, const double* wparams, int nw, int64_t* n_pairs);
 int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pair_v);

@@ -17,8 +17,8 @@
 namespace pmk {
 // launchers defined in the kernel translation units
 void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const double* dX, const double* dy, cudaStream_t s);
-void launch_chol(int D, const LeafTable& lt, const int* d_order, KParams kp, double sigma2, cudaStream_t s);
-void launch_solve(const LeafTable& lt, const int* d_order, int max_npad, cudaStream_t s);
+void launch_chol(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, cudaStream_t s);
+void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
 void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, cudaStream_t s);
 void launch_neighbours(int D, bool fill, const TreeDev& tr, const QueryPlan& q, double radius, double delta, int wkind,
@@ -75,10 +75,12 @@ struct pmk_handle {
   // model
   bool fitted = false;
   int D = 0;
-  int64_t n_leaves = 0, leaf_base = 0, total_leaves = 0;
+  int64_t n_leaves = 0, total_leaves = 0;
+  int64_t fit_first = 0, fit_count = -1;   // leaves factorised by this handle (multi-GPU: leaf -> rank map)
   KParams kp{0, 1.0};
   double sigma2 = 0.0;
   int max_npad = 0;
+  int64_t L_doubles = 0, Linv_doubles = 0, x_points = 0;
   std::vector<int> h_n, h_npad;
   std::vector<int64_t> h_xoff, h_loff, h_ioff;
   int64_t xstride = 0;
@@ -301,11 +303,38 @@ int pmk_cross_gram(pmk_handle* h, int D, int64_t n, const double* X, int64_t m, 
 
 // ---------------------------------------------------------------------------------------------
 // fit
-int pmk_set_leaf_base(pmk_handle* h, int64_t leaf_base, int64_t total_leaves) {
+int pmk_set_fit_range(pmk_handle* h, int64_t first_leaf, int64_t n_leaves) {
   if (!h) return PMK_ERR_ARG;
-  if (leaf_base < 0 || total_leaves < 1 || leaf_base >= total_leaves) return fail(h, PMK_ERR_ARG, "bad leaf_base/total_leaves");
-  h->leaf_base = leaf_base;
-  h->total_leaves = total_leaves;
+  if (first_leaf < 0 || n_leaves < -1) return fail(h, PMK_ERR_ARG, "bad fit range");
+  h->fit_first = first_leaf;
+  h->fit_count = n_leaves;
+  return PMK_OK;
+}
+
+int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_leaves, void** dptr, int64_t* bytes) {
+  if (!h || !dptr || !bytes) return PMK_ERR_ARG;
+  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
+  if (first_leaf < 0 || n_leaves < 0 || first_leaf + n_leaves > h->n_leaves) return fail(h, PMK_ERR_ARG, "leaf range out of bounds");
+  auto span = [&](const std::vector<int64_t>& off, int64_t end_total, double* base) {
+    const int64_t a0 = first_leaf < h->n_leaves ? off[first_leaf] : end_total;
+    const int64_t a1 = first_leaf + n_leaves < h->n_leaves ? off[first_leaf + n_leaves] : end_total;
+    *dptr = (void*)(base + a0);
+    *bytes = (a1 - a0) * (int64_t)sizeof(double);
+  };
+  switch (which) {
+    case PMK_BUF_L: span(h->h_loff, h->L_doubles, h->d_L.as<double>()); break;
+    case PMK_BUF_LINV: span(h->h_ioff, h->Linv_doubles, h->d_Linv.as<double>()); break;
+    case PMK_BUF_ALPHA: span(h->h_xoff, h->x_points, h->d_alpha.as<double>()); break;
+    default: return fail(h, PMK_ERR_ARG, "unknown buffer id %d", which);
+  }
+  return PMK_OK;
+}
+
+int pmk_mark_fitted(pmk_handle* h) {
+  if (!h) return PMK_ERR_ARG;
+  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
+  h->fitted = true;
+  h->plan_valid = false;
   return PMK_OK;
 }
 
@@ -348,12 +377,13 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   }
   const int64_t total_pts = leaf_off[n_leaves];
   h->xstride = xo + 256;   // slack: the Gram kernel's TMA tiles may read past the last leaf
+  h->L_doubles = lo;
+  h->Linv_doubles = io;
+  h->x_points = xo;
   h->max_npad = max_npad;
   h->D = D;
   h->n_leaves = n_leaves;
-  if (h->total_leaves == 0 || h->leaf_base + n_leaves > h->total_leaves) {
-    h->total_leaves = h->leaf_base + n_leaves;
-  }
+  h->total_leaves = n_leaves;
   h->kp = kp;
   h->sigma2 = sigma2;
 
@@ -372,10 +402,13 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   CU(h, h->d_Linv.ensure(sizeof(double) * (size_t)io));
   (void)total_pts;
 
-  // LPT order: largest leaves first
-  std::vector<int> order(n_leaves);
-  std::iota(order.begin(), order.end(), 0);
+  // leaves this handle factorises (all of them unless pmk_set_fit_range narrowed it), LPT order
+  const int64_t f0 = std::min<int64_t>(h->fit_first, n_leaves);
+  const int64_t f1 = h->fit_count < 0 ? n_leaves : std::min<int64_t>(n_leaves, f0 + h->fit_count);
+  std::vector<int> order;
+  for (int64_t p = f0; p < f1; ++p) order.push_back((int)p);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->h_npad[a] > h->h_npad[b]; });
+  const int n_order = (int)order.size();
   // query size classes
   std::vector<int> cls[3];
   for (int64_t p = 0; p < n_leaves; ++p) cls[query_class_of(h->h_npad[p])].push_back((int)p);
@@ -393,7 +426,7 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   CU(h, cudaMemcpyAsync(h->d_xoff.p, h->h_xoff.data(), sizeof(int64_t) * n_leaves, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_loff.p, h->h_loff.data(), sizeof(int64_t) * n_leaves, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_ioff.p, h->h_ioff.data(), sizeof(int64_t) * n_leaves, cudaMemcpyHostToDevice, h->stream));
-  CU(h, cudaMemcpyAsync(h->d_order.p, order.data(), sizeof(int) * n_leaves, cudaMemcpyHostToDevice, h->stream));
+  if (n_order) CU(h, cudaMemcpyAsync(h->d_order.p, order.data(), sizeof(int) * n_order, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_leafoff.p, leaf_off, sizeof(int64_t) * (n_leaves + 1), cudaMemcpyHostToDevice, h->stream));
   // the host vectors above are pageable: the async copies have completed staging on return, but
   // `order`/`cls` die at scope exit, so drain the stream before that.
@@ -421,12 +454,12 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   KCHECK(h, "k_pack_leaves");
   {
     Timer t(h, PMK_T_FIT_CHOL);
-    launch_chol(D, lt, h->d_order.as<int>(), kp, sigma2, h->stream);
+    launch_chol(D, lt, h->d_order.as<int>(), n_order, kp, sigma2, h->stream);
   }
   KCHECK(h, "k_chol");
   {
     Timer t(h, PMK_T_FIT_SOLVE);
-    launch_solve(lt, h->d_order.as<int>(), max_npad, h->stream);
+    launch_solve(lt, h->d_order.as<int>(), n_order, max_npad, h->stream);
   }
   KCHECK(h, "k_solve_alpha");
   // status: first failing leaf
@@ -435,13 +468,13 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   CU(h, cudaStreamSynchronize(h->stream));
   for (int64_t p = 0; p < n_leaves; ++p) {
     if (h_info[p] != 0) {
-      if (bad_leaf) *bad_leaf = h->leaf_base + p + 1;
+      if (bad_leaf) *bad_leaf = p + 1;
       if (info) *info = h_info[p];
       return fail(h, PMK_ERR_NOT_POSDEF, "leaf %lld: K + sigma2*I is not positive definite (info=%d)",
-                  (long long)(h->leaf_base + p + 1), h_info[p]);
+                  (long long)(p + 1), h_info[p]);
     }
   }
-  h->fitted = true;
+  h->fitted = (n_order == n_leaves);   // a partial fit becomes usable after the peers' factors arrive (pmk_mark_fitted)
   h->plan_valid = false;
   return PMK_OK;
 }
@@ -464,8 +497,8 @@ int pmk_fit(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, con
 
 static int check_leaf(pmk_handle* h, int64_t leaf, int64_t* local) {
   if (!h) return PMK_ERR_ARG;
-  if (!h->fitted) return fail(h, PMK_ERR_STATE, "model is not fitted");
-  const int64_t p = leaf - 1 - h->leaf_base;
+  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "model is not fitted");
+  const int64_t p = leaf - 1;
   if (p < 0 || p >= h->n_leaves) return fail(h, PMK_ERR_ARG, "leaf %lld not owned by this handle", (long long)leaf);
   *local = p;
   return PMK_OK;
@@ -670,10 +703,6 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const int mean_only = flags & 1;
   h->last_flags = flags;
   Timer tt(h, PMK_T_Q_PAIRS);
-  if (h->n_leaves != h->total_leaves) {
-    CU(h, cudaMemsetAsync(d_pair_u, 0, sizeof(double) * q.n_pairs, h->stream));
-    CU(h, cudaMemsetAsync(d_pair_v, 0, sizeof(double) * q.n_pairs, h->stream));
-  }
   for (int c = 0; c < 3; ++c) {
     if (h->n_class[c] == 0) continue;
     PairWork w;
@@ -682,7 +711,7 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     w.tile_off = h->d_tile_off[c].as<int64_t>();
     w.leaf_pair_start = h->d_leaf_pair_start.as<int64_t>();
     w.sorted_pair = h->d_sorted_pair.as<int32_t>();
-    w.leaf_base = h->leaf_base;
+    w.leaf_base = 0;
     const int mq = query_class_mq(c);
     launch_class_tiles(w, mq, h->d_class_tiles[c].as<int32_t>(), h->stream);
     KCHECK(h, "k_class_tiles");
@@ -764,11 +793,11 @@ int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_
   if (pair_t) CU(h, cudaMemcpyAsync(pair_t, q.pair_t, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
   if (pair_w) CU(h, cudaMemcpyAsync(pair_w, q.pair_w, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
   if (pair_u) {
-    if (!h->d_pair_u.p) return fail(h, PMK_ERR_STATE, "pair_u is caller-owned in the split (multi-GPU) query");
+    if (!h->d_pair_u.p) return fail(h, PMK_ERR_STATE, "pair_u is caller-owned in the split query");
     CU(h, cudaMemcpyAsync(pair_u, h->d_pair_u.p, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
   }
   if (pair_v) {
-    if (!h->d_pair_v.p) return fail(h, PMK_ERR_STATE, "pair_v is caller-owned in the split (multi-GPU) query");
+    if (!h->d_pair_v.p) return fail(h, PMK_ERR_STATE, "pair_v is caller-owned in the split query");
     CU(h, cudaMemcpyAsync(pair_v, h->d_pair_v.p, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
   }
   CU(h, cudaStreamSynchronize(s));

@@ -360,20 +360,22 @@ void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const do
   }
 }
 
-void launch_chol(int D, const LeafTable& lt, const int* d_order, KParams kp, double sigma2, cudaStream_t s) {
+void launch_chol(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, cudaStream_t s) {
   constexpr int NW = 8, R = 2;
+  if (n_order <= 0) return;
   switch (D) {
-    case 1: k_chol<1, NW, R><<<lt.n_leaves, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
-    case 2: k_chol<2, NW, R><<<lt.n_leaves, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
-    case 3: k_chol<3, NW, R><<<lt.n_leaves, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
+    case 1: k_chol<1, NW, R><<<n_order, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
+    case 2: k_chol<2, NW, R><<<n_order, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
+    case 3: k_chol<3, NW, R><<<n_order, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
     default: break;
   }
 }
 
-void launch_solve(const LeafTable& lt, const int* d_order, int max_npad, cudaStream_t s) {
+void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s) {
   constexpr int NW = 8;
+  if (n_order <= 0) return;
   const size_t smem = (size_t)(max_npad + NW * 32 + 32) * sizeof(double);
-  k_solve_alpha<NW><<<lt.n_leaves, NW * 32, smem, s>>>(lt, d_order);
+  k_solve_alpha<NW><<<n_order, NW * 32, smem, s>>>(lt, d_order);
 }
 
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s) {

@@ -61,7 +61,7 @@ class _LazyLeafList:
         if not eta._fitted:
             raise PMKError(_lib.PMK_ERR_STATE, "MixtureGPType is not fitted (Julia: UndefRefError on c_set[n])")
         n = eta.X_parts[i].shape[0]
-        leaf = eta._leaf_base + i + 1
+        leaf = i + 1
         L = lib()
         if self._what == "c":
             out = np.empty(n)
@@ -78,8 +78,7 @@ class MixtureGPType:
     The fitted state lives in HBM; c_set / L_set / U_set materialise a leaf on the host on demand
     (U_set is the Gram matrix WITHOUT σ², mixtureGP.jl:99)."""
 
-    def __init__(self, X_parts: Sequence[np.ndarray], hps, device: int = 0, leaf_base: int = 0,
-                 total_leaves: Optional[int] = None):
+    def __init__(self, X_parts: Sequence[np.ndarray], hps, device: int = 0, fit_range: Optional[tuple] = None):
         self.X_parts = [_as_points(X) for X in X_parts]
         self.hps = hps                     # (hps_v, hps_c) as returned by fetchhyperplanes
         self.σ2_set: List[float] = []
@@ -88,8 +87,7 @@ class MixtureGPType:
         self.U_set = _LazyLeafList(self, "K")
         self._h = Handle(device)
         self._fitted = False
-        self._leaf_base = leaf_base
-        self._total_leaves = total_leaves
+        self._fit_range = fit_range        # (first_leaf 0-based, n_leaves): leaf -> rank map slice, None = all
         self._tree_key = None
         self.θ = None
 
@@ -117,8 +115,8 @@ def fitmixtureGP_(η: MixtureGPType, y_parts: Sequence[np.ndarray], θ, σ2: flo
     X_packed = np.ascontiguousarray(np.concatenate(η.X_parts, axis=0))
     y_packed = np.ascontiguousarray(np.concatenate([np.asarray(y, dtype=np.float64) for y in y_parts]))
     L = lib()
-    if η._total_leaves is not None:
-        η._h.check(L.pmk_set_leaf_base(η._h.raw, η._leaf_base, η._total_leaves))
+    if η._fit_range is not None:
+        η._h.check(L.pmk_set_fit_range(η._h.raw, int(η._fit_range[0]), int(η._fit_range[1])))
     bad, info = C.c_int64(0), C.c_int(0)
     kp = θ.params
     η._fitted = False
@@ -127,10 +125,24 @@ def fitmixtureGP_(η: MixtureGPType, y_parts: Sequence[np.ndarray], θ, σ2: flo
     if rc == _lib.PMK_ERR_NOT_POSDEF:
         raise PosDefException(info.value, bad.value, L.pmk_last_error(η._h.raw).decode())
     η._h.check(rc)
-    η._fitted = True
+    η._fitted = η._fit_range is None or (η._fit_range[0] == 0 and η._fit_range[1] >= N_parts)
     η.θ = θ
     η.σ2_set = [float(σ2)] * N_parts
     return η
+
+
+def model_buffer(η: MixtureGPType, which: int, first_leaf: int, n_leaves: int):
+    """(device address, bytes) of the contiguous span holding leaves [first_leaf, first_leaf+n_leaves) of
+    buffer `which` (_lib.BUF_L / BUF_LINV / BUF_ALPHA) -- what the ranks exchange after a sharded fit."""
+    dptr, nbytes = C.c_void_p(), C.c_int64(0)
+    η._h.check(lib().pmk_model_buffer(η._h.raw, which, first_leaf, n_leaves, C.byref(dptr), C.byref(nbytes)))
+    return int(dptr.value or 0), int(nbytes.value)
+
+
+def mark_fitted(η: MixtureGPType):
+    """Declare the replicated model complete after the peers' factors have been copied in."""
+    η._h.check(lib().pmk_mark_fitted(η._h.raw))
+    η._fitted = True
 
 
 def _set_tree(η: MixtureGPType, root: Optional[BSPTree], levels: int):

@@ -134,3 +134,30 @@ def test_single_gp_ibb1d():
     c = O.fitRKHS(case["X"], case["y"], th, 1e-5)
     yq = O.query_rkhs(case["X"], case["X"], c, th)
     assert np.abs(yq - case["y"]).max() < 1e-3                      # near-interpolation at sigma2 = 1e-5
+
+
+def test_c_restatement_matches_numpy_oracle():
+    """oracle/pmk_oracle.c (the timed CPU baseline) against oracle/pmk_oracle.py on the mixGP.jl workload."""
+    from oracle import c_oracle
+    case = cases.mixgp_file()
+    m = helpers.oracle_model(case)
+    eta = m["eta"]
+    wth, _ = helpers.kernels(case["wkernel"])
+    y_set = [case["y"][i - 1] for i in m["X_set_inds"]]
+    alpha, L, off, Xp = c_oracle.fit(eta.X_parts, y_set, m["th"].kind, m["th"].param, case["sigma2"])
+    loff = np.concatenate([[0], np.cumsum(np.diff(off) ** 2)])
+    for p in range(len(eta.X_parts)):
+        n = off[p + 1] - off[p]
+        Lc = L[loff[p]:loff[p + 1]].reshape(n, n, order="F")
+        assert np.abs(Lc - eta.L_set[p]).max() < 1e-10 * np.abs(eta.L_set[p]).max()
+        K = c_oracle.gram(eta.X_parts[p], m["th"].kind, m["th"].param)
+        np.testing.assert_allclose(K, O.constructkernelmatrix(eta.X_parts[p], m["th"]), rtol=2e-15, atol=0)   # pow(t,6): libm vs numpy, 1-2 ulp
+    Xq = case["Xq"][::7]
+    Yc, Vc, home, npairs, absent = c_oracle.query(m["hv"], m["hc"], 3, off, Xp, alpha, L, m["th"].kind, m["th"].param, Xq, 0.3, 1e-5,
+                                          wth.kind, wth.param)
+    Yo, Vo, od = O.querymixtureGP_vec(Xq, eta, 3, 0.3, 1e-5, m["th"], wth)
+    assert not absent.any()
+    assert np.array_equal(home, od["home"])
+    assert np.array_equal(npairs, np.diff(od["pair_off"]))
+    assert np.abs(Yc - Yo).max() <= 2e-9 * np.abs(Yo).max()
+    assert np.abs(Vc - Vo).max() <= 2e-8 * np.abs(Vo).max()
