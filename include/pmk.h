@@ -164,6 +164,12 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
 int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pair_v);
 int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d_pair_v, double* dYq, double* dVq);
 
+/* ---- options ----------------------------------------------------------------------------- */
+/* PMK_OPT_FULL_HYPERPLANE_SCAN: 1 = findneighbourpartitions scans ALL hyperplanes per query exactly as the
+ * reference loop does (mixtureGP.jl:354); 0 (default) = exact per-leaf candidate lists (same result). */
+enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1 };
+int pmk_set_option(pmk_handle* h, int option, int64_t value);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 int pmk_get_timings(pmk_handle* h, double* ms /* PMK_T_COUNT entries */);
 /* number of kernel launches issued by this handle since creation */

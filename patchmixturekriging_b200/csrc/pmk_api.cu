@@ -20,9 +20,15 @@ void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const do
 void launch_chol(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
-void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, cudaStream_t s);
-void launch_neighbours(int D, bool fill, const TreeDev& tr, const QueryPlan& q, double radius, double delta, int wkind,
-                       double wparam, int32_t* d_leaf_count, cudaStream_t s);
+void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, int32_t* d_leaf_qcount,
+                 cudaStream_t s);
+void launch_leaf_bbox(int D, int n_leaves, int64_t Nq, const double* dXq, const int32_t* qperm, const int64_t* leaf_qstart,
+                      double* bbox, cudaStream_t s);
+void launch_leaf_candidates(int D, bool fill, int n_leaves, const TreeDev& tr, const double* bbox, double radius,
+                            int32_t* cand_count, const int64_t* cand_start, int32_t* cand, cudaStream_t s);
+void launch_neighbours(int D, bool fill, bool pruned, const TreeDev& tr, const QueryPlan& q, double radius, double delta,
+                       int wkind, double wparam, int32_t* d_leaf_count, const int32_t* qperm, const int64_t* cand_start,
+                       const int32_t* cand, cudaStream_t s);
 void launch_combine(int64_t Nq, const int64_t* pair_off, const double* pw, const double* pu, const double* pv, double* dYq,
                     double* dVq, int mean_only, cudaStream_t s);
 void launch_scan_small(const int32_t* in, int64_t* out, int n, cudaStream_t s);
@@ -99,6 +105,8 @@ struct pmk_handle {
   DBuf d_Xq, d_home, d_npairs, d_pair_off, d_Yq, d_Vq;
   DBuf d_pair_leaf, d_pair_q, d_pair_hp, d_pair_t, d_pair_w, d_pair_u, d_pair_v, d_sorted_pair, d_keys_out, d_iota;
   DBuf d_leaf_count, d_leaf_pair_start, d_cub;
+  DBuf d_leaf_qcount, d_leaf_qstart, d_qperm, d_qkeys, d_bbox, d_cand_count, d_cand_start, d_cand;
+  bool full_scan = false;   // PMK_OPT_FULL_HYPERPLANE_SCAN
   DBuf d_scratch;   // Gram scratch
   QueryPlan plan{};
   bool plan_valid = false;
@@ -212,7 +220,8 @@ void pmk_destroy(pmk_handle* h) {
                   &h->d_info, &h->d_order, &h->d_leafoff, &h->d_Xin, &h->d_yin, &h->d_hv, &h->d_hc, &h->d_Xq, &h->d_home,
                   &h->d_npairs, &h->d_pair_off, &h->d_Yq, &h->d_Vq, &h->d_pair_leaf, &h->d_pair_q, &h->d_pair_hp, &h->d_pair_t,
                   &h->d_pair_w, &h->d_pair_u, &h->d_pair_v, &h->d_sorted_pair, &h->d_keys_out, &h->d_iota, &h->d_leaf_count,
-                  &h->d_leaf_pair_start, &h->d_cub, &h->d_scratch};
+                  &h->d_leaf_pair_start, &h->d_cub, &h->d_scratch, &h->d_leaf_qcount, &h->d_leaf_qstart, &h->d_qperm,
+                  &h->d_qkeys, &h->d_bbox, &h->d_cand_count, &h->d_cand_start, &h->d_cand};
   for (DBuf* b : bufs) b->release();
   for (int c = 0; c < 3; ++c) {
     h->d_class_leaves[c].release();
@@ -234,6 +243,14 @@ int pmk_synchronize(pmk_handle* h) {
 }
 
 int64_t pmk_launch_count(const pmk_handle* h) { return h ? h->launches : 0; }
+
+int pmk_set_option(pmk_handle* h, int option, int64_t value) {
+  if (!h) return PMK_ERR_ARG;
+  switch (option) {
+    case PMK_OPT_FULL_HYPERPLANE_SCAN: h->full_scan = value != 0; h->plan_valid = false; return PMK_OK;
+    default: return fail(h, PMK_ERR_ARG, "unknown option %d", option);
+  }
+}
 
 int pmk_get_timings(pmk_handle* h, double* ms) {
   if (!h || !ms) return PMK_ERR_ARG;
@@ -595,7 +612,7 @@ int pmk_find_partition(pmk_handle* h, int64_t Nq, const double* Xq, int32_t* lea
   CU(h, h->d_Xq.ensure(sizeof(double) * Nq * D));
   CU(h, h->d_home.ensure(sizeof(int32_t) * Nq));
   CU(h, cudaMemcpyAsync(h->d_Xq.p, Xq, sizeof(double) * Nq * D, cudaMemcpyHostToDevice, h->stream));
-  launch_home(D, h->tree, Nq, h->d_Xq.as<double>(), h->d_home.as<int32_t>(), h->stream);
+  launch_home(D, h->tree, Nq, h->d_Xq.as<double>(), h->d_home.as<int32_t>(), nullptr, h->stream);
   KCHECK(h, "k_home");
   CU(h, cudaMemcpyAsync(leaf_out, h->d_home.p, sizeof(int32_t) * Nq, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -638,11 +655,63 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
   q.pair_off = h->d_pair_off.as<int64_t>();
 
   Timer tt(h, PMK_T_Q_TREE);
-  launch_home(D, h->tree, Nq, dXq, q.home, h->stream);
-  KCHECK(h, "k_home");
+  const bool pruned = !h->full_scan && h->n_hp > 0;
+  // iota (pair / query ids for the radix sorts)
+  auto ensure_iota = [&](int64_t n) -> int {
+    if (h->d_iota.cap < sizeof(int32_t) * (size_t)n) {
+      CU(h, h->d_iota.ensure(sizeof(int32_t) * n));
+      std::vector<int32_t> iota((size_t)(h->d_iota.cap / sizeof(int32_t)));
+      std::iota(iota.begin(), iota.end(), 0);
+      CU(h, cudaMemcpyAsync(h->d_iota.p, iota.data(), sizeof(int32_t) * iota.size(), cudaMemcpyHostToDevice, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+    }
+    return PMK_OK;
+  };
+  int end_bit = 1;
+  while ((1ll << end_bit) <= TL) ++end_bit;
   CU(h, cudaMemsetAsync(h->d_npairs.as<int32_t>() + Nq, 0, sizeof(int32_t), h->stream));
   CU(h, cudaMemsetAsync(h->d_leaf_count.p, 0, sizeof(int32_t) * TL, h->stream));
-  launch_neighbours(D, false, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(), h->stream);
+  if (pruned) {
+    CU(h, h->d_leaf_qcount.ensure(sizeof(int32_t) * TL));
+    CU(h, h->d_leaf_qstart.ensure(sizeof(int64_t) * (TL + 1)));
+    CU(h, h->d_qperm.ensure(sizeof(int32_t) * Nq));
+    CU(h, h->d_qkeys.ensure(sizeof(int32_t) * Nq));
+    CU(h, h->d_bbox.ensure(sizeof(double) * TL * 2 * D));
+    CU(h, h->d_cand_count.ensure(sizeof(int32_t) * TL));
+    CU(h, h->d_cand_start.ensure(sizeof(int64_t) * (TL + 1)));
+    if (int rc = ensure_iota(Nq)) return rc;
+    CU(h, cudaMemsetAsync(h->d_leaf_qcount.p, 0, sizeof(int32_t) * TL, h->stream));
+  }
+  launch_home(D, h->tree, Nq, dXq, q.home, pruned ? h->d_leaf_qcount.as<int32_t>() : nullptr, h->stream);
+  KCHECK(h, "k_home");
+  if (pruned) {
+    launch_scan_small(h->d_leaf_qcount.as<int32_t>(), h->d_leaf_qstart.as<int64_t>(), (int)TL, h->stream);
+    KCHECK(h, "k_scan_small");
+    {   // queries sorted (stably) by home leaf
+      size_t tb = 0;
+      cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, q.home, h->d_qkeys.as<int32_t>(), h->d_iota.as<int32_t>(),
+                                      h->d_qperm.as<int32_t>(), (int)Nq, 0, end_bit, h->stream);
+      CU(h, h->d_cub.ensure(tb));
+      CU(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, q.home, h->d_qkeys.as<int32_t>(), h->d_iota.as<int32_t>(),
+                                            h->d_qperm.as<int32_t>(), (int)Nq, 0, end_bit, h->stream));
+    }
+    launch_leaf_bbox(D, (int)TL, Nq, dXq, h->d_qperm.as<int32_t>(), h->d_leaf_qstart.as<int64_t>(), h->d_bbox.as<double>(), h->stream);
+    KCHECK(h, "k_leaf_bbox");
+    launch_leaf_candidates(D, false, (int)TL, h->tree, h->d_bbox.as<double>(), radius, h->d_cand_count.as<int32_t>(), nullptr,
+                           nullptr, h->stream);
+    KCHECK(h, "k_leaf_candidates<count>");
+    launch_scan_small(h->d_cand_count.as<int32_t>(), h->d_cand_start.as<int64_t>(), (int)TL, h->stream);
+    KCHECK(h, "k_scan_small");
+    int64_t n_cand = 0;
+    CU(h, cudaMemcpyAsync(&n_cand, h->d_cand_start.as<int64_t>() + TL, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    CU(h, h->d_cand.ensure(sizeof(int32_t) * std::max<int64_t>(n_cand, 1)));
+    launch_leaf_candidates(D, true, (int)TL, h->tree, h->d_bbox.as<double>(), radius, h->d_cand_count.as<int32_t>(),
+                           h->d_cand_start.as<int64_t>(), h->d_cand.as<int32_t>(), h->stream);
+    KCHECK(h, "k_leaf_candidates<fill>");
+  }
+  launch_neighbours(D, false, pruned, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(),
+                    h->d_qperm.as<int32_t>(), h->d_cand_start.as<int64_t>(), h->d_cand.as<int32_t>(), h->stream);
   KCHECK(h, "k_neighbours<count>");
   {
     size_t tb = 0;
@@ -667,21 +736,14 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
   q.pair_hp = h->d_pair_hp.as<int32_t>();
   q.pair_t = h->d_pair_t.as<double>();
   q.pair_w = h->d_pair_w.as<double>();
-  launch_neighbours(D, true, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(), h->stream);
+  launch_neighbours(D, true, pruned, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(),
+                    h->d_qperm.as<int32_t>(), h->d_cand_start.as<int64_t>(), h->d_cand.as<int32_t>(), h->stream);
   KCHECK(h, "k_neighbours<fill>");
   launch_scan_small(h->d_leaf_count.as<int32_t>(), h->d_leaf_pair_start.as<int64_t>(), (int)TL, h->stream);
   KCHECK(h, "k_scan_small");
   // stable sort of pair ids by leaf
   {
-    if (h->d_iota.cap < sizeof(int32_t) * (size_t)n_pairs) {
-      CU(h, h->d_iota.ensure(sizeof(int32_t) * n_pairs));
-      std::vector<int32_t> iota((size_t)(h->d_iota.cap / sizeof(int32_t)));
-      std::iota(iota.begin(), iota.end(), 0);
-      CU(h, cudaMemcpyAsync(h->d_iota.p, iota.data(), sizeof(int32_t) * iota.size(), cudaMemcpyHostToDevice, h->stream));
-      CU(h, cudaStreamSynchronize(h->stream));
-    }
-    int end_bit = 1;
-    while ((1ll << end_bit) <= TL) ++end_bit;
+    if (int rc = ensure_iota(n_pairs)) return rc;
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, q.pair_leaf, h->d_keys_out.as<int32_t>(), h->d_iota.as<int32_t>(),
                                     h->d_sorted_pair.as<int32_t>(), (int)n_pairs, 0, end_bit, h->stream);

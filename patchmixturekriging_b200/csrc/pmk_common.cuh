@@ -20,10 +20,22 @@ struct KParams {
 // C/D: lane holds C[lane>>2][2*(lane&3)+{0,1}].
 // ---------------------------------------------------------------------------------------
 __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-               : "+d"(d0), "+d"(d1)
-               : "d"(a), "d"(b));
+  asm("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+      : "+d"(d0), "+d"(d1)
+      : "d"(a), "d"(b));
 }
+
+// A warp-uniform condition that ptxas must turn into a BRANCH, never into predication.
+// Measured on B200 (profiles/ncu_r01_v0_summary.md): a predicated-off DMMA still occupies the FP64
+// tensor pipe for its full 16 cycles, so if-converted "skip this tile" guards cost as much as the
+// work they skip.  The opaque trip count makes the guarded block a loop body, which cannot be
+// if-converted.
+__device__ __forceinline__ int opaque_int(int x) {
+  int y;
+  asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+#define PMK_UNIFORM_IF(cond) for (int pmk_r_ = pmk::opaque_int((cond) ? 1 : 0); pmk_r_ > 0; --pmk_r_)
 
 // ---------------------------------------------------------------------------------------
 // Packed storage of a leaf's lower-triangular factor L (n_pad x n_pad, n_pad % 32 == 0).

@@ -78,6 +78,30 @@ __device__ __noinline__ int factor_block32(double* Dbuf, double* Ibuf, int lane)
   return 0;
 }
 
+// trailing-update inner loop of k_chol for NV valid row tiles (NV is warp-uniform)
+template <int R, int NV>
+__device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2* __restrict__ Lp, const int (&bo)[4],
+                                           const int (&ao)[R], int nct) {
+#pragma unroll 4
+  for (int ct = 0; ct < nct; ++ct) {
+    double2 bf[4], af[NV];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf[b] = Lp[bo[b] + ct * 32];
+#pragma unroll
+    for (int r = 0; r < NV; ++r) af[r] = Lp[ao[r] + ct * 32];
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af[r].x, bf[b].x);
+    }
+#pragma unroll
+    for (int r = 0; r < NV; ++r) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af[r].y, bf[b].y);
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 template <int D, int NW, int R>
 __global__ void __launch_bounds__(NW * 32, 3)
@@ -147,24 +171,11 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
         for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
 #pragma unroll
         for (int r = 0; r < R; ++r) ao[r] = (int)tri(tv[r] ? t[r] : t0) * 32 + lane;
-        const int nct = 4 * J;
-#pragma unroll 2
-        for (int ct = 0; ct < nct; ++ct) {
-          double2 bf[4];
-#pragma unroll
-          for (int b = 0; b < 4; ++b) bf[b] = Lp[bo[b] + ct * 32];
-#pragma unroll
-          for (int r = 0; r < R; ++r) {
-            if (tv[r]) {
-              const double2 af = Lp[ao[r] + ct * 32];
-#pragma unroll
-              for (int b = 0; b < 4; ++b) {
-                dmma884(acc[r][b][0], acc[r][b][1], af.x, bf[b].x);
-                dmma884(acc[r][b][0], acc[r][b][1], af.y, bf[b].y);
-              }
-            }
-          }
-        }
+        // the number of valid row tiles of this warp is uniform: pick a loop specialised for it, so
+        // that no DMMA is predicated (a predicated-off DMMA still occupies the pipe) and the loads of
+        // the unrolled iterations can be hoisted freely
+        if (tv[R - 1]) chol_kloop<R, R>(acc, Lp, bo, ao, 4 * J);
+        else if (R > 1 && tv[0]) chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J);
       }
       // ---- diagonal block: factor + invert (chunk 0 carries row tiles t0..t0+3 on warps 0..3) ----
       if (c == 0) {
@@ -202,7 +213,7 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
       // ---- panel rows below the diagonal block: L[t, J] = C * inv(L_JJ)^T ------------------------
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        if (tv[r] && t[r] >= t0 + 4) {
+        PMK_UNIFORM_IF(tv[r] && t[r] >= t0 + 4) {
           double alo[4], ahi[4];
 #pragma unroll
           for (int kb = 0; kb < 4; ++kb) {

@@ -18,8 +18,18 @@ namespace pmk {
 
 static constexpr unsigned kFullQ = 0xffffffffu;
 
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  // .cg: cache in L2 only -- an L tile is consumed once per CTA, other CTAs of the same leaf find it in L2
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 
-template <int D, int NW, int NT, int NQT>
+
+template <int D, int NW, int NT, int NQT, int DEPTH>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, double* __restrict__ pair_u,
               double* __restrict__ pair_v) {
@@ -123,7 +133,51 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 #pragma unroll
   for (int k = 0; k < OT; ++k) vacc[k][0] = vacc[k][1] = 0.0;
 
+  // Per-warp cp.async ring of L tiles.  The sequence of tiles a warp consumes -- for J, for ct, for its
+  // active row tiles -- does not depend on the solve, so the copies run DEPTH-1 tiles ahead of the DMMAs
+  // (across the block barriers too) without costing a register; every lane copies and later reads back
+  // exactly its own 16 bytes of the fragment-major tile.
+  extern __shared__ __align__(16) unsigned char pmk_dyn_smem[];
+  double2* ring = reinterpret_cast<double2*>(pmk_dyn_smem) + (size_t)warp * (DEPTH * 32) + lane;
+  int pJ = 0, pct = 0, pi = -1;
+  bool pdone = false;
+  auto p_advance = [&]() {
+    for (;;) {
+      ++pi;
+      if (pi == NT) {
+        pi = 0;
+        if (++pct == 4) { pct = 0; ++pJ; }
+      }
+      if (pJ + 1 >= nblk) { pdone = true; return; }
+      const int t = warp + NW * pi;
+      if (t >= 4 * pJ + 4 && t < ntl) return;
+    }
+  };
+  auto p_issue = [&](int slot) {
+    if (!pdone) {
+      const int t = warp + NW * pi;
+      cp_async16(ring + slot * 32, Lp + (tri(t) + 4 * pJ + pct) * 32 + lane);
+      p_advance();
+    }
+    cp_async_commit();     // always commit: keeps the group count in step with the consumer
+  };
+  p_advance();
+#pragma unroll
+  for (int s_ = 0; s_ < DEPTH - 1; ++s_) p_issue(s_);
+  int cslot = 0, fslot = DEPTH - 1;   // slot to consume next / free slot to refill
+
   for (int J = 0; J < nblk; ++J) {
+    // prefetch this warp's inverse-diagonal-block tiles for step 2 (latency hidden behind the barrier)
+    double2 fI[OT][4];
+#pragma unroll
+    for (int k = 0; k < OT; ++k) {
+      const int ot = warp + NW * k;
+      const int a = ot / NQT;
+#pragma unroll
+      for (int b = 0; b < 4; ++b)
+        fI[k][b] = (ot < 4 * NQT && b <= a) ? Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane]
+                                            : make_double2(0.0, 0.0);
+    }
     // 1. owners of block J's four row tiles publish C_J = -acc
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
@@ -141,18 +195,23 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 #pragma unroll
     for (int k = 0; k < OT; ++k) {
       const int ot = warp + NW * k;
-      if (ot < 4 * NQT) {
+      PMK_UNIFORM_IF(ot < 4 * NQT) {
         const int a = ot / NQT, nt = ot % NQT;
         double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
-        const double2* It = Ip + (size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2) * 32 + lane;
-#pragma unroll
-        for (int b = 0; b < 4; ++b) {
-          if (b <= a) {
-            const double2 f = It[b * 32];
-            const double b0 = Cbuf[(8 * b + l) * LDQ + nt * 8 + g];
-            const double b1 = Cbuf[(8 * b + 4 + l) * LDQ + nt * 8 + g];
-            dmma884(s0, s1, f.x, b0);
-            dmma884(r0, r1, f.y, b1);
+        const double* Cb = &Cbuf[l * LDQ + nt * 8 + g];
+        // b = 0 always; b = 1..a behind real (uniform) branches
+        dmma884(s0, s1, fI[k][0].x, Cb[0]);
+        dmma884(r0, r1, fI[k][0].y, Cb[4 * LDQ]);
+        PMK_UNIFORM_IF(a >= 1) {
+          dmma884(s0, s1, fI[k][1].x, Cb[8 * LDQ]);
+          dmma884(r0, r1, fI[k][1].y, Cb[12 * LDQ]);
+          PMK_UNIFORM_IF(a >= 2) {
+            dmma884(s0, s1, fI[k][2].x, Cb[16 * LDQ]);
+            dmma884(r0, r1, fI[k][2].y, Cb[20 * LDQ]);
+            PMK_UNIFORM_IF(a >= 3) {
+              dmma884(s0, s1, fI[k][3].x, Cb[24 * LDQ]);
+              dmma884(r0, r1, fI[k][3].y, Cb[28 * LDQ]);
+            }
           }
         }
         s0 += r0;
@@ -163,8 +222,11 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
       }
     }
     __syncthreads();
-    // 3. acc[I] += L_IJ * S_J for the row tiles below block J
+    // 3. acc[I] += L_IJ * S_J for the row tiles below block J.  Tile guards are REAL branches
+    //    (PMK_UNIFORM_IF); within a tile the DMMAs are ordered k-step-major so that consecutive
+    //    ones hit different accumulators.
     if (J + 1 < nblk) {
+      const int t_lo = 4 * J + 4;
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct) {
         double bf[2][NQT];
@@ -175,18 +237,22 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 #pragma unroll
         for (int i = 0; i < NT; ++i) {
           const int t = warp + NW * i;
-          if (t >= 4 * J + 4 && t < ntl) {
-            const double2 af = Lp[(tri(t) + 4 * J + ct) * 32 + lane];
+          PMK_UNIFORM_IF(t >= t_lo && t < ntl) {
+            cp_async_wait<DEPTH - 2>();
+            const double2 af = ring[cslot * 32];
+            p_issue(fslot);              // refill the slot consumed one step ago (its data is in registers by now)
+            fslot = cslot;
+            cslot = (cslot + 1 == DEPTH) ? 0 : cslot + 1;
 #pragma unroll
-            for (int nt = 0; nt < NQT; ++nt) {
-              dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[0][nt]);
-              dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[1][nt]);
-            }
+            for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[0][nt]);
+#pragma unroll
+            for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[1][nt]);
           }
         }
       }
     }
   }
+  cp_async_wait<0>();
 
   // ---- reduce ||s||^2 and finish --------------------------------------------------------------
 #pragma unroll
@@ -226,13 +292,26 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 
 // one translation unit per D (pmk_query_d{1,2,3}.cu) instantiates the three size classes
 //   class 0: n_pad <=  512, MQ = 32     class 1: n_pad <= 1024, MQ = 16     class 2: n_pad <= 2048, MQ = 8
+template <int D, int NW, int NT, int NQT, int DEPTH>
+static void launch_one(unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int mean_only,
+                       double* pu, double* pv, cudaStream_t s) {
+  constexpr size_t dyn = (size_t)NW * DEPTH * 32 * sizeof(double2);
+  static bool configured = false;   // one attribute call per instantiation (per process; all devices are B200)
+  auto kern = k_query_pairs<D, NW, NT, NQT, DEPTH>;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    configured = true;
+  }
+  kern<<<grid, NW * 32, dyn, s>>>(lt, w, q, kp, mean_only, pu, pv);
+}
+
 template <int D>
 void launch_pairs_d(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                     int mean_only, double* pu, double* pv, cudaStream_t s) {
-  constexpr int NW = 16;
-  if (cls == 0) k_query_pairs<D, NW, 4, 4><<<grid, NW * 32, 0, s>>>(lt, w, q, kp, mean_only, pu, pv);
-  else if (cls == 1) k_query_pairs<D, NW, 8, 2><<<grid, NW * 32, 0, s>>>(lt, w, q, kp, mean_only, pu, pv);
-  else k_query_pairs<D, NW, 16, 1><<<grid, NW * 32, 0, s>>>(lt, w, q, kp, mean_only, pu, pv);
+  constexpr int NW = 16, DEPTH = 6;
+  if (cls == 0) launch_one<D, NW, 4, 4, DEPTH>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else if (cls == 1) launch_one<D, NW, 8, 2, DEPTH>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else launch_one<D, NW, 16, 1, DEPTH>(grid, lt, w, q, kp, mean_only, pu, pv, s);
 }
 
 }  // namespace pmk

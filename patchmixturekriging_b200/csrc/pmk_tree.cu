@@ -26,65 +26,190 @@ __device__ __forceinline__ int descend(const TreeDev& tr, const double* x) {
 }
 
 template <int D>
-__global__ void k_home(TreeDev tr, int64_t Nq, const double* __restrict__ Xq, int32_t* __restrict__ home) {
+__global__ void k_home(TreeDev tr, int64_t Nq, const double* __restrict__ Xq, int32_t* __restrict__ home,
+                       int32_t* __restrict__ leaf_qcount /* may be null */) {
   const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
   if (j >= Nq) return;
   double x[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) x[d] = Xq[j * D + d];
-  home[j] = descend<D>(tr, x);
+  const int h = descend<D>(tr, x);
+  home[j] = h;
+  if (leaf_qcount) atomicAdd(&leaf_qcount[h - 1], 1);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Exact pruning of findneighbourpartitions' scan over ALL hyperplanes (mixtureGP.jl:354).
+// A hyperplane i can only pass the reference's test norm(z - p) < radius for a query p of leaf l if
+// its plane comes within ~radius of the bounding box of l's queries.  Per leaf we therefore build the
+// ascending list of such hyperplanes (interval arithmetic with a generous slack), and every query then
+// runs the reference's test -- same operations, same order -- on its home leaf's list only.  The kept
+// set, its order and every t are identical to the full scan (checked against the brute-force kernel
+// in tests/test_gpu_parity.py::test_pruned_neighbour_search_equals_full_scan).
+template <int D>
+__global__ void k_leaf_bbox(int64_t Nq, const double* __restrict__ Xq, const int32_t* __restrict__ qperm,
+                            const int64_t* __restrict__ leaf_qstart, double* __restrict__ bbox /* [leaf][2][D] */) {
+  const int leaf = blockIdx.x;
+  const int64_t a = leaf_qstart[leaf], b = leaf_qstart[leaf + 1];
+  double lo[D], hi[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) { lo[d] = INFINITY; hi[d] = -INFINITY; }
+  for (int64_t k = a + threadIdx.x; k < b; k += blockDim.x) {
+    const int64_t j = qperm[k];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      const double x = Xq[j * D + d];
+      lo[d] = fmin(lo[d], x);
+      hi[d] = fmax(hi[d], x);
+    }
+  }
+  __shared__ double red[2 * D][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+      lo[d] = fmin(lo[d], __shfl_xor_sync(0xffffffffu, lo[d], m));
+      hi[d] = fmax(hi[d], __shfl_xor_sync(0xffffffffu, hi[d], m));
+    }
+    if (lane == 0) { red[d][warp] = lo[d]; red[D + d][warp] = hi[d]; }
+  }
+  __syncthreads();
+  if (threadIdx.x < D) {
+    double l = INFINITY, h = -INFINITY;
+    for (int w = 0; w < nw; ++w) { l = fmin(l, red[threadIdx.x][w]); h = fmax(h, red[D + threadIdx.x][w]); }
+    bbox[(leaf * 2 + 0) * D + threadIdx.x] = l;
+    bbox[(leaf * 2 + 1) * D + threadIdx.x] = h;
+  }
+}
+
+template <int D, bool FILL>
+__global__ void __launch_bounds__(256)
+k_leaf_candidates(TreeDev tr, const double* __restrict__ bbox, double radius, int32_t* __restrict__ cand_count,
+                  const int64_t* __restrict__ cand_start, int32_t* __restrict__ cand) {
+  const int leaf = blockIdx.x;
+  double lo[D], hi[D];
+  double amax = 0.0;
+  bool empty = false;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    lo[d] = bbox[(leaf * 2 + 0) * D + d];
+    hi[d] = bbox[(leaf * 2 + 1) * D + d];
+    if (!(lo[d] <= hi[d])) empty = true;
+    amax += fmax(fabs(lo[d]), fabs(hi[d]));
+  }
+  if (empty) {
+    if (!FILL && threadIdx.x == 0) cand_count[leaf] = 0;
+    return;
+  }
+  __shared__ int wsum[8];
+  __shared__ int s_base;
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t out0 = FILL ? cand_start[leaf] : 0;
+  for (int base = 0; base < tr.n_hp; base += 256) {
+    const int i = base + threadIdx.x;
+    bool f = false;
+    if (i < tr.n_hp) {
+      double slo = 0.0, shi = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double u = tr.hv[d * tr.n_hp + i];
+        const double a = u * lo[d], b = u * hi[d];
+        slo += fmin(a, b);
+        shi += fmax(a, b);
+      }
+      const double c = tr.hc[i];
+      const double dist = fmax(0.0, fmax(c - shi, slo - c));       // min |c - u.p| over the box
+      f = dist <= radius * (1.0 + 1e-6) + 1e-9 * (1.0 + fabs(c) + amax);
+    }
+    const unsigned bal = __ballot_sync(0xffffffffu, f);
+    const int wpre = __popc(bal & ((1u << lane) - 1));
+    if (lane == 0) wsum[warp] = __popc(bal);
+    __syncthreads();
+    int off = s_base;
+    for (int w = 0; w < warp; ++w) off += wsum[w];
+    if (FILL && f) cand[out0 + off + wpre] = i;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int w = 0; w < 8; ++w) tot += wsum[w];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (!FILL && threadIdx.x == 0) cand_count[leaf] = s_base;
 }
 
 // Pass FILL=false counts the slots of every query (kept neighbours + 1); FILL=true writes them.
 // Slot order = reference order: kept hyperplanes in increasing index, home leaf last.
-template <int D, bool FILL>
+// The reference's per-hyperplane test (mixtureGP.jl:357-399) for hyperplane i; returns the neighbour leaf or 0.
+template <int D>
+__device__ __forceinline__ int neighbour_test(const TreeDev& tr, const double* p, int home, int i, double radius,
+                                              double delta, double* t_out) {
+  double u[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) u[d] = tr.hv[d * tr.n_hp + i];
+  const double c = tr.hc[i];
+  const double t = __dadd_rn(-dot_seq<D>(u, p), c);              // mixtureGP.jl:361  t = -dot(u,p) + c
+  // z = p + t.*u ; norm(z - p)                                     mixtureGP.jl:362,367
+  double s = 0.0;
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    const double z = __dadd_rn(p[d], __dmul_rn(t, u[d]));
+    const double dd = __dsub_rn(z, p[d]);
+    s = (d == 0) ? __dmul_rn(dd, dd) : __dadd_rn(s, __dmul_rn(dd, dd));
+  }
+  if (!(__dsqrt_rn(s) < radius)) return 0;
+  double z1[D], z2[D];
+  const double tp = __dadd_rn(t, delta), tm = __dsub_rn(t, delta);
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    z1[d] = __dadd_rn(p[d], __dmul_rn(tp, u[d]));                // mixtureGP.jl:370-371
+    z2[d] = __dadd_rn(p[d], __dmul_rn(tm, u[d]));
+  }
+  const int r1 = descend<D>(tr, z1);
+  const int r2 = descend<D>(tr, z2);
+  if ((r2 == home) == (r1 == home)) return 0;                    // mixtureGP.jl:387 xor
+  *t_out = t;
+  return (r1 == home) ? r2 : r1;                                 // mixtureGP.jl:392-395
+}
+
+// Pass FILL=false counts the slots of every query (kept neighbours + 1); FILL=true writes them.
+// Slot order = reference order: kept hyperplanes in increasing index, home leaf last.
+// PRUNED: thread k handles query qperm[k] (queries sorted by home leaf, so a warp shares one candidate
+// list) and scans its leaf's candidate hyperplanes; otherwise thread j scans all hyperplanes.
+template <int D, bool FILL, bool PRUNED>
 __global__ void k_neighbours(TreeDev tr, QueryPlan q, double radius, double delta, int wkind, double wparam,
-                             int32_t* __restrict__ leaf_count /* global leaf ids, 0-based slot */) {
-  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
-  if (j >= q.Nq) return;
+                             int32_t* __restrict__ leaf_count /* pairs per global leaf */, const int32_t* __restrict__ qperm,
+                             const int64_t* __restrict__ cand_start, const int32_t* __restrict__ cand) {
+  const int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (k >= q.Nq) return;
+  const int64_t j = PRUNED ? (int64_t)qperm[k] : k;
   double p[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) p[d] = q.Xq[j * D + d];
   const int home = q.home[j];
   int64_t slot = FILL ? q.pair_off[j] : 0;
   int kept = 0;
-  for (int i = 0; i < tr.n_hp; ++i) {
-    double u[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) u[d] = tr.hv[d * tr.n_hp + i];
-    const double c = tr.hc[i];
-    const double t = __dadd_rn(-dot_seq<D>(u, p), c);            // mixtureGP.jl:361  t = -dot(u,p) + c
-    // z = p + t.*u ; norm(z - p)                                   mixtureGP.jl:362,367
-    double s = 0.0;
-#pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double z = __dadd_rn(p[d], __dmul_rn(t, u[d]));
-      const double dd = __dsub_rn(z, p[d]);
-      s = (d == 0) ? __dmul_rn(dd, dd) : __dadd_rn(s, __dmul_rn(dd, dd));
-    }
-    if (__dsqrt_rn(s) < radius) {
-      double z1[D], z2[D];
-      const double tp = __dadd_rn(t, delta), tm = __dsub_rn(t, delta);
-#pragma unroll
-      for (int d = 0; d < D; ++d) {
-        z1[d] = __dadd_rn(p[d], __dmul_rn(tp, u[d]));              // mixtureGP.jl:370-371
-        z2[d] = __dadd_rn(p[d], __dmul_rn(tm, u[d]));
+  const int64_t c0 = PRUNED ? cand_start[home - 1] : 0;
+  const int64_t c1 = PRUNED ? cand_start[home] : tr.n_hp;
+  for (int64_t cc = c0; cc < c1; ++cc) {
+    const int i = PRUNED ? cand[cc] : (int)cc;
+    double t;
+    const int nb = neighbour_test<D>(tr, p, home, i, radius, delta, &t);
+    if (nb != 0) {
+      if (FILL) {
+        q.pair_leaf[slot] = nb;
+        q.pair_q[slot] = (int32_t)j;
+        q.pair_hp[slot] = i + 1;
+        q.pair_t[slot] = t;
+        q.pair_w[slot] = k_tau(wkind, wparam, fabs(t));            // mixtureGP.jl:231
+        atomicAdd(&leaf_count[nb - 1], 1);
+        ++slot;
       }
-      const int r1 = descend<D>(tr, z1);
-      const int r2 = descend<D>(tr, z2);
-      if ((r2 == home) != (r1 == home)) {                          // mixtureGP.jl:387 xor
-        if (FILL) {
-          const int nb = (r1 == home) ? r2 : r1;                   // mixtureGP.jl:392-395
-          q.pair_leaf[slot] = nb;
-          q.pair_q[slot] = (int32_t)j;
-          q.pair_hp[slot] = i + 1;
-          q.pair_t[slot] = t;
-          q.pair_w[slot] = k_tau(wkind, wparam, fabs(t));          // mixtureGP.jl:231
-          atomicAdd(&leaf_count[nb - 1], 1);
-          ++slot;
-        }
-        ++kept;
-      }
+      ++kept;
     }
   }
   if (FILL) {
@@ -144,36 +269,71 @@ __global__ void k_scan_small(const int32_t* __restrict__ in, int64_t* __restrict
 }
 
 // ---------------------------------------------------------------------------------------------
-void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, cudaStream_t s) {
+void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, int32_t* d_leaf_qcount,
+                 cudaStream_t s) {
   const int T = 256;
   const unsigned B = (unsigned)((Nq + T - 1) / T);
   if (B == 0) return;
   switch (D) {
-    case 1: k_home<1><<<B, T, 0, s>>>(tr, Nq, dXq, d_home); break;
-    case 2: k_home<2><<<B, T, 0, s>>>(tr, Nq, dXq, d_home); break;
-    case 3: k_home<3><<<B, T, 0, s>>>(tr, Nq, dXq, d_home); break;
+    case 1: k_home<1><<<B, T, 0, s>>>(tr, Nq, dXq, d_home, d_leaf_qcount); break;
+    case 2: k_home<2><<<B, T, 0, s>>>(tr, Nq, dXq, d_home, d_leaf_qcount); break;
+    case 3: k_home<3><<<B, T, 0, s>>>(tr, Nq, dXq, d_home, d_leaf_qcount); break;
+    default: break;
+  }
+}
+
+void launch_leaf_bbox(int D, int n_leaves, int64_t Nq, const double* dXq, const int32_t* qperm, const int64_t* leaf_qstart,
+                      double* bbox, cudaStream_t s) {
+  switch (D) {
+    case 1: k_leaf_bbox<1><<<n_leaves, 128, 0, s>>>(Nq, dXq, qperm, leaf_qstart, bbox); break;
+    case 2: k_leaf_bbox<2><<<n_leaves, 128, 0, s>>>(Nq, dXq, qperm, leaf_qstart, bbox); break;
+    case 3: k_leaf_bbox<3><<<n_leaves, 128, 0, s>>>(Nq, dXq, qperm, leaf_qstart, bbox); break;
     default: break;
   }
 }
 
 template <bool FILL>
-static void launch_nb_t(int D, const TreeDev& tr, const QueryPlan& q, double radius, double delta, int wkind,
-                        double wparam, int32_t* d_leaf_count, cudaStream_t s) {
-  const int T = 128;
-  const unsigned B = (unsigned)((q.Nq + T - 1) / T);
-  if (B == 0) return;
+static void launch_cand_t(int D, int n_leaves, const TreeDev& tr, const double* bbox, double radius, int32_t* cand_count,
+                          const int64_t* cand_start, int32_t* cand, cudaStream_t s) {
   switch (D) {
-    case 1: k_neighbours<1, FILL><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count); break;
-    case 2: k_neighbours<2, FILL><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count); break;
-    case 3: k_neighbours<3, FILL><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count); break;
+    case 1: k_leaf_candidates<1, FILL><<<n_leaves, 256, 0, s>>>(tr, bbox, radius, cand_count, cand_start, cand); break;
+    case 2: k_leaf_candidates<2, FILL><<<n_leaves, 256, 0, s>>>(tr, bbox, radius, cand_count, cand_start, cand); break;
+    case 3: k_leaf_candidates<3, FILL><<<n_leaves, 256, 0, s>>>(tr, bbox, radius, cand_count, cand_start, cand); break;
     default: break;
   }
 }
 
-void launch_neighbours(int D, bool fill, const TreeDev& tr, const QueryPlan& q, double radius, double delta, int wkind,
-                       double wparam, int32_t* d_leaf_count, cudaStream_t s) {
-  if (fill) launch_nb_t<true>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, s);
-  else launch_nb_t<false>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, s);
+void launch_leaf_candidates(int D, bool fill, int n_leaves, const TreeDev& tr, const double* bbox, double radius,
+                            int32_t* cand_count, const int64_t* cand_start, int32_t* cand, cudaStream_t s) {
+  if (fill) launch_cand_t<true>(D, n_leaves, tr, bbox, radius, cand_count, cand_start, cand, s);
+  else launch_cand_t<false>(D, n_leaves, tr, bbox, radius, cand_count, cand_start, cand, s);
+}
+
+template <bool FILL, bool PRUNED>
+static void launch_nb_t(int D, const TreeDev& tr, const QueryPlan& q, double radius, double delta, int wkind,
+                        double wparam, int32_t* d_leaf_count, const int32_t* qperm, const int64_t* cand_start,
+                        const int32_t* cand, cudaStream_t s) {
+  const int T = 128;
+  const unsigned B = (unsigned)((q.Nq + T - 1) / T);
+  if (B == 0) return;
+  switch (D) {
+    case 1: k_neighbours<1, FILL, PRUNED><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand); break;
+    case 2: k_neighbours<2, FILL, PRUNED><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand); break;
+    case 3: k_neighbours<3, FILL, PRUNED><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand); break;
+    default: break;
+  }
+}
+
+void launch_neighbours(int D, bool fill, bool pruned, const TreeDev& tr, const QueryPlan& q, double radius, double delta,
+                       int wkind, double wparam, int32_t* d_leaf_count, const int32_t* qperm, const int64_t* cand_start,
+                       const int32_t* cand, cudaStream_t s) {
+  if (pruned) {
+    if (fill) launch_nb_t<true, true>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
+    else launch_nb_t<false, true>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
+  } else {
+    if (fill) launch_nb_t<true, false>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
+    else launch_nb_t<false, false>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
+  }
 }
 
 void launch_combine(int64_t Nq, const int64_t* pair_off, const double* pw, const double* pu, const double* pv,

@@ -242,3 +242,59 @@ def test_leaf_size_edges(built_lib):
         assert np.abs(eta.L_set[i] - Lref).max() < 1e-11
         cref = O.backslash(U, y)
         assert np.abs(U @ eta.c_set[i] - y).max() < 1e-12 * max(1.0, np.abs(cref).max())
+
+
+@pytest.mark.parametrize("name", ["c3_mini", "c4_mini", "mixgp_file"])
+def test_pruned_neighbour_search_equals_full_scan(built_lib, name):
+    """The per-leaf candidate lists must reproduce the reference's scan over ALL hyperplanes bit for bit:
+    same kept hyperplanes, same order, same t, same weights (and therefore the same Yq, Vq)."""
+    case, m, root, eta, pk = _setup(name)
+    _, wk = helpers.kernels(case["wkernel"])
+    Xq = case["Xq"]
+    L = _lib.lib()
+    out = {}
+    for full in (1, 0):
+        eta.handle.check(L.pmk_set_option(eta.handle.raw, _lib.OPT_FULL_HYPERPLANE_SCAN, full))
+        Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk,
+                                      debug_flag=True)
+        out[full] = (Yq, Vq, dv._flat)
+    for key in ("home", "pair_off", "pair_leaf", "pair_hp", "pair_t", "pair_w", "pair_u", "pair_v"):
+        assert np.array_equal(out[0][2][key], out[1][2][key]), key
+    assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
+
+
+def test_sharded_fit_equals_single_fit(built_lib):
+    """leaf -> rank map on one GPU: two handles each factorise half of the leaves, exchange their L / inverse-block /
+    alpha spans (device-to-device copies standing in for the NCCL broadcasts of bench.py) and must then answer
+    queries bit-identically to the handle that fitted everything."""
+    import torch
+    from patchmixturekriging_b200 import mixturegp
+    case, m, root, eta, pk = _setup("c3_mini")
+    _, wk = helpers.kernels(case["wkernel"])
+    X, y = case["X"], case["y"]
+    X_set, X_set_inds, _, _ = P.organizetrainingsets(root, case["levels"], X, case["eps"])
+    y_set = [y[i - 1] for i in X_set_inds]
+    nl = len(X_set)
+    ranges = [(0, nl // 2), (nl // 2, nl - nl // 2)]
+    etas = [P.MixtureGPType(X_set, P.fetchhyperplanes(root), fit_range=r) for r in ranges]
+    for e in etas:
+        P.fitmixtureGP_(e, y_set, pk, case["sigma2"])
+
+    class Span:
+        def __init__(self, ptr, nbytes):
+            self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 2}
+
+    for which in (_lib.BUF_L, _lib.BUF_LINV, _lib.BUF_ALPHA):
+        for src, (a, n) in enumerate(ranges):
+            sp, sb = mixturegp.model_buffer(etas[src], which, a, n)
+            dp, db = mixturegp.model_buffer(etas[1 - src], which, a, n)
+            assert sb == db and sb > 0
+            torch.as_tensor(Span(dp, db), device="cuda:0").copy_(torch.as_tensor(Span(sp, sb), device="cuda:0"))
+    torch.cuda.synchronize()
+    Xq = case["Xq"][:5000]
+    Y0, V0, _ = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
+    for e in etas:
+        mixturegp.mark_fitted(e)
+        Y1, V1, _ = P.querymixtureGP(Xq, e, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
+        assert np.array_equal(Y0, Y1) and np.array_equal(V0, V1)
+        e.close()
