@@ -67,7 +67,8 @@ enum {
   PMK_T_Q_PAIRS = 4,       /* fused cross-covariance / mean / TRSM-variance kernel (K3)        */
   PMK_T_Q_COMBINE = 5,     /* convex mixture combine                                           */
   PMK_T_GRAM = 6,          /* standalone Gram kernel                                           */
-  PMK_T_COUNT = 8
+  PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +3: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=2048)  */
+  PMK_T_COUNT = 12
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

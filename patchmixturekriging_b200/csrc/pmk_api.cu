@@ -72,6 +72,8 @@ thread_local std::string g_create_error;
 
 }  // namespace
 
+static constexpr int kNumClasses = 4;   // query size classes (pmk_query.cu)
+
 struct pmk_handle {
   int device = 0;
   cudaStream_t stream = nullptr;
@@ -91,8 +93,8 @@ struct pmk_handle {
   std::vector<int64_t> h_xoff, h_loff, h_ioff;
   int64_t xstride = 0;
   DBuf d_n, d_npad, d_xoff, d_loff, d_ioff, d_xs, d_y, d_alpha, d_L, d_Linv, d_info, d_order, d_leafoff, d_Xin, d_yin;
-  DBuf d_class_leaves[3], d_class_tiles[3], d_tile_off[3];
-  int n_class[3] = {0, 0, 0};
+  DBuf d_class_leaves[kNumClasses], d_class_tiles[kNumClasses], d_tile_off[kNumClasses];
+  int n_class[kNumClasses] = {};
   LeafTable lt{};
 
   // tree
@@ -223,7 +225,7 @@ void pmk_destroy(pmk_handle* h) {
                   &h->d_leaf_pair_start, &h->d_cub, &h->d_scratch, &h->d_leaf_qcount, &h->d_leaf_qstart, &h->d_qperm,
                   &h->d_qkeys, &h->d_bbox, &h->d_cand_count, &h->d_cand_start, &h->d_cand};
   for (DBuf* b : bufs) b->release();
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < kNumClasses; ++c) {
     h->d_class_leaves[c].release();
     h->d_class_tiles[c].release();
     h->d_tile_off[c].release();
@@ -427,9 +429,9 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->h_npad[a] > h->h_npad[b]; });
   const int n_order = (int)order.size();
   // query size classes
-  std::vector<int> cls[3];
+  std::vector<int> cls[kNumClasses];
   for (int64_t p = 0; p < n_leaves; ++p) cls[query_class_of(h->h_npad[p])].push_back((int)p);
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < kNumClasses; ++c) {
     h->n_class[c] = (int)cls[c].size();
     if (!cls[c].empty()) {
       CU(h, h->d_class_leaves[c].ensure(sizeof(int) * cls[c].size()));
@@ -765,7 +767,9 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const int mean_only = flags & 1;
   h->last_flags = flags;
   Timer tt(h, PMK_T_Q_PAIRS);
-  for (int c = 0; c < 3; ++c) {
+  for (int c = 0; c < kNumClasses; ++c) {
+    h->ev_used[PMK_T_Q_PAIRS_CLASS0 + c] = false;
+    h->ms[PMK_T_Q_PAIRS_CLASS0 + c] = 0.0;
     if (h->n_class[c] == 0) continue;
     PairWork w;
     w.class_leaves = h->d_class_leaves[c].as<int>();
@@ -781,7 +785,10 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     KCHECK(h, "k_scan_small");
     // upper bound on the tile count without a host round trip: excess CTAs exit at once
     const int64_t ub = q.n_pairs / mq + h->n_class[c];
-    launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
+    {
+      Timer tc(h, PMK_T_Q_PAIRS_CLASS0 + c);
+      launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
+    }
     KCHECK(h, "k_query_pairs");
   }
   return PMK_OK;

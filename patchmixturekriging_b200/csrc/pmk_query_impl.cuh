@@ -29,12 +29,12 @@ __device__ __forceinline__ void cp_async_wait() {
 }
 
 
-template <int D, int NW, int NT, int NQT, int DEPTH>
+template <int D, int NW, int NT, int NQT, int DEPTH, int GI>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, double* __restrict__ pair_u,
               double* __restrict__ pair_v) {
   constexpr int MQ = 8 * NQT;
-  constexpr int LDQ = MQ + 4;                 // == 4 (mod 16) for MQ in {8,16,32}: conflict-free fragment loads
+  constexpr int LDQ = MQ + 4;                 // == 4 or 12 (mod 16) for MQ in {8,16,24,32}: conflict-free fragment loads
   constexpr int OT = (4 * NQT + NW - 1) / NW; // diagonal-solve output tiles per warp
   __shared__ __align__(16) double Cbuf[32 * LDQ];
   __shared__ __align__(16) double Sbuf[32 * LDQ];
@@ -133,38 +133,38 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 #pragma unroll
   for (int k = 0; k < OT; ++k) vacc[k][0] = vacc[k][1] = 0.0;
 
-  // Per-warp cp.async ring of L tiles.  The sequence of tiles a warp consumes -- for J, for ct, for its
-  // active row tiles -- does not depend on the solve, so the copies run DEPTH-1 tiles ahead of the DMMAs
-  // (across the block barriers too) without costing a register; every lane copies and later reads back
-  // exactly its own 16 bytes of the fragment-major tile.
+  // Per-warp cp.async ring of L tiles.  What a warp consumes in step 3 -- for J, for ct: the tiles
+  // (t_i, 4J+ct) of its active row tiles -- does not depend on the solve, so the copies run DEPTH-1
+  // groups ahead of the DMMAs (across the block barriers too) without costing a register.  One commit
+  // group = one (J, ct) = up to NT tiles at fixed ring positions; every lane copies and later reads
+  // back exactly its own 16 bytes of each fragment-major tile.
   extern __shared__ __align__(16) unsigned char pmk_dyn_smem[];
-  double2* ring = reinterpret_cast<double2*>(pmk_dyn_smem) + (size_t)warp * (DEPTH * 32) + lane;
-  int pJ = 0, pct = 0, pi = -1;
-  bool pdone = false;
-  auto p_advance = [&]() {
-    for (;;) {
-      ++pi;
-      if (pi == NT) {
-        pi = 0;
+  constexpr int NG = NT / GI;        // groups per (J, ct): GI row tiles each
+  double2* ring = reinterpret_cast<double2*>(pmk_dyn_smem) + (size_t)warp * (DEPTH * GI * 32) + lane;
+  int toff[NT];                      // tile-row base (in double2 units) of this warp's row tiles
+#pragma unroll
+  for (int i = 0; i < NT; ++i) toff[i] = (int)tri(warp + NW * i) * 32 + lane;
+  int pJ = 0, pct = 0, pslot = 0;    // producer cursor: next (J, ct) to copy, ring slot to fill
+  auto p_issue = [&](int ih) {       // ih: which GI-sized part of the row tiles (compile-time at every call site)
+    if (pJ + 1 < nblk) {
+#pragma unroll
+      for (int ii = 0; ii < GI; ++ii) {
+        const int i = ih * GI + ii;
+        const int t = warp + NW * i;
+        if (t >= 4 * pJ + 4 && t < ntl) cp_async16(ring + (pslot * GI + ii) * 32, Lp + toff[i] + (4 * pJ + pct) * 32);
+      }
+      if (ih == NG - 1) {
         if (++pct == 4) { pct = 0; ++pJ; }
       }
-      if (pJ + 1 >= nblk) { pdone = true; return; }
-      const int t = warp + NW * pi;
-      if (t >= 4 * pJ + 4 && t < ntl) return;
     }
+    cp_async_commit();               // always commit: keeps the group count in step with the consumer
+    pslot = (pslot + 1 == DEPTH) ? 0 : pslot + 1;
   };
-  auto p_issue = [&](int slot) {
-    if (!pdone) {
-      const int t = warp + NW * pi;
-      cp_async16(ring + slot * 32, Lp + (tri(t) + 4 * pJ + pct) * 32 + lane);
-      p_advance();
-    }
-    cp_async_commit();     // always commit: keeps the group count in step with the consumer
-  };
-  p_advance();
+  // prologue: DEPTH-1 groups in flight.  The group sequence is (J, ct, ih) with ih fastest.
+  static_assert((DEPTH - 1) % NG == 0 || NG == 1 || DEPTH - 1 < NG, "prologue must stay aligned with the ih cycle");
 #pragma unroll
-  for (int s_ = 0; s_ < DEPTH - 1; ++s_) p_issue(s_);
-  int cslot = 0, fslot = DEPTH - 1;   // slot to consume next / free slot to refill
+  for (int s_ = 0; s_ < DEPTH - 1; ++s_) p_issue(s_ % NG);
+  int cslot = 0;                     // ring slot of the group consumed next
 
   for (int J = 0; J < nblk; ++J) {
     // prefetch this warp's inverse-diagonal-block tiles for step 2 (latency hidden behind the barrier)
@@ -226,7 +226,12 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     //    (PMK_UNIFORM_IF); within a tile the DMMAs are ordered k-step-major so that consecutive
     //    ones hit different accumulators.
     if (J + 1 < nblk) {
-      const int t_lo = 4 * J + 4;
+      unsigned active = 0;
+#pragma unroll
+      for (int i = 0; i < NT; ++i) {
+        const int t = warp + NW * i;
+        if (t >= 4 * J + 4 && t < ntl) active |= 1u << i;
+      }
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct) {
         double bf[2][NQT];
@@ -235,18 +240,21 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 #pragma unroll
           for (int nt = 0; nt < NQT; ++nt) bf[ks][nt] = Sbuf[(8 * ct + 4 * ks + l) * LDQ + nt * 8 + g];
 #pragma unroll
-        for (int i = 0; i < NT; ++i) {
-          const int t = warp + NW * i;
-          PMK_UNIFORM_IF(t >= t_lo && t < ntl) {
-            cp_async_wait<DEPTH - 2>();
-            const double2 af = ring[cslot * 32];
-            p_issue(fslot);              // refill the slot consumed one step ago (its data is in registers by now)
-            fslot = cslot;
-            cslot = (cslot + 1 == DEPTH) ? 0 : cslot + 1;
+        for (int ih = 0; ih < NG; ++ih) {
+          cp_async_wait<DEPTH - 2>();        // group (J, ct, ih) has landed
+          const double2* rs = ring + cslot * (GI * 32);
+          cslot = (cslot + 1 == DEPTH) ? 0 : cslot + 1;
+          p_issue((ih + DEPTH - 1) % NG);    // next group goes into the slot consumed one group ago
 #pragma unroll
-            for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[0][nt]);
+          for (int ii = 0; ii < GI; ++ii) {
+            const int i = ih * GI + ii;
+            PMK_UNIFORM_IF(active & (1u << i)) {
+              const double2 af = rs[ii * 32];
 #pragma unroll
-            for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[1][nt]);
+              for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[0][nt]);
+#pragma unroll
+              for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[1][nt]);
+            }
           }
         }
       }
@@ -292,12 +300,13 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 
 // one translation unit per D (pmk_query_d{1,2,3}.cu) instantiates the three size classes
 //   class 0: n_pad <=  512, MQ = 32     class 1: n_pad <= 1024, MQ = 16     class 2: n_pad <= 2048, MQ = 8
-template <int D, int NW, int NT, int NQT, int DEPTH>
+template <int D, int NW, int NT, int NQT, int DEPTH, int GI>
 static void launch_one(unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int mean_only,
                        double* pu, double* pv, cudaStream_t s) {
-  constexpr size_t dyn = (size_t)NW * DEPTH * 32 * sizeof(double2);
+  constexpr size_t dyn = (size_t)NW * DEPTH * GI * 32 * sizeof(double2);
+  static_assert(dyn <= 200 * 1024, "ring does not fit in shared memory");
   static bool configured = false;   // one attribute call per instantiation (per process; all devices are B200)
-  auto kern = k_query_pairs<D, NW, NT, NQT, DEPTH>;
+  auto kern = k_query_pairs<D, NW, NT, NQT, DEPTH, GI>;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     configured = true;
@@ -308,10 +317,13 @@ static void launch_one(unsigned grid, const LeafTable& lt, const PairWork& w, co
 template <int D>
 void launch_pairs_d(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                     int mean_only, double* pu, double* pv, cudaStream_t s) {
-  constexpr int NW = 16, DEPTH = 6;
-  if (cls == 0) launch_one<D, NW, 4, 4, DEPTH>(grid, lt, w, q, kp, mean_only, pu, pv, s);
-  else if (cls == 1) launch_one<D, NW, 8, 2, DEPTH>(grid, lt, w, q, kp, mean_only, pu, pv, s);
-  else launch_one<D, NW, 16, 1, DEPTH>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  constexpr int NW = 16;   // ring bytes = NW * DEPTH * GI * 512
+  // class:   0: n_pad <= 512, 32 pairs/CTA | 1: <= 768, 24 | 2: <= 1024, 16 | 3: <= 2048, 8
+  // (the accumulators of n_pad x MQ doubles must fit the register file: NT * NQT * 4 registers per thread)
+  if (cls == 0) launch_one<D, NW, 4, 4, 3, 4>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else if (cls == 1) launch_one<D, NW, 6, 3, 3, 6>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else if (cls == 2) launch_one<D, NW, 8, 2, 2, 8>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else launch_one<D, NW, 16, 1, 2, 8>(grid, lt, w, q, kp, mean_only, pu, pv, s);
 }
 
 }  // namespace pmk
