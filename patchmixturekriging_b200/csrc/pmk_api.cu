@@ -26,9 +26,10 @@ void launch_leaf_bbox(int D, int n_leaves, int64_t Nq, const double* dXq, const 
                       double* bbox, cudaStream_t s);
 void launch_leaf_candidates(int D, bool fill, int n_leaves, const TreeDev& tr, const double* bbox, double radius,
                             int32_t* cand_count, const int64_t* cand_start, int32_t* cand, cudaStream_t s);
-void launch_neighbours(int D, bool fill, bool pruned, const TreeDev& tr, const QueryPlan& q, double radius, double delta,
-                       int wkind, double wparam, int32_t* d_leaf_count, const int32_t* qperm, const int64_t* cand_start,
-                       const int32_t* cand, cudaStream_t s);
+void launch_neighbours(int D, bool fill, bool pruned, int n_leaves, const TreeDev& tr, const QueryPlan& q, double radius,
+                       double delta, int wkind, double wparam, int32_t* d_leaf_count, const int32_t* qperm,
+                       const int64_t* leaf_qstart, const int64_t* cand_start, const int32_t* cand, uint16_t* kept_rec,
+                       cudaStream_t s);
 void launch_combine(int64_t Nq, const int64_t* pair_off, const double* pw, const double* pu, const double* pv, double* dYq,
                     double* dVq, int mean_only, cudaStream_t s);
 void launch_scan_small(const int32_t* in, int64_t* out, int n, cudaStream_t s);
@@ -107,7 +108,7 @@ struct pmk_handle {
   DBuf d_Xq, d_home, d_npairs, d_pair_off, d_Yq, d_Vq;
   DBuf d_pair_leaf, d_pair_q, d_pair_hp, d_pair_t, d_pair_w, d_pair_u, d_pair_v, d_sorted_pair, d_keys_out, d_iota;
   DBuf d_leaf_count, d_leaf_pair_start, d_cub;
-  DBuf d_leaf_qcount, d_leaf_qstart, d_qperm, d_qkeys, d_bbox, d_cand_count, d_cand_start, d_cand;
+  DBuf d_leaf_qcount, d_leaf_qstart, d_qperm, d_qkeys, d_bbox, d_cand_count, d_cand_start, d_cand, d_kept;
   bool full_scan = false;   // PMK_OPT_FULL_HYPERPLANE_SCAN
   DBuf d_scratch;   // Gram scratch
   QueryPlan plan{};
@@ -223,7 +224,7 @@ void pmk_destroy(pmk_handle* h) {
                   &h->d_npairs, &h->d_pair_off, &h->d_Yq, &h->d_Vq, &h->d_pair_leaf, &h->d_pair_q, &h->d_pair_hp, &h->d_pair_t,
                   &h->d_pair_w, &h->d_pair_u, &h->d_pair_v, &h->d_sorted_pair, &h->d_keys_out, &h->d_iota, &h->d_leaf_count,
                   &h->d_leaf_pair_start, &h->d_cub, &h->d_scratch, &h->d_leaf_qcount, &h->d_leaf_qstart, &h->d_qperm,
-                  &h->d_qkeys, &h->d_bbox, &h->d_cand_count, &h->d_cand_start, &h->d_cand};
+                  &h->d_qkeys, &h->d_bbox, &h->d_cand_count, &h->d_cand_start, &h->d_cand, &h->d_kept};
   for (DBuf* b : bufs) b->release();
   for (int c = 0; c < kNumClasses; ++c) {
     h->d_class_leaves[c].release();
@@ -681,6 +682,7 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
     CU(h, h->d_bbox.ensure(sizeof(double) * TL * 2 * D));
     CU(h, h->d_cand_count.ensure(sizeof(int32_t) * TL));
     CU(h, h->d_cand_start.ensure(sizeof(int64_t) * (TL + 1)));
+    CU(h, h->d_kept.ensure(sizeof(uint16_t) * 8 * Nq));
     if (int rc = ensure_iota(Nq)) return rc;
     CU(h, cudaMemsetAsync(h->d_leaf_qcount.p, 0, sizeof(int32_t) * TL, h->stream));
   }
@@ -712,8 +714,9 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
                            h->d_cand_start.as<int64_t>(), h->d_cand.as<int32_t>(), h->stream);
     KCHECK(h, "k_leaf_candidates<fill>");
   }
-  launch_neighbours(D, false, pruned, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(),
-                    h->d_qperm.as<int32_t>(), h->d_cand_start.as<int64_t>(), h->d_cand.as<int32_t>(), h->stream);
+  launch_neighbours(D, false, pruned, (int)TL, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(),
+                    h->d_qperm.as<int32_t>(), h->d_leaf_qstart.as<int64_t>(), h->d_cand_start.as<int64_t>(),
+                    h->d_cand.as<int32_t>(), h->d_kept.as<uint16_t>(), h->stream);
   KCHECK(h, "k_neighbours<count>");
   {
     size_t tb = 0;
@@ -738,8 +741,9 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
   q.pair_hp = h->d_pair_hp.as<int32_t>();
   q.pair_t = h->d_pair_t.as<double>();
   q.pair_w = h->d_pair_w.as<double>();
-  launch_neighbours(D, true, pruned, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(),
-                    h->d_qperm.as<int32_t>(), h->d_cand_start.as<int64_t>(), h->d_cand.as<int32_t>(), h->stream);
+  launch_neighbours(D, true, pruned, (int)TL, h->tree, q, radius, delta, wk.kind, wk.p, h->d_leaf_count.as<int32_t>(),
+                    h->d_qperm.as<int32_t>(), h->d_leaf_qstart.as<int64_t>(), h->d_cand_start.as<int64_t>(),
+                    h->d_cand.as<int32_t>(), h->d_kept.as<uint16_t>(), h->stream);
   KCHECK(h, "k_neighbours<fill>");
   launch_scan_small(h->d_leaf_count.as<int32_t>(), h->d_leaf_pair_start.as<int64_t>(), (int)TL, h->stream);
   KCHECK(h, "k_scan_small");

@@ -224,6 +224,179 @@ __global__ void k_neighbours(TreeDev tr, QueryPlan q, double radius, double delt
   }
 }
 
+// Pruned search, one CTA per home leaf (scan pass).  The leaf's candidate hyperplanes (u, c) and the
+// hyperplanes of its ANCESTORS are staged in shared memory once.  Per query:
+//   A. every candidate gets the cheap conservative rejection |t| > radius(1+1e-9)+... (norm(z - p)
+//      equals |t| up to a few ulp of |p|, so the reference's test would fail as well); survivors are
+//      only recorded, so the warp does not diverge into the expensive path per candidate;
+//   B. each survivor runs the reference's exact test.  "findpartition(z) == home" is evaluated as
+//      "z takes home's branch at each of home's ancestors" -- the same comparisons findpartition makes
+//      on the way to home, but as independent shared-memory dot products instead of two dependent
+//      pointer-chasing descents.
+// The kept candidates (slot numbers in the leaf's list, at most 7, else an overflow mark) go to a
+// 16-byte record per query; the fill pass replays only those.
+static constexpr int kKeptMax = 7;
+static constexpr int kCandCap = 768;
+
+template <int D>
+__global__ void __launch_bounds__(256)
+k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const int32_t* __restrict__ qperm,
+                  const int64_t* __restrict__ leaf_qstart, const int64_t* __restrict__ cand_start,
+                  const int32_t* __restrict__ cand, uint16_t* __restrict__ kept_rec /* [Nq][8] */) {
+  __shared__ double s_u[D][kCandCap];
+  __shared__ double s_c[kCandCap];
+  __shared__ double a_u[D][32];
+  __shared__ double a_c[32];
+  const int leaf = blockIdx.x;
+  const int64_t qa = leaf_qstart[leaf], qb = leaf_qstart[leaf + 1];
+  if (qa == qb) return;
+  const int64_t ca = cand_start[leaf];
+  const int nc = (int)(cand_start[leaf + 1] - ca);
+  const int ns = nc < kCandCap ? nc : kCandCap;
+  const int Lv = tr.levels - 1;
+  for (int k = threadIdx.x; k < ns; k += blockDim.x) {
+    const int i = cand[ca + k];
+    s_c[k] = tr.hc[i];
+#pragma unroll
+    for (int d = 0; d < D; ++d) s_u[d][k] = tr.hv[d * tr.n_hp + i];
+  }
+  if (threadIdx.x == 0) {        // home's ancestors: node_0 = 0, node_{d+1} = node_d + (right ? 2^(Lv-1-d) : 1)
+    int node = 0;
+    for (int d = 0; d < Lv; ++d) {
+      a_c[d] = tr.hc[node];
+      for (int dd = 0; dd < D; ++dd) a_u[dd][d] = tr.hv[dd * tr.n_hp + node];
+      const int right = (leaf >> (Lv - 1 - d)) & 1;
+      node += right ? (1 << (Lv - 1 - d)) : 1;
+    }
+  }
+  __syncthreads();
+  auto in_home = [&](const double* x) -> bool {
+    for (int d = 0; d < Lv; ++d) {
+      double v[D];
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) v[dd] = a_u[dd][d];
+      const int right = !(dot_seq<D>(v, x) < a_c[d]);              // partition.jl:254
+      if (right != ((leaf >> (Lv - 1 - d)) & 1)) return false;
+    }
+    return true;
+  };
+  for (int64_t kq = qa + threadIdx.x; kq < qb; kq += blockDim.x) {
+    const int64_t j = qperm[kq];
+    double p[D];
+    double pabs = 1.0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+      p[d] = q.Xq[j * D + d];
+      pabs += fabs(p[d]);
+    }
+    const double thr = radius * (1.0 + 1e-9) + 1e-12 * pabs;
+    unsigned short surv[64];
+    int nsurv = 0, kept = 0;
+    unsigned short kl[kKeptMax];
+    auto process = [&](int k) {
+      double u[D], c;
+      if (k < ns) {
+        c = s_c[k];
+#pragma unroll
+        for (int d = 0; d < D; ++d) u[d] = s_u[d][k];
+      } else {
+        const int i = cand[ca + k];
+        c = tr.hc[i];
+#pragma unroll
+        for (int d = 0; d < D; ++d) u[d] = tr.hv[d * tr.n_hp + i];
+      }
+      const double t = __dadd_rn(-dot_seq<D>(u, p), c);            // mixtureGP.jl:361
+      double s = 0.0;
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        const double z = __dadd_rn(p[d], __dmul_rn(t, u[d]));      // mixtureGP.jl:362
+        const double dd = __dsub_rn(z, p[d]);
+        s = (d == 0) ? __dmul_rn(dd, dd) : __dadd_rn(s, __dmul_rn(dd, dd));
+      }
+      if (!(__dsqrt_rn(s) < radius)) return;                       // mixtureGP.jl:367
+      double z1[D], z2[D];
+      const double tp = __dadd_rn(t, delta), tm = __dsub_rn(t, delta);
+#pragma unroll
+      for (int d = 0; d < D; ++d) {
+        z1[d] = __dadd_rn(p[d], __dmul_rn(tp, u[d]));              // mixtureGP.jl:370-371
+        z2[d] = __dadd_rn(p[d], __dmul_rn(tm, u[d]));
+      }
+      if (in_home(z1) != in_home(z2)) {                            // mixtureGP.jl:387 xor
+        if (kept < kKeptMax) kl[kept] = (unsigned short)k;
+        ++kept;
+      }
+    };
+    for (int k = 0; k < nc; ++k) {
+      double tq;
+      if (k < ns) {
+        double u[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) u[d] = s_u[d][k];
+        tq = __dadd_rn(-dot_seq<D>(u, p), s_c[k]);
+      } else {
+        const int i = cand[ca + k];
+        double u[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) u[d] = tr.hv[d * tr.n_hp + i];
+        tq = __dadd_rn(-dot_seq<D>(u, p), tr.hc[i]);
+      }
+      if (fabs(tq) > thr) continue;
+      if (nsurv < 64) surv[nsurv++] = (unsigned short)k;
+      else {                      // list full: flush it in order, then keep collecting (order must stay ascending)
+        for (int s_ = 0; s_ < nsurv; ++s_) process(surv[s_]);
+        nsurv = 0;
+        surv[nsurv++] = (unsigned short)k;
+      }
+    }
+    for (int s_ = 0; s_ < nsurv; ++s_) process(surv[s_]);
+    q.npairs[j] = kept + 1;
+    uint16_t* rec = kept_rec + j * 8;
+#pragma unroll
+    for (int m = 0; m < kKeptMax; ++m) rec[m] = m < kept ? kl[m] : (uint16_t)0;
+    rec[7] = kept <= kKeptMax ? (uint16_t)kept : (uint16_t)0xFFFF;
+  }
+}
+
+// Fill pass: replay the kept candidates of every query (the reference's exact test again, now with the real
+// descents that also yield the neighbour leaf id) and write the pair slots in reference order.
+template <int D>
+__global__ void k_neighbours_fill(TreeDev tr, QueryPlan q, double radius, double delta, int wkind, double wparam,
+                                  int32_t* __restrict__ leaf_count, const int64_t* __restrict__ cand_start,
+                                  const int32_t* __restrict__ cand, const uint16_t* __restrict__ kept_rec) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= q.Nq) return;
+  double p[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) p[d] = q.Xq[j * D + d];
+  const int home = q.home[j];
+  int64_t slot = q.pair_off[j];
+  const uint16_t* rec = kept_rec + j * 8;
+  const int64_t ca = cand_start[home - 1];
+  const int nk = rec[7];
+  const int n_iter = nk == 0xFFFF ? (int)(cand_start[home] - ca) : nk;
+  for (int m = 0; m < n_iter; ++m) {
+    const int k = nk == 0xFFFF ? m : (int)rec[m];
+    const int i = cand[ca + k];
+    double t;
+    const int nb = neighbour_test<D>(tr, p, home, i, radius, delta, &t);
+    if (nb != 0) {
+      q.pair_leaf[slot] = nb;
+      q.pair_q[slot] = (int32_t)j;
+      q.pair_hp[slot] = i + 1;
+      q.pair_t[slot] = t;
+      q.pair_w[slot] = k_tau(wkind, wparam, fabs(t));              // mixtureGP.jl:231
+      atomicAdd(&leaf_count[nb - 1], 1);
+      ++slot;
+    }
+  }
+  q.pair_leaf[slot] = home;                                         // mixtureGP.jl:237-239, w[end] = 1
+  q.pair_q[slot] = (int32_t)j;
+  q.pair_hp[slot] = 0;
+  q.pair_t[slot] = 0.0;
+  q.pair_w[slot] = 1.0;
+  atomicAdd(&leaf_count[home - 1], 1);
+}
+
 // Yq = dot(w,u), Vq = dot(w, v.*w) with w = w_tilde / sum(w_tilde)   (mixtureGP.jl:263-272)
 __global__ void k_combine(int64_t Nq, const int64_t* __restrict__ pair_off, const double* __restrict__ pw,
                           const double* __restrict__ pu, const double* __restrict__ pv, double* __restrict__ Yq,
@@ -324,15 +497,31 @@ static void launch_nb_t(int D, const TreeDev& tr, const QueryPlan& q, double rad
   }
 }
 
-void launch_neighbours(int D, bool fill, bool pruned, const TreeDev& tr, const QueryPlan& q, double radius, double delta,
-                       int wkind, double wparam, int32_t* d_leaf_count, const int32_t* qperm, const int64_t* cand_start,
-                       const int32_t* cand, cudaStream_t s) {
-  if (pruned) {
-    if (fill) launch_nb_t<true, true>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
-    else launch_nb_t<false, true>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
-  } else {
+void launch_neighbours(int D, bool fill, bool pruned, int n_leaves, const TreeDev& tr, const QueryPlan& q, double radius,
+                       double delta, int wkind, double wparam, int32_t* d_leaf_count, const int32_t* qperm,
+                       const int64_t* leaf_qstart, const int64_t* cand_start, const int32_t* cand, uint16_t* kept_rec,
+                       cudaStream_t s) {
+  if (!pruned) {
     if (fill) launch_nb_t<true, false>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
     else launch_nb_t<false, false>(D, tr, q, radius, delta, wkind, wparam, d_leaf_count, qperm, cand_start, cand, s);
+    return;
+  }
+  if (!fill) {
+    switch (D) {
+      case 1: k_neighbours_scan<1><<<n_leaves, 256, 0, s>>>(tr, q, radius, delta, qperm, leaf_qstart, cand_start, cand, kept_rec); break;
+      case 2: k_neighbours_scan<2><<<n_leaves, 256, 0, s>>>(tr, q, radius, delta, qperm, leaf_qstart, cand_start, cand, kept_rec); break;
+      case 3: k_neighbours_scan<3><<<n_leaves, 256, 0, s>>>(tr, q, radius, delta, qperm, leaf_qstart, cand_start, cand, kept_rec); break;
+      default: break;
+    }
+  } else {
+    const int T = 128;
+    const unsigned B = (unsigned)((q.Nq + T - 1) / T);
+    switch (D) {
+      case 1: k_neighbours_fill<1><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count, cand_start, cand, kept_rec); break;
+      case 2: k_neighbours_fill<2><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count, cand_start, cand, kept_rec); break;
+      case 3: k_neighbours_fill<3><<<B, T, 0, s>>>(tr, q, radius, delta, wkind, wparam, d_leaf_count, cand_start, cand, kept_rec); break;
+      default: break;
+    }
   }
 }
 
