@@ -35,7 +35,8 @@ __device__ __forceinline__ int opaque_int(int x) {
   asm volatile("mov.b32 %0, %1;" : "=r"(y) : "r"(x));
   return y;
 }
-#define PMK_UNIFORM_IF(cond) for (int pmk_r_ = pmk::opaque_int((cond) ? 1 : 0); pmk_r_ > 0; --pmk_r_)
+#define PMK_UNIFORM_IF(cond) \
+  _Pragma("unroll 1") for (int pmk_r_ = pmk::opaque_int((cond) ? 1 : 0); pmk_r_ > 0; --pmk_r_)
 
 // ---------------------------------------------------------------------------------------
 // Packed storage of a leaf's lower-triangular factor L (n_pad x n_pad, n_pad % 32 == 0).

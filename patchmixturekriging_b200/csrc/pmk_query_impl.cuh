@@ -22,6 +22,9 @@ __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   // .cg: cache in L2 only -- an L tile is consumed once per CTA, other CTAs of the same leaf find it in L2
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async16_u32(uint32_t smem_addr, const void* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() {
@@ -141,27 +144,38 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
   extern __shared__ __align__(16) unsigned char pmk_dyn_smem[];
   constexpr int NG = NT / GI;        // groups per (J, ct): GI row tiles each
   double2* ring = reinterpret_cast<double2*>(pmk_dyn_smem) + (size_t)warp * (DEPTH * GI * 32) + lane;
-  int toff[NT];                      // tile-row base (in double2 units) of this warp's row tiles
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  // producer state, kept deliberately cheap: one global pointer per owned row tile (advanced by one tile =
+  // 512 B per (J, ct) group), a bit mask of the row tiles that exist (t < ntl), and the row-tile threshold
+  // 4*pJ+4 below which a tile is already solved.
+  const double2* srcb = Lp + lane;   // + (4*pJ + pct) tiles, advanced by one tile per (J, ct)
+  int toff[NT];                      // tri(t_i) * 32: start of row tile t_i (double2 units)
+  unsigned exists = 0;
 #pragma unroll
-  for (int i = 0; i < NT; ++i) toff[i] = (int)tri(warp + NW * i) * 32 + lane;
-  int pJ = 0, pct = 0, pslot = 0;    // producer cursor: next (J, ct) to copy, ring slot to fill
+  for (int i = 0; i < NT; ++i) {
+    const int t = warp + NW * i;
+    toff[i] = (int)tri(t) * 32;
+    if (t < ntl) exists |= 1u << i;
+  }
+  int pthr = 4, pct = 0, pslot = 0;  // next group: column tile 4*pJ + pct with pthr = 4*pJ + 4
+  const int pthr_end = 4 * nblk;     // pJ + 1 < nblk  <=>  pthr < 4 * nblk
   auto p_issue = [&](int ih) {       // ih: which GI-sized part of the row tiles (compile-time at every call site)
-    if (pJ + 1 < nblk) {
+    if (pthr < pthr_end) {
+      const uint32_t dst = ring_u32 + (uint32_t)(pslot * (GI * 512));
 #pragma unroll
       for (int ii = 0; ii < GI; ++ii) {
         const int i = ih * GI + ii;
-        const int t = warp + NW * i;
-        if (t >= 4 * pJ + 4 && t < ntl) cp_async16(ring + (pslot * GI + ii) * 32, Lp + toff[i] + (4 * pJ + pct) * 32);
+        if (((exists >> i) & 1u) && warp + NW * i >= pthr) cp_async16_u32(dst + ii * 512, srcb + toff[i]);
       }
       if (ih == NG - 1) {
-        if (++pct == 4) { pct = 0; ++pJ; }
+        srcb += 32;
+        if (++pct == 4) { pct = 0; pthr += 4; }
       }
     }
     cp_async_commit();               // always commit: keeps the group count in step with the consumer
     pslot = (pslot + 1 == DEPTH) ? 0 : pslot + 1;
   };
   // prologue: DEPTH-1 groups in flight.  The group sequence is (J, ct, ih) with ih fastest.
-  static_assert((DEPTH - 1) % NG == 0 || NG == 1 || DEPTH - 1 < NG, "prologue must stay aligned with the ih cycle");
 #pragma unroll
   for (int s_ = 0; s_ < DEPTH - 1; ++s_) p_issue(s_ % NG);
   int cslot = 0;                     // ring slot of the group consumed next
@@ -229,9 +243,9 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
       unsigned active = 0;
 #pragma unroll
       for (int i = 0; i < NT; ++i) {
-        const int t = warp + NW * i;
-        if (t >= 4 * J + 4 && t < ntl) active |= 1u << i;
+        if (warp + NW * i >= 4 * J + 4) active |= 1u << i;
       }
+      active &= exists;
 #pragma unroll
       for (int ct = 0; ct < 4; ++ct) {
         double bf[2][NQT];
