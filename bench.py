@@ -237,7 +237,7 @@ def main():
     import torch
     import torch.distributed as dist
     import patchmixturekriging_b200 as P
-    from patchmixturekriging_b200 import _lib, mixturegp
+    from patchmixturekriging_b200 import _lib, mixturegp, sharding
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
@@ -249,10 +249,11 @@ def main():
     root, sizes, leaf_off, Xp, yp = partition(w)
     n_leaves = len(sizes)
     Nq = w["nq"]
-    q0, q1 = (Nq * rank) // world, (Nq * (rank + 1)) // world
+    q0, q1 = sharding.query_slice(rank, world, Nq)
     Xq_h = gen_queries(w, q0, q1 - q0)
     nq_loc = q1 - q0
-    l0, l1 = (n_leaves * rank) // world, (n_leaves * (rank + 1)) // world
+    l0, lc = sharding.leaf_range(rank, world, n_leaves)
+    l1 = l0 + lc
 
     θ = P.GaussianKernel1DType(w["eps_sq"])
     wθ = P.Spline34KernelType(1.0 / w["radius"])
@@ -268,20 +269,18 @@ def main():
 
     dX = torch.from_numpy(Xp).cuda(); dy = torch.from_numpy(yp).cuda(); dXq = torch.from_numpy(Xq_h).cuda()
     dYq = torch.empty(nq_loc, dtype=torch.float64, device="cuda"); dVq = torch.empty_like(dYq)
-    dY_all = torch.empty(Nq, dtype=torch.float64, device="cuda") if world > 1 else None
-    dV_all = torch.empty(Nq, dtype=torch.float64, device="cuda") if world > 1 else None
+    gathered = [None, None]
     kp = θ.params; wp = wθ.params
     stream = torch.cuda.ExternalStream(int(L.pmk_stream(h.raw)), device=dev)
     bad, info = C.c_int64(0), C.c_int(0)
 
+    def span_of(which, first, count):
+        ptr, nb = mixturegp.model_buffer(η, which, first, count)
+        return torch.as_tensor(_CudaSpan(ptr, nb), device=f"cuda:{dev}") if nb else torch.empty(0, dtype=torch.float64, device="cuda")
+
     def exchange_factors():
         """leaf -> rank map: every rank broadcasts the spans it factorised (NCCL over NVLink)."""
-        for which in (_lib.BUF_L, _lib.BUF_LINV, _lib.BUF_ALPHA):
-            for r in range(world):
-                a, b = (n_leaves * r) // world, (n_leaves * (r + 1)) // world
-                ptr, nb = mixturegp.model_buffer(η, which, a, b - a)
-                if nb:
-                    dist.broadcast(torch.as_tensor(_CudaSpan(ptr, nb), device=f"cuda:{dev}"), src=r)
+        sharding.exchange_spans(span_of, n_leaves, (_lib.BUF_L, _lib.BUF_LINV, _lib.BUF_ALPHA))
         torch.cuda.current_stream().synchronize()
         mixturegp.mark_fitted(η)
 
@@ -299,8 +298,8 @@ def main():
                                 dYq.data_ptr(), dVq.data_ptr()))
         if world > 1:
             h.synchronize()
-            dist.all_gather_into_tensor(dY_all, dYq) if Nq % world == 0 else None
-            dist.all_gather_into_tensor(dV_all, dVq) if Nq % world == 0 else None
+            gathered[0] = sharding.gather_slices(dYq, Nq)
+            gathered[1] = sharding.gather_slices(dVq, Nq)
             torch.cuda.current_stream().synchronize()
         e[2].record(stream)
         e[2].synchronize()
@@ -362,7 +361,8 @@ def main():
             t1 = time.perf_counter()
             P.querymixtureGP_(hYq, hVq, hXq, η, root, w["levels"], w["radius"], w["delta"], θ, w["sigma2"], wθ)
             if world > 1:
-                dist.all_gather_into_tensor(dY_all, torch.from_numpy(hYq).cuda()) if Nq % world == 0 else None
+                gathered[0] = sharding.gather_slices(torch.from_numpy(hYq).cuda(), Nq)
+                gathered[1] = sharding.gather_slices(torch.from_numpy(hVq).cuda(), Nq)
                 torch.cuda.synchronize()
             t2 = time.perf_counter()
             return 1e3 * (t1 - t0), 1e3 * (t2 - t1)
