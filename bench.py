@@ -285,15 +285,17 @@ def main():
         mixturegp.mark_fitted(η)
 
     def step_device():
-        """fit + query with inputs resident in HBM; returns (fit_ms, query_ms) from CUDA events on the handle's stream."""
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+        """fit + query with inputs resident in HBM; returns (fit_ms, exchange_ms, query_ms) from CUDA events on the
+        handle's stream (the NCCL work is bracketed by stream synchronisation, so the events see it)."""
+        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record(stream)
         h.check(L.pmk_fit_dev(h.raw, 2, n_leaves, _lib.ptr(leaf_off), dX.data_ptr(), dy.data_ptr(), θ.kernel_id, _lib.ptr(kp), 1,
                               w["sigma2"], C.byref(bad), C.byref(info)))
+        e[1].record(stream)
         if world > 1:
             h.synchronize()
             exchange_factors()
-        e[1].record(stream)
+        e[2].record(stream)
         h.check(L.pmk_query_dev(h.raw, nq_loc, dXq.data_ptr(), w["radius"], w["delta"], wθ.kernel_id, _lib.ptr(wp), 1, 0,
                                 dYq.data_ptr(), dVq.data_ptr()))
         if world > 1:
@@ -301,9 +303,9 @@ def main():
             gathered[0] = sharding.gather_slices(dYq, Nq)
             gathered[1] = sharding.gather_slices(dVq, Nq)
             torch.cuda.current_stream().synchronize()
-        e[2].record(stream)
-        e[2].synchronize()
-        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2])
+        e[3].record(stream)
+        e[3].synchronize()
+        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])
 
     def barrier():
         if world > 1:
@@ -320,10 +322,10 @@ def main():
     t_wall0 = time.perf_counter()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record(stream)
-    fit_ms, query_ms, kt = [], [], []
+    fit_ms, exch_ms, query_ms, kt = [], [], [], []
     for _ in range(args.steps):
-        f, q = step_device()
-        fit_ms.append(f); query_ms.append(q)
+        f, x, q = step_device()
+        fit_ms.append(f + x); exch_ms.append(x); query_ms.append(q)
         kt.append(h.timings().copy())
     ev1.record(stream)
     barrier()
@@ -333,10 +335,11 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches = h.launch_count() - launches0
 
-    t = torch.tensor([total_ms, float(np.mean(fit_ms)), float(np.mean(query_ms))], dtype=torch.float64, device="cuda")
+    t = torch.tensor([total_ms, float(np.mean(fit_ms)), float(np.mean(query_ms)), float(np.mean(exch_ms))], dtype=torch.float64,
+                     device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, fit_ms_m, query_ms_m = (float(x) for x in t.cpu())
+    total_ms, fit_ms_m, query_ms_m, exch_ms_m = (float(x) for x in t.cpu())
     kt = np.mean(np.array(kt), axis=0)
 
     # ---------------- e2e through the public host API, pinned host buffers --------------------
@@ -418,6 +421,7 @@ def main():
         line = {"metric": "query_pts_per_s (mixture-GP query; fit throughput in fit_leaves_per_s)", "value": Nq / (query_ms_m * 1e-3),
                 "unit": "pts/s", "fit_leaves_per_s": n_leaves / (fit_ms_m * 1e-3), "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "ms_fit": fit_ms_m, "ms_query": query_ms_m,
+                "ms_factor_exchange": exch_ms_m, "fit_compute_leaves_per_s": n_leaves / max((fit_ms_m - exch_ms_m) * 1e-3, 1e-9),
                 "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                 "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
                 "roofline": roofline, "phases": phases}

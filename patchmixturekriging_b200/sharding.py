@@ -37,20 +37,39 @@ def gather_slices(local, nq: int, group=None):
         out = torch.empty(nq, dtype=local.dtype, device=local.device)
         dist.all_gather_into_tensor(out, local.contiguous(), group=group)
         return out
-    parts = [torch.empty(query_slice(r, world, nq)[1] - query_slice(r, world, nq)[0], dtype=local.dtype, device=local.device)
-             for r in range(world)]
-    dist.all_gather(parts, local.contiguous(), group=group)
-    return torch.cat(parts)
+    # uneven slices (they differ by at most one element): pad to the longest, gather, trim
+    sizes = [query_slice(r, world, nq)[1] - query_slice(r, world, nq)[0] for r in range(world)]
+    m = max(sizes)
+    padded = torch.zeros(m, dtype=local.dtype, device=local.device)
+    padded[:local.shape[0]] = local
+    out = torch.empty(m * world, dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, padded, group=group)
+    return torch.cat([out[r * m:r * m + sizes[r]] for r in range(world)])
 
 
 def exchange_spans(span_of, n_leaves: int, buffers, group=None):
-    """After a sharded fit: every rank broadcasts the device spans it factorised.
-    span_of(which, first_leaf, count) -> 1-D tensor aliasing that span of the local model (may be empty)."""
+    """After a sharded fit: every rank sends the device spans it factorised to every peer and receives theirs.
+    span_of(which, first_leaf, count) -> 1-D tensor aliasing that span of the local model (may be empty).
+    All transfers of one buffer go out as ONE batch of point-to-point operations (a single NCCL group), so they
+    run concurrently over NVLink / NVSwitch in both directions instead of as serialised broadcasts."""
     import torch.distributed as dist
     world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if world == 1:
+        return
     for which in buffers:
+        a, n = leaf_range(rank, world, n_leaves)
+        mine = span_of(which, a, n)
+        ops = []
         for r in range(world):
-            a, n = leaf_range(r, world, n_leaves)
-            t = span_of(which, a, n)
-            if t.numel():
-                dist.broadcast(t, src=r, group=group)
+            if r == rank:
+                continue
+            ar, nr = leaf_range(r, world, n_leaves)
+            theirs = span_of(which, ar, nr)
+            if theirs.numel():
+                ops.append(dist.P2POp(dist.irecv, theirs, r, group))
+            if mine.numel():
+                ops.append(dist.P2POp(dist.isend, mine, r, group))
+        if ops:
+            for req in dist.batch_isend_irecv(ops):
+                req.wait()
