@@ -21,7 +21,7 @@ SYMBOLS = [
     "pmk_create", "pmk_destroy", "pmk_last_error", "pmk_version", "pmk_gram", "pmk_cross_gram", "pmk_fit", "pmk_fit_dev",
     "pmk_leaf_size", "pmk_get_alpha", "pmk_get_L", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_query",
     "pmk_query_dev", "pmk_last_query_pairs", "pmk_last_query_debug", "pmk_set_fit_range", "pmk_model_buffer", "pmk_mark_fitted", "pmk_query_plan_dev",
-    "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_option", "pmk_get_timings", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
+    "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_option", "pmk_get_timings", "pmk_debug_counters", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
 ]
 
 _lib = None
@@ -82,6 +82,7 @@ def lib() -> C.CDLL:
     L.pmk_query_combine_dev.argtypes = [vp, dp, dp, dp, dp]
     L.pmk_set_option.argtypes = [vp, i32, i64]
     L.pmk_get_timings.argtypes = [vp, dp]
+    L.pmk_debug_counters.argtypes = [vp, dp, i32]
     L.pmk_launch_count.argtypes = [vp]
     L.pmk_launch_count.restype = i64
     L.pmk_stream.argtypes = [vp]

@@ -20,6 +20,7 @@ void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const do
 void launch_chol(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
+void read_chol_cycles(unsigned long long* out, bool reset);
 void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, int32_t* d_leaf_qcount,
                  cudaStream_t s);
 void launch_leaf_bbox(int D, int n_leaves, int64_t Nq, const double* dXq, const int32_t* qperm, const int64_t* leaf_qstart,
@@ -253,6 +254,14 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
     case PMK_OPT_FULL_HYPERPLANE_SCAN: h->full_scan = value != 0; h->plan_valid = false; return PMK_OK;
     default: return fail(h, PMK_ERR_ARG, "unknown option %d", option);
   }
+}
+
+int pmk_debug_counters(pmk_handle* h, uint64_t* out8, int reset) {
+  if (!h || !out8) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  CU(h, cudaStreamSynchronize(h->stream));
+  read_chol_cycles(reinterpret_cast<unsigned long long*>(out8), reset != 0);
+  return PMK_OK;
 }
 
 int pmk_get_timings(pmk_handle* h, double* ms) {

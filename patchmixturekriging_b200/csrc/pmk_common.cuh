@@ -38,6 +38,18 @@ __device__ __forceinline__ int opaque_int(int x) {
 #define PMK_UNIFORM_IF(cond) \
   _Pragma("unroll 1") for (int pmk_r_ = pmk::opaque_int((cond) ? 1 : 0); pmk_r_ > 0; --pmk_r_)
 
+// cp.async (LDGSTS) helpers: 16-byte asynchronous global -> shared copies, used as register-free prefetch
+// rings for the packed L tiles (each lane copies, and later reads back, exactly its own 16 bytes of a tile).
+__device__ __forceinline__ void cp_async16_u32(uint32_t smem_addr, const void* gmem) {
+  // .cg: cache in L2 only -- a tile is consumed once per CTA; other CTAs of the same leaf find it in L2
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------------------------------
 // Packed storage of a leaf's lower-triangular factor L (n_pad x n_pad, n_pad % 32 == 0).
 // 8x8 tiles, row-tile-major, lower tiles only: tile (t, c), c <= t, sits at tile index
@@ -184,6 +196,27 @@ __device__ __forceinline__ double eval_kernel(const KParams& kp, const double* x
     zz.v[d] = z[d];
   }
   return eval_kernel_generic<D>(kp.kind, kp.p, xx, zz);
+}
+
+// N independent evaluations, written stage by stage (all distances, then all square roots, then all
+// exponentials) so that the FP64 dependency chains of different evaluations interleave: the hot kernels
+// evaluate dozens of independent entries per thread, and one evaluation alone is a ~50-instruction chain.
+template <int D, int N>
+__device__ __forceinline__ void eval_kernel_batch(const KParams& kp, const double (&xa)[N][D], const double (&xb)[N][D],
+                                                  const bool (&valid)[N], double (&out)[N]) {
+  if (kp.kind == PMK_KERNEL_SQEXP) {
+    double arg[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double tau = stationary_tau<D>(xa[i], xb[i]);
+      arg[i] = __dmul_rn(-kp.p, __dmul_rn(tau, tau));
+    }
+#pragma unroll
+    for (int i = 0; i < N; ++i) out[i] = valid[i] ? exp(arg[i]) : 0.0;
+    return;
+  }
+#pragma unroll
+  for (int i = 0; i < N; ++i) out[i] = valid[i] ? eval_kernel<D>(kp, xa[i], xb[i]) : 0.0;
 }
 
 // sequential dot product, no contraction (contract of partition.jl:69,254,285 and mixtureGP.jl:361)

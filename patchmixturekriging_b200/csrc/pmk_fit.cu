@@ -16,6 +16,10 @@
 namespace pmk {
 
 static constexpr unsigned kFull = 0xffffffffu;
+
+// per-phase cycle counters of k_chol (warp 0 of every CTA), read by tools via pmk_debug_counters
+__device__ unsigned long long g_chol_cycles[8];
+
 static constexpr int LD = 36;   // smem row stride (doubles), == 4 (mod 16): fragment loads are conflict-free
 
 // ---------------------------------------------------------------------------------------------
@@ -43,63 +47,92 @@ __global__ void k_pack_leaves(LeafTable lt, const int64_t* __restrict__ leaf_off
 // returns 0 or the (block-local, 1-based) order of the first non-positive pivot.
 static constexpr int LDD = 33;
 __device__ __noinline__ int factor_block32(double* Dbuf, double* Ibuf, int lane) {
-  // left-looking (dot-product form) Cholesky, column j: lane i >= j owns L[i][j]
+  // Left-looking (dot-product form) Cholesky, column j: lane i >= j owns L[i][j].  Fully unrolled: every
+  // shared-memory address is an immediate and the inner products have static trip counts -- this serial
+  // phase is latency-bound on a single warp, so instruction count is what matters.
+  const double* rowp = Dbuf + lane * LDD;
+  int info = 0;
+#pragma unroll
   for (int j = 0; j < 32; ++j) {
-    double s0 = Dbuf[lane * LDD + j], s1 = 0.0;
-    int k = 0;
-    for (; k + 1 < j; k += 2) {
-      s0 = fma(-Dbuf[lane * LDD + k], Dbuf[j * LDD + k], s0);
-      s1 = fma(-Dbuf[lane * LDD + k + 1], Dbuf[j * LDD + k + 1], s1);
+    double s0 = rowp[j], s1 = 0.0;
+#pragma unroll
+    for (int k = 0; k < j; ++k) {
+      if (k & 1) s1 = fma(-rowp[k], Dbuf[j * LDD + k], s1);
+      else s0 = fma(-rowp[k], Dbuf[j * LDD + k], s0);
     }
-    if (k < j) s0 = fma(-Dbuf[lane * LDD + k], Dbuf[j * LDD + k], s0);
     const double s = s0 + s1;
     const double d = __shfl_sync(kFull, s, j);
-    if (!(d > 0.0)) return j + 1;                 // uniform: d is a broadcast
-    const double ljj = sqrt(d);
-    const double inv = 1.0 / ljj;
+    if (!(d > 0.0) && info == 0) info = j + 1;    // uniform: d is a broadcast
+    const double inv = rsqrt(d);                  // 1/ajj (dpotf2 scales the column by 1/ajj)
     __syncwarp();
-    if (lane == j) Dbuf[lane * LDD + j] = ljj;
-    else if (lane > j) Dbuf[lane * LDD + j] = s * inv;
-    else Dbuf[lane * LDD + j] = 0.0;              // zero the upper triangle
+    Dbuf[lane * LDD + j] = lane > j ? s * inv : (lane == j ? d * inv : 0.0);
+    if (lane == j) Ibuf[j * LD + j] = inv;        // 1/L[j][j], reused by the inverse below
     __syncwarp();
   }
-  // column `lane` of X = inv(L): x_i = (delta_i,lane - sum_{k<i} L[i][k] x_k) / L[i][i]
+  if (info != 0) return info;
+  // column `lane` of X = inv(L): x_i = (delta_i,lane - sum_{k<i} L[i][k] x_k) / L[i][i]; x kept in registers
+  double x[32];
+#pragma unroll
   for (int i = 0; i < 32; ++i) {
     double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
-    int k = 0;
-    for (; k + 1 < i; k += 2) {
-      s0 = fma(-Dbuf[i * LDD + k], Ibuf[k * LD + lane], s0);
-      s1 = fma(-Dbuf[i * LDD + k + 1], Ibuf[(k + 1) * LD + lane], s1);
+#pragma unroll
+    for (int k = 0; k < i; ++k) {
+      if (k & 1) s1 = fma(-Dbuf[i * LDD + k], x[k], s1);
+      else s0 = fma(-Dbuf[i * LDD + k], x[k], s0);
     }
-    if (k < i) s0 = fma(-Dbuf[i * LDD + k], Ibuf[k * LD + lane], s0);
-    Ibuf[i * LD + lane] = (i >= lane) ? (s0 + s1) / Dbuf[i * LDD + i] : 0.0;
+    x[i] = (i >= lane) ? (s0 + s1) * Ibuf[i * LD + i] : 0.0;
   }
+  __syncwarp();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) Ibuf[i * LD + lane] = x[i];
   __syncwarp();
   return 0;
 }
 
-// trailing-update inner loop of k_chol for NV valid row tiles (NV is warp-uniform)
+// trailing-update inner loop of k_chol for NV valid row tiles (NV is warp-uniform).
+// The warp's own operand tiles L[t_r, ct] stream through a per-warp cp.async ring kDepth-1 column tiles ahead
+// (register-free prefetch: without it every iteration exposed an L2 round trip and a leaf took ~3.5 M cycles);
+// the panel's row tiles L[J, ct] are shared by all warps of the CTA and come through L1.
+static constexpr int kCholDepth = 4;
 template <int R, int NV>
 __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2* __restrict__ Lp, const int (&bo)[4],
-                                           const int (&ao)[R], int nct) {
-#pragma unroll 4
-  for (int ct = 0; ct < nct; ++ct) {
-    double2 bf[4], af[NV];
+                                           const int (&ao)[R], int nct, uint32_t ring_u32, const double2* ring) {
+  auto issue = [&](int ct, int slot) {
+    if (ct < nct) {
 #pragma unroll
-    for (int b = 0; b < 4; ++b) bf[b] = Lp[bo[b] + ct * 32];
-#pragma unroll
-    for (int r = 0; r < NV; ++r) af[r] = Lp[ao[r] + ct * 32];
-#pragma unroll
-    for (int r = 0; r < NV; ++r) {
-#pragma unroll
-      for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af[r].x, bf[b].x);
+      for (int r = 0; r < NV; ++r) cp_async16_u32(ring_u32 + (uint32_t)((slot * R + r) * 512), Lp + ao[r] + ct * 32);
     }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int s = 0; s < kCholDepth - 1; ++s) issue(s, s);
+  int cslot = 0, fslot = kCholDepth - 1;
+  double2 bn[4];                                   // panel-row fragments, loaded one column tile ahead
+#pragma unroll
+  for (int b = 0; b < 4; ++b) bn[b] = nct > 0 ? Lp[bo[b]] : make_double2(0.0, 0.0);
+  for (int ct = 0; ct < nct; ++ct) {
+    double2 bf[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf[b] = bn[b];
+    if (ct + 1 < nct) {
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bn[b] = Lp[bo[b] + (ct + 1) * 32];
+    }
+    cp_async_wait<kCholDepth - 2>();
+    const double2* rs = ring + cslot * (R * 32);
+    issue(ct + kCholDepth - 1, fslot);      // refill the slot consumed one iteration ago
+    fslot = cslot;
+    cslot = (cslot + 1 == kCholDepth) ? 0 : cslot + 1;
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
+      const double2 af = rs[r * 32];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af[r].y, bf[b].y);
+      for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af.x, bf[b].x);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af.y, bf[b].y);
     }
   }
+  cp_async_wait<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -120,10 +153,14 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
   double2* Ip = reinterpret_cast<double2*>(lt.Linv + lt.ioff[p]);
   if (threadIdx.x == 0) s_fail = 0;
   __syncthreads();
+  extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
+  const double2* ring = reinterpret_cast<const double2*>(pmk_chol_smem) + (size_t)warp * (kCholDepth * R * 32) + lane;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
 
   const int src_lo = (lane & ~3) | (l >> 1);
   const int src_hi = (lane & ~3) | (2 + (l >> 1));
 
+  long long c_total = clock64(), c_factor = 0, c_kloop = 0, c_init = 0, c_solve = 0, c_wait = 0;
   for (int J = 0; J < nblk; ++J) {
     const int t0 = 4 * J;
     const int nchunks = (ntl - t0 + NW * R - 1) / (NW * R);
@@ -137,6 +174,7 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
         tv[r] = t[r] < ntl;
       }
       // ---- Gram entries straight into the (negated) accumulators: acc = -(K + sigma2*I) ----------
+      long long c0 = clock64();
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         const int row = 8 * (tv[r] ? t[r] : t0) + g;
@@ -164,6 +202,7 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
           }
         }
       }
+      { long long c1 = clock64(); c_init += c1 - c0; c0 = c1; }
       // ---- acc += L[t, 0:J] * L[J, 0:J]^T on the FP64 tensor cores -------------------------------
       {
         int bo[4], ao[R];
@@ -174,9 +213,15 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
         // the number of valid row tiles of this warp is uniform: pick a loop specialised for it, so
         // that no DMMA is predicated (a predicated-off DMMA still occupies the pipe) and the loads of
         // the unrolled iterations can be hoisted freely
-        if (tv[R - 1]) chol_kloop<R, R>(acc, Lp, bo, ao, 4 * J);
-        else if (R > 1 && tv[0]) chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J);
+        int nv = 0;
+#pragma unroll
+        for (int r = 0; r < R; ++r) nv += tv[r] ? 1 : 0;
+        if (nv == R) chol_kloop<R, R>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+        else if (R > 3 && nv == 3) chol_kloop<R, (R > 3 ? 3 : 1)>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+        else if (R > 2 && nv == 2) chol_kloop<R, (R > 2 ? 2 : 1)>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+        else if (nv >= 1) chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
       }
+      { long long c1 = clock64(); c_kloop += c1 - c0; c0 = c1; }
       // ---- diagonal block: factor + invert (chunk 0 carries row tiles t0..t0+3 on warps 0..3) ----
       if (c == 0) {
         if (warp < 4) {
@@ -187,6 +232,7 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
           }
         }
         __syncthreads();
+        { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
         if (warp == 0) {
           const int info = factor_block32(Dbuf, Ibuf, lane);
           if (info != 0) {
@@ -208,6 +254,7 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
           }
         }
         __syncthreads();
+        { long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; }
         if (s_fail) return;
       }
       // ---- panel rows below the diagonal block: L[t, J] = C * inv(L_JJ)^T ------------------------
@@ -237,14 +284,24 @@ k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
             }
             // C-fragment (row g, cols 2l, 2l+1) -> packed fragment-major tile
             double* tile = tile_row + cb * 64;
-            const int c0 = 2 * l, c1 = 2 * l + 1;
-            tile[(g * 4 + (c0 & 3)) * 2 + (c0 >> 2)] = o0;
-            tile[(g * 4 + (c1 & 3)) * 2 + (c1 >> 2)] = o1;
+            const int q0 = 2 * l, q1 = 2 * l + 1;
+            tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0;
+            tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1;
           }
         }
       }
+      { long long c1 = clock64(); c_solve += c1 - c0; c0 = c1; }
     }
-    __syncthreads();   // panel J complete and visible before panel J+1 reads it
+    { long long c1 = clock64(); __syncthreads(); c_wait += clock64() - c1; }   // panel J complete and visible before panel J+1 reads it
+  }
+  if (threadIdx.x == 0) {
+    atomicAdd(&g_chol_cycles[0], (unsigned long long)(clock64() - c_total));
+    atomicAdd(&g_chol_cycles[1], (unsigned long long)c_init);
+    atomicAdd(&g_chol_cycles[2], (unsigned long long)c_kloop);
+    atomicAdd(&g_chol_cycles[3], (unsigned long long)c_factor);
+    atomicAdd(&g_chol_cycles[4], (unsigned long long)c_solve);
+    atomicAdd(&g_chol_cycles[5], (unsigned long long)c_wait);
+    atomicAdd(&g_chol_cycles[6], 1ull);
   }
 }
 
@@ -374,10 +431,18 @@ void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const do
 void launch_chol(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, cudaStream_t s) {
   constexpr int NW = 8, R = 2;
   if (n_order <= 0) return;
+  const size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings (64 KB)
+  static bool configured = false;   // static + dynamic shared memory exceeds the 48 KB default
+  if (!configured) {
+    cudaFuncSetAttribute(k_chol<1, NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_chol<2, NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    cudaFuncSetAttribute(k_chol<3, NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    configured = true;
+  }
   switch (D) {
-    case 1: k_chol<1, NW, R><<<n_order, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
-    case 2: k_chol<2, NW, R><<<n_order, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
-    case 3: k_chol<3, NW, R><<<n_order, NW * 32, 0, s>>>(lt, d_order, kp, sigma2); break;
+    case 1: k_chol<1, NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order, kp, sigma2); break;
+    case 2: k_chol<2, NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order, kp, sigma2); break;
+    case 3: k_chol<3, NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order, kp, sigma2); break;
     default: break;
   }
 }
@@ -387,6 +452,14 @@ void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_
   if (n_order <= 0) return;
   const size_t smem = (size_t)(max_npad + NW * 32 + 32) * sizeof(double);
   k_solve_alpha<NW><<<n_order, NW * 32, smem, s>>>(lt, d_order);
+}
+
+void read_chol_cycles(unsigned long long* out, bool reset) {
+  cudaMemcpyFromSymbol(out, g_chol_cycles, sizeof(unsigned long long) * 8);
+  if (reset) {
+    unsigned long long z[8] = {0};
+    cudaMemcpyToSymbol(g_chol_cycles, z, sizeof z);
+  }
 }
 
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s) {

@@ -18,20 +18,6 @@ namespace pmk {
 
 static constexpr unsigned kFullQ = 0xffffffffu;
 
-__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
-  // .cg: cache in L2 only -- an L tile is consumed once per CTA, other CTAs of the same leaf find it in L2
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async16_u32(uint32_t smem_addr, const void* gmem) {
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gmem) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-
-
 template <int D, int NW, int NT, int NQT, int DEPTH, int GI>
 __global__ void __launch_bounds__(NW * 32, 1)
 k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, double* __restrict__ pair_u,
