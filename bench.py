@@ -403,11 +403,12 @@ def main():
                     "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
                     "algorithmic_flops_per_launch": flops_pairs, "ms_per_launch": float(kt[_lib.T_Q_PAIRS]),
                     "pairs_per_launch": int(npairs.value)}
-        fit_ach = flops_fit / (kt[_lib.T_FIT_CHOL] * 1e-3) / 1e12
-        phases = {"fit_pack_ms": float(kt[_lib.T_FIT_PACK]), "fit_chol_ms": float(kt[_lib.T_FIT_CHOL]),
+        fit_ach = flops_fit / ((kt[_lib.T_FIT_CHOL] + kt[_lib.T_FIT_GRAM]) * 1e-3) / 1e12
+        phases = {"fit_pack_ms": float(kt[_lib.T_FIT_PACK]), "fit_gram_ms": float(kt[_lib.T_FIT_GRAM]),
+                  "fit_chol_ms": float(kt[_lib.T_FIT_CHOL]),
                   "fit_solve_ms": float(kt[_lib.T_FIT_SOLVE]), "query_tree_ms": float(kt[_lib.T_Q_TREE]),
                   "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]), "query_combine_ms": float(kt[_lib.T_Q_COMBINE]),
-                  "fit_chol_tflops": fit_ach, "fit_chol_frac_of_fp64_peak": fit_ach / peak}
+                  "fit_gram_chol_tflops": fit_ach, "fit_gram_chol_frac_of_fp64_peak": fit_ach / peak}
         # per leaf-size class of the pair kernel: ms and achieved TFLOP/s
         npad_ = (sizes + 31) // 32 * 32
         cls_ = np.where(npad_ <= 512, 0, np.where(npad_ <= 768, 1, np.where(npad_ <= 1024, 2, 3)))

@@ -61,12 +61,13 @@ typedef enum {
 /* timing slots of pmk_get_timings (milliseconds, CUDA events on the handle's stream) */
 enum {
   PMK_T_FIT_PACK = 0,      /* AoS -> padded SoA leaf packing                                   */
-  PMK_T_FIT_CHOL = 1,      /* fused Gram + blocked Cholesky (K1+K2)                            */
+  PMK_T_FIT_CHOL = 1,      /* batched blocked Cholesky (K2)                                    */
   PMK_T_FIT_SOLVE = 2,     /* forward/back solves for alpha                                    */
   PMK_T_Q_TREE = 3,        /* home leaf + neighbour search + pair build + binning              */
   PMK_T_Q_PAIRS = 4,       /* fused cross-covariance / mean / TRSM-variance kernel (K3)        */
   PMK_T_Q_COMBINE = 5,     /* convex mixture combine                                           */
-  PMK_T_GRAM = 6,          /* standalone Gram kernel                                           */
+  PMK_T_GRAM = 6,          /* standalone Gram kernel (constructkernelmatrix / U_set)           */
+  PMK_T_FIT_GRAM = 7,      /* per-leaf Gram tiles of the fit (K1)                              */
   PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +3: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=2048)  */
   PMK_T_COUNT = 12
 };

@@ -15,6 +15,7 @@ BUF_L, BUF_LINV, BUF_ALPHA = 0, 1, 2
 OPT_FULL_HYPERPLANE_SCAN = 1
 T_FIT_PACK, T_FIT_CHOL, T_FIT_SOLVE, T_Q_TREE, T_Q_PAIRS, T_Q_COMBINE, T_GRAM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 12
 T_Q_PAIRS_CLASS0 = 8
+T_FIT_GRAM = 7
 
 # every symbol include/pmk.h declares
 SYMBOLS = [

@@ -17,7 +17,9 @@
 namespace pmk {
 // launchers defined in the kernel translation units
 void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const double* dX, const double* dy, cudaStream_t s);
-void launch_chol(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, cudaStream_t s);
+void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_order, int max_npad, KParams kp, double sigma2,
+                       cudaStream_t s);
+void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
 void read_chol_cycles(unsigned long long* out, bool reset);
@@ -482,8 +484,13 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   }
   KCHECK(h, "k_pack_leaves");
   {
+    Timer t(h, PMK_T_FIT_GRAM);
+    launch_gram_tiles(D, lt, h->d_order.as<int>(), n_order, max_npad, kp, sigma2, h->stream);
+  }
+  KCHECK(h, "k_gram_tiles");
+  {
     Timer t(h, PMK_T_FIT_CHOL);
-    launch_chol(D, lt, h->d_order.as<int>(), n_order, kp, sigma2, h->stream);
+    launch_chol(lt, h->d_order.as<int>(), n_order, h->stream);
   }
   KCHECK(h, "k_chol");
   {

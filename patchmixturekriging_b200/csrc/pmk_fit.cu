@@ -47,18 +47,29 @@ __global__ void k_pack_leaves(LeafTable lt, const int64_t* __restrict__ leaf_off
 // returns 0 or the (block-local, 1-based) order of the first non-positive pivot.
 static constexpr int LDD = 33;
 __device__ __noinline__ int factor_block32(double* Dbuf, double* Ibuf, int lane) {
-  // Left-looking (dot-product form) Cholesky, column j: lane i >= j owns L[i][j].  Fully unrolled: every
-  // shared-memory address is an immediate and the inner products have static trip counts -- this serial
-  // phase is latency-bound on a single warp, so instruction count is what matters.
+  // Step j does column j of the left-looking (dot-product form) Cholesky -- lane i >= j owns L[i][j] -- and,
+  // fused into the same step, row j of X = inv(L) by forward substitution (lane c owns column c of X):
+  //     x_jc = (delta_jc - sum_{k<j} L[j][k] x_kc) / L[j][j].
+  // Both need row j of L (k < j), loaded once; the two dependency chains are independent, so they overlap.
+  // Fully unrolled: every shared-memory address is an immediate and the inner products have static trip
+  // counts -- this serial phase is latency-bound on a single warp, instruction count is what matters.
   const double* rowp = Dbuf + lane * LDD;
+  const double* xcol = Ibuf + lane;
   int info = 0;
 #pragma unroll
   for (int j = 0; j < 32; ++j) {
     double s0 = rowp[j], s1 = 0.0;
+    double t0 = (j == lane) ? 1.0 : 0.0, t1 = 0.0;
 #pragma unroll
     for (int k = 0; k < j; ++k) {
-      if (k & 1) s1 = fma(-rowp[k], Dbuf[j * LDD + k], s1);
-      else s0 = fma(-rowp[k], Dbuf[j * LDD + k], s0);
+      const double ljk = Dbuf[j * LDD + k];
+      if (k & 1) {
+        s1 = fma(-rowp[k], ljk, s1);
+        t1 = fma(-ljk, xcol[k * LD], t1);
+      } else {
+        s0 = fma(-rowp[k], ljk, s0);
+        t0 = fma(-ljk, xcol[k * LD], t0);
+      }
     }
     const double s = s0 + s1;
     const double d = __shfl_sync(kFull, s, j);
@@ -66,27 +77,10 @@ __device__ __noinline__ int factor_block32(double* Dbuf, double* Ibuf, int lane)
     const double inv = rsqrt(d);                  // 1/ajj (dpotf2 scales the column by 1/ajj)
     __syncwarp();
     Dbuf[lane * LDD + j] = lane > j ? s * inv : (lane == j ? d * inv : 0.0);
-    if (lane == j) Ibuf[j * LD + j] = inv;        // 1/L[j][j], reused by the inverse below
+    Ibuf[j * LD + lane] = (j >= lane) ? (t0 + t1) * inv : 0.0;
     __syncwarp();
   }
-  if (info != 0) return info;
-  // column `lane` of X = inv(L): x_i = (delta_i,lane - sum_{k<i} L[i][k] x_k) / L[i][i]; x kept in registers
-  double x[32];
-#pragma unroll
-  for (int i = 0; i < 32; ++i) {
-    double s0 = (i == lane) ? 1.0 : 0.0, s1 = 0.0;
-#pragma unroll
-    for (int k = 0; k < i; ++k) {
-      if (k & 1) s1 = fma(-Dbuf[i * LDD + k], x[k], s1);
-      else s0 = fma(-Dbuf[i * LDD + k], x[k], s0);
-    }
-    x[i] = (i >= lane) ? (s0 + s1) * Ibuf[i * LD + i] : 0.0;
-  }
-  __syncwarp();
-#pragma unroll
-  for (int i = 0; i < 32; ++i) Ibuf[i * LD + lane] = x[i];
-  __syncwarp();
-  return 0;
+  return info;
 }
 
 // trailing-update inner loop of k_chol for NV valid row tiles (NV is warp-uniform).
@@ -136,168 +130,223 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
 }
 
 // ---------------------------------------------------------------------------------------------
-template <int D, int NW, int R>
-__global__ void __launch_bounds__(NW * 32, 3)
-k_chol(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
-  __shared__ double Dbuf[32 * LDD];
-  __shared__ double Ibuf[32 * LD];
-  __shared__ int s_fail;
+// K1 for the fit: the lower tiles of K + sigma2*I (identity on the padding) written into the leaf's L tile
+// slots in C-FRAGMENT-major order (lane (g,l) holds {M[g][2l], M[g][2l+1]}), i.e. exactly as k_chol's
+// accumulators want them.  A tile slot goes K (here) -> raw panel block C (k_chol, parked) -> L (final,
+// A-fragment-major).  Full-occupancy elementwise kernel: the evaluations (sqrt + exp chains) run at FP64
+// pipe throughput here instead of stalling the low-occupancy factorisation (measured: evaluating them
+// inside k_chol took 31 % of its cycles).  One warp per row tile.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
   const int p = order[blockIdx.x];
-  const int n = lt.n[p], npad = lt.npad[p];
-  const int nblk = npad >> 5, ntl = npad >> 3;
+  const int n = lt.n[p], ntl = lt.npad[p] >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.y * 8 + warp;
+  if (t >= ntl) return;
   const int g = lane >> 2, l = lane & 3;
   const double* __restrict__ xs = lt.xs + lt.xoff[p];
   const int64_t xstride = lt.xstride;
+  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]) + tri(t) * 32 + lane;
+  const int row = 8 * t + g;
+  double xr[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) xr[d] = xs[d * xstride + row];
+#pragma unroll 4
+  for (int c = 0; c <= t; ++c) {
+    double kv[2];
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int col = 8 * c + 2 * l + e;
+      double v = 0.0;
+      if (col <= row) {
+        if (row < n) {          // col <= row < n
+          double xc[D];
+#pragma unroll
+          for (int d = 0; d < D; ++d) xc[d] = xs[d * xstride + col];
+          v = eval_kernel<D>(kp, xr, xc);               // evalkernel(X[i], X[j]), i >= j  (RKHS.jl:21-25)
+          if (row == col) v = __dadd_rn(v, sigma2);     // mixtureGP.jl:102-104
+        } else {
+          v = (row == col) ? 1.0 : 0.0;                 // identity padding
+        }
+      }
+      kv[e] = v;
+    }
+    Lp[c * 32] = make_double2(kv[0], kv[1]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K2: blocked left-looking Cholesky of one leaf per CTA (see the file header).  Per 32-column panel J:
+//   A. warps 0-3: diagonal block  D = K_JJ - L[J,0:J] L[J,0:J]^T  -> shared memory (named barrier of 4 warps)
+//   B. warp 0 factors + inverts D (serial, latency-bound) WHILE all other warps (and warp 0 afterwards) pull
+//      row-tile groups off a shared counter, compute C = K[t,J] - L[t,0:J] L[J,0:J]^T on DMMA and park the raw
+//      C tiles in their L slots
+//   C. all warps: L[t,J] = C inv(L_JJ)^T on DMMA, final A-fragment-major tiles.
+template <int NW, int R>
+__global__ void __launch_bounds__(NW * 32, 3)
+k_chol(LeafTable lt, const int* __restrict__ order) {
+  __shared__ double Dbuf[32 * LDD];
+  __shared__ double Ibuf[32 * LD];
+  __shared__ int s_fail, s_next;
+  const int p = order[blockIdx.x];
+  const int npad = lt.npad[p];
+  const int nblk = npad >> 5, ntl = npad >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, l = lane & 3;
   double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
   double2* Ip = reinterpret_cast<double2*>(lt.Linv + lt.ioff[p]);
-  if (threadIdx.x == 0) s_fail = 0;
+  if (threadIdx.x == 0) {
+    s_fail = 0;
+    s_next = 4;
+  }
   __syncthreads();
   extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
   const double2* ring = reinterpret_cast<const double2*>(pmk_chol_smem) + (size_t)warp * (kCholDepth * R * 32) + lane;
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
-
   const int src_lo = (lane & ~3) | (l >> 1);
   const int src_hi = (lane & ~3) | (2 + (l >> 1));
 
-  long long c_total = clock64(), c_factor = 0, c_kloop = 0, c_init = 0, c_solve = 0, c_wait = 0;
+  long long c_total = clock64(), c_diag = 0, c_work = 0, c_factor = 0, c_solve = 0, c_wait = 0;
   for (int J = 0; J < nblk; ++J) {
     const int t0 = 4 * J;
-    const int nchunks = (ntl - t0 + NW * R - 1) / (NW * R);
-    for (int c = 0; c < nchunks; ++c) {
-      int t[R];
-      bool tv[R];
+    int bo[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
+    long long c0 = clock64();
+    // ---- A: diagonal block ----------------------------------------------------------------------
+    if (warp < 4) {
       double acc[R][4][2];
+      int ao[R];
 #pragma unroll
-      for (int r = 0; r < R; ++r) {
-        t[r] = t0 + c * NW * R + warp + NW * r;
-        tv[r] = t[r] < ntl;
+      for (int r = 0; r < R; ++r) ao[r] = (int)tri(t0 + warp) * 32 + lane;
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double2 kt = (b <= warp) ? Lp[ao[0] + (t0 + b) * 32] : make_double2(0.0, 0.0);
+        acc[0][b][0] = -kt.x;
+        acc[0][b][1] = -kt.y;
       }
-      // ---- Gram entries straight into the (negated) accumulators: acc = -(K + sigma2*I) ----------
-      long long c0 = clock64();
+      chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 0] = -acc[0][b][0];
+        Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 1] = -acc[0][b][1];
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");      // the four diagonal-row warps only
+      { long long c1 = clock64(); c_diag += c1 - c0; c0 = c1; }
+      if (warp == 0) {
+        const int info = factor_block32(Dbuf, Ibuf, lane);
+        if (info != 0) {
+          if (lane == 0) {
+            lt.info[p] = 32 * J + info;
+            s_fail = 1;
+          }
+        } else {
+#pragma unroll
+          for (int a = 0; a < 4; ++a) {
+            for (int b = 0; b <= a; ++b) {
+              const int rd = (8 * a + g) * LDD + 8 * b + l;
+              const int ri = (8 * a + g) * LD + 8 * b + l;
+              Lp[(tri(t0 + a) + t0 + b) * 32 + lane] = make_double2(Dbuf[rd], Dbuf[rd + 4]);
+              Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane] =
+                  make_double2(Ibuf[ri], Ibuf[ri + 4]);
+            }
+          }
+        }
+        { long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; }
+      }
+    }
+    // ---- B: off-diagonal row tiles, dynamically dealt; raw C parked in the tile slots -------------
+    for (;;) {
+      int tb = 0;
+      if (lane == 0) tb = atomicAdd(&s_next, R);
+      tb = __shfl_sync(kFull, tb, 0);
+      if (tb >= ntl) break;
+      double acc[R][4][2];
+      int ao[R];
+      int nv = 0;
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        const int row = 8 * (tv[r] ? t[r] : t0) + g;
-        double xr[D];
-#pragma unroll
-        for (int d = 0; d < D; ++d) xr[d] = xs[d * xstride + row];
+        const bool tv = tb + r < ntl;
+        nv += tv ? 1 : 0;
+        ao[r] = (int)tri(tv ? tb + r : tb) * 32 + lane;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int col = 32 * J + 8 * b + 2 * l + e;
-            double kv = 0.0;
-            if (tv[r] && col <= row) {
-              if (row < n) {   // col <= row < n
-                double xc[D];
-#pragma unroll
-                for (int d = 0; d < D; ++d) xc[d] = xs[d * xstride + col];
-                kv = eval_kernel<D>(kp, xr, xc);      // evalkernel(X[i], X[j]), i >= j  (RKHS.jl:21-25)
-                if (row == col) kv = __dadd_rn(kv, sigma2);   // mixtureGP.jl:102-104
-              } else {
-                kv = (row == col) ? 1.0 : 0.0;        // identity padding
-              }
-            }
-            acc[r][b][e] = -kv;
-          }
+          const double2 kt = tv ? Lp[ao[r] + (t0 + b) * 32] : make_double2(0.0, 0.0);
+          acc[r][b][0] = -kt.x;
+          acc[r][b][1] = -kt.y;
         }
       }
-      { long long c1 = clock64(); c_init += c1 - c0; c0 = c1; }
-      // ---- acc += L[t, 0:J] * L[J, 0:J]^T on the FP64 tensor cores -------------------------------
-      {
-        int bo[4], ao[R];
-#pragma unroll
-        for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
-#pragma unroll
-        for (int r = 0; r < R; ++r) ao[r] = (int)tri(tv[r] ? t[r] : t0) * 32 + lane;
-        // the number of valid row tiles of this warp is uniform: pick a loop specialised for it, so
-        // that no DMMA is predicated (a predicated-off DMMA still occupies the pipe) and the loads of
-        // the unrolled iterations can be hoisted freely
-        int nv = 0;
-#pragma unroll
-        for (int r = 0; r < R; ++r) nv += tv[r] ? 1 : 0;
-        if (nv == R) chol_kloop<R, R>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
-        else if (R > 3 && nv == 3) chol_kloop<R, (R > 3 ? 3 : 1)>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
-        else if (R > 2 && nv == 2) chol_kloop<R, (R > 2 ? 2 : 1)>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
-        else if (nv >= 1) chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
-      }
-      { long long c1 = clock64(); c_kloop += c1 - c0; c0 = c1; }
-      // ---- diagonal block: factor + invert (chunk 0 carries row tiles t0..t0+3 on warps 0..3) ----
-      if (c == 0) {
-        if (warp < 4) {
-#pragma unroll
-          for (int b = 0; b < 4; ++b) {
-            Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 0] = -acc[0][b][0];
-            Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 1] = -acc[0][b][1];
-          }
-        }
-        __syncthreads();
-        { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
-        if (warp == 0) {
-          const int info = factor_block32(Dbuf, Ibuf, lane);
-          if (info != 0) {
-            if (lane == 0) {
-              lt.info[p] = 32 * J + info;
-              s_fail = 1;
-            }
-          } else {
-#pragma unroll
-            for (int a = 0; a < 4; ++a) {
-              for (int b = 0; b <= a; ++b) {
-                const int rd = (8 * a + g) * LDD + 8 * b + l;
-                const int ri = (8 * a + g) * LD + 8 * b + l;
-                Lp[(tri(t0 + a) + t0 + b) * 32 + lane] = make_double2(Dbuf[rd], Dbuf[rd + 4]);
-                Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane] =
-                    make_double2(Ibuf[ri], Ibuf[ri + 4]);
-              }
-            }
-          }
-        }
-        __syncthreads();
-        { long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; }
-        if (s_fail) return;
-      }
-      // ---- panel rows below the diagonal block: L[t, J] = C * inv(L_JJ)^T ------------------------
+      if (nv == R) chol_kloop<R, R>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+      else chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);     // R == 2: one valid tile
 #pragma unroll
       for (int r = 0; r < R; ++r) {
-        PMK_UNIFORM_IF(tv[r] && t[r] >= t0 + 4) {
-          double alo[4], ahi[4];
+        if (r < nv) {
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) {
-            const double v0 = __shfl_sync(kFull, acc[r][kb][0], src_lo);
-            const double v1 = __shfl_sync(kFull, acc[r][kb][1], src_lo);
-            const double w0 = __shfl_sync(kFull, acc[r][kb][0], src_hi);
-            const double w1 = __shfl_sync(kFull, acc[r][kb][1], src_hi);
-            alo[kb] = -((l & 1) ? v1 : v0);
-            ahi[kb] = -((l & 1) ? w1 : w0);
-          }
-          double* tile_row = reinterpret_cast<double*>(Lp + (tri(t[r]) + t0) * 32);
-#pragma unroll
-          for (int cb = 0; cb < 4; ++cb) {
-            double o0 = 0.0, o1 = 0.0;
-#pragma unroll
-            for (int kb = 0; kb <= cb; ++kb) {
-              const double blo = Ibuf[(8 * cb + g) * LD + 8 * kb + l];
-              const double bhi = Ibuf[(8 * cb + g) * LD + 8 * kb + 4 + l];
-              dmma884(o0, o1, alo[kb], blo);
-              dmma884(o0, o1, ahi[kb], bhi);
-            }
-            // C-fragment (row g, cols 2l, 2l+1) -> packed fragment-major tile
-            double* tile = tile_row + cb * 64;
-            const int q0 = 2 * l, q1 = 2 * l + 1;
-            tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0;
-            tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1;
-          }
+          for (int b = 0; b < 4; ++b) Lp[ao[r] + (t0 + b) * 32] = make_double2(-acc[r][b][0], -acc[r][b][1]);
         }
       }
-      { long long c1 = clock64(); c_solve += c1 - c0; c0 = c1; }
     }
-    { long long c1 = clock64(); __syncthreads(); c_wait += clock64() - c1; }   // panel J complete and visible before panel J+1 reads it
+    { long long c1 = clock64(); c_work += c1 - c0; c0 = c1; }
+    __syncthreads();     // inverse block ready, every C tile parked
+    { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+    if (s_fail) return;
+    // ---- C: L[t, J] = C * inv(L_JJ)^T -----------------------------------------------------------
+    {
+      int t = t0 + 4 + warp;
+      double2 cf[4], cn[4];
+      if (t < ntl) {
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) cf[kb] = Lp[(tri(t) + t0 + kb) * 32 + lane];
+      }
+      for (; t < ntl; t += NW) {
+        double2* trow = Lp + (tri(t) + t0) * 32;
+        if (t + NW < ntl) {               // next row tile's parked block, one iteration ahead
+#pragma unroll
+          for (int kb = 0; kb < 4; ++kb) cn[kb] = Lp[(tri(t + NW) + t0 + kb) * 32 + lane];
+        }
+        double alo[4], ahi[4];
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {     // C-fragment (cols 2l, 2l+1) -> A-fragment (cols l, l+4) inside the quad
+          const double v0 = __shfl_sync(kFull, cf[kb].x, src_lo);
+          const double v1 = __shfl_sync(kFull, cf[kb].y, src_lo);
+          const double w0 = __shfl_sync(kFull, cf[kb].x, src_hi);
+          const double w1 = __shfl_sync(kFull, cf[kb].y, src_hi);
+          alo[kb] = (l & 1) ? v1 : v0;
+          ahi[kb] = (l & 1) ? w1 : w0;
+        }
+        double* tile_row = reinterpret_cast<double*>(trow);
+        double o0[4], o1[4], p0[4], p1[4];
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) o0[cb] = o1[cb] = p0[cb] = p1[cb] = 0.0;
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) {     // kb outermost: the four output tiles advance in lock step
+#pragma unroll
+          for (int cb = kb; cb < 4; ++cb) dmma884(o0[cb], o1[cb], alo[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + l]);
+#pragma unroll
+          for (int cb = kb; cb < 4; ++cb) dmma884(p0[cb], p1[cb], ahi[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + 4 + l]);
+        }
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) {
+          // C-fragment (row g, cols 2l, 2l+1) -> packed A-fragment-major tile
+          double* tile = tile_row + cb * 64;
+          const int q0 = 2 * l, q1 = 2 * l + 1;
+          tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0[cb] + p0[cb];
+          tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1[cb] + p1[cb];
+        }
+#pragma unroll
+        for (int kb = 0; kb < 4; ++kb) cf[kb] = cn[kb];
+      }
+    }
+    if (threadIdx.x == 0) s_next = t0 + 8;     // first off-diagonal row tile of the next panel
+    { long long c1 = clock64(); c_solve += c1 - c0; c0 = c1; }
+    __syncthreads();     // panel J complete and visible before panel J+1 reads it
+    { long long c1 = clock64(); c_wait += c1 - c0; }
   }
   if (threadIdx.x == 0) {
     atomicAdd(&g_chol_cycles[0], (unsigned long long)(clock64() - c_total));
-    atomicAdd(&g_chol_cycles[1], (unsigned long long)c_init);
-    atomicAdd(&g_chol_cycles[2], (unsigned long long)c_kloop);
+    atomicAdd(&g_chol_cycles[1], (unsigned long long)c_diag);
+    atomicAdd(&g_chol_cycles[2], (unsigned long long)c_work);
     atomicAdd(&g_chol_cycles[3], (unsigned long long)c_factor);
     atomicAdd(&g_chol_cycles[4], (unsigned long long)c_solve);
     atomicAdd(&g_chol_cycles[5], (unsigned long long)c_wait);
@@ -428,23 +477,28 @@ void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const do
   }
 }
 
-void launch_chol(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, cudaStream_t s) {
-  constexpr int NW = 8, R = 2;
+void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_order, int max_npad, KParams kp, double sigma2,
+                       cudaStream_t s) {
   if (n_order <= 0) return;
-  const size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings (64 KB)
-  static bool configured = false;   // static + dynamic shared memory exceeds the 48 KB default
-  if (!configured) {
-    cudaFuncSetAttribute(k_chol<1, NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_chol<2, NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    cudaFuncSetAttribute(k_chol<3, NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    configured = true;
-  }
+  dim3 grid(n_order, (max_npad / 8 + 7) / 8);
   switch (D) {
-    case 1: k_chol<1, NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order, kp, sigma2); break;
-    case 2: k_chol<2, NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order, kp, sigma2); break;
-    case 3: k_chol<3, NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order, kp, sigma2); break;
+    case 1: k_gram_tiles<1><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2); break;
+    case 2: k_gram_tiles<2><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2); break;
+    case 3: k_gram_tiles<3><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2); break;
     default: break;
   }
+}
+
+void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s) {
+  constexpr int NW = 8, R = 2;
+  if (n_order <= 0) return;
+  const size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings (32 KB)
+  static bool configured = false;   // static + dynamic shared memory exceeds the 48 KB default
+  if (!configured) {
+    cudaFuncSetAttribute(k_chol<NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    configured = true;
+  }
+  k_chol<NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order);
 }
 
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s) {

@@ -15,6 +15,6 @@ out = np.zeros(8, dtype=np.uint64)
 eta.handle.check(_lib.lib().pmk_debug_counters(eta.handle.raw, _lib.ptr(out), 1))
 P.fitmixtureGP_(eta, y_set, th, w["sigma2"])
 eta.handle.check(_lib.lib().pmk_debug_counters(eta.handle.raw, _lib.ptr(out), 1))
-names = ["total", "gram_init", "update_loop", "diag_factor", "panel_solve", "barrier_wait", "ctas"]
+names = ["total", "diag_block(warp0)", "offdiag_work(warp0)", "factor(warp0)", "panel_solve", "barrier_wait", "ctas"]
 n = float(out[6])
-print({k: round(float(v) / n) for k, v in zip(names, out[:6])}, "ctas", int(n), "ms", eta.handle.timings()[_lib.T_FIT_CHOL])
+print({k: round(float(v) / n) for k, v in zip(names, out[:6])}, "ctas", int(n), "chol ms", eta.handle.timings()[_lib.T_FIT_CHOL], "gram tiles ms", eta.handle.timings()[_lib.T_FIT_GRAM])
