@@ -175,8 +175,9 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value);
 /* ---- instrumentation --------------------------------------------------------------------- */
 int pmk_get_timings(pmk_handle* h, double* ms /* PMK_T_COUNT entries */);
 /* cycle counters of the fit kernel, summed over CTAs (warp 0): total, gram-init, update loop, diagonal factor,
- * panel solve, barrier wait, #CTAs, reserved.  reset != 0 zeroes them after reading. */
-int pmk_debug_counters(pmk_handle* h, uint64_t* out8, int reset);
+ * panel solve, barrier wait, #CTAs, reserved.  flags: bit0 = zero them after reading; bit1 = read the pair kernel's
+ * counters instead (total, cross-covariance init, publish+barrier, diagonal solve+barrier, update, #CTAs). */
+int pmk_debug_counters(pmk_handle* h, uint64_t* out8, int flags);
 /* number of kernel launches issued by this handle since creation */
 int64_t pmk_launch_count(const pmk_handle* h);
 /* stream the handle launches on, as a cudaStream_t cast to void* (for event timing by the caller) */

@@ -23,6 +23,7 @@ void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStrea
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
 void read_chol_cycles(unsigned long long* out, bool reset);
+void read_query_cycles(int D, unsigned long long* out, bool reset);
 void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, int32_t* d_leaf_qcount,
                  cudaStream_t s);
 void launch_leaf_bbox(int D, int n_leaves, int64_t Nq, const double* dXq, const int32_t* qperm, const int64_t* leaf_qstart,
@@ -262,7 +263,8 @@ int pmk_debug_counters(pmk_handle* h, uint64_t* out8, int reset) {
   if (!h || !out8) return PMK_ERR_ARG;
   if (int rc = set_device(h)) return rc;
   CU(h, cudaStreamSynchronize(h->stream));
-  read_chol_cycles(reinterpret_cast<unsigned long long*>(out8), reset != 0);
+  if (reset & 2) read_query_cycles(h->D, reinterpret_cast<unsigned long long*>(out8), (reset & 1) != 0);
+  else read_chol_cycles(reinterpret_cast<unsigned long long*>(out8), (reset & 1) != 0);
   return PMK_OK;
 }
 

@@ -3,6 +3,15 @@
 
 namespace pmk {
 
+void read_query_cycles_d1(unsigned long long* out, bool reset);
+void read_query_cycles_d2(unsigned long long* out, bool reset);
+void read_query_cycles_d3(unsigned long long* out, bool reset);
+void read_query_cycles(int D, unsigned long long* out, bool reset) {
+  if (D == 1) read_query_cycles_d1(out, reset);
+  else if (D == 2) read_query_cycles_d2(out, reset);
+  else read_query_cycles_d3(out, reset);
+}
+
 __global__ void k_class_tiles(PairWork w, int mq, int32_t* __restrict__ tiles) {
   const int s = blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= w.n_class_leaves) return;

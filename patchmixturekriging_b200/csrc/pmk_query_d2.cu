@@ -5,4 +5,5 @@ void launch_pairs_d2(int cls, unsigned grid, const LeafTable& lt, const PairWork
                       int mean_only, double* pu, double* pv, cudaStream_t s) {
   launch_pairs_d<2>(cls, grid, lt, w, q, kp, mean_only, pu, pv, s);
 }
+void read_query_cycles_d2(unsigned long long* out, bool reset) { read_query_cycles_tu(out, reset); }
 }  // namespace pmk
