@@ -11,6 +11,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpmk_b200.so")
 SOURCES = ["pmk_api.cu", "pmk_fit.cu", "pmk_tree.cu", "pmk_query.cu", "pmk_query_d1.cu", "pmk_query_d2.cu", "pmk_query_d3.cu", "pmk_gram.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+EXTRA = os.environ.get("PMK_NVCC_EXTRA", "").split()     # e.g. PMK_NVCC_EXTRA=-DPMK_PROFILE_CYCLES for the phase counters
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
@@ -33,7 +34,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(HERE, "build", src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
-            jobs.append([NVCC, *FLAGS, "-c", s, "-o", o])
+            jobs.append([NVCC, *FLAGS, *EXTRA, "-c", s, "-o", o])
 
     def run(cmd):
         r = subprocess.run(cmd, capture_output=True, text=True)

@@ -7,6 +7,14 @@
 #include <stdint.h>
 #include "../../include/pmk.h"
 
+// Per-phase cycle counters (tools/chol_phases.py, tools/query_phases.py) are compiled in only with
+// -DPMK_PROFILE_CYCLES: reading the clock between phases costs ~10 % in the pair kernel.
+#ifdef PMK_PROFILE_CYCLES
+#define PMK_CYC(...) __VA_ARGS__
+#else
+#define PMK_CYC(...)
+#endif
+
 namespace pmk {
 
 struct KParams {

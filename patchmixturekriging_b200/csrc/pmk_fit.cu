@@ -207,13 +207,13 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
   const int src_lo = (lane & ~3) | (l >> 1);
   const int src_hi = (lane & ~3) | (2 + (l >> 1));
 
-  long long c_total = clock64(), c_diag = 0, c_work = 0, c_factor = 0, c_solve = 0, c_wait = 0;
+  PMK_CYC(long long c_total = clock64(), c_diag = 0, c_work = 0, c_factor = 0, c_solve = 0, c_wait = 0;)
   for (int J = 0; J < nblk; ++J) {
     const int t0 = 4 * J;
     int bo[4];
 #pragma unroll
     for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
-    long long c0 = clock64();
+    PMK_CYC(long long c0 = clock64();)
     // ---- A: diagonal block ----------------------------------------------------------------------
     if (warp < 4) {
       double acc[R][4][2];
@@ -233,7 +233,7 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
         Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 1] = -acc[0][b][1];
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");      // the four diagonal-row warps only
-      { long long c1 = clock64(); c_diag += c1 - c0; c0 = c1; }
+      PMK_CYC({ long long c1 = clock64(); c_diag += c1 - c0; c0 = c1; })
       if (warp == 0) {
         const int info = factor_block32(Dbuf, Ibuf, lane);
         if (info != 0) {
@@ -253,7 +253,7 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
             }
           }
         }
-        { long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; }
+        PMK_CYC({ long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; })
       }
     }
     // ---- B: off-diagonal row tiles, dynamically dealt; raw C parked in the tile slots -------------
@@ -287,9 +287,9 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
         }
       }
     }
-    { long long c1 = clock64(); c_work += c1 - c0; c0 = c1; }
+    PMK_CYC({ long long c1 = clock64(); c_work += c1 - c0; c0 = c1; })
     __syncthreads();     // inverse block ready, every C tile parked
-    { long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; }
+    PMK_CYC({ long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; })
     if (s_fail) return;
     // ---- C: L[t, J] = C * inv(L_JJ)^T -----------------------------------------------------------
     {
@@ -339,10 +339,11 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
       }
     }
     if (threadIdx.x == 0) s_next = t0 + 8;     // first off-diagonal row tile of the next panel
-    { long long c1 = clock64(); c_solve += c1 - c0; c0 = c1; }
+    PMK_CYC({ long long c1 = clock64(); c_solve += c1 - c0; c0 = c1; })
     __syncthreads();     // panel J complete and visible before panel J+1 reads it
-    { long long c1 = clock64(); c_wait += c1 - c0; }
+    PMK_CYC({ long long c1 = clock64(); c_wait += c1 - c0; })
   }
+#ifdef PMK_PROFILE_CYCLES
   if (threadIdx.x == 0) {
     atomicAdd(&g_chol_cycles[0], (unsigned long long)(clock64() - c_total));
     atomicAdd(&g_chol_cycles[1], (unsigned long long)c_diag);
@@ -352,6 +353,7 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
     atomicAdd(&g_chol_cycles[5], (unsigned long long)c_wait);
     atomicAdd(&g_chol_cycles[6], 1ull);
   }
+#endif
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -67,7 +67,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
   const double2* __restrict__ Lp = reinterpret_cast<const double2*>(lt.L + lt.loff[p]);
   const double2* __restrict__ Ip = reinterpret_cast<const double2*>(lt.Linv + lt.ioff[p]);
 
-  long long q_total = clock64(), q_init = 0, q_pub = 0, q_diag = 0, q_upd = 0;
+  PMK_CYC(long long q_total = clock64(), q_init = 0, q_pub = 0, q_diag = 0, q_upd = 0;)
   if (tid < MQ) {
     const int qi = tid < cnt ? tid : cnt - 1;
     const int64_t gp = w.sorted_pair[pstart + qi];
@@ -130,7 +130,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     return;
   }
 
-  q_init = clock64() - q_total;
+  PMK_CYC(q_init = clock64() - q_total;)
   // ---- right-looking blocked TRSM:  s = L^-1 k  (mixtureGP.jl:311), ||s||^2 on the fly ----------
   double vacc[OT][2];
 #pragma unroll
@@ -181,7 +181,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
   int cslot = 0;                     // ring slot of the group consumed next
 
   for (int J = 0; J < nblk; ++J) {
-    long long qc = clock64();
+    PMK_CYC(long long qc = clock64();)
     // prefetch this warp's inverse-diagonal-block tiles for step 2 (latency hidden behind the barrier)
     double2 fI[OT][4];
 #pragma unroll
@@ -206,7 +206,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
       }
     }
     __syncthreads();
-    { long long c1 = clock64(); q_pub += c1 - qc; qc = c1; }
+    PMK_CYC({ long long c1 = clock64(); q_pub += c1 - qc; qc = c1; })
     // 2. S_J = inv(L_JJ) * C_J : 4 x NQT output tiles spread over the warps
 #pragma unroll
     for (int k = 0; k < OT; ++k) {
@@ -238,7 +238,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
       }
     }
     __syncthreads();
-    { long long c1 = clock64(); q_diag += c1 - qc; qc = c1; }
+    PMK_CYC({ long long c1 = clock64(); q_diag += c1 - qc; qc = c1; })
     // 3. acc[I] += L_IJ * S_J for the row tiles below block J.  Tile guards are REAL branches
     //    (PMK_UNIFORM_IF); within a tile the DMMAs are ordered k-step-major so that consecutive
     //    ones hit different accumulators.
@@ -276,7 +276,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
         }
       }
     }
-    q_upd += clock64() - qc;
+    PMK_CYC(q_upd += clock64() - qc;)
   }
   cp_async_wait<0>();
 
@@ -313,6 +313,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     pair_u[gp] = u;
     pair_v[gp] = v;
   }
+#ifdef PMK_PROFILE_CYCLES
   if (tid == 0) {
     atomicAdd(&g_query_cycles[0], (unsigned long long)(clock64() - q_total));
     atomicAdd(&g_query_cycles[1], (unsigned long long)q_init);
@@ -321,6 +322,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     atomicAdd(&g_query_cycles[4], (unsigned long long)q_upd);
     atomicAdd(&g_query_cycles[5], 1ull);
   }
+#endif
 }
 
 
