@@ -398,9 +398,14 @@ def main():
             float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * EVAL_FLOPS_2D).sum())
         peak, peak_src = fp64_peak()
         ach = flops_pairs / (kt[_lib.T_Q_PAIRS] * 1e-3) / 1e12
+        try:      # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch, leaf class <=512)
+            tr_ = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic_r01.json")))
+            traffic = {"bytes": tr_["dram_bytes_read"] + tr_["dram_bytes_write"], "of": tr_["kernel"], "source": tr_["source"]}
+        except Exception:
+            traffic = None
         roofline = {"kernel": "k_query_pairs (fused cross-covariance + mean + DMMA TRSM variance)", "bound": "tensor",
                     "pipe": "FP64 DMMA.8x8x4 (mma.sync.m8n8k4.f64); tcgen05 has no f64 kind", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": None,
+                    "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
                     "algorithmic_flops_per_launch": flops_pairs, "ms_per_launch": float(kt[_lib.T_Q_PAIRS]),
                     "pairs_per_launch": int(npairs.value)}
         fit_ach = flops_fit / ((kt[_lib.T_FIT_CHOL] + kt[_lib.T_FIT_GRAM]) * 1e-3) / 1e12

@@ -108,6 +108,8 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
  *   K: U_set[leaf] = Gram WITHOUT sigma2 (mixtureGP.jl:99), recomputed on demand. */
 int pmk_leaf_size(pmk_handle* h, int64_t leaf, int64_t* n_out);
 int pmk_get_alpha(pmk_handle* h, int64_t leaf, double* out);
+/* overwrite a leaf's weights (setupGPquery(c, X, theta, sigma2), src/RKHS/querying.jl:43-58, takes c from the caller) */
+int pmk_set_alpha(pmk_handle* h, int64_t leaf, const double* c);
 int pmk_get_L(pmk_handle* h, int64_t leaf, double* out);
 int pmk_get_K(pmk_handle* h, int64_t leaf, double* out);
 
@@ -121,12 +123,23 @@ int pmk_set_tree(pmk_handle* h, int D, int levels, const double* hp_v, const dou
 /* findpartition (partition.jl:248-262) for many points: leaf_out[j] 1-based. */
 int pmk_find_partition(pmk_handle* h, int64_t Nq, const double* Xq, int32_t* leaf_out);
 
+/* organizetrainingsets(root, levels, X0, eps) (partition.jl:301-357; findεpartitions! :269-298) on the device, for the
+ * tree given to pmk_set_tree.  X0 is D x N.  leaf_off_out gets n_leaves+1 0-based prefix offsets, *total_out the number of
+ * (leaf, point) memberships.  pmk_organize_fetch then returns
+ *   inds_out[total]          X_set_inds, leaf after leaf, ascending 1-based global point ids inside each leaf
+ *   point_off_out[N+1], point_leaves_out[total]   regions_list_set: every point's leaves, left-to-right, 1-based
+ * (any pointer may be NULL).  Bit-exact against the reference's comparisons (v.x < c+eps / v.x > c-eps, un-fused). */
+int pmk_organize_training_sets(pmk_handle* h, int64_t N, const double* X0, double eps, int64_t* leaf_off_out,
+                               int64_t* total_out);
+int pmk_organize_fetch(pmk_handle* h, int32_t* inds_out, int64_t* point_off_out, int32_t* point_leaves_out);
+
 /* ---- query ------------------------------------------------------------------------------- */
 /* querymixtureGP!(Yq, Vq, Xq, eta, root, levels, radius, delta, theta, sigma2, weight_theta, ...)
  * (mixtureGP.jl:159-294; inner: queryinner! :296-316, findneighbourpartitions :339-405,
  * findpartition partition.jl:248-262).  Xq is D x Nq.  wkernel_id/wparams = weight_theta (a stationary
  * kernel evaluated at abs(t)).  theta and sigma2 are those given to pmk_fit.
- * flags: bit0 = mean only (Vq untouched; this is query!(Yq,Xq,eta), RKHS.jl:220-247, when levels==1). */
+ * flags: bit0 = mean only (Vq untouched; this is query!(Yq,Xq,eta), RKHS.jl:220-247, when levels==1);
+ *        bit1 = variance without the clamp(., 1e-12, Inf) of queryinner! (evalqueryGP!, querying.jl:60-79). */
 int pmk_query(pmk_handle* h, int64_t Nq, const double* Xq, double radius, double delta, int wkernel_id,
               const double* wparams, int nw, int flags, double* Yq, double* Vq);
 int pmk_query_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radius, double delta, int wkernel_id,

@@ -5,16 +5,17 @@ julia/PatchMixtureKrigingB200.jl is the same layer written for the reference's o
 from .kernels import (BrownianBridge10, BrownianBridge1eps, BrownianBridge1ϵ, BrownianBridge20, BrownianBridge2eps,
                       BrownianBridge2ϵ, GaussianKernel1DType, RationalQuadraticKernelType, Spline12KernelType,
                       Spline32KernelType, Spline34KernelType)
-from .partition import BSPTree, fetchhyperplanes, findpartition, gethyperplane, organizetrainingsets, setuppartition
+from .partition import (BSPTree, fetchhyperplanes, findpartition, gethyperplane, organizetrainingsets,
+                        organizetrainingsets_device, setuppartition)
 from ._lib import Handle, PMKError, PosDefException, LIB_PATH
 from .mixturegp import MixtureGPDebugType, MixtureGPType, fitmixtureGP_, querymixtureGP, querymixtureGP_
-from .rkhs import RKHSProblemType, constructkernelmatrix, evalkernel, fitRKHS_, query_
+from .rkhs import RKHSProblemType, constructkernelmatrix, evalkernel, evalquery, fitRKHS_, query_, setupGPquery
 
 __all__ = [
     "BrownianBridge10", "BrownianBridge20", "BrownianBridge1ϵ", "BrownianBridge2ϵ", "BrownianBridge1eps", "BrownianBridge2eps",
     "GaussianKernel1DType", "Spline34KernelType", "Spline12KernelType", "Spline32KernelType", "RationalQuadraticKernelType",
-    "BSPTree", "setuppartition", "organizetrainingsets", "fetchhyperplanes", "findpartition", "gethyperplane",
+    "BSPTree", "setuppartition", "organizetrainingsets", "organizetrainingsets_device", "fetchhyperplanes", "findpartition", "gethyperplane",
     "MixtureGPType", "MixtureGPDebugType", "fitmixtureGP_", "querymixtureGP", "querymixtureGP_",
-    "RKHSProblemType", "fitRKHS_", "query_", "constructkernelmatrix", "evalkernel",
+    "RKHSProblemType", "fitRKHS_", "query_", "constructkernelmatrix", "evalkernel", "evalquery", "setupGPquery",
     "Handle", "PMKError", "PosDefException", "LIB_PATH",
 ]

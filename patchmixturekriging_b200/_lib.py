@@ -20,7 +20,7 @@ T_FIT_GRAM = 7
 # every symbol include/pmk.h declares
 SYMBOLS = [
     "pmk_create", "pmk_destroy", "pmk_last_error", "pmk_version", "pmk_gram", "pmk_cross_gram", "pmk_fit", "pmk_fit_dev",
-    "pmk_leaf_size", "pmk_get_alpha", "pmk_get_L", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_query",
+    "pmk_leaf_size", "pmk_get_alpha", "pmk_set_alpha", "pmk_get_L", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_organize_training_sets", "pmk_organize_fetch", "pmk_query",
     "pmk_query_dev", "pmk_last_query_pairs", "pmk_last_query_debug", "pmk_set_fit_range", "pmk_model_buffer", "pmk_mark_fitted", "pmk_query_plan_dev",
     "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_option", "pmk_get_timings", "pmk_debug_counters", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
 ]
@@ -67,10 +67,13 @@ def lib() -> C.CDLL:
     L.pmk_fit_dev.argtypes = L.pmk_fit.argtypes
     L.pmk_leaf_size.argtypes = [vp, i64, C.POINTER(i64)]
     L.pmk_get_alpha.argtypes = [vp, i64, dp]
+    L.pmk_set_alpha.argtypes = [vp, i64, dp]
     L.pmk_get_L.argtypes = [vp, i64, dp]
     L.pmk_get_K.argtypes = [vp, i64, dp]
     L.pmk_set_tree.argtypes = [vp, i32, i32, dp, dp]
     L.pmk_find_partition.argtypes = [vp, i64, dp, dp]
+    L.pmk_organize_training_sets.argtypes = [vp, i64, dp, dbl, dp, C.POINTER(i64)]
+    L.pmk_organize_fetch.argtypes = [vp, dp, dp, dp]
     L.pmk_query.argtypes = [vp, i64, dp, dbl, dbl, i32, dp, i32, i32, dp, dp]
     L.pmk_query_dev.argtypes = L.pmk_query.argtypes
     L.pmk_last_query_pairs.argtypes = [vp, C.POINTER(i64)]

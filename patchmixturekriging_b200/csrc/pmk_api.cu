@@ -37,6 +37,8 @@ void launch_neighbours(int D, bool fill, bool pruned, int n_leaves, const TreeDe
 void launch_combine(int64_t Nq, const int64_t* pair_off, const double* pw, const double* pu, const double* pv, double* dYq,
                     double* dVq, int mean_only, cudaStream_t s);
 void launch_scan_small(const int32_t* in, int64_t* out, int n, cudaStream_t s);
+void launch_eps_partitions(int D, bool fill, const TreeDev& tr, int64_t N, const double* dX, double eps, int32_t* counts,
+                           const int64_t* off, int32_t* pair_leaf, int32_t* pair_pt, int32_t* leaf_count, cudaStream_t s);
 void launch_aos_to_soa(int D, const double* dX, int64_t n, int64_t stride, double* xs, cudaStream_t s);
 void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double* xc, int64_t xc_stride, int m, KParams kp,
                  double sigma2, int symmetric, double* dK, cudaStream_t s);
@@ -114,6 +116,9 @@ struct pmk_handle {
   DBuf d_leaf_count, d_leaf_pair_start, d_cub;
   DBuf d_leaf_qcount, d_leaf_qstart, d_qperm, d_qkeys, d_bbox, d_cand_count, d_cand_start, d_cand, d_kept;
   bool full_scan = false;   // PMK_OPT_FULL_HYPERPLANE_SCAN
+  // organizetrainingsets on the device (results of the last call)
+  DBuf o_X, o_counts, o_off, o_pl, o_pp, o_sl, o_sp, o_lcount, o_lstart;
+  int64_t o_N = 0, o_total = 0, o_leaves = 0;
   DBuf d_scratch;   // Gram scratch
   QueryPlan plan{};
   bool plan_valid = false;
@@ -228,7 +233,8 @@ void pmk_destroy(pmk_handle* h) {
                   &h->d_npairs, &h->d_pair_off, &h->d_Yq, &h->d_Vq, &h->d_pair_leaf, &h->d_pair_q, &h->d_pair_hp, &h->d_pair_t,
                   &h->d_pair_w, &h->d_pair_u, &h->d_pair_v, &h->d_sorted_pair, &h->d_keys_out, &h->d_iota, &h->d_leaf_count,
                   &h->d_leaf_pair_start, &h->d_cub, &h->d_scratch, &h->d_leaf_qcount, &h->d_leaf_qstart, &h->d_qperm,
-                  &h->d_qkeys, &h->d_bbox, &h->d_cand_count, &h->d_cand_start, &h->d_cand, &h->d_kept};
+                  &h->d_qkeys, &h->d_bbox, &h->d_cand_count, &h->d_cand_start, &h->d_cand, &h->d_kept, &h->o_X, &h->o_counts, &h->o_off, &h->o_pl, &h->o_pp, &h->o_sl,
+                  &h->o_sp, &h->o_lcount, &h->o_lstart};
   for (DBuf* b : bufs) b->release();
   for (int c = 0; c < kNumClasses; ++c) {
     h->d_class_leaves[c].release();
@@ -559,6 +565,16 @@ int pmk_get_alpha(pmk_handle* h, int64_t leaf, double* out) {
   return PMK_OK;
 }
 
+int pmk_set_alpha(pmk_handle* h, int64_t leaf, const double* c) {
+  int64_t p;
+  if (int rc = check_leaf(h, leaf, &p)) return rc;
+  if (!c) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (int rc = set_device(h)) return rc;
+  CU(h, cudaMemcpyAsync(h->d_alpha.as<double>() + h->h_xoff[p], c, sizeof(double) * h->h_n[p], cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
 int pmk_get_L(pmk_handle* h, int64_t leaf, double* out) {
   int64_t p;
   if (int rc = check_leaf(h, leaf, &p)) return rc;
@@ -638,6 +654,80 @@ int pmk_find_partition(pmk_handle* h, int64_t Nq, const double* Xq, int32_t* lea
   CU(h, cudaMemcpyAsync(leaf_out, h->d_home.p, sizeof(int32_t) * Nq, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
   h->plan_valid = false;
+  return PMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// organizetrainingsets on the device
+int pmk_organize_training_sets(pmk_handle* h, int64_t N, const double* X0, double eps, int64_t* leaf_off_out,
+                               int64_t* total_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->tree_set || h->n_hp == 0) return fail(h, PMK_ERR_STATE, "pmk_set_tree (levels >= 2) has not been called");
+  if (N < 1 || N > INT32_MAX - 1 || !X0) return fail(h, PMK_ERR_ARG, "bad N or NULL X0");
+  const int D = h->tree_D;
+  const int64_t TL = (int64_t)h->n_hp + 1;
+  CU(h, h->o_X.ensure(sizeof(double) * N * D));
+  CU(h, h->o_counts.ensure(sizeof(int32_t) * (N + 1)));
+  CU(h, h->o_off.ensure(sizeof(int64_t) * (N + 1)));
+  CU(h, h->o_lcount.ensure(sizeof(int32_t) * TL));
+  CU(h, h->o_lstart.ensure(sizeof(int64_t) * (TL + 1)));
+  CU(h, cudaMemcpyAsync(h->o_X.p, X0, sizeof(double) * N * D, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemsetAsync(h->o_counts.as<int32_t>() + N, 0, sizeof(int32_t), h->stream));
+  CU(h, cudaMemsetAsync(h->o_lcount.p, 0, sizeof(int32_t) * TL, h->stream));
+  launch_eps_partitions(D, false, h->tree, N, h->o_X.as<double>(), eps, h->o_counts.as<int32_t>(), nullptr, nullptr, nullptr,
+                        nullptr, h->stream);
+  KCHECK(h, "k_eps_partitions<count>");
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveScan((void*)nullptr, tb, h->o_counts.as<int32_t>(), h->o_off.as<int64_t>(), cub::Sum(), (int64_t)0,
+                                   (int)(N + 1), h->stream);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceScan::ExclusiveScan(h->d_cub.p, tb, h->o_counts.as<int32_t>(), h->o_off.as<int64_t>(), cub::Sum(),
+                                         (int64_t)0, (int)(N + 1), h->stream));
+  }
+  int64_t total = 0;
+  CU(h, cudaMemcpyAsync(&total, h->o_off.as<int64_t>() + N, sizeof(int64_t), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (total < N || total > INT32_MAX) return fail(h, PMK_ERR_UNSUPPORTED, "pair count %lld out of range", (long long)total);
+  CU(h, h->o_pl.ensure(sizeof(int32_t) * total));
+  CU(h, h->o_pp.ensure(sizeof(int32_t) * total));
+  CU(h, h->o_sl.ensure(sizeof(int32_t) * total));
+  CU(h, h->o_sp.ensure(sizeof(int32_t) * total));
+  launch_eps_partitions(D, true, h->tree, N, h->o_X.as<double>(), eps, nullptr, h->o_off.as<int64_t>(), h->o_pl.as<int32_t>(),
+                        h->o_pp.as<int32_t>(), h->o_lcount.as<int32_t>(), h->stream);
+  KCHECK(h, "k_eps_partitions<fill>");
+  launch_scan_small(h->o_lcount.as<int32_t>(), h->o_lstart.as<int64_t>(), (int)TL, h->stream);
+  KCHECK(h, "k_scan_small");
+  {
+    int end_bit = 1;
+    while ((1ll << end_bit) <= TL) ++end_bit;
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, h->o_pl.as<int32_t>(), h->o_sl.as<int32_t>(), h->o_pp.as<int32_t>(),
+                                    h->o_sp.as<int32_t>(), (int)total, 0, end_bit, h->stream);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->o_pl.as<int32_t>(), h->o_sl.as<int32_t>(), h->o_pp.as<int32_t>(),
+                                          h->o_sp.as<int32_t>(), (int)total, 0, end_bit, h->stream));
+  }
+  if (leaf_off_out)
+    CU(h, cudaMemcpyAsync(leaf_off_out, h->o_lstart.p, sizeof(int64_t) * (TL + 1), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->o_N = N;
+  h->o_total = total;
+  h->o_leaves = TL;
+  if (total_out) *total_out = total;
+  return PMK_OK;
+}
+
+int pmk_organize_fetch(pmk_handle* h, int32_t* inds_out, int64_t* point_off_out, int32_t* point_leaves_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (h->o_total == 0) return fail(h, PMK_ERR_STATE, "pmk_organize_training_sets has not been called");
+  cudaStream_t s = h->stream;
+  if (inds_out) CU(h, cudaMemcpyAsync(inds_out, h->o_sp.p, sizeof(int32_t) * h->o_total, cudaMemcpyDeviceToHost, s));
+  if (point_off_out) CU(h, cudaMemcpyAsync(point_off_out, h->o_off.p, sizeof(int64_t) * (h->o_N + 1), cudaMemcpyDeviceToHost, s));
+  if (point_leaves_out) CU(h, cudaMemcpyAsync(point_leaves_out, h->o_pl.p, sizeof(int32_t) * h->o_total, cudaMemcpyDeviceToHost, s));
+  CU(h, cudaStreamSynchronize(s));
   return PMK_OK;
 }
 
@@ -786,7 +876,7 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
   if (!d_pair_u || !d_pair_v) return fail(h, PMK_ERR_ARG, "NULL pointer");
   const QueryPlan& q = h->plan;
-  const int mean_only = flags & 1;
+  const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
   h->last_flags = flags;
   Timer tt(h, PMK_T_Q_PAIRS);
   for (int c = 0; c < kNumClasses; ++c) {

@@ -120,7 +120,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     }
   }
 
-  if (mean_only) {
+  if (mean_only & 1) {
     __syncthreads();
     if (tid < cnt) {
       double u = 0.0;
@@ -308,7 +308,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     for (int d = 0; d < D; ++d) xq[d] = s_xq[d * MQ + tid];
     const double kxx = eval_kernel<D>(kp, xq, xq);
     double v = kxx - vs;                               // mixtureGP.jl:312, clamp(., 1e-12, Inf)
-    if (v < 1e-12) v = 1e-12;
+    if (!(mean_only & 2) && v < 1e-12) v = 1e-12;   // flag bit1: no clamp (evalqueryGP!, querying.jl:76-78)
     const int64_t gp = s_pair[tid];
     pair_u[gp] = u;
     pair_v[gp] = v;

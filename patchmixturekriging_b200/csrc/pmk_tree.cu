@@ -397,6 +397,64 @@ __global__ void k_neighbours_fill(TreeDev tr, QueryPlan q, double radius, double
   atomicAdd(&leaf_count[home - 1], 1);
 }
 
+// ε-overlap training sets on the device: findεpartitions! (partition.jl:269-298) per training point -- left iff
+// v.x < c + ε, right iff v.x > c - ε, both possible -- as an explicit-stack DFS (left first, so a point's leaves
+// come out in the reference's left-to-right order).  FILL=false counts, FILL=true writes (leaf, point) pairs at the
+// point's offset; a stable sort by leaf then yields every leaf's point list in ascending global index, which is
+// exactly X_set_inds of organizetrainingsets (partition.jl:301-357).
+template <int D, bool FILL>
+__global__ void k_eps_partitions(TreeDev tr, int64_t N, const double* __restrict__ X, double eps,
+                                 int32_t* __restrict__ counts, const int64_t* __restrict__ off,
+                                 int32_t* __restrict__ pair_leaf, int32_t* __restrict__ pair_pt,
+                                 int32_t* __restrict__ leaf_count) {
+  const int64_t n = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  double x[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) x[d] = X[n * D + d];
+  const int Lv = tr.levels - 1;
+  int st_node[26], st_prefix[26];
+  signed char st_depth[26];
+  int sp = 0;
+  st_node[0] = 0; st_prefix[0] = 0; st_depth[0] = 0; sp = 1;
+  int cnt = 0;
+  int64_t slot = FILL ? off[n] : 0;
+  while (sp > 0) {
+    --sp;
+    const int node = st_node[sp], prefix = st_prefix[sp], depth = st_depth[sp];
+    if (depth == Lv) {
+      if (FILL) {
+        pair_leaf[slot] = prefix + 1;
+        pair_pt[slot] = (int32_t)n + 1;
+        atomicAdd(&leaf_count[prefix], 1);
+        ++slot;
+      }
+      ++cnt;
+      continue;
+    }
+    double v[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) v[d] = tr.hv[d * tr.n_hp + node];
+    const double h = dot_seq<D>(v, x);
+    const double c = tr.hc[node];
+    const bool go_l = h < __dadd_rn(c, eps);       // partition.jl:287
+    const bool go_r = h > __dsub_rn(c, eps);       // partition.jl:292
+    if (go_r) {                                     // pushed first, popped last: left subtree is visited first
+      st_node[sp] = node + (1 << (Lv - 1 - depth));
+      st_prefix[sp] = prefix * 2 + 1;
+      st_depth[sp] = (signed char)(depth + 1);
+      ++sp;
+    }
+    if (go_l) {
+      st_node[sp] = node + 1;
+      st_prefix[sp] = prefix * 2;
+      st_depth[sp] = (signed char)(depth + 1);
+      ++sp;
+    }
+  }
+  if (!FILL) counts[n] = cnt;
+}
+
 // Yq = dot(w,u), Vq = dot(w, v.*w) with w = w_tilde / sum(w_tilde)   (mixtureGP.jl:263-272)
 __global__ void k_combine(int64_t Nq, const int64_t* __restrict__ pair_off, const double* __restrict__ pw,
                           const double* __restrict__ pu, const double* __restrict__ pv, double* __restrict__ Yq,
@@ -523,6 +581,23 @@ void launch_neighbours(int D, bool fill, bool pruned, int n_leaves, const TreeDe
       default: break;
     }
   }
+}
+
+void launch_eps_partitions(int D, bool fill, const TreeDev& tr, int64_t N, const double* dX, double eps, int32_t* counts,
+                           const int64_t* off, int32_t* pair_leaf, int32_t* pair_pt, int32_t* leaf_count, cudaStream_t s) {
+  const int T = 128;
+  const unsigned B = (unsigned)((N + T - 1) / T);
+  if (B == 0) return;
+#define PMK_EPS(DD)                                                                                              \
+  if (fill) k_eps_partitions<DD, true><<<B, T, 0, s>>>(tr, N, dX, eps, counts, off, pair_leaf, pair_pt, leaf_count); \
+  else k_eps_partitions<DD, false><<<B, T, 0, s>>>(tr, N, dX, eps, counts, off, pair_leaf, pair_pt, leaf_count);
+  switch (D) {
+    case 1: PMK_EPS(1) break;
+    case 2: PMK_EPS(2) break;
+    case 3: PMK_EPS(3) break;
+    default: break;
+  }
+#undef PMK_EPS
 }
 
 void launch_combine(int64_t Nq, const int64_t* pair_off, const double* pw, const double* pu, const double* pv,

@@ -6,6 +6,8 @@ bodies go through the C ABI to the same CUDA kernels as the mixture path (one le
   RKHSProblemType(c, X, θ, σ²)               declarations.jl:226-231
   fitRKHS_(η, y)                             fitRKHS!   RKHS.jl:182-217
   query_(Yq, Xq, η)                          query!     RKHS.jl:220-247   (mean only)
+  evalquery(x, c, X, θ)                      querying.jl:2-5   Σ c_n k(x, X_n)
+  setupGPquery(c, X, θ, σ²) -> fq            querying.jl:43-58; fq(xq) -> (mean, variance) = evalqueryGP! :60-79
 """
 from __future__ import annotations
 
@@ -114,3 +116,48 @@ def query_(Yq: np.ndarray, Xq, η: RKHSProblemType) -> None:
     wp = np.array([1.0])
     η._h.check(lib().pmk_query(η._h.raw, Xq.shape[0], ptr(Xq), 0.0, 0.0, 1, ptr(wp), 1, 1, ptr(Yq), None))
     return None
+
+
+def setupGPquery(c, X, θ, σ2: float):
+    """setupGPquery(c, X, θ, σ²) (src/RKHS/querying.jl:43-58).  Returns fq with fq(xq) -> (mean, variance) for one point
+    (evalqueryGP!, :60-79: mean = Σ c_n k(xq,X_n), variance = k(xq,xq) - kᵀ(K+σ²I)⁻¹k, NOT clamped) or, for an (m, D)
+    array of points, two arrays.  The reference solves A\\k by LU per query; here ‖L⁻¹k‖² through the fused pair kernel."""
+    X = _as_points(X)
+    c = np.ascontiguousarray(np.asarray(c, dtype=np.float64))
+    if c.shape[0] != X.shape[0]:
+        raise PMKError(_lib.PMK_ERR_ARG, "DimensionMismatch: length(c) != length(X)")
+    h = Handle(0)
+    L = lib()
+    n, D = X.shape
+    leaf_off = np.array([0, n], dtype=np.int64)
+    kp = θ.params
+    bad, info = C.c_int64(0), C.c_int(0)
+    rc = L.pmk_fit(h.raw, D, 1, ptr(leaf_off), ptr(X), ptr(np.zeros(n)), θ.kernel_id, ptr(kp), kp.shape[0], float(σ2),
+                   C.byref(bad), C.byref(info))
+    if rc == _lib.PMK_ERR_NOT_POSDEF:
+        raise PosDefException(info.value, bad.value, L.pmk_last_error(h.raw).decode())
+    h.check(rc)
+    h.check(L.pmk_set_alpha(h.raw, 1, ptr(c)))
+    h.check(L.pmk_set_tree(h.raw, D, 1, None, None))
+    wp = np.array([1.0])
+
+    def fq(xq):
+        xq = np.asarray(xq, dtype=np.float64)
+        single = xq.ndim == 1 and (D > 1 or xq.shape[0] == 1)
+        Xq = _as_points(xq[None, :] if single else xq)
+        Yq, Vq = np.empty(Xq.shape[0]), np.empty(Xq.shape[0])
+        h.check(L.pmk_query(h.raw, Xq.shape[0], ptr(Xq), 0.0, 0.0, 1, ptr(wp), 1, 2, ptr(Yq), ptr(Vq)))
+        return (float(Yq[0]), float(Vq[0])) if single else (Yq, Vq)
+
+    fq.handle = h
+    return fq
+
+
+def evalquery(x, c, X, θ):
+    """evalquery(x, c, X, θ) = Σ c_n k(x, X_n) (src/RKHS/querying.jl:2-5), for one point or an (m, D) array."""
+    x = np.asarray(x, dtype=np.float64)
+    Xp = _as_points(X)
+    single = x.ndim == 1 and (Xp.shape[1] > 1 or x.shape[0] == 1)
+    K = constructkernelmatrix(x[None, :] if single else x, θ, Xp)
+    out = K @ np.asarray(c, dtype=np.float64)
+    return float(out[0]) if single else out

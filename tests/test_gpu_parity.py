@@ -298,3 +298,43 @@ def test_sharded_fit_equals_single_fit(built_lib):
         Y1, V1, _ = P.querymixtureGP(Xq, e, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
         assert np.array_equal(Y0, Y1) and np.array_equal(V0, V1)
         e.close()
+
+
+def test_single_gp_variance_query(built_lib):
+    """setupGPquery / evalqueryGP! (src/RKHS/querying.jl:43-79): mean from the caller's c, unclamped variance k** - kᵀA⁻¹k."""
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(31, 300, [-1.0, -1.0], [1.0, 1.0])
+    y = np.sin(3 * X[:, 0]) * X[:, 1]
+    ok, pk = helpers.kernels(("SQEXP", 6.0))
+    s2 = 1e-3
+    A = O.constructkernelmatrix(X, ok) + s2 * np.eye(len(X))
+    c = O.backslash(A, y)
+    Xq = synth.uniform_points(32, 64, [-1.2, -1.2], [1.2, 1.2])
+    kq = O.kernel_cross(Xq, X, ok)
+    mean_ref = kq @ c
+    var_ref = 1.0 - np.einsum("ij,ij->i", kq, np.linalg.solve(A, kq.T).T)      # evalqueryGP!: A\\k by LU, no clamp
+    fq = P.setupGPquery(c, X, pk, s2)
+    m, v = fq(Xq)
+    assert_close("evalqueryGP mean", m, mean_ref)
+    assert_close("evalqueryGP var", v, var_ref, 1e-8)
+    m0, v0 = fq(Xq[5])
+    assert m0 == m[5] and v0 == v[5]
+    np.testing.assert_allclose(P.evalquery(Xq, c, X, pk), mean_ref, rtol=1e-12, atol=1e-13)
+    # a query on top of a training point: variance ~ sigma2-level, may dip below the 1e-12 clamp of queryinner! but is not clamped here
+    mm, vv = fq(X[:8])
+    assert np.all(np.abs(vv) < 5 * s2)
+
+
+@pytest.mark.parametrize("name,eps", [("mixgp_file", 1.5), ("c3_mini", 0.31), ("c4_mini", 0.35), ("c3_mini", 0.0)])
+def test_organizetrainingsets_device_bit_exact(built_lib, name, eps):
+    """ε-overlap training sets on the GPU, bit-exact X_set_inds / regions_list_set."""
+    case = CASES[name]()
+    X = case["X"]
+    root, _, _ = P.setuppartition(X, case["levels"])
+    Xs_h, inds_h, rl_h, _ = P.organizetrainingsets(root, case["levels"], X, eps)
+    Xs_d, inds_d, rl_d, prob = P.organizetrainingsets_device(root, case["levels"], X, eps)
+    assert prob == [] and len(inds_d) == len(inds_h)
+    for a, b, xa in zip(inds_d, inds_h, Xs_d):
+        assert np.array_equal(a, b) and np.array_equal(xa, X[b - 1])
+    for i in range(0, len(X), 53):
+        assert list(rl_d[i]) == list(rl_h[i])
