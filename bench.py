@@ -34,48 +34,63 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 FP64_PEAK_FALLBACK_TFLOPS = 37.1   # tools/fp64_peak.cu on this pool's B200 (profiles/fp64_peaks_r01.json)
-EVAL_FLOPS_2D = 3 * 2 + 2 + 20     # one SqExp evaluation: differences/squares/sum + sqrt + exp (DESIGN.md "flop counts")
+def eval_flops(D):                 # one SqExp evaluation: differences/squares/sum + sqrt + exp (DESIGN.md "flop counts")
+    return 3 * D + 2 + 20
 
 
 # --------------------------------------------------------------------------------------------
 def workload(name: str, nq_override: int | None = None):
     from patchmixturekriging_b200 import synth
+    lo, hi = [-5.0, -10.0], [5.0, 10.0]
     if name == "c3":          # BASELINE configs[2]: 2-D, N = 1M, 4096 leaves of ~512 points with overlap, 10M queries
         N, levels, eps, nq = 1_000_000, 13, 0.043, 10_000_000
-    elif name == "c3_mini":   # same shape, 1/16 size (for quick runs)
+    elif name == "c3_mini":   # same shape, 1/16 size (for quick runs), same point density
         N, levels, eps, nq = 62_500, 9, 0.043, 625_000
+        lo, hi = [-1.25, -2.5], [1.25, 2.5]
     elif name == "c2":        # BASELINE configs[1]: examples/mixGP.jl, SqExp, N = 20k, 64 leaves
         N, levels, eps, nq = 20_000, 7, 0.5, 20_000
+    elif name == "c4":        # BASELINE configs[3]: 3-D, N = 4M, 8192 leaves of ~1024 points
+        N, levels, eps, nq = 4_000_000, 14, 0.075, 10_000_000
+        lo, hi = [-5.0, -10.0, -5.0], [5.0, 10.0, 5.0]
+    elif name == "c4_mini":   # 1/16 of c4, same density
+        N, levels, eps, nq = 250_000, 10, 0.075, 625_000
+        lo, hi = [-2.5, -5.0, -1.25], [2.5, 5.0, 1.25]
     else:
         raise SystemExit(f"unknown workload {name}")
-    lo, hi = [-5.0, -10.0], [5.0, 10.0]
-    if name == "c3_mini":     # keep the point density of c3
-        lo, hi = [-1.25, -2.5], [1.25, 2.5]
+    D = len(lo)
     nq = nq_override or nq
     X = synth.uniform_points(25, N, lo, hi)
     y = synth.f_mixgp(X)
-    spacing = np.sqrt((hi[0] - lo[0]) * (hi[1] - lo[1]) / N)
-    eps_sq = 8.0 if name == "c2" else round(1.0 / (3.5 * spacing) ** 2)      # c3: 408 ~ SURVEY's "eps_sq ~ 400"
+    vol = float(np.prod(np.asarray(hi) - np.asarray(lo)))
+    spacing = (vol / N) ** (1.0 / D)
+    if name == "c2":
+        eps_sq = 8.0
+    elif D == 2:
+        eps_sq = round(1.0 / (3.5 * spacing) ** 2)      # c3: 408 ~ SURVEY's "eps_sq ~ 400" (length-scale ~3.5 spacings)
+    else:
+        eps_sq = round(1.0 / (2.0 * spacing) ** 2)      # 3-D: length-scale ~2 spacings
     radius = 0.3 if name == "c2" else eps
     return dict(name=name, X=X, y=y, levels=levels, eps=eps, radius=radius, delta=1e-5, sigma2=1e-3, eps_sq=float(eps_sq),
-                nq=nq, lo=lo, hi=hi)
+                nq=nq, lo=lo, hi=hi, D=D)
 
 
 def gen_queries(w, first: int, count: int) -> np.ndarray:
     """queries [first, first+count) of the workload's stream (uniform on the domain)."""
     from patchmixturekriging_b200 import synth
     lo, hi = np.asarray(w["lo"]), np.asarray(w["hi"])
-    Xq = np.empty((count, 2))
-    for d in range(2):
+    D = len(lo)
+    Xq = np.empty((count, D))
+    for d in range(D):
         u = synth.uniform01(1234567, count, d * w["nq"] + first)
         Xq[:, d] = u * (hi[d] - lo[d]) + lo[d]
     return Xq
 
 
-def partition(w):
+def partition(w, device: bool = False):
     import patchmixturekriging_b200 as P
     root, X_parts, X_parts_inds = P.setuppartition(w["X"], w["levels"])
-    X_set, X_set_inds, _, _ = P.organizetrainingsets(root, w["levels"], w["X"], w["eps"])
+    org = P.organizetrainingsets_device if device else P.organizetrainingsets
+    X_set, X_set_inds, _, _ = org(root, w["levels"], w["X"], w["eps"])
     sizes = np.array([len(i) for i in X_set_inds], dtype=np.int64)
     leaf_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     idx = np.concatenate(X_set_inds) - 1
@@ -167,7 +182,7 @@ def cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=1, warmup=0, sample_lea
         home = P.findpartition(Xq, root)
         cand.append(Xq[home <= nl])
         first += cnt
-    cand = np.concatenate(cand) if cand else np.zeros((0, 2))
+    cand = np.concatenate(cand) if cand else np.zeros((0, w["D"]))
     _, _, _, _, absent = c_oracle.query(hv, hc, w["levels"], off_s, Xs, np.zeros(len(Xs)), np.zeros(1), SQEXP, w["eps_sq"], cand,
                                         w["radius"], w["delta"], SPLINE34, 1.0 / w["radius"], threads, structure_only=True)
     Xq_s = np.ascontiguousarray(cand[absent == 0][:sample_queries])
@@ -212,7 +227,7 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
     w = workload(args.workload, args.nq)
-    cfg = {"workload": f"{w['name']}: 2-D mixture-GP, N={len(w['X'])}, {1 << (w['levels'] - 1)} BSP leaves, eps={w['eps']}, "
+    cfg = {"workload": f"{w['name']}: {w['D']}-D mixture-GP, N={len(w['X'])}, {1 << (w['levels'] - 1)} BSP leaves, eps={w['eps']}, "
                        f"radius={w['radius']}, delta={w['delta']}, SqExp eps_sq={w['eps_sq']}, sigma2={w['sigma2']}, Nq={w['nq']}",
            "l2": "inputs larger than L2 (packed factors + queries + pair arrays are GBs per step vs 126 MB L2)"}
 
@@ -246,7 +261,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
 
-    root, sizes, leaf_off, Xp, yp = partition(w)
+    root, sizes, leaf_off, Xp, yp = partition(w, device=True)
     n_leaves = len(sizes)
     Nq = w["nq"]
     q0, q1 = sharding.query_slice(rank, world, Nq)
@@ -263,7 +278,7 @@ def main():
     h = η.handle
     L = _lib.lib()
     hv = np.ascontiguousarray(root.hps_v); hc = np.ascontiguousarray(root.hps_c)
-    h.check(L.pmk_set_tree(h.raw, 2, w["levels"], _lib.ptr(hv), _lib.ptr(hc)))
+    h.check(L.pmk_set_tree(h.raw, w["D"], w["levels"], _lib.ptr(hv), _lib.ptr(hc)))
     if world > 1:
         h.check(L.pmk_set_fit_range(h.raw, l0, l1 - l0))
 
@@ -289,7 +304,7 @@ def main():
         handle's stream (the NCCL work is bracketed by stream synchronisation, so the events see it)."""
         e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
         e[0].record(stream)
-        h.check(L.pmk_fit_dev(h.raw, 2, n_leaves, _lib.ptr(leaf_off), dX.data_ptr(), dy.data_ptr(), θ.kernel_id, _lib.ptr(kp), 1,
+        h.check(L.pmk_fit_dev(h.raw, w["D"], n_leaves, _lib.ptr(leaf_off), dX.data_ptr(), dy.data_ptr(), θ.kernel_id, _lib.ptr(kp), 1,
                               w["sigma2"], C.byref(bad), C.byref(info)))
         e[1].record(stream)
         if world > 1:
@@ -356,7 +371,7 @@ def main():
         def step_host():
             t0 = time.perf_counter()
             # fitmixtureGP_ packs the leaf list; the packed arrays are what crosses the ABI
-            h.check(L.pmk_fit(h.raw, 2, n_leaves, _lib.ptr(leaf_off), _lib.ptr(hXp), _lib.ptr(hyp), θ.kernel_id, _lib.ptr(kp), 1,
+            h.check(L.pmk_fit(h.raw, w["D"], n_leaves, _lib.ptr(leaf_off), _lib.ptr(hXp), _lib.ptr(hyp), θ.kernel_id, _lib.ptr(kp), 1,
                               w["sigma2"], C.byref(bad), C.byref(info)))
             if world > 1:
                 exchange_factors()
@@ -393,9 +408,9 @@ def main():
         h.check(L.pmk_last_query_debug(h.raw, None, None, _lib.ptr(pl), None, None, None, None, None))
         per_leaf = np.bincount(pl - 1, minlength=n_leaves).astype(np.float64)
         nn = sizes.astype(np.float64)
-        flops_pairs = float((per_leaf * (nn * nn + nn * (EVAL_FLOPS_2D + 4))).sum())      # TRSM n^2 + n*(eval + mean 2 + ||s||^2 2)
-        flops_fit = float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * EVAL_FLOPS_2D).sum()) * (l1 - l0) / n_leaves if world > 1 else \
-            float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * EVAL_FLOPS_2D).sum())
+        flops_pairs = float((per_leaf * (nn * nn + nn * (eval_flops(w["D"]) + 4))).sum())      # TRSM n^2 + n*(eval + mean 2 + ||s||^2 2)
+        flops_fit = float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * eval_flops(w["D"])).sum()) * (l1 - l0) / n_leaves if world > 1 else \
+            float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * eval_flops(w["D"])).sum())
         peak, peak_src = fp64_peak()
         ach = flops_pairs / (kt[_lib.T_Q_PAIRS] * 1e-3) / 1e12
         try:      # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch, leaf class <=512)
@@ -417,7 +432,8 @@ def main():
         # per leaf-size class of the pair kernel: ms and achieved TFLOP/s
         npad_ = (sizes + 31) // 32 * 32
         cls_ = np.where(npad_ <= 512, 0, np.where(npad_ <= 768, 1, np.where(npad_ <= 1024, 2, 3)))
-        fl_leaf = per_leaf * (nn * nn + nn * (EVAL_FLOPS_2D + 4))
+        phases["leaf_points_min_mean_max"] = [int(sizes.min()), float(sizes.mean()), int(sizes.max())]
+        fl_leaf = per_leaf * (nn * nn + nn * (eval_flops(w["D"]) + 4))
         phases["pairs_by_class"] = [
             {"class": c, "leaves": int((cls_ == c).sum()), "pairs": int(per_leaf[cls_ == c].sum()),
              "ms": float(kt[_lib.T_Q_PAIRS_CLASS0 + c]),
