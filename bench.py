@@ -431,14 +431,14 @@ def main():
                   "fit_gram_chol_tflops": fit_ach, "fit_gram_chol_frac_of_fp64_peak": fit_ach / peak}
         # per leaf-size class of the pair kernel: ms and achieved TFLOP/s
         npad_ = (sizes + 31) // 32 * 32
-        cls_ = np.where(npad_ <= 512, 0, np.where(npad_ <= 768, 1, np.where(npad_ <= 1024, 2, 3)))
+        cls_ = np.where(npad_ <= 512, 0, np.where(npad_ <= 768, 1, np.where(npad_ <= 1024, 2, np.where(npad_ <= 1536, 3, 4))))
         phases["leaf_points_min_mean_max"] = [int(sizes.min()), float(sizes.mean()), int(sizes.max())]
         fl_leaf = per_leaf * (nn * nn + nn * (eval_flops(w["D"]) + 4))
         phases["pairs_by_class"] = [
             {"class": c, "leaves": int((cls_ == c).sum()), "pairs": int(per_leaf[cls_ == c].sum()),
              "ms": float(kt[_lib.T_Q_PAIRS_CLASS0 + c]),
              "tflops": float(fl_leaf[cls_ == c].sum() / max(kt[_lib.T_Q_PAIRS_CLASS0 + c], 1e-9) / 1e9)}
-            for c in range(4) if (cls_ == c).any()]
+            for c in range(5) if (cls_ == c).any()]
 
         line = {"metric": "query_pts_per_s (mixture-GP query; fit throughput in fit_leaves_per_s)", "value": Nq / (query_ms_m * 1e-3),
                 "unit": "pts/s", "fit_leaves_per_s": n_leaves / (fit_ms_m * 1e-3), "n_gpus": world, "steps": args.steps,

@@ -68,8 +68,8 @@ enum {
   PMK_T_Q_COMBINE = 5,     /* convex mixture combine                                           */
   PMK_T_GRAM = 6,          /* standalone Gram kernel (constructkernelmatrix / U_set)           */
   PMK_T_FIT_GRAM = 7,      /* per-leaf Gram tiles of the fit (K1)                              */
-  PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +3: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=2048)  */
-  PMK_T_COUNT = 12
+  PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +4: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=1536, <=2048) */
+  PMK_T_COUNT = 13
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

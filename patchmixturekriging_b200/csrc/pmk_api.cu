@@ -79,7 +79,7 @@ thread_local std::string g_create_error;
 
 }  // namespace
 
-static constexpr int kNumClasses = 4;   // query size classes (pmk_query.cu)
+static constexpr int kNumClasses = 5;   // query size classes (pmk_query.cu)
 
 struct pmk_handle {
   int device = 0;

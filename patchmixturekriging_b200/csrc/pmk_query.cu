@@ -26,8 +26,8 @@ void launch_pairs_d2(int, unsigned, const LeafTable&, const PairWork&, const Que
 void launch_pairs_d3(int, unsigned, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, double*, double*, cudaStream_t);
 
 // size classes: n_pad <= 8 * NT * NW
-int query_class_of(int npad) { return npad <= 512 ? 0 : (npad <= 768 ? 1 : (npad <= 1024 ? 2 : 3)); }
-int query_class_mq(int cls) { return cls == 0 ? 32 : (cls == 1 ? 24 : (cls == 2 ? 16 : 8)); }
+int query_class_of(int npad) { return npad <= 512 ? 0 : (npad <= 768 ? 1 : (npad <= 1024 ? 2 : (npad <= 1536 ? 3 : 4))); }
+int query_class_mq(int cls) { return cls == 0 ? 32 : (cls == 1 ? 24 : (cls <= 3 ? 16 : 8)); }
 
 void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q,
                         KParams kp, int mean_only, double* pu, double* pv, cudaStream_t s) {

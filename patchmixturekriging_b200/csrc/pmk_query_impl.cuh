@@ -346,11 +346,12 @@ template <int D>
 void launch_pairs_d(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                     int mean_only, double* pu, double* pv, cudaStream_t s) {
   constexpr int NW = 16;   // ring bytes = NW * DEPTH * GI * 512
-  // class:   0: n_pad <= 512, 32 pairs/CTA | 1: <= 768, 24 | 2: <= 1024, 16 | 3: <= 2048, 8
+  // class:   0: n_pad <= 512, 32 pairs/CTA | 1: <= 768, 24 | 2: <= 1024, 16 | 3: <= 1536, 16 | 4: <= 2048, 8
   // (the accumulators of n_pad x MQ doubles must fit the register file: NT * NQT * 4 registers per thread)
   if (cls == 0) launch_one<D, NW, 4, 4, 3, 4>(grid, lt, w, q, kp, mean_only, pu, pv, s);
   else if (cls == 1) launch_one<D, NW, 6, 3, 3, 6>(grid, lt, w, q, kp, mean_only, pu, pv, s);
   else if (cls == 2) launch_one<D, NW, 8, 2, 2, 8>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else if (cls == 3) launch_one<D, NW, 12, 2, 2, 6>(grid, lt, w, q, kp, mean_only, pu, pv, s);
   else launch_one<D, NW, 16, 1, 2, 8>(grid, lt, w, q, kp, mean_only, pu, pv, s);
 }
 
