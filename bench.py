@@ -427,7 +427,8 @@ def main():
         phases = {"fit_pack_ms": float(kt[_lib.T_FIT_PACK]), "fit_gram_ms": float(kt[_lib.T_FIT_GRAM]),
                   "fit_chol_ms": float(kt[_lib.T_FIT_CHOL]),
                   "fit_solve_ms": float(kt[_lib.T_FIT_SOLVE]), "query_tree_ms": float(kt[_lib.T_Q_TREE]),
-                  "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]), "query_combine_ms": float(kt[_lib.T_Q_COMBINE]),
+                  "query_make_M_ms": float(kt[_lib.T_Q_MAKE_M]), "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]),
+                  "query_combine_ms": float(kt[_lib.T_Q_COMBINE]),
                   "fit_gram_chol_tflops": fit_ach, "fit_gram_chol_frac_of_fp64_peak": fit_ach / peak}
         # per leaf-size class of the pair kernel: ms and achieved TFLOP/s
         npad_ = (sizes + 31) // 32 * 32

@@ -69,7 +69,8 @@ enum {
   PMK_T_GRAM = 6,          /* standalone Gram kernel (constructkernelmatrix / U_set)           */
   PMK_T_FIT_GRAM = 7,      /* per-leaf Gram tiles of the fit (K1)                              */
   PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +4: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=1536, <=2048) */
-  PMK_T_COUNT = 13
+  PMK_T_Q_MAKE_M = 13,       /* M_IJ = L_IJ inv(L_JJ), built once per fit by the first variance query               */
+  PMK_T_COUNT = 14
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------- */

@@ -21,6 +21,7 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
                        cudaStream_t s);
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
+void launch_make_M(const LeafTable& lt, int max_npad, cudaStream_t s);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
 void read_chol_cycles(unsigned long long* out, bool reset);
 void read_query_cycles(int D, unsigned long long* out, bool reset);
@@ -89,6 +90,7 @@ struct pmk_handle {
 
   // model
   bool fitted = false;
+  bool m_ready = false;    // M (pair-kernel operand) built for the current factors
   int D = 0;
   int64_t n_leaves = 0, total_leaves = 0;
   int64_t fit_first = 0, fit_count = -1;   // leaves factorised by this handle (multi-GPU: leaf -> rank map)
@@ -99,7 +101,7 @@ struct pmk_handle {
   std::vector<int> h_n, h_npad;
   std::vector<int64_t> h_xoff, h_loff, h_ioff;
   int64_t xstride = 0;
-  DBuf d_n, d_npad, d_xoff, d_loff, d_ioff, d_xs, d_y, d_alpha, d_L, d_Linv, d_info, d_order, d_leafoff, d_Xin, d_yin;
+  DBuf d_n, d_npad, d_xoff, d_loff, d_ioff, d_xs, d_y, d_alpha, d_L, d_M, d_Linv, d_info, d_order, d_leafoff, d_Xin, d_yin;
   DBuf d_class_leaves[kNumClasses], d_class_tiles[kNumClasses], d_tile_off[kNumClasses];
   int n_class[kNumClasses] = {};
   LeafTable lt{};
@@ -228,7 +230,7 @@ void pmk_destroy(pmk_handle* h) {
   if (!h) return;
   cudaSetDevice(h->device);
   cudaStreamSynchronize(h->stream);
-  DBuf* bufs[] = {&h->d_n, &h->d_npad, &h->d_xoff, &h->d_loff, &h->d_ioff, &h->d_xs, &h->d_y, &h->d_alpha, &h->d_L, &h->d_Linv,
+  DBuf* bufs[] = {&h->d_n, &h->d_npad, &h->d_xoff, &h->d_loff, &h->d_ioff, &h->d_xs, &h->d_y, &h->d_alpha, &h->d_L, &h->d_M, &h->d_Linv,
                   &h->d_info, &h->d_order, &h->d_leafoff, &h->d_Xin, &h->d_yin, &h->d_hv, &h->d_hc, &h->d_Xq, &h->d_home,
                   &h->d_npairs, &h->d_pair_off, &h->d_Yq, &h->d_Vq, &h->d_pair_leaf, &h->d_pair_q, &h->d_pair_hp, &h->d_pair_t,
                   &h->d_pair_w, &h->d_pair_u, &h->d_pair_v, &h->d_sorted_pair, &h->d_keys_out, &h->d_iota, &h->d_leaf_count,
@@ -373,6 +375,7 @@ int pmk_mark_fitted(pmk_handle* h) {
   if (!h) return PMK_ERR_ARG;
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->fitted = true;
+  h->m_ready = false;
   h->plan_valid = false;
   return PMK_OK;
 }
@@ -483,6 +486,7 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   lt.y = h->d_y.as<double>();
   lt.alpha = h->d_alpha.as<double>();
   lt.L = h->d_L.as<double>();
+  lt.M = nullptr;          // allocated and built on the first variance query after a fit (ensure_M)
   lt.Linv = h->d_Linv.as<double>();
   lt.info = h->d_info.as<int>();
 
@@ -518,6 +522,7 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
                   (long long)(p + 1), h_info[p]);
     }
   }
+  h->m_ready = false;
   h->fitted = (n_order == n_leaves);   // a partial fit becomes usable after the peers' factors arrive (pmk_mark_fitted)
   h->plan_valid = false;
   return PMK_OK;
@@ -878,6 +883,15 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const QueryPlan& q = h->plan;
   const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
   h->last_flags = flags;
+  if (!(flags & 1) && !h->m_ready) {     // variance wanted: the pair kernel streams M, built once per fit
+    Timer tm(h, PMK_T_Q_MAKE_M);
+    CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
+    h->lt.M = h->d_M.as<double>();
+    launch_make_M(h->lt, h->max_npad, h->stream);
+    KCHECK(h, "k_make_M");
+    h->m_ready = true;
+  }
+  if (h->lt.M == nullptr) h->lt.M = h->lt.L;   // mean-only queries never touch the factor
   Timer tt(h, PMK_T_Q_PAIRS);
   for (int c = 0; c < kNumClasses; ++c) {
     h->ev_used[PMK_T_Q_PAIRS_CLASS0 + c] = false;

@@ -357,6 +357,47 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// M_IJ = L_IJ inv(L_JJ) for every strictly-lower 32x32 block (one warp per row tile; full occupancy, HBM-bound:
+// reads L once, writes M once).  With M the pair kernel's blocked TRSM needs no diagonal solve between its
+// updates:  W_J := L_JJ S_J obeys  W_I = C_I - sum_{J<I} M_IJ W_J.
+__global__ void __launch_bounds__(256)
+k_make_M(LeafTable lt, int first_leaf) {
+  const int p = first_leaf + blockIdx.x;
+  const int ntl = lt.npad[p] >> 3;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t = blockIdx.y * 8 + warp;
+  if (t >= ntl) return;
+  const int g = lane >> 2, l = lane & 3;
+  const double2* __restrict__ Lrow = reinterpret_cast<const double2*>(lt.L + lt.loff[p]) + tri(t) * 32 + lane;
+  double* Mrow = lt.M + lt.loff[p] + tri(t) * 64;
+  const double* __restrict__ Ib = lt.Linv + lt.ioff[p];
+  const int nJ = t >> 2;                         // column blocks strictly left of the row tile's own block
+  for (int J = 0; J < nJ; ++J) {
+    const double* Iblk = Ib + (size_t)J * kInvDoublesPerBlock;
+    double2 af[4];
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) af[kb] = Lrow[(4 * J + kb) * 32];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      double o0 = 0.0, o1 = 0.0, p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int kb = cb; kb < 4; ++kb) {          // inv(L_JJ) is lower triangular: rows kb >= cb of column block cb
+        // B[k][n] = Linv[8kb + k][8cb + n]; lane holds k = l (and l + 4), n = g
+        const int tl = (kb * (kb + 1) / 2 + cb) * 32;
+        const double b0 = Iblk[(tl + l * 4 + (g & 3)) * 2 + (g >> 2)];
+        const double b1 = Iblk[(tl + (l + 4) * 4 + (g & 3)) * 2 + (g >> 2)];
+        dmma884(o0, o1, af[kb].x, b0);
+        dmma884(p0, p1, af[kb].y, b1);
+      }
+      double* tile = Mrow + (4 * J + cb) * 64;
+      const int q0 = 2 * l, q1 = 2 * l + 1;
+      tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0 + p0;
+      tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1 + p1;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // alpha = L^-T L^-1 y per leaf (the reference solves U\y by LU, mixtureGP.jl:106; same solution up to
 // rounding -- see DESIGN.md "alpha").  Blocked substitution: GEMV updates stream the packed tiles,
 // diagonal blocks use the stored 32x32 inverses.
@@ -501,6 +542,12 @@ void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStrea
     configured = true;
   }
   k_chol<NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order);
+}
+
+void launch_make_M(const LeafTable& lt, int max_npad, cudaStream_t s) {
+  if (lt.n_leaves <= 0) return;
+  dim3 grid(lt.n_leaves, (max_npad / 8 + 7) / 8);
+  k_make_M<<<grid, 256, 0, s>>>(lt, 0);
 }
 
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s) {

@@ -10,6 +10,7 @@ namespace pmk {
 //  L     : packed lower Cholesky factors (pmk_common.cuh layout), leaf p at L + loff[p];
 //          rows/cols >= n[p] are identity padding
 //  Linv  : inverses of the 32x32 diagonal blocks of L, leaf p block J at Linv + ioff[p] + J*640
+//  M     : L with every strictly-lower 32x32 block right-multiplied by its column block's inverse (k_make_M)
 struct LeafTable {
   int n_leaves;
   const int* n;
@@ -22,6 +23,7 @@ struct LeafTable {
   double* y;
   double* alpha;
   double* L;
+  double* M;          // same tile layout as L: M_IJ = L_IJ inv(L_JJ) for the strictly-lower 32x32 blocks (pair kernel operand)
   double* Linv;
   int* info;          // per leaf: 0 ok, >0 = order of the first non-positive leading minor
 };

@@ -7,10 +7,12 @@
 // lives in REGISTERS as DMMA accumulators for the whole kernel (row tiles dealt cyclically to the
 // warps so the shrinking triangular work stays balanced); a right-looking blocked TRSM walks the
 // 32-row blocks J:
-//     S_J = inv(L_JJ) * C_J                    (stored 32x32 inverse, DMMA; C_J via shared memory)
-//     C_I -= L_IJ * S_J   for all I > J        (DMMA; L_IJ streamed from L2/HBM as packed fragment
-//                                               tiles, one LDG.128 per lane; S_J from shared memory)
-// Only S_J (32 x MQ) ever sits in shared memory; ||s||^2 and dot(k, alpha) are reduced on the fly.
+//     W_J = C_J                                (rows of block J are final; W_J = L_JJ S_J, published via smem)
+//     C_I -= M_IJ * W_J   for all I > J        (DMMA; M_IJ = L_IJ inv(L_JJ) precomputed by k_make_M, streamed
+//                                               from L2/HBM as packed fragment tiles through a cp.async ring)
+//     S_J = inv(L_JJ) * W_J                    (DMMA side job, only for ||s||^2 -- not on the critical path)
+// One block barrier per J.  Only W_J (32 x MQ, double-buffered) ever sits in shared memory; ||s||^2 and
+// dot(k, alpha) are reduced on the fly.
 #pragma once
 #include "pmk_internal.cuh"
 
@@ -37,8 +39,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
   constexpr int MQ = 8 * NQT;
   constexpr int LDQ = MQ + 4;                 // == 4 or 12 (mod 16) for MQ in {8,16,24,32}: conflict-free fragment loads
   constexpr int OT = (4 * NQT + NW - 1) / NW; // diagonal-solve output tiles per warp
-  __shared__ __align__(16) double Cbuf[32 * LDQ];
-  __shared__ __align__(16) double Sbuf[32 * LDQ];
+  __shared__ __align__(16) double Wbuf[2][32 * LDQ];   // W_J = L_JJ S_J of two consecutive blocks
   __shared__ double s_xq[D * MQ];
   __shared__ int64_t s_pair[MQ];
   __shared__ double ured[NW * MQ];
@@ -64,7 +65,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
   const double* __restrict__ xs = lt.xs + lt.xoff[p];
   const double* __restrict__ al = lt.alpha + lt.xoff[p];
   const int64_t xstride = lt.xstride;
-  const double2* __restrict__ Lp = reinterpret_cast<const double2*>(lt.L + lt.loff[p]);
+  const double2* __restrict__ Lp = reinterpret_cast<const double2*>(lt.M + lt.loff[p]);   // M_IJ = L_IJ inv(L_JJ)
   const double2* __restrict__ Ip = reinterpret_cast<const double2*>(lt.Linv + lt.ioff[p]);
 
   PMK_CYC(long long q_total = clock64(), q_init = 0, q_pub = 0, q_diag = 0, q_upd = 0;)
@@ -193,7 +194,8 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
         fI[k][b] = (ot < 4 * NQT && b <= a) ? Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane]
                                             : make_double2(0.0, 0.0);
     }
-    // 1. owners of block J's four row tiles publish C_J = -acc
+    // 1. owners of block J's four row tiles publish W_J = -acc (their rows are final: W_J = L_JJ S_J)
+    double* Wb = Wbuf[J & 1];
 #pragma unroll
     for (int i = 0; i < NT; ++i) {
       const int t = warp + NW * i;
@@ -201,20 +203,20 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
         const int a = t & 3;
 #pragma unroll
         for (int nt = 0; nt < NQT; ++nt)
-          *reinterpret_cast<double2*>(&Cbuf[(8 * a + g) * LDQ + nt * 8 + 2 * l]) =
+          *reinterpret_cast<double2*>(&Wb[(8 * a + g) * LDQ + nt * 8 + 2 * l]) =
               make_double2(-acc[i][nt][0], -acc[i][nt][1]);
       }
     }
-    __syncthreads();
+    __syncthreads();      // the ONLY block barrier per J (W is double-buffered)
     PMK_CYC({ long long c1 = clock64(); q_pub += c1 - qc; qc = c1; })
-    // 2. S_J = inv(L_JJ) * C_J : 4 x NQT output tiles spread over the warps
+    // 2. side job, off the critical path: S_J = inv(L_JJ) * W_J only feeds ||s||^2 (4 x NQT tiles over the warps)
 #pragma unroll
     for (int k = 0; k < OT; ++k) {
       const int ot = warp + NW * k;
       PMK_UNIFORM_IF(ot < 4 * NQT) {
         const int a = ot / NQT, nt = ot % NQT;
         double s0 = 0.0, s1 = 0.0, r0 = 0.0, r1 = 0.0;
-        const double* Cb = &Cbuf[l * LDQ + nt * 8 + g];
+        const double* Cb = &Wb[l * LDQ + nt * 8 + g];
         // b = 0 always; b = 1..a behind real (uniform) branches
         dmma884(s0, s1, fI[k][0].x, Cb[0]);
         dmma884(r0, r1, fI[k][0].y, Cb[4 * LDQ]);
@@ -232,14 +234,12 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
         }
         s0 += r0;
         s1 += r1;
-        *reinterpret_cast<double2*>(&Sbuf[(8 * a + g) * LDQ + nt * 8 + 2 * l]) = make_double2(s0, s1);
         vacc[k][0] = fma(s0, s0, vacc[k][0]);
         vacc[k][1] = fma(s1, s1, vacc[k][1]);
       }
     }
-    __syncthreads();
     PMK_CYC({ long long c1 = clock64(); q_diag += c1 - qc; qc = c1; })
-    // 3. acc[I] += L_IJ * S_J for the row tiles below block J.  Tile guards are REAL branches
+    // 3. acc[I] += M_IJ * W_J for the row tiles below block J (M_IJ W_J = L_IJ S_J).  Tile guards are REAL branches
     //    (PMK_UNIFORM_IF); within a tile the DMMAs are ordered k-step-major so that consecutive
     //    ones hit different accumulators.
     if (J + 1 < nblk) {
@@ -255,7 +255,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
 #pragma unroll
         for (int ks = 0; ks < 2; ++ks)
 #pragma unroll
-          for (int nt = 0; nt < NQT; ++nt) bf[ks][nt] = Sbuf[(8 * ct + 4 * ks + l) * LDQ + nt * 8 + g];
+          for (int nt = 0; nt < NQT; ++nt) bf[ks][nt] = Wb[(8 * ct + 4 * ks + l) * LDQ + nt * 8 + g];
 #pragma unroll
         for (int ih = 0; ih < NG; ++ih) {
           cp_async_wait<DEPTH - 2>();        // group (J, ct, ih) has landed
