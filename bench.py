@@ -295,9 +295,11 @@ def main():
 
     def exchange_factors():
         """leaf -> rank map: every rank broadcasts the spans it factorised (NCCL over NVLink)."""
-        sharding.exchange_spans(span_of, n_leaves, (_lib.BUF_L, _lib.BUF_LINV, _lib.BUF_ALPHA))
+        mixturegp.build_M(η)          # M for the leaves this rank factorised; only M (not L) travels
+        h.synchronize()
+        sharding.exchange_spans(span_of, n_leaves, (_lib.BUF_M, _lib.BUF_LINV, _lib.BUF_ALPHA))
         torch.cuda.current_stream().synchronize()
-        mixturegp.mark_fitted(η)
+        mixturegp.mark_fitted(η, m_exchanged=True)
 
     def step_device():
         """fit + query with inputs resident in HBM; returns (fit_ms, exchange_ms, query_ms) from CUDA events on the

@@ -164,12 +164,16 @@ int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_
  * the leaves the leaf->rank map gives it: pmk_set_fit_range(first_leaf 0-based, n) BEFORE pmk_fit (which
  * still receives ALL leaves' inputs, so every rank lays the model out identically).  After the fit each
  * rank's L / inv-diagonal-block / alpha ranges are contiguous device spans (pmk_model_buffer) that the
- * host layer exchanges with NCCL over NVLink; pmk_mark_fitted then declares the replicated model
+ * host layer exchanges with NCCL over NVLink (PMK_BUF_M, after pmk_build_M, in place of PMK_BUF_L when only queries
+ * follow); pmk_mark_fitted then declares the replicated model
  * complete.  Queries are sliced across ranks with no data-path collective; results are gathered once. */
-enum { PMK_BUF_L = 0, PMK_BUF_LINV = 1, PMK_BUF_ALPHA = 2 };
+enum { PMK_BUF_L = 0, PMK_BUF_LINV = 1, PMK_BUF_ALPHA = 2, PMK_BUF_M = 3 };
 int pmk_set_fit_range(pmk_handle* h, int64_t first_leaf, int64_t n_leaves /* -1 = to the end */);
 int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_leaves, void** dptr, int64_t* bytes);
-int pmk_mark_fitted(pmk_handle* h);
+/* M_IJ = L_IJ inv(L_JJ) (the pair kernel's operand) for the leaves of the fit range; single-GPU queries build it lazily */
+int pmk_build_M(pmk_handle* h);
+/* m_exchanged != 0: the peers' M spans were copied in as well (PMK_BUF_M), so no rank rebuilds M for foreign leaves */
+int pmk_mark_fitted(pmk_handle* h, int m_exchanged);
 
 /* The query in three stages on DEVICE buffers (pmk_query_dev = the three in sequence):
  *   pmk_query_plan_dev   : home leaves, neighbours, weights, pair list binned by leaf; returns n_pairs

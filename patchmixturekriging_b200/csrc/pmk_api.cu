@@ -21,7 +21,7 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
                        cudaStream_t s);
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
-void launch_make_M(const LeafTable& lt, int max_npad, cudaStream_t s);
+void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_npad, cudaStream_t s);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
 void read_chol_cycles(unsigned long long* out, bool reset);
 void read_query_cycles(int D, unsigned long long* out, bool reset);
@@ -366,16 +366,35 @@ int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_lea
     case PMK_BUF_L: span(h->h_loff, h->L_doubles, h->d_L.as<double>()); break;
     case PMK_BUF_LINV: span(h->h_ioff, h->Linv_doubles, h->d_Linv.as<double>()); break;
     case PMK_BUF_ALPHA: span(h->h_xoff, h->x_points, h->d_alpha.as<double>()); break;
+    case PMK_BUF_M:
+      if (!h->d_M.p) return fail(h, PMK_ERR_STATE, "M has not been built (pmk_build_M)");
+      span(h->h_loff, h->L_doubles, h->d_M.as<double>());
+      break;
     default: return fail(h, PMK_ERR_ARG, "unknown buffer id %d", which);
   }
   return PMK_OK;
 }
 
-int pmk_mark_fitted(pmk_handle* h) {
+int pmk_build_M(pmk_handle* h) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
+  const int64_t f0 = std::min<int64_t>(h->fit_first, h->n_leaves);
+  const int64_t f1 = h->fit_count < 0 ? h->n_leaves : std::min<int64_t>(h->n_leaves, f0 + h->fit_count);
+  Timer tm(h, PMK_T_Q_MAKE_M);
+  CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
+  h->lt.M = h->d_M.as<double>();
+  launch_make_M(h->lt, (int)f0, (int)(f1 - f0), h->max_npad, h->stream);
+  KCHECK(h, "k_make_M");
+  h->m_ready = (f0 == 0 && f1 == h->n_leaves);
+  return PMK_OK;
+}
+
+int pmk_mark_fitted(pmk_handle* h, int m_exchanged) {
   if (!h) return PMK_ERR_ARG;
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->fitted = true;
-  h->m_ready = false;
+  h->m_ready = m_exchanged != 0 && h->d_M.p != nullptr;
   h->plan_valid = false;
   return PMK_OK;
 }
@@ -486,7 +505,7 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   lt.y = h->d_y.as<double>();
   lt.alpha = h->d_alpha.as<double>();
   lt.L = h->d_L.as<double>();
-  lt.M = nullptr;          // allocated and built on the first variance query after a fit (ensure_M)
+  lt.M = nullptr;          // allocated and built on the first variance query after a fit (or by pmk_build_M)
   lt.Linv = h->d_Linv.as<double>();
   lt.info = h->d_info.as<int>();
 
@@ -887,7 +906,7 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     Timer tm(h, PMK_T_Q_MAKE_M);
     CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
     h->lt.M = h->d_M.as<double>();
-    launch_make_M(h->lt, h->max_npad, h->stream);
+    launch_make_M(h->lt, 0, (int)h->n_leaves, h->max_npad, h->stream);
     KCHECK(h, "k_make_M");
     h->m_ready = true;
   }

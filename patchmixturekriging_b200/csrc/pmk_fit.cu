@@ -544,10 +544,10 @@ void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStrea
   k_chol<NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order);
 }
 
-void launch_make_M(const LeafTable& lt, int max_npad, cudaStream_t s) {
-  if (lt.n_leaves <= 0) return;
-  dim3 grid(lt.n_leaves, (max_npad / 8 + 7) / 8);
-  k_make_M<<<grid, 256, 0, s>>>(lt, 0);
+void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_npad, cudaStream_t s) {
+  if (n_leaves <= 0) return;
+  dim3 grid(n_leaves, (max_npad / 8 + 7) / 8);
+  k_make_M<<<grid, 256, 0, s>>>(lt, first_leaf);
 }
 
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s) {

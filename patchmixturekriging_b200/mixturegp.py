@@ -139,9 +139,14 @@ def model_buffer(η: MixtureGPType, which: int, first_leaf: int, n_leaves: int):
     return int(dptr.value or 0), int(nbytes.value)
 
 
-def mark_fitted(η: MixtureGPType):
+def build_M(η: MixtureGPType):
+    """M_IJ = L_IJ inv(L_JJ) for the leaves this handle factorised (what a sharded run exchanges instead of L)."""
+    η._h.check(lib().pmk_build_M(η._h.raw))
+
+
+def mark_fitted(η: MixtureGPType, m_exchanged: bool = False):
     """Declare the replicated model complete after the peers' factors have been copied in."""
-    η._h.check(lib().pmk_mark_fitted(η._h.raw))
+    η._h.check(lib().pmk_mark_fitted(η._h.raw, 1 if m_exchanged else 0))
     η._fitted = True
 
 

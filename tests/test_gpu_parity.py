@@ -284,7 +284,9 @@ def test_sharded_fit_equals_single_fit(built_lib):
         def __init__(self, ptr, nbytes):
             self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 2}
 
-    for which in (_lib.BUF_L, _lib.BUF_LINV, _lib.BUF_ALPHA):
+    for e in etas:
+        mixturegp.build_M(e)
+    for which in (_lib.BUF_L, _lib.BUF_M, _lib.BUF_LINV, _lib.BUF_ALPHA):
         for src, (a, n) in enumerate(ranges):
             sp, sb = mixturegp.model_buffer(etas[src], which, a, n)
             dp, db = mixturegp.model_buffer(etas[1 - src], which, a, n)
@@ -294,7 +296,7 @@ def test_sharded_fit_equals_single_fit(built_lib):
     Xq = case["Xq"][:5000]
     Y0, V0, _ = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
     for e in etas:
-        mixturegp.mark_fitted(e)
+        mixturegp.mark_fitted(e, m_exchanged=True)
         Y1, V1, _ = P.querymixtureGP(Xq, e, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
         assert np.array_equal(Y0, Y1) and np.array_equal(V0, V1)
         e.close()
