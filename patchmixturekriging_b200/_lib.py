@@ -8,7 +8,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpmk_b200.so")
+LIB_PATH = os.environ.get("PMK_LIB") or os.path.join(_HERE, "libpmk_b200.so")   # PMK_LIB: experiment builds (build.py PMK_VARIANT)
 
 PMK_OK, PMK_ERR_CUDA, PMK_ERR_ARG, PMK_ERR_NOT_POSDEF, PMK_ERR_STATE, PMK_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 BUF_L, BUF_LINV, BUF_ALPHA, BUF_M = 0, 1, 2, 3

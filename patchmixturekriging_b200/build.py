@@ -8,7 +8,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libpmk_b200.so")
+# PMK_VARIANT=name builds an experiment (different PMK_NVCC_EXTRA) next to the product as libpmk_b200_<name>.so;
+# load it with PMK_LIB=<path> (see _lib.py).  The product library is always libpmk_b200.so.
+VARIANT = os.environ.get("PMK_VARIANT", "")
+LIB = os.path.join(HERE, f"libpmk_b200_{VARIANT}.so" if VARIANT else "libpmk_b200.so")
+BUILD_DIR = os.path.join(HERE, f"build_{VARIANT}" if VARIANT else "build")
 SOURCES = ["pmk_api.cu", "pmk_fit.cu", "pmk_tree.cu", "pmk_query.cu", "pmk_query_d1.cu", "pmk_query_d2.cu", "pmk_query_d3.cu", "pmk_gram.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("PMK_NVCC_EXTRA", "").split()     # e.g. PMK_NVCC_EXTRA=-DPMK_PROFILE_CYCLES for the phase counters
@@ -28,10 +32,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
     hdrs.append(os.path.join(HERE, "..", "include", "pmk.h"))
     hdrs.append(os.path.abspath(__file__))
     objs, jobs = [], []
-    os.makedirs(os.path.join(HERE, "build"), exist_ok=True)
+    os.makedirs(BUILD_DIR, exist_ok=True)
+    only = os.environ.get("PMK_VARIANT_ONLY", "").split()   # variant builds: recompile just these, link the rest from build/
     for src in SOURCES:
         s = os.path.join(CSRC, src)
-        o = os.path.join(HERE, "build", src.replace(".cu", ".o"))
+        o = os.path.join(BUILD_DIR, src.replace(".cu", ".o"))
+        if VARIANT and only and src not in only:
+            objs.append(os.path.join(HERE, "build", src.replace(".cu", ".o")))
+            continue
         objs.append(o)
         if force or _stale(o, [s] + hdrs):
             jobs.append([NVCC, *FLAGS, *EXTRA, "-c", s, "-o", o])
@@ -42,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, max(1, len(jobs)))) as ex:
         for cmd, r in ex.map(run, jobs):
-            log = os.path.join(HERE, "build", os.path.basename(cmd[-1]) + ".log")
+            log = os.path.join(BUILD_DIR, os.path.basename(cmd[-1]) + ".log")
             with open(log, "w") as f:
                 f.write(r.stdout + r.stderr)
             if verbose or r.returncode != 0:
