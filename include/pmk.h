@@ -70,7 +70,8 @@ enum {
   PMK_T_FIT_GRAM = 7,      /* per-leaf Gram tiles of the fit (K1)                              */
   PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +4: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=1536, <=2048) */
   PMK_T_Q_MAKE_M = 13,       /* M_IJ = L_IJ inv(L_JJ), built once per fit by the first variance query               */
-  PMK_T_COUNT = 14
+  PMK_T_Q_INVERT = 14,       /* P = inv(L) (operand of the explicit-inverse pair kernel), built once per fit        */
+  PMK_T_COUNT = 15
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -112,6 +113,8 @@ int pmk_get_alpha(pmk_handle* h, int64_t leaf, double* out);
 /* overwrite a leaf's weights (setupGPquery(c, X, theta, sigma2), src/RKHS/querying.jl:43-58, takes c from the caller) */
 int pmk_set_alpha(pmk_handle* h, int64_t leaf, const double* c);
 int pmk_get_L(pmk_handle* h, int64_t leaf, double* out);
+/* dense n x n column-major inv(L) as the explicit-inverse solver uses it (built on demand) */
+int pmk_get_Linv(pmk_handle* h, int64_t leaf, double* out);
 int pmk_get_K(pmk_handle* h, int64_t leaf, double* out);
 
 /* ---- tree -------------------------------------------------------------------------------- */
@@ -167,13 +170,15 @@ int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_
  * host layer exchanges with NCCL over NVLink (PMK_BUF_M, after pmk_build_M, in place of PMK_BUF_L when only queries
  * follow); pmk_mark_fitted then declares the replicated model
  * complete.  Queries are sliced across ranks with no data-path collective; results are gathered once. */
-enum { PMK_BUF_L = 0, PMK_BUF_LINV = 1, PMK_BUF_ALPHA = 2, PMK_BUF_M = 3 };
+enum { PMK_BUF_L = 0, PMK_BUF_LINV = 1, PMK_BUF_ALPHA = 2, PMK_BUF_M = 3, PMK_BUF_P = 4 };
 int pmk_set_fit_range(pmk_handle* h, int64_t first_leaf, int64_t n_leaves /* -1 = to the end */);
 int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_leaves, void** dptr, int64_t* bytes);
-/* M_IJ = L_IJ inv(L_JJ) (the pair kernel's operand) for the leaves of the fit range; single-GPU queries build it lazily */
+/* The pair kernel's operands for the leaves of the fit range: M_IJ = L_IJ inv(L_JJ) (substitution solver) and
+ * P = inv(L) (explicit-inverse solver, the default; packed like L).  Single-GPU queries build them lazily. */
 int pmk_build_M(pmk_handle* h);
-/* m_exchanged != 0: the peers' M spans were copied in as well (PMK_BUF_M), so no rank rebuilds M for foreign leaves */
-int pmk_mark_fitted(pmk_handle* h, int m_exchanged);
+/* exchanged: bit0 = the peers' M spans were copied in (PMK_BUF_M), bit1 = the peers' P spans (PMK_BUF_P); an operand
+ * that was not exchanged cannot be rebuilt for foreign leaves unless their L and Linv spans were exchanged too */
+int pmk_mark_fitted(pmk_handle* h, int exchanged);
 
 /* The query in three stages on DEVICE buffers (pmk_query_dev = the three in sequence):
  *   pmk_query_plan_dev   : home leaves, neighbours, weights, pair list binned by leaf; returns n_pairs
@@ -187,7 +192,12 @@ int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d
 /* ---- options ----------------------------------------------------------------------------- */
 /* PMK_OPT_FULL_HYPERPLANE_SCAN: 1 = findneighbourpartitions scans ALL hyperplanes per query exactly as the
  * reference loop does (mixtureGP.jl:354); 0 (default) = exact per-leaf candidate lists (same result). */
-enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1 };
+/* PMK_OPT_QUERY_SOLVER: how queryinner!'s v = L \ kq (mixtureGP.jl:311) is carried out for a tile of queries:
+ *   0 (default) = s = P kq with P = inv(L) formed once per fit by blocked substitution -- no dependency between row
+ *                 blocks, so the tensor pipe never waits (measured vs dtrsv: <= 3e-11 at sigma2 = 1e-3);
+ *   1           = blocked forward substitution with 32x32 diagonal-block inverses (closest to dtrsv; use it for
+ *                 very ill-conditioned leaves, cond(K) >~ 1e6). */
+enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2 };
 int pmk_set_option(pmk_handle* h, int option, int64_t value);
 
 /* ---- instrumentation --------------------------------------------------------------------- */

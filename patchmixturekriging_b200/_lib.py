@@ -11,17 +11,19 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PMK_LIB") or os.path.join(_HERE, "libpmk_b200.so")   # PMK_LIB: experiment builds (build.py PMK_VARIANT)
 
 PMK_OK, PMK_ERR_CUDA, PMK_ERR_ARG, PMK_ERR_NOT_POSDEF, PMK_ERR_STATE, PMK_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
-BUF_L, BUF_LINV, BUF_ALPHA, BUF_M = 0, 1, 2, 3
-OPT_FULL_HYPERPLANE_SCAN = 1
-T_FIT_PACK, T_FIT_CHOL, T_FIT_SOLVE, T_Q_TREE, T_Q_PAIRS, T_Q_COMBINE, T_GRAM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 14
+BUF_L, BUF_LINV, BUF_ALPHA, BUF_M, BUF_P = 0, 1, 2, 3, 4
+OPT_FULL_HYPERPLANE_SCAN, OPT_QUERY_SOLVER = 1, 2
+SOLVER_INVERSE, SOLVER_SUBSTITUTION = 0, 1
+T_FIT_PACK, T_FIT_CHOL, T_FIT_SOLVE, T_Q_TREE, T_Q_PAIRS, T_Q_COMBINE, T_GRAM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 15
 T_Q_MAKE_M = 13
+T_Q_INVERT = 14
 T_Q_PAIRS_CLASS0 = 8
 T_FIT_GRAM = 7
 
 # every symbol include/pmk.h declares
 SYMBOLS = [
     "pmk_create", "pmk_destroy", "pmk_last_error", "pmk_version", "pmk_gram", "pmk_cross_gram", "pmk_fit", "pmk_fit_dev",
-    "pmk_leaf_size", "pmk_get_alpha", "pmk_set_alpha", "pmk_get_L", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_organize_training_sets", "pmk_organize_fetch", "pmk_query",
+    "pmk_leaf_size", "pmk_get_alpha", "pmk_set_alpha", "pmk_get_L", "pmk_get_Linv", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_organize_training_sets", "pmk_organize_fetch", "pmk_query",
     "pmk_query_dev", "pmk_last_query_pairs", "pmk_last_query_debug", "pmk_set_fit_range", "pmk_model_buffer", "pmk_build_M", "pmk_mark_fitted", "pmk_query_plan_dev",
     "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_option", "pmk_get_timings", "pmk_debug_counters", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
 ]
@@ -71,6 +73,7 @@ def lib() -> C.CDLL:
     L.pmk_set_alpha.argtypes = [vp, i64, dp]
     L.pmk_get_L.argtypes = [vp, i64, dp]
     L.pmk_get_K.argtypes = [vp, i64, dp]
+    L.pmk_get_Linv.argtypes = [vp, i64, dp]
     L.pmk_set_tree.argtypes = [vp, i32, i32, dp, dp]
     L.pmk_find_partition.argtypes = [vp, i64, dp, dp]
     L.pmk_organize_training_sets.argtypes = [vp, i64, dp, dbl, dp, C.POINTER(i64)]

@@ -22,7 +22,7 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
 void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_npad, cudaStream_t s);
-void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s);
+void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s, int which = 0);
 void read_chol_cycles(unsigned long long* out, bool reset);
 void read_query_cycles(int D, unsigned long long* out, bool reset);
 void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, int32_t* d_leaf_qcount,
@@ -90,7 +90,9 @@ struct pmk_handle {
 
   // model
   bool fitted = false;
-  bool m_ready = false;    // M (pair-kernel operand) built for the current factors
+  bool m_ready = false;    // M (operand of the substitution pair kernel) built for the current factors
+  bool p_ready = false;    // P = inv(L) (operand of the explicit-inverse pair kernel) built for the current factors
+  int solver = 0;          // PMK_OPT_QUERY_SOLVER: 0 = explicit inverse (TRMM), 1 = blocked substitution (TRSM)
   int D = 0;
   int64_t n_leaves = 0, total_leaves = 0;
   int64_t fit_first = 0, fit_count = -1;   // leaves factorised by this handle (multi-GPU: leaf -> rank map)
@@ -104,6 +106,10 @@ struct pmk_handle {
   DBuf d_n, d_npad, d_xoff, d_loff, d_ioff, d_xs, d_y, d_alpha, d_L, d_M, d_Linv, d_info, d_order, d_leafoff, d_Xin, d_yin;
   DBuf d_class_leaves[kNumClasses], d_class_tiles[kNumClasses], d_tile_off[kNumClasses];
   int n_class[kNumClasses] = {};
+  // inversion work lists (leaves of the fit range, per size class): tile = MQ columns of inv(L)
+  DBuf d_P, d_inv_leaves[kNumClasses], d_inv_tile_off[kNumClasses];
+  int n_inv_class[kNumClasses] = {};
+  int64_t inv_tiles[kNumClasses] = {};
   LeafTable lt{};
 
   // tree
@@ -263,6 +269,10 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
   if (!h) return PMK_ERR_ARG;
   switch (option) {
     case PMK_OPT_FULL_HYPERPLANE_SCAN: h->full_scan = value != 0; h->plan_valid = false; return PMK_OK;
+    case PMK_OPT_QUERY_SOLVER:
+      if (value != 0 && value != 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: 0 (explicit inverse) or 1 (substitution)");
+      h->solver = (int)value;
+      return PMK_OK;
     default: return fail(h, PMK_ERR_ARG, "unknown option %d", option);
   }
 }
@@ -370,7 +380,46 @@ int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_lea
       if (!h->d_M.p) return fail(h, PMK_ERR_STATE, "M has not been built (pmk_build_M)");
       span(h->h_loff, h->L_doubles, h->d_M.as<double>());
       break;
+    case PMK_BUF_P:
+      if (!h->d_P.p) return fail(h, PMK_ERR_STATE, "P has not been built (pmk_build_M)");
+      span(h->h_loff, h->L_doubles, h->d_P.as<double>());
+      break;
     default: return fail(h, PMK_ERR_ARG, "unknown buffer id %d", which);
+  }
+  return PMK_OK;
+}
+
+// M (and P = inv(L) when want_P) for the leaves of the fit range.  P comes from the substitution pair kernel itself,
+// run on identity right-hand sides (tile = MQ columns of the inverse, starting at the column's own block).
+static int build_operands(pmk_handle* h, bool want_P) {
+  const int64_t f0 = std::min<int64_t>(h->fit_first, h->n_leaves);
+  const int64_t f1 = h->fit_count < 0 ? h->n_leaves : std::min<int64_t>(h->n_leaves, f0 + h->fit_count);
+  const bool all = (f0 == 0 && f1 == h->n_leaves);
+  if (!h->m_ready) {
+    Timer tm(h, PMK_T_Q_MAKE_M);
+    CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
+    h->lt.M = h->d_M.as<double>();
+    launch_make_M(h->lt, (int)f0, (int)(f1 - f0), h->max_npad, h->stream);
+    KCHECK(h, "k_make_M");
+    h->m_ready = all;
+  }
+  if (want_P && !h->p_ready) {
+    Timer tm(h, PMK_T_Q_INVERT);
+    CU(h, h->d_P.ensure(sizeof(double) * (size_t)h->L_doubles));
+    h->lt.P = h->d_P.as<double>();
+    h->lt.M = h->d_M.as<double>();
+    for (int c = 0; c < kNumClasses; ++c) {
+      if (h->n_inv_class[c] == 0) continue;
+      PairWork w{};
+      w.class_leaves = h->d_inv_leaves[c].as<int>();
+      w.n_class_leaves = h->n_inv_class[c];
+      w.tile_off = h->d_inv_tile_off[c].as<int64_t>();
+      w.leaf_base = 0;
+      QueryPlan q{};
+      launch_query_pairs(h->D, c, (unsigned)h->inv_tiles[c], h->lt, w, q, h->kp, 4, nullptr, nullptr, h->stream);
+      KCHECK(h, "k_query_pairs (inversion)");
+    }
+    h->p_ready = all;
   }
   return PMK_OK;
 }
@@ -379,22 +428,17 @@ int pmk_build_M(pmk_handle* h) {
   if (!h) return PMK_ERR_ARG;
   if (int rc = set_device(h)) return rc;
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
-  const int64_t f0 = std::min<int64_t>(h->fit_first, h->n_leaves);
-  const int64_t f1 = h->fit_count < 0 ? h->n_leaves : std::min<int64_t>(h->n_leaves, f0 + h->fit_count);
-  Timer tm(h, PMK_T_Q_MAKE_M);
-  CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
-  h->lt.M = h->d_M.as<double>();
-  launch_make_M(h->lt, (int)f0, (int)(f1 - f0), h->max_npad, h->stream);
-  KCHECK(h, "k_make_M");
-  h->m_ready = (f0 == 0 && f1 == h->n_leaves);
-  return PMK_OK;
+  h->m_ready = false;
+  h->p_ready = false;
+  return build_operands(h, h->solver == 0);
 }
 
-int pmk_mark_fitted(pmk_handle* h, int m_exchanged) {
+int pmk_mark_fitted(pmk_handle* h, int exchanged) {
   if (!h) return PMK_ERR_ARG;
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->fitted = true;
-  h->m_ready = m_exchanged != 0 && h->d_M.p != nullptr;
+  h->m_ready = (exchanged & 1) != 0 && h->d_M.p != nullptr;
+  h->p_ready = (exchanged & 2) != 0 && h->d_P.p != nullptr;
   h->plan_valid = false;
   return PMK_OK;
 }
@@ -482,6 +526,22 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
       CU(h, cudaMemcpyAsync(h->d_class_leaves[c].p, cls[c].data(), sizeof(int) * cls[c].size(), cudaMemcpyHostToDevice, h->stream));
     }
   }
+  std::vector<int> icls[kNumClasses];
+  std::vector<int64_t> ioff_t[kNumClasses];
+  for (int64_t p = f0; p < f1; ++p) icls[query_class_of(h->h_npad[p])].push_back((int)p);
+  for (int c = 0; c < kNumClasses; ++c) {
+    h->n_inv_class[c] = (int)icls[c].size();
+    h->inv_tiles[c] = 0;
+    if (icls[c].empty()) continue;
+    const int mq = query_class_mq(c);
+    ioff_t[c].push_back(0);
+    for (int p : icls[c]) ioff_t[c].push_back(ioff_t[c].back() + (h->h_npad[p] + mq - 1) / mq);
+    h->inv_tiles[c] = ioff_t[c].back();
+    CU(h, h->d_inv_leaves[c].ensure(sizeof(int) * icls[c].size()));
+    CU(h, h->d_inv_tile_off[c].ensure(sizeof(int64_t) * ioff_t[c].size()));
+    CU(h, cudaMemcpyAsync(h->d_inv_leaves[c].p, icls[c].data(), sizeof(int) * icls[c].size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_inv_tile_off[c].p, ioff_t[c].data(), sizeof(int64_t) * ioff_t[c].size(), cudaMemcpyHostToDevice, h->stream));
+  }
   CU(h, cudaMemcpyAsync(h->d_n.p, h->h_n.data(), sizeof(int) * n_leaves, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_npad.p, h->h_npad.data(), sizeof(int) * n_leaves, cudaMemcpyHostToDevice, h->stream));
   CU(h, cudaMemcpyAsync(h->d_xoff.p, h->h_xoff.data(), sizeof(int64_t) * n_leaves, cudaMemcpyHostToDevice, h->stream));
@@ -506,6 +566,7 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   lt.alpha = h->d_alpha.as<double>();
   lt.L = h->d_L.as<double>();
   lt.M = nullptr;          // allocated and built on the first variance query after a fit (or by pmk_build_M)
+  lt.P = nullptr;
   lt.Linv = h->d_Linv.as<double>();
   lt.info = h->d_info.as<int>();
 
@@ -542,6 +603,7 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
     }
   }
   h->m_ready = false;
+  h->p_ready = false;
   h->fitted = (n_order == n_leaves);   // a partial fit becomes usable after the peers' factors arrive (pmk_mark_fitted)
   h->plan_valid = false;
   return PMK_OK;
@@ -607,6 +669,21 @@ int pmk_get_L(pmk_handle* h, int64_t leaf, double* out) {
   const int n = h->h_n[p];
   CU(h, h->d_scratch.ensure(sizeof(double) * (size_t)n * n));
   launch_unpack_L(h->lt, (int)p, n, h->d_scratch.as<double>(), h->stream);
+  KCHECK(h, "k_unpack_L");
+  CU(h, cudaMemcpyAsync(out, h->d_scratch.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_get_Linv(pmk_handle* h, int64_t leaf, double* out) {
+  int64_t p;
+  if (int rc = check_leaf(h, leaf, &p)) return rc;
+  if (!out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (int rc = set_device(h)) return rc;
+  if (int rc = build_operands(h, true)) return rc;
+  const int n = h->h_n[p];
+  CU(h, h->d_scratch.ensure(sizeof(double) * (size_t)n * n));
+  launch_unpack_L(h->lt, (int)p, n, h->d_scratch.as<double>(), h->stream, 1);
   KCHECK(h, "k_unpack_L");
   CU(h, cudaMemcpyAsync(out, h->d_scratch.p, sizeof(double) * (size_t)n * n, cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -902,13 +979,8 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const QueryPlan& q = h->plan;
   const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
   h->last_flags = flags;
-  if (!(flags & 1) && !h->m_ready) {     // variance wanted: the pair kernel streams M, built once per fit
-    Timer tm(h, PMK_T_Q_MAKE_M);
-    CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
-    h->lt.M = h->d_M.as<double>();
-    launch_make_M(h->lt, 0, (int)h->n_leaves, h->max_npad, h->stream);
-    KCHECK(h, "k_make_M");
-    h->m_ready = true;
+  if (!(flags & 1)) {     // variance wanted: the pair kernel streams M (substitution) or P = inv(L), built once per fit
+    if (int rc = build_operands(h, h->solver == 0)) return rc;
   }
   if (h->lt.M == nullptr) h->lt.M = h->lt.L;   // mean-only queries never touch the factor
   Timer tt(h, PMK_T_Q_PAIRS);

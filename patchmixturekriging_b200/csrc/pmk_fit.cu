@@ -499,9 +499,9 @@ k_solve_alpha(LeafTable lt, const int* __restrict__ order) {
 }
 
 // dense column-major n x n lower-triangular copy of leaf p's factor (pmk_get_L)
-__global__ void k_unpack_L(LeafTable lt, int p, double* __restrict__ out) {
+__global__ void k_unpack_L(LeafTable lt, int p, double* __restrict__ out, int which) {
   const int n = lt.n[p];
-  const double* __restrict__ Lp = lt.L + lt.loff[p];
+  const double* __restrict__ Lp = (which ? lt.P : lt.L) + lt.loff[p];
   const int64_t total = (int64_t)n * n;
   for (int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; idx < total; idx += (int64_t)gridDim.x * blockDim.x) {
     const int r = (int)(idx % n), c = (int)(idx / n);
@@ -565,12 +565,12 @@ void read_chol_cycles(unsigned long long* out, bool reset) {
   }
 }
 
-void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s) {
+void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s, int which) {
   int64_t total = (int64_t)n * n;
   int blocks = (int)((total + 255) / 256);
   if (blocks > 4096) blocks = 4096;
   if (blocks < 1) blocks = 1;
-  k_unpack_L<<<blocks, 256, 0, s>>>(lt, p, d_out);
+  k_unpack_L<<<blocks, 256, 0, s>>>(lt, p, d_out, which);
 }
 
 }  // namespace pmk

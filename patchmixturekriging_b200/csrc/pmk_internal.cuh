@@ -25,6 +25,7 @@ struct LeafTable {
   double* L;
   double* M;          // same tile layout as L: M_IJ = L_IJ inv(L_JJ) for the strictly-lower 32x32 blocks (pair kernel operand)
   double* Linv;
+  double* P;          // same tile layout as L: the full inverse inv(L) (operand of the explicit-inverse pair kernel)
   int* info;          // per leaf: 0 ok, >0 = order of the first non-positive leading minor
 };
 

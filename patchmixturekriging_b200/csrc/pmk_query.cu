@@ -1,4 +1,4 @@
-// K3 dispatch: size classes and the per-D launchers (kernel in pmk_query_impl.cuh).
+// K3 dispatch: size classes and the per-D launchers (kernel in pmk_query_trsm.cuh).
 #include "pmk_internal.cuh"
 
 namespace pmk {
@@ -27,7 +27,7 @@ void launch_pairs_d3(int, unsigned, const LeafTable&, const PairWork&, const Que
 
 // size classes: n_pad <= 8 * NT * NW
 int query_class_of(int npad) { return npad <= 512 ? 0 : (npad <= 768 ? 1 : (npad <= 1024 ? 2 : (npad <= 1536 ? 3 : 4))); }
-int query_class_mq(int cls) { return cls == 0 ? 32 : (cls == 1 ? 24 : (cls <= 3 ? 16 : 8)); }
+int query_class_mq(int cls) { return cls == 0 ? 32 : (cls == 1 ? 24 : (cls == 2 ? 16 : 8)); }
 
 void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q,
                         KParams kp, int mean_only, double* pu, double* pv, cudaStream_t s) {

@@ -1,5 +1,5 @@
-// K3 instantiations for D = 3 (see pmk_query_impl.cuh)
-#include "pmk_query_impl.cuh"
+// K3 instantiations for D = 3 (see pmk_query_trsm.cuh)
+#include "pmk_query_trsm.cuh"
 namespace pmk {
 void launch_pairs_d3(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                       int mean_only, double* pu, double* pv, cudaStream_t s) {

@@ -3,8 +3,8 @@
 // touches HBM.  Replaces queryinner! (reference src/RKHS/mixtureGP.jl:296-316) for all pairs
 // of a leaf at once (the reference does one dtrsv per pair).
 //
-// Persistent, warp-specialised CTAs (one per SM, 640 threads):
-//   * 16 CONSUMER warps (setmaxnreg 112) own the tile of work (leaf p, MQ = 8*NQT pairs binned to p).  The
+// Persistent, warp-specialised CTAs (one per SM, 512 threads):
+//   * 12 CONSUMER warps (setmaxnreg 160) own the tile of work (leaf p, MQ = 8*NQT pairs binned to p).  The
 //     n_pad x MQ cross-covariance tile lives in REGISTERS as DMMA accumulators for the whole tile (row tiles dealt
 //     cyclically to the warps so the shrinking triangular work stays balanced); a right-looking blocked TRSM
 //     walks the 32-row blocks J:
@@ -24,7 +24,7 @@
 namespace pmk {
 
 static constexpr unsigned kFullQ = 0xffffffffu;
-static constexpr int kCW = 16;                 // consumer warps
+static constexpr int kCW = 12;                 // consumer warps (3 per SM sub-partition)
 static constexpr int kPW = 4;                  // producer warps (one warpgroup: setmaxnreg is per warpgroup)
 static constexpr int kConsumerThreads = kCW * 32;
 static constexpr int kK3Threads = (kCW + kPW) * 32;
@@ -124,20 +124,23 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     // ================================ producers ================================================
     asm volatile("setmaxnreg.dec.sync.aligned.u32 32;\n");
     if (mean_only & 1) return;
-    constexpr int LPC = NT <= 8 ? 8 : 16;     // lanes per consumer warp (one lane per row tile)
+    constexpr int LPC = NT <= 8 ? 8 : (NT <= 16 ? 16 : 32);   // lanes per consumer warp (one lane per row tile)
     constexpr int CPR = 32 / LPC;             // consumer warps served per round
     constexpr int ROUNDS = 4 / CPR;
     const int pw = warp - kCW;
+    if (4 * pw >= kCW) return;                // producer warp pw serves consumer warps 4pw .. 4pw+3
     const int i = lane % LPC, sub = lane / LPC;
     uint32_t slot[ROUNDS], ph[ROUNDS];        // ring position of this lane's consumer warp (both sides count groups alike)
 #pragma unroll
     for (int r = 0; r < ROUNDS; ++r) slot[r] = ph[r] = 0;
     for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int p = w.class_leaves[find_tile_leaf(w, tile)];
+      const int lo_p = find_tile_leaf(w, tile);
+      const int p = w.class_leaves[lo_p];
       const int npad = lt.npad[p];
       const int nblk = npad >> 5, ntl = npad >> 3;
       const char* Mp = reinterpret_cast<const char*>(lt.M + lt.loff[p]);
-      for (int J = 0; J + 1 < nblk; ++J) {
+      const int J0 = (mean_only & 4) ? (int)((tile - w.tile_off[lo_p]) * MQ) >> 5 : 0;   // inversion: first non-zero block
+      for (int J = J0; J + 1 < nblk; ++J) {
         const int thr = 4 * J + 4;
         bool act[ROUNDS];
         unsigned msk[ROUNDS];             // active row tiles of this lane's consumer warp (bit i)
@@ -146,7 +149,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
           const int t = 4 * pw + r * CPR + sub + kCW * i;
           act[r] = (i < NT) && (t < ntl) && (t >= thr);
           const unsigned bal = __ballot_sync(kFullQ, act[r]);
-          msk[r] = (bal >> (sub * LPC)) & ((1u << LPC) - 1u);
+          msk[r] = LPC == 32 ? bal : ((bal >> (sub * LPC)) & ((1u << (LPC & 31)) - 1u));
         }
 #pragma unroll 1
         for (int cg = 0; cg < NG; ++cg) {
@@ -181,7 +184,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
   }
 
   // ================================== consumers ==================================================
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 112;\n");
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 160;\n");
   const int g = lane >> 2, l = lane & 3;
   const double2* ring = reinterpret_cast<const double2*>(pmk_dyn_smem) + (size_t)warp * (DEPTH * SLOT_BYTES / 16) + lane;
   const uint32_t my_full = q_smem_u32(&full_bar[warp * DEPTH]);
@@ -193,8 +196,10 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     const int lo = find_tile_leaf(w, tile);
     const int p = w.class_leaves[lo];
     const int64_t gleaf = w.leaf_base + p;
-    const int64_t pstart = w.leaf_pair_start[gleaf] + (tile - w.tile_off[lo]) * MQ;
-    const int64_t pend = w.leaf_pair_start[gleaf + 1];
+    const bool invert = (mean_only & 4) != 0;      // RHS = MQ identity columns: the tile computes columns of inv(L)
+    const int col0 = invert ? (int)(tile - w.tile_off[lo]) * MQ : 0;
+    const int64_t pstart = invert ? 0 : w.leaf_pair_start[gleaf] + (tile - w.tile_off[lo]) * MQ;
+    const int64_t pend = invert ? 0 : w.leaf_pair_start[gleaf + 1];
     const int cnt = (int)((pend - pstart) < (int64_t)MQ ? (pend - pstart) : (int64_t)MQ);
     const int n = lt.n[p], npad = lt.npad[p];
     const int nblk = npad >> 5, ntl = npad >> 3;
@@ -203,7 +208,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     const double* __restrict__ Ip = lt.Linv + lt.ioff[p];
 
     PMK_CYC(long long q_total = clock64(), q_init = 0, q_pub = 0, q_diag = 0, q_upd = 0;)
-    if (tid < MQ) {
+    if (!invert && tid < MQ) {
       const int qi = tid < cnt ? tid : cnt - 1;
       const int64_t gp = w.sorted_pair[pstart + qi];
       s_pair[tid] = tid < cnt ? gp : (int64_t)-1;
@@ -213,7 +218,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     }
     // inv(L_00) for the first side job (cp.async: every thread waits for its own 16 bytes before the block barrier)
     if (!(mean_only & 1) && tid < kInvDoublesPerBlock / 2)
-      cp_async16_u32(q_smem_u32(&Ibuf[0][2 * tid]), Ip + 2 * tid);
+      cp_async16_u32(q_smem_u32(&Ibuf[(col0 >> 5) & 1][2 * tid]), Ip + (size_t)(col0 >> 5) * kInvDoublesPerBlock + 2 * tid);
     cp_async_commit();
     consumer_bar();
 
@@ -234,7 +239,11 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
         const int t = warp + kCW * i;
         const int row = 8 * t + g;
         double k0 = 0.0, k1 = 0.0;
-        if ((t < ntl) && (row < n)) {
+        if (invert) {
+          const int col = col0 + nt * 8 + 2 * l;
+          k0 = row == col ? 1.0 : 0.0;
+          k1 = row == col + 1 ? 1.0 : 0.0;
+        } else if ((t < ntl) && (row < n)) {
           double xr[D];
 #pragma unroll
           for (int d = 0; d < D; ++d) xr[d] = xs[d * xstride + row];
@@ -285,7 +294,8 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     for (int i = 0; i < NT; ++i)
       if (warp + kCW * i < ntl) exists |= 1u << i;
 
-    for (int J = 0; J < nblk; ++J) {
+    double* __restrict__ Pout = invert ? lt.P + lt.loff[p] : nullptr;
+    for (int J = invert ? (col0 >> 5) : 0; J < nblk; ++J) {
       PMK_CYC(long long qc = clock64();)
       // 1. owners of block J's four row tiles publish W_J = -acc (their rows are final: W_J = L_JJ S_J)
       double* Wb = Wbuf[J & 1];
@@ -339,6 +349,16 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
           s1 += r1;
           vacc[k][0] = fma(s0, s0, vacc[k][0]);
           vacc[k][1] = fma(s1, s1, vacc[k][1]);
+          PMK_UNIFORM_IF(invert) {
+            // S_J tile (a, nt) = rows 32J+8a.., columns col0+8nt.. of inv(L): store it in the packed fragment-major layout
+            const int rt = 4 * J + a, cth = (col0 >> 3) + nt;
+            if (cth <= rt) {
+              double* tp = Pout + (tri(rt) + cth) * 64;
+              const int q0 = 2 * l, q1 = 2 * l + 1;
+              tp[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = s0;
+              tp[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = s1;
+            }
+          }
         }
       }
       PMK_CYC({ long long c1 = clock64(); q_diag += c1 - qc; qc = c1; })
@@ -406,7 +426,7 @@ k_query_pairs(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int mean_only, 
     }
     cp_async_wait<0>();
     consumer_bar();
-    if (tid < cnt) {
+    if (!invert && tid < cnt) {
       const int nt = tid >> 3, qi = tid & 7;
       double vs = 0.0;
 #pragma unroll
@@ -457,25 +477,32 @@ static void launch_one(unsigned grid, const LeafTable& lt, const PairWork& w, co
   kern<<<ctas, kK3Threads, dyn, s>>>(lt, w, q, kp, mean_only, pu, pv);
 }
 
-#ifndef PMK_K3_CFG0
-#define PMK_K3_CFG0 2, 4, 2
+// ring geometry of the two headline classes (overridable for tuning builds): column tiles per group, ring slots
+#ifndef PMK_K3_CG0
+#define PMK_K3_CG0 2
 #endif
-#ifndef PMK_K3_CFG1
-#define PMK_K3_CFG1 1, 6, 3
+#ifndef PMK_K3_DEPTH0
+#define PMK_K3_DEPTH0 2
+#endif
+#ifndef PMK_K3_CG1
+#define PMK_K3_CG1 1
+#endif
+#ifndef PMK_K3_DEPTH1
+#define PMK_K3_DEPTH1 3
 #endif
 
 template <int D>
 void launch_pairs_d(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                     int mean_only, double* pu, double* pv, cudaStream_t s) {
-  // class:   0: n_pad <= 512, 32 pairs/tile | 1: <= 768, 24 | 2: <= 1024, 16 | 3: <= 1536, 16 | 4: <= 2048, 8
+  // class:   0: n_pad <= 512, 32 pairs/tile | 1: <= 768, 24 | 2: <= 1024, 16 | 3: <= 1536, 8 | 4: <= 2048, 8
   // (the accumulators of n_pad x MQ doubles must fit the consumers' registers: NT * NQT * 4 per thread)
   // template arguments: NT row tiles per warp, NQT query tiles, CG column tiles x GI row tiles per operand group,
   // DEPTH ring slots per consumer warp
-  if (cls == 0) launch_one<D, 4, 4, PMK_K3_CFG0>(grid, lt, w, q, kp, mean_only, pu, pv, s);
-  else if (cls == 1) launch_one<D, 6, 3, PMK_K3_CFG1>(grid, lt, w, q, kp, mean_only, pu, pv, s);
-  else if (cls == 2) launch_one<D, 8, 2, 1, 8, 3>(grid, lt, w, q, kp, mean_only, pu, pv, s);
-  else if (cls == 3) launch_one<D, 12, 2, 1, 6, 3>(grid, lt, w, q, kp, mean_only, pu, pv, s);
-  else launch_one<D, 16, 1, 1, 8, 3>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  if (cls == 0) launch_one<D, 6, 4, PMK_K3_CG0, 6, PMK_K3_DEPTH0>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else if (cls == 1) launch_one<D, 8, 3, PMK_K3_CG1, 8, PMK_K3_DEPTH1>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else if (cls == 2) launch_one<D, 11, 2, 1, 11, 3>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else if (cls == 3) launch_one<D, 16, 1, 1, 8, 3>(grid, lt, w, q, kp, mean_only, pu, pv, s);
+  else launch_one<D, 22, 1, 1, 11, 3>(grid, lt, w, q, kp, mean_only, pu, pv, s);
 }
 
 }  // namespace pmk

@@ -68,7 +68,7 @@ class _LazyLeafList:
             eta._h.check(L.pmk_get_alpha(eta._h.raw, leaf, ptr(out)))
             return out
         out = np.empty((n, n), order="F")
-        fn = L.pmk_get_L if self._what == "L" else L.pmk_get_K
+        fn = {"L": L.pmk_get_L, "Linv": L.pmk_get_Linv}.get(self._what, L.pmk_get_K)
         eta._h.check(fn(eta._h.raw, leaf, ptr(out)))
         return out
 
@@ -139,14 +139,22 @@ def model_buffer(η: MixtureGPType, which: int, first_leaf: int, n_leaves: int):
     return int(dptr.value or 0), int(nbytes.value)
 
 
+def set_query_solver(η: MixtureGPType, solver: int):
+    """_lib.SOLVER_INVERSE (default: s = inv(L) kq, inverse formed once per fit) or _lib.SOLVER_SUBSTITUTION
+    (blocked forward substitution, closest to the reference's dtrsv)."""
+    η._h.check(lib().pmk_set_option(η._h.raw, _lib.OPT_QUERY_SOLVER, solver))
+
+
 def build_M(η: MixtureGPType):
-    """M_IJ = L_IJ inv(L_JJ) for the leaves this handle factorised (what a sharded run exchanges instead of L)."""
+    """The pair kernel's operands (M_IJ = L_IJ inv(L_JJ), and P = inv(L) for the default solver) for the leaves this
+    handle factorised -- what a sharded run exchanges instead of L."""
     η._h.check(lib().pmk_build_M(η._h.raw))
 
 
-def mark_fitted(η: MixtureGPType, m_exchanged: bool = False):
-    """Declare the replicated model complete after the peers' factors have been copied in."""
-    η._h.check(lib().pmk_mark_fitted(η._h.raw, 1 if m_exchanged else 0))
+def mark_fitted(η: MixtureGPType, m_exchanged: bool = False, p_exchanged: bool = False):
+    """Declare the replicated model complete after the peers' factors have been copied in (m/p_exchanged: the
+    peers' pair-kernel operands M / P = inv(L) came along, so nothing is rebuilt for foreign leaves)."""
+    η._h.check(lib().pmk_mark_fitted(η._h.raw, (1 if m_exchanged else 0) | (2 if p_exchanged else 0)))
     η._fitted = True
 
 

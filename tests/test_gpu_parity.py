@@ -122,6 +122,25 @@ def test_fit_factor_and_weights(built_lib, name):
 
 
 @pytest.mark.parametrize("name", list(CASES))
+def test_explicit_inverse_operand(built_lib, name):
+    """P = inv(L), the operand of the default (explicit-inverse) query solver: formed on the device by blocked
+    substitution on identity right-hand sides.  Checked as a residual, P L = I, and for exact triangularity."""
+    from patchmixturekriging_b200.mixturegp import _LazyLeafList
+    case, m, root, eta, pk = _setup(name)
+    P_set = _LazyLeafList(eta, "Linv")
+    n_leaves = len(eta.X_parts)
+    worst = 0.0
+    for leaf in sorted({0, 1, n_leaves // 2, n_leaves - 1}):
+        L = eta.L_set[leaf]
+        Pm = P_set[leaf]
+        assert np.array_equal(np.triu(Pm, 1), np.zeros_like(Pm))
+        R = Pm @ L - np.eye(L.shape[0])
+        worst = max(worst, np.abs(R).max() / (np.abs(Pm) @ np.abs(L)).max())
+    print(f"{name}: |P L - I| / (|P||L|) = {worst:.3e}")
+    assert worst < 1e-14
+
+
+@pytest.mark.parametrize("name", list(CASES))
 def test_query_structure_bit_exact(built_lib, name):
     case, m, root, eta, pk = _setup(name)
     _, wk = helpers.kernels(case["wkernel"])
