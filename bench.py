@@ -295,11 +295,11 @@ def main():
 
     def exchange_factors():
         """leaf -> rank map: every rank broadcasts the spans it factorised (NCCL over NVLink)."""
-        mixturegp.build_M(η)          # M for the leaves this rank factorised; only M (not L) travels
+        mixturegp.build_M(η)          # pair-kernel operands of the leaves this rank factorised; only P = inv(L) travels
         h.synchronize()
-        sharding.exchange_spans(span_of, n_leaves, (_lib.BUF_M, _lib.BUF_LINV, _lib.BUF_ALPHA))
+        sharding.exchange_spans(span_of, n_leaves, (_lib.BUF_P, _lib.BUF_ALPHA))
         torch.cuda.current_stream().synchronize()
-        mixturegp.mark_fitted(η, m_exchanged=True)
+        mixturegp.mark_fitted(η, p_exchanged=True)
 
     def step_device():
         """fit + query with inputs resident in HBM; returns (fit_ms, exchange_ms, query_ms) from CUDA events on the
@@ -420,7 +420,7 @@ def main():
             traffic = {"bytes": tr_["dram_bytes_read"] + tr_["dram_bytes_write"], "of": tr_["kernel"], "source": tr_["source"]}
         except Exception:
             traffic = None
-        roofline = {"kernel": "k_query_pairs (fused cross-covariance + mean + DMMA TRSM variance)", "bound": "tensor",
+        roofline = {"kernel": "k_query_trmm (fused cross-covariance + mean + variance s = inv(L) kq on DMMA, per (query, leaf) pair)", "bound": "tensor",
                     "pipe": "FP64 DMMA.8x8x4 (mma.sync.m8n8k4.f64); tcgen05 has no f64 kind", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
                     "algorithmic_flops_per_launch": flops_pairs, "ms_per_launch": float(kt[_lib.T_Q_PAIRS]),
@@ -429,7 +429,7 @@ def main():
         phases = {"fit_pack_ms": float(kt[_lib.T_FIT_PACK]), "fit_gram_ms": float(kt[_lib.T_FIT_GRAM]),
                   "fit_chol_ms": float(kt[_lib.T_FIT_CHOL]),
                   "fit_solve_ms": float(kt[_lib.T_FIT_SOLVE]), "query_tree_ms": float(kt[_lib.T_Q_TREE]),
-                  "query_make_M_ms": float(kt[_lib.T_Q_MAKE_M]), "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]),
+                  "query_make_M_ms": float(kt[_lib.T_Q_MAKE_M]), "query_invert_ms": float(kt[_lib.T_Q_INVERT]), "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]),
                   "query_combine_ms": float(kt[_lib.T_Q_COMBINE]),
                   "fit_gram_chol_tflops": fit_ach, "fit_gram_chol_frac_of_fp64_peak": fit_ach / peak}
         # per leaf-size class of the pair kernel: ms and achieved TFLOP/s

@@ -48,6 +48,8 @@ int query_class_mq(int cls);
 void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                         int mean_only, double* pu, double* pv, cudaStream_t s);
 void launch_class_tiles(const PairWork& w, int mq, int32_t* tiles, cudaStream_t s);
+void launch_query_trmm(int D, int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags,
+                       double* pu, double* pv, cudaStream_t s);
 }  // namespace pmk
 
 using namespace pmk;
@@ -430,7 +432,7 @@ int pmk_build_M(pmk_handle* h) {
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->m_ready = false;
   h->p_ready = false;
-  return build_operands(h, h->solver == 0);
+  return build_operands(h, h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP);
 }
 
 int pmk_mark_fitted(pmk_handle* h, int exchanged) {
@@ -980,7 +982,7 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
   h->last_flags = flags;
   if (!(flags & 1)) {     // variance wanted: the pair kernel streams M (substitution) or P = inv(L), built once per fit
-    if (int rc = build_operands(h, h->solver == 0)) return rc;
+    if (int rc = build_operands(h, h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP)) return rc;
   }
   if (h->lt.M == nullptr) h->lt.M = h->lt.L;   // mean-only queries never touch the factor
   Timer tt(h, PMK_T_Q_PAIRS);
@@ -1004,7 +1006,10 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     const int64_t ub = q.n_pairs / mq + h->n_class[c];
     {
       Timer tc(h, PMK_T_Q_PAIRS_CLASS0 + c);
-      launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
+      if (!(mean_only & 1) && h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP)
+        launch_query_trmm(h->D, c, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
+      else
+        launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
     }
     KCHECK(h, "k_query_pairs");
   }

@@ -1,9 +1,13 @@
-// K3 instantiations for D = 1 (see pmk_query_trsm.cuh)
-#include "pmk_query_trsm.cuh"
+// K3 instantiations for D = 1 (see pmk_query_trsm.cuh, pmk_query_trmm.cuh)
+#include "pmk_query_trmm.cuh"
 namespace pmk {
 void launch_pairs_d1(int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                       int mean_only, double* pu, double* pv, cudaStream_t s) {
   launch_pairs_d<1>(cls, grid, lt, w, q, kp, mean_only, pu, pv, s);
+}
+void launch_trmm_d1(int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags, double* pu,
+                    double* pv, cudaStream_t s) {
+  launch_trmm_d<1>(cls, lt, w, q, kp, flags, pu, pv, s);
 }
 void read_query_cycles_d1(unsigned long long* out, bool reset) { read_query_cycles_tu(out, reset); }
 }  // namespace pmk

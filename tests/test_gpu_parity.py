@@ -167,13 +167,21 @@ def test_query_structure_bit_exact(built_lib, name):
     assert np.array_equal(P.findpartition(Xq, root), home)
 
 
+@pytest.mark.parametrize("solver", [_lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION])
 @pytest.mark.parametrize("name", list(CASES))
-def test_query_mean_variance(built_lib, name):
+def test_query_mean_variance(built_lib, name, solver):
+    """Both query solvers against the oracle's dtrsv path: s = inv(L) kq with the explicit inverse (default; taken for
+    the squared-exponential kernel) and blocked forward substitution."""
+    from patchmixturekriging_b200 import mixturegp
     case, m, root, eta, pk = _setup(name)
     wth, wk = helpers.kernels(case["wkernel"])
     Xq = case["Xq"]
-    Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk,
-                                  debug_flag=True)
+    mixturegp.set_query_solver(eta, solver)
+    try:
+        Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk,
+                                      debug_flag=True)
+    finally:
+        mixturegp.set_query_solver(eta, _lib.SOLVER_INVERSE)
     Yo, Vo, od = O.querymixtureGP_vec(Xq, m["eta"], case["levels"], case["radius"], case["delta"], m["th"], wth)
     f = dv._flat
     assert np.array_equal(f["pair_leaf"], od["pair_leaf"])
@@ -305,7 +313,7 @@ def test_sharded_fit_equals_single_fit(built_lib):
 
     for e in etas:
         mixturegp.build_M(e)
-    for which in (_lib.BUF_L, _lib.BUF_M, _lib.BUF_LINV, _lib.BUF_ALPHA):
+    for which in (_lib.BUF_L, _lib.BUF_M, _lib.BUF_P, _lib.BUF_LINV, _lib.BUF_ALPHA):
         for src, (a, n) in enumerate(ranges):
             sp, sb = mixturegp.model_buffer(etas[src], which, a, n)
             dp, db = mixturegp.model_buffer(etas[1 - src], which, a, n)
@@ -315,7 +323,7 @@ def test_sharded_fit_equals_single_fit(built_lib):
     Xq = case["Xq"][:5000]
     Y0, V0, _ = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
     for e in etas:
-        mixturegp.mark_fitted(e, m_exchanged=True)
+        mixturegp.mark_fitted(e, m_exchanged=True, p_exchanged=True)
         Y1, V1, _ = P.querymixtureGP(Xq, e, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
         assert np.array_equal(Y0, Y1) and np.array_equal(V0, V1)
         e.close()
