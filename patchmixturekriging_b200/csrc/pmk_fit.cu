@@ -11,6 +11,7 @@
 //             L[J+1:, J] = C * inv(L_JJ)^T on DMMA, stored once in packed-tile form.
 // Several CTAs are resident per SM so that one leaf's serial diagonal-block phase overlaps the
 // other leaves' DMMA phases.
+#include <cstdlib>
 #include "pmk_internal.cuh"
 
 namespace pmk {
@@ -183,8 +184,11 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
 //      row-tile groups off a shared counter, compute C = K[t,J] - L[t,0:J] L[J,0:J]^T on DMMA and park the raw
 //      C tiles in their L slots
 //   C. all warps: L[t,J] = C inv(L_JJ)^T on DMMA, final A-fragment-major tiles.
+#ifndef PMK_CHOL_MINB
+#define PMK_CHOL_MINB 3      // resident leaves per SM the register allocation targets (4 forces 64 registers: measured below)
+#endif
 template <int NW, int R>
-__global__ void __launch_bounds__(NW * 32, 3)
+__global__ void __launch_bounds__(NW * 32, PMK_CHOL_MINB)
 k_chol(LeafTable lt, const int* __restrict__ order) {
   __shared__ double Dbuf[32 * LDD];
   __shared__ double Ibuf[32 * LD];
@@ -535,7 +539,12 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s) {
   constexpr int NW = 8, R = 2;
   if (n_order <= 0) return;
-  const size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings (32 KB)
+  size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings (32 KB)
+  // tuning knob: PMK_CHOL_CTAS_PER_SM=1|2 pads the dynamic shared memory so that fewer leaves are resident per SM
+  // (fewer concurrent leaves = smaller L2 working set of the left-looking re-reads, but fewer warps to hide latency)
+  static int ctas_per_sm = [] { const char* e = getenv("PMK_CHOL_CTAS_PER_SM"); return e ? atoi(e) : 3; }();
+  if (ctas_per_sm == 2) dyn = 100 * 1024;
+  else if (ctas_per_sm == 1) dyn = 150 * 1024;
   static bool configured = false;   // static + dynamic shared memory exceeds the 48 KB default
   if (!configured) {
     cudaFuncSetAttribute(k_chol<NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);

@@ -262,10 +262,12 @@ k_query_trmm(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, doubl
       const int sb = (int)(kt % kSB);
       q_mbar_wait(q_smem_u32(&stage_full[sb]), (uint32_t)((kt / kSB) & 1));
       const int p = s_desc[sb].p;
-      const int npad = s_desc[sb].npad;
+      const int n_pts = s_desc[sb].n;
       __syncwarp();
       if (lane == 0) q_mbar_arrive(q_smem_u32(&stage_empty[sb]));
-      const int nblk = npad >> 5, ntl = npad >> 3;
+      // only the row / column tiles that hold real points take part: the identity padding of the fit (n_pad is a multiple
+      // of 32) contributes exact zeros, so the pair kernel works on ceil(n/8) tiles
+      const int ntl = (n_pts + 7) >> 3, nblk = (ntl + 3) >> 2;
       const char* Pp = reinterpret_cast<const char*>(lt.P + lt.loff[p]);
       for (int J = 0; J < nblk; ++J) {
 #pragma unroll 1
@@ -340,8 +342,8 @@ k_query_trmm(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, doubl
     PMK_CYC(long long c_t0 = clock64(), c_eval = 0, c_bar = 0, c_full = 0, c_stage = 0, c_end = 0;)
     q_mbar_wait(q_smem_u32(&stage_full[sb]), (uint32_t)((kt / kSB) & 1));
     PMK_CYC(c_stage = clock64() - c_t0;)
-    const int p = s_desc[sb].p, npad = s_desc[sb].npad, n = s_desc[sb].n;
-    const int nblk = npad >> 5, ntl = npad >> 3;
+    const int p = s_desc[sb].p, n = s_desc[sb].n;
+    const int ntl = (n + 7) >> 3, nblk = (ntl + 3) >> 2;      // tiles with real points only (see the producer)
     const double* __restrict__ xs = lt.xs + lt.xoff[p];
     const double* __restrict__ al = lt.alpha + lt.xoff[p];
     const double* sX = s_X + (size_t)sb * (D + 1) * (NPMAX > 0 ? NPMAX : 1);

@@ -16,5 +16,5 @@ eta.handle.check(_lib.lib().pmk_debug_counters(eta.handle.raw, _lib.ptr(out), 1)
 P.fitmixtureGP_(eta, y_set, th, w["sigma2"])
 eta.handle.check(_lib.lib().pmk_debug_counters(eta.handle.raw, _lib.ptr(out), 1))
 names = ["total", "diag_block(warp0)", "offdiag_work(warp0)", "factor(warp0)", "panel_solve", "barrier_wait", "ctas"]
-n = float(out[6])
+n = max(float(out[6]), 1.0)   # counters are zero unless built with -DPMK_PROFILE_CYCLES
 print({k: round(float(v) / n) for k, v in zip(names, out[:6])}, "ctas", int(n), "chol ms", eta.handle.timings()[_lib.T_FIT_CHOL], "gram tiles ms", eta.handle.timings()[_lib.T_FIT_GRAM])
