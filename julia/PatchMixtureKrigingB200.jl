@@ -122,6 +122,13 @@ function fitmixtureGP!(Î·::MixtureGPType{T}, y_parts::Vector{Vector{T}}, Î¸, ÏƒÂ
     return Î·
 end
 
+"""How `L \\ kq` of `queryinner!` (mixtureGP.jl:311) is carried out: 0 = explicit inverse formed once per fit (default),
+1 = blocked forward substitution (closest to `dtrsv`).  `PMK_OPT_QUERY_SOLVER` of include/pmk.h."""
+function setsolver!(Î·::MixtureGPType, solver::Integer)
+    check(Î·.h, ccall((:pmk_set_option, libpmk), Cint, (Ptr{Cvoid}, Cint, Int64), Î·.h.ptr, 2, solver))
+    return Î·
+end
+
 # flatten the reference's BinaryNode tree for the device: hyperplanes in fetchhyperplanes order (mixtureGP.jl:322-334)
 function settree!(Î·::MixtureGPType, levels::Integer)
     D = length(Î·.X_parts[1][1]); hps = Î·.hps
