@@ -48,6 +48,8 @@ int query_class_mq(int cls);
 void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
                         int mean_only, double* pu, double* pv, cudaStream_t s);
 void launch_class_tiles(const PairWork& w, int mq, int32_t* tiles, cudaStream_t s);
+bool launch_query_rowp(int D, int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags, int npmax,
+                       double* pu, double* pv, cudaStream_t s);
 void launch_query_trmm(int D, int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags,
                        double* pu, double* pv, cudaStream_t s);
 }  // namespace pmk
@@ -94,7 +96,9 @@ struct pmk_handle {
   bool fitted = false;
   bool m_ready = false;    // M (operand of the substitution pair kernel) built for the current factors
   bool p_ready = false;    // P = inv(L) (operand of the explicit-inverse pair kernel) built for the current factors
-  int solver = 0;          // PMK_OPT_QUERY_SOLVER: 0 = explicit inverse (TRMM), 1 = blocked substitution (TRSM)
+  int solver = 0;          // PMK_OPT_QUERY_SOLVER: 0 = explicit inverse, row-panel product; 1 = blocked substitution (TRSM);
+                           // 2 = explicit inverse, column-sweep product (round-1 kernel, kept for comparison)
+  int class_max_npad[5] = {};
   int D = 0;
   int64_t n_leaves = 0, total_leaves = 0;
   int64_t fit_first = 0, fit_count = -1;   // leaves factorised by this handle (multi-GPU: leaf -> rank map)
@@ -272,7 +276,8 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
   switch (option) {
     case PMK_OPT_FULL_HYPERPLANE_SCAN: h->full_scan = value != 0; h->plan_valid = false; return PMK_OK;
     case PMK_OPT_QUERY_SOLVER:
-      if (value != 0 && value != 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: 0 (explicit inverse) or 1 (substitution)");
+      if (value < 0 || value > 2)
+        return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: 0 (explicit inverse), 1 (substitution) or 2 (explicit inverse, column sweep)");
       h->solver = (int)value;
       return PMK_OK;
     default: return fail(h, PMK_ERR_ARG, "unknown option %d", option);
@@ -432,7 +437,7 @@ int pmk_build_M(pmk_handle* h) {
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->m_ready = false;
   h->p_ready = false;
-  return build_operands(h, h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP);
+  return build_operands(h, h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP);
 }
 
 int pmk_mark_fitted(pmk_handle* h, int exchanged) {
@@ -518,7 +523,12 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   const int n_order = (int)order.size();
   // query size classes
   std::vector<int> cls[kNumClasses];
-  for (int64_t p = 0; p < n_leaves; ++p) cls[query_class_of(h->h_npad[p])].push_back((int)p);
+  for (int c = 0; c < kNumClasses; ++c) h->class_max_npad[c] = 0;
+  for (int64_t p = 0; p < n_leaves; ++p) {
+    const int c = query_class_of(h->h_npad[p]);
+    cls[c].push_back((int)p);
+    h->class_max_npad[c] = std::max(h->class_max_npad[c], h->h_npad[p]);
+  }
   for (int c = 0; c < kNumClasses; ++c) {
     h->n_class[c] = (int)cls[c].size();
     if (!cls[c].empty()) {
@@ -982,7 +992,7 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
   h->last_flags = flags;
   if (!(flags & 1)) {     // variance wanted: the pair kernel streams M (substitution) or P = inv(L), built once per fit
-    if (int rc = build_operands(h, h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP)) return rc;
+    if (int rc = build_operands(h, h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP)) return rc;
   }
   if (h->lt.M == nullptr) h->lt.M = h->lt.L;   // mean-only queries never touch the factor
   Timer tt(h, PMK_T_Q_PAIRS);
@@ -1006,7 +1016,10 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     const int64_t ub = q.n_pairs / mq + h->n_class[c];
     {
       Timer tc(h, PMK_T_Q_PAIRS_CLASS0 + c);
-      if (!(mean_only & 1) && h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP)
+      if (!(mean_only & 1) && h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP) {
+        if (!launch_query_rowp(h->D, c, h->lt, w, q, h->kp, mean_only, h->class_max_npad[c], d_pair_u, d_pair_v, h->stream))
+          return fail(h, PMK_ERR_UNSUPPORTED, "row-panel pair kernel: no shared-memory configuration for size class %d", c);
+      } else if (!(mean_only & 1) && h->solver == 2 && h->kp.kind == PMK_KERNEL_SQEXP)
         launch_query_trmm(h->D, c, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
       else
         launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);

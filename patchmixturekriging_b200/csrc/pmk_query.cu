@@ -55,6 +55,21 @@ void launch_query_trmm(int D, int cls, const LeafTable& lt, const PairWork& w, c
   }
 }
 
+bool launch_rowp_d1(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, int, double*, double*, cudaStream_t);
+bool launch_rowp_d2(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, int, double*, double*, cudaStream_t);
+bool launch_rowp_d3(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, int, double*, double*, cudaStream_t);
+
+// explicit-inverse pair kernel, row-panel product (pmk_query_rowp.cuh); persistent, reads its tile count on the device
+bool launch_query_rowp(int D, int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags,
+                       int npmax, double* pu, double* pv, cudaStream_t s) {
+  switch (D) {
+    case 1: return launch_rowp_d1(cls, lt, w, q, kp, flags, npmax, pu, pv, s);
+    case 2: return launch_rowp_d2(cls, lt, w, q, kp, flags, npmax, pu, pv, s);
+    case 3: return launch_rowp_d3(cls, lt, w, q, kp, flags, npmax, pu, pv, s);
+    default: return false;
+  }
+}
+
 void launch_class_tiles(const PairWork& w, int mq, int32_t* tiles, cudaStream_t s) {
   if (w.n_class_leaves == 0) return;
   k_class_tiles<<<(w.n_class_leaves + 255) / 256, 256, 0, s>>>(w, mq, tiles);

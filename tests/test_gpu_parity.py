@@ -167,11 +167,11 @@ def test_query_structure_bit_exact(built_lib, name):
     assert np.array_equal(P.findpartition(Xq, root), home)
 
 
-@pytest.mark.parametrize("solver", [_lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION])
+@pytest.mark.parametrize("solver", [_lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION, _lib.SOLVER_INVERSE_COLSWEEP])
 @pytest.mark.parametrize("name", list(CASES))
 def test_query_mean_variance(built_lib, name, solver):
-    """Both query solvers against the oracle's dtrsv path: s = inv(L) kq with the explicit inverse (default; taken for
-    the squared-exponential kernel) and blocked forward substitution."""
+    """Every query solver against the oracle's dtrsv path: s = inv(L) kq with the explicit inverse (default row-panel
+    kernel and the column-sweep kernel; taken for the squared-exponential kernel) and blocked forward substitution."""
     from patchmixturekriging_b200 import mixturegp
     case, m, root, eta, pk = _setup(name)
     wth, wk = helpers.kernels(case["wkernel"])

@@ -17,7 +17,7 @@ out = np.zeros(8, dtype=np.uint64)
 for rep in range(2):
     P.querymixtureGP_(Yq, Vq, Xq, eta, root, w["levels"], w["radius"], w["delta"], th, w["sigma2"], wth)
     eta.handle.check(_lib.lib().pmk_debug_counters(eta.handle.raw, _lib.ptr(out), 3))
-# explicit-inverse kernel (default solver): cycles per tile seen by warp 0, and the waits of warp 11
-names = ["total", "evaluations", "block barrier", "operand wait", "tile start+end", "tiles", "w11 block barrier", "w11 operand wait"]
+# row-panel kernel (default solver): cycles per tile, averaged over the 16 compute warps
+names = ["total", "tile start (staging waits, ring prefill)", "phase E", "wait K complete", "phase M", "tiles", "operand waits in M", "epilogue + wait K free"]
 n = float(out[5])
 print({k: round(float(v) / n) for k, v in zip(names, out) if k != "tiles"}, "tiles", int(n), "pairs ms", eta.handle.timings()[_lib.T_Q_PAIRS])
