@@ -26,7 +26,10 @@
 
 namespace pmk {
 
-static constexpr int kRW = 16;                  // compute warps (4 per SM sub-partition)
+#ifndef PMK_ROWP_WARPS
+#define PMK_ROWP_WARPS 16
+#endif
+static constexpr int kRW = PMK_ROWP_WARPS;      // compute warps (4 per SM sub-partition)
 static constexpr int kRowpCompute = kRW * 32;
 static constexpr int kRowpThreads = kRowpCompute + 32;
 static constexpr int kRSB = 2;                  // staged tiles: the one being worked on and the next
@@ -75,8 +78,19 @@ __device__ __forceinline__ double exp_neg_tab(double t, const double* __restrict
 // R row tiles per unit, CW column tiles per chunk, DEPTH chunks in flight per warp.
 // Dynamic shared memory: [kRW][DEPTH][R][CW][512 B] rings | K fragments: npmax * MQ doubles | per-unit ||S||^2:
 // [2][ucap][MQ] | (STAGE_X) inputs + alpha: [D+1][npmax]
+#ifndef PMK_ROWP_SWP
+#define PMK_ROWP_SWP 0
+#endif
+#ifndef PMK_ROWP_FASTISSUE
+#define PMK_ROWP_FASTISSUE 1
+#endif
+#ifdef PMK_ROWP_MAXNREG
+#define PMK_ROWP_BOUNDS __maxnreg__(PMK_ROWP_MAXNREG)
+#else
+#define PMK_ROWP_BOUNDS __launch_bounds__(kRowpThreads, 1)
+#endif
 template <int D, int NQT, int R, int CW, int DEPTH, bool STAGE_X>
-__global__ void __launch_bounds__(kRowpThreads, 1)
+__global__ void PMK_ROWP_BOUNDS
 k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int npmax, double* __restrict__ pair_u,
              double* __restrict__ pair_v) {
   constexpr int MQ = 8 * NQT;
@@ -242,13 +256,13 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
         nc = nc > CW ? CW : nc;
         if (t < ntl && nc > 0) total += (uint32_t)nc * 512u;
       }
-      q_mbar_expect_tx(fb, total);
+      q_mbar_expect_tx(fb, (PMK_K3_X & 4) ? 0u : total);
 #pragma unroll
       for (int i = 0; i < R; ++i) {
         const int t = R * m + i;
         int nc = t + 1 - c0;
         nc = nc > CW ? CW : nc;
-        if (t < ntl && nc > 0)
+        if (t < ntl && nc > 0 && !(PMK_K3_X & 4))
           q_bulk_g2s(ring_u32 + (uint32_t)(slot * SLOT_BYTES + i * (CW * 512)), Pp + (tri(t) + (size_t)c0) * 512,
                      (uint32_t)nc * 512u, fb);
       }
@@ -257,27 +271,43 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
     // The operand stream of this warp: units claimed largest first (index i counts from the largest: unit n_units-1-i),
     // the first one statically, the following ones from the tile's counter when the stream reaches the end of a unit.
     // Claimed-but-not-yet-consumed units wait in a byte queue (at most DEPTH + 1 of them).
+    // A unit's leading chunks are "full" (every row tile meets every column tile): R copies of CW tiles from a running
+    // pointer; only its last chunks (the diagonal end) take the general path.
+    auto full_chunks = [&](int m) { return R * m + R - 1 < ntl ? (R * m + 1) / CW : 0; };
     uint64_t uq = 0;
     int uqn = 0;
-    int im = n_units - 1 - warp, ich = 0, inch = im >= 0 ? unit_chunks(im) : 0;
-    if (im >= 0) {
-      uq = (uint64_t)im;
-      uqn = 1;
-    }
+    int im = n_units - 1 - warp, ich = 0, inch = 0, ifull = 0;
+    const char* isrc = Pp;
+    auto begin_unit = [&]() {
+      inch = unit_chunks(im);
+      ifull = full_chunks(im);
+      isrc = Pp + tri(R * im) * 512;
+      uq |= (uint64_t)im << (8 * uqn);
+      ++uqn;
+    };
+    if (im >= 0) begin_unit();
     auto issue_next = [&](int slot) {
       if (im >= 0) {
-        if (lane == 0) issue(im, ich, slot);
+        if (PMK_ROWP_FASTISSUE && ich < ifull) {
+          if (lane == 0) {
+            const uint32_t fb = my_full + slot * 8;
+            q_mbar_expect_tx(fb, (PMK_K3_X & 4) ? 0u : (uint32_t)SLOT_BYTES);
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+              if (!(PMK_K3_X & 4)) q_bulk_g2s(ring_u32 + (uint32_t)(slot * SLOT_BYTES + i * (CW * 512)),
+                         isrc + (uint32_t)((i * R * im + i * (i + 1) / 2) * 512), CW * 512, fb);
+          }
+        } else if (lane == 0) {
+          issue(im, ich, slot);
+        }
+        isrc += CW * 512;
         if (++ich == inch) {
           int idx = 0;
           if (lane == 0) idx = atomicAdd(&s_next[sb], 1);
           idx = __shfl_sync(kFullQ, idx, 0);
           im = n_units - 1 - idx;
           ich = 0;
-          if (im >= 0) {
-            inch = unit_chunks(im);
-            uq |= (uint64_t)im << (8 * uqn);
-            ++uqn;
-          }
+          if (im >= 0) begin_unit();
         }
       }
     };
@@ -356,79 +386,109 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
 
     // ---- phase M: this warp's units of S = P K, each squared and summed per query ----------------------------------
     int slot = 0;
+    auto load_b = [&](double2 (&bf)[NQT], int c) {
+#pragma unroll
+      for (int nt = 0; nt < NQT; ++nt) bf[nt] = Kfl[(c * NQT + nt) * 32];
+    };
+    auto mma_tile = [&](double (&a)[NQT][2], const double2& af, const double2 (&bf)[NQT]) {
+#pragma unroll
+      for (int nt = 0; nt < NQT; ++nt) dmma884(a[nt][0], a[nt][1], af.x, bf[nt].x);
+#pragma unroll
+      for (int nt = 0; nt < NQT; ++nt) dmma884(a[nt][0], a[nt][1], af.y, bf[nt].y);
+    };
     while (uqn > 0) {
       const int m = (int)(uq & 255u);
       uq >>= 8;
       --uqn;
-      const int nch = unit_chunks(m);
+      const int nch = unit_chunks(m), nfull = full_chunks(m);
       double acc[R][NQT][2];
 #pragma unroll
       for (int i = 0; i < R; ++i)
 #pragma unroll
         for (int nt = 0; nt < NQT; ++nt) acc[i][nt][0] = acc[i][nt][1] = 0.0;
-      const bool whole = R * m + R - 1 < ntl;       // all R row tiles of the unit exist
-      for (int ch = 0; ch < nch; ++ch) {
+      // ---- full chunks: every row tile of the unit meets every column tile of the chunk.  Software-pipelined: the K
+      // fragments (B) of the next column tile are loaded before the current tile's DMMAs -- across the chunk boundary too,
+      // they do not depend on the ring -- and the P fragments (A) of the next column tile of the chunk likewise.
+      double2 bf[2][NQT];
+      if (PMK_ROWP_SWP && nfull > 0) load_b(bf[0], 0);
+      for (int ch = 0; ch < nfull; ++ch) {
         PMK_CYC(c_a = clock64();)
         q_mbar_wait(my_full + slot * 8, (phbits >> slot) & 1u);
         PMK_CYC(c_full += clock64() - c_a;)
         phbits ^= 1u << slot;
         const double2* rs = ring_g + slot * (SLOT_BYTES / 16);
         const int c0 = ch * CW;
-        if (whole && c0 + CW - 1 <= R * m) {
-          // every row tile of the unit meets every column tile of the chunk
+        double2 af[2][R];
+#pragma unroll
+        for (int i = 0; i < R; ++i) af[0][i] = rs[(i * CW) * 32];
+#pragma unroll
+        for (int cc = 0; cc < CW; ++cc) {
+          // column c0 + cc + 1 exists in K: it is at most R m + 1 <= the unit's last row tile
+          if (PMK_ROWP_SWP) load_b(bf[(cc + 1) & 1], c0 + cc + 1);
+          else load_b(bf[cc & 1], c0 + cc);
+          if (cc + 1 < CW) {
+#pragma unroll
+            for (int i = 0; i < R; ++i) af[(cc + 1) & 1][i] = rs[(i * CW + cc + 1) * 32];
+          }
+#pragma unroll
+          for (int i = 0; i < R; ++i) mma_tile(acc[i], af[cc & 1][i], bf[cc & 1]);
+        }
+        if (PMK_ROWP_SWP && (CW & 1)) {       // odd chunk width: the prefetched fragments sit in the other buffer
+#pragma unroll
+          for (int nt = 0; nt < NQT; ++nt) bf[0][nt] = bf[1][nt];
+        }
+        __syncwarp();                 // every lane has read the slot: refill it with the chunk DEPTH ahead
+        issue_next(slot);
+        if (++slot == DEPTH) slot = 0;
+      }
+      // ---- the unit's diagonal end (P is lower triangular: row tile t meets column tile c only if c <= t) and short
+      // units at the end of the leaf
+      for (int ch = nfull; ch < nch; ++ch) {
+        PMK_CYC(c_a = clock64();)
+        q_mbar_wait(my_full + slot * 8, (phbits >> slot) & 1u);
+        PMK_CYC(c_full += clock64() - c_a;)
+        phbits ^= 1u << slot;
+        const double2* rs = ring_g + slot * (SLOT_BYTES / 16);
+        const int c0 = ch * CW;
+        if (R * m + R - 1 < ntl) {
+          // whole unit: the leading columns of the chunk (c <= R m) meet every row tile, then the triangle
+          // c = R m + 1 + j meets the row tiles i > j
+          const int ncf = R * m + 1 - c0;           // full columns in this chunk (may be <= 0 or > CW)
 #pragma unroll
           for (int cc = 0; cc < CW; ++cc) {
-            double2 bf[NQT];
+            PMK_UNIFORM_IF(cc < ncf) {
+              double2 b[NQT];
+              load_b(b, c0 + cc);
 #pragma unroll
-            for (int nt = 0; nt < NQT; ++nt) bf[nt] = Kfl[((c0 + cc) * NQT + nt) * 32];
-#pragma unroll
-            for (int i = 0; i < R; ++i) {
-              const double2 af = rs[(i * CW + cc) * 32];
-#pragma unroll
-              for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[nt].x);
-#pragma unroll
-              for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[nt].y);
+              for (int i = 0; i < R; ++i) mma_tile(acc[i], rs[(i * CW + cc) * 32], b);
             }
           }
-        } else if (CW == R && whole && c0 == R * m) {
-          // the unit's diagonal chunk (P is lower triangular): row tile i meets column tile cc only if cc <= i
 #pragma unroll
-          for (int cc = 0; cc < CW; ++cc) {
-            double2 bf[NQT];
+          for (int j = 0; j < R - 1; ++j) {
+            const int cc = R * m + 1 + j - c0;      // position of the triangle's column j in this chunk
+            PMK_UNIFORM_IF(cc >= 0 && cc < CW) {
+              double2 b[NQT];
+              load_b(b, c0 + cc);
 #pragma unroll
-            for (int nt = 0; nt < NQT; ++nt) bf[nt] = Kfl[((c0 + cc) * NQT + nt) * 32];
-#pragma unroll
-            for (int i = cc; i < R; ++i) {
-              const double2 af = rs[(i * CW + cc) * 32];
-#pragma unroll
-              for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[nt].x);
-#pragma unroll
-              for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[nt].y);
+              for (int i = j + 1; i < R; ++i) mma_tile(acc[i], rs[(i * CW + cc) * 32], b);
             }
           }
         } else {
-          // diagonal chunks of other shapes, short units at the end of the leaf: guarded, with real branches
+          // short unit at the end of the leaf: guarded tile by tile, with real branches
 #pragma unroll
           for (int cc = 0; cc < CW; ++cc) {
             const int c = c0 + cc;
             PMK_UNIFORM_IF(c <= R * m + R - 1 && c < ntl) {      // c <= the unit's last row tile
-              double2 bf[NQT];
-#pragma unroll
-              for (int nt = 0; nt < NQT; ++nt) bf[nt] = Kfl[(c * NQT + nt) * 32];
+              double2 b[NQT];
+              load_b(b, c);
 #pragma unroll
               for (int i = 0; i < R; ++i) {
-                PMK_UNIFORM_IF(R * m + i < ntl && c <= R * m + i) {
-                  const double2 af = rs[(i * CW + cc) * 32];
-#pragma unroll
-                  for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.x, bf[nt].x);
-#pragma unroll
-                  for (int nt = 0; nt < NQT; ++nt) dmma884(acc[i][nt][0], acc[i][nt][1], af.y, bf[nt].y);
-                }
+                PMK_UNIFORM_IF(R * m + i < ntl && c <= R * m + i) mma_tile(acc[i], rs[(i * CW + cc) * 32], b);
               }
             }
           }
         }
-        __syncwarp();                 // every lane has read the slot: refill it with the chunk DEPTH ahead
+        __syncwarp();
         issue_next(slot);
         if (++slot == DEPTH) slot = 0;
       }
@@ -507,24 +567,26 @@ static bool launch_rowp_one(const LeafTable& lt, const PairWork& w, const QueryP
 }
 
 #ifndef PMK_ROWP_CW
-#define PMK_ROWP_CW 2
+#define PMK_ROWP_CW 4
 #endif
 #ifndef PMK_ROWP_DEPTH
-#define PMK_ROWP_DEPTH 2
+#define PMK_ROWP_DEPTH 1
 #endif
 
 // npmax: largest n_pad among the class's leaves (sizes the K buffer); same size classes / MQ as the other pair kernels.
-// The K buffer (n_pad x MQ doubles) has priority over the rings: a class whose largest leaf leaves no room for
-// 2 x 2-tile chunks per warp runs with single-tile chunks.
+// Measured on c3_mini (16 warps): chunks of 2 column tiles x 2 slots 10.71 ms, 3 x 1 10.43, 4 x 1 10.47, 1 x 4 11.51;
+// 12 warps 4 x 1 10.62, 5 x 1 10.53; 8 warps 8 x 1 11.24 -- the per-chunk cost (barrier wait, refill) outweighs a second
+// slot: the other three warps of the sub-partition hide the refill latency.  The K buffer (n_pad x MQ doubles) has
+// priority over the rings: a class whose largest leaf leaves no room for 4-tile chunks runs with 2-tile chunks.
 template <int D>
 bool launch_rowp_d(int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags, int npmax,
                    double* pu, double* pv, cudaStream_t s) {
   if (cls == 0)
     return launch_rowp_one<D, 4, 2, PMK_ROWP_CW, PMK_ROWP_DEPTH>(lt, w, q, kp, flags, npmax, pu, pv, s) ||
-           launch_rowp_one<D, 4, 2, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
+           launch_rowp_one<D, 4, 2, 2, 1>(lt, w, q, kp, flags, npmax, pu, pv, s);
   if (cls == 1)
     return launch_rowp_one<D, 3, 2, PMK_ROWP_CW, PMK_ROWP_DEPTH>(lt, w, q, kp, flags, npmax, pu, pv, s) ||
-           launch_rowp_one<D, 3, 2, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
+           launch_rowp_one<D, 3, 2, 2, 1>(lt, w, q, kp, flags, npmax, pu, pv, s);
   if (cls == 2) return launch_rowp_one<D, 2, 4, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
   return launch_rowp_one<D, 1, 4, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
 }
