@@ -420,7 +420,7 @@ def main():
             traffic = {"bytes": tr_["dram_bytes_read"] + tr_["dram_bytes_write"], "of": tr_["kernel"], "source": tr_["source"]}
         except Exception:
             traffic = None
-        roofline = {"kernel": "k_query_trmm (fused cross-covariance + mean + variance s = inv(L) kq on DMMA, per (query, leaf) pair)", "bound": "tensor",
+        roofline = {"kernel": "k_query_rowp (fused cross-covariance + mean + variance, s = inv(L) kq as a row-panel product on DMMA, per (query, leaf) pair)", "bound": "tensor",
                     "pipe": "FP64 DMMA.8x8x4 (mma.sync.m8n8k4.f64); tcgen05 has no f64 kind", "achieved": ach, "peak": peak,
                     "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
                     "algorithmic_flops_per_launch": flops_pairs, "ms_per_launch": float(kt[_lib.T_Q_PAIRS]),

@@ -64,7 +64,7 @@ enum {
   PMK_T_FIT_CHOL = 1,      /* batched blocked Cholesky (K2)                                    */
   PMK_T_FIT_SOLVE = 2,     /* forward/back solves for alpha                                    */
   PMK_T_Q_TREE = 3,        /* home leaf + neighbour search + pair build + binning              */
-  PMK_T_Q_PAIRS = 4,       /* fused cross-covariance / mean / TRSM-variance kernel (K3)        */
+  PMK_T_Q_PAIRS = 4,       /* fused cross-covariance / mean / variance pair kernel (K3)        */
   PMK_T_Q_COMBINE = 5,     /* convex mixture combine                                           */
   PMK_T_GRAM = 6,          /* standalone Gram kernel (constructkernelmatrix / U_set)           */
   PMK_T_FIT_GRAM = 7,      /* per-leaf Gram tiles of the fit (K1)                              */
@@ -193,10 +193,13 @@ int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d
 /* PMK_OPT_FULL_HYPERPLANE_SCAN: 1 = findneighbourpartitions scans ALL hyperplanes per query exactly as the
  * reference loop does (mixtureGP.jl:354); 0 (default) = exact per-leaf candidate lists (same result). */
 /* PMK_OPT_QUERY_SOLVER: how queryinner!'s v = L \ kq (mixtureGP.jl:311) is carried out for a tile of queries:
- *   0 (default) = s = P kq with P = inv(L) formed once per fit by blocked substitution -- no dependency between row
- *                 blocks, so the tensor pipe never waits (measured vs dtrsv: <= 3e-11 at sigma2 = 1e-3);
+ *   0 (default) = s = P kq with P = inv(L) formed once per fit by blocked substitution, as a ROW-PANEL product: the
+ *                 cross-covariance tile is evaluated once into shared memory, every warp streams its own rows of P and
+ *                 keeps only ||s||^2 -- no dependency between warps, so the tensor pipe never waits
+ *                 (measured vs dtrsv: <= 3e-11 at sigma2 = 1e-3);
  *   1           = blocked forward substitution with 32x32 diagonal-block inverses (closest to dtrsv; use it for
- *                 very ill-conditioned leaves, cond(K) >~ 1e6). */
+ *                 very ill-conditioned leaves, cond(K) >~ 1e6);
+ *   2           = s = P kq as a column sweep with the tile of s in registers (round-1 mid kernel, kept for comparison). */
 enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2 };
 int pmk_set_option(pmk_handle* h, int option, int64_t value);
 

@@ -123,7 +123,8 @@ function fitmixtureGP!(Î·::MixtureGPType{T}, y_parts::Vector{Vector{T}}, Î¸, ÏƒÂ
 end
 
 """How `L \\ kq` of `queryinner!` (mixtureGP.jl:311) is carried out: 0 = explicit inverse formed once per fit (default),
-1 = blocked forward substitution (closest to `dtrsv`).  `PMK_OPT_QUERY_SOLVER` of include/pmk.h."""
+1 = blocked forward substitution (closest to `dtrsv`), 2 = explicit inverse with the round-1 column-sweep kernel.
+`PMK_OPT_QUERY_SOLVER` of include/pmk.h."""
 function setsolver!(Î·::MixtureGPType, solver::Integer)
     check(Î·.h, ccall((:pmk_set_option, libpmk), Cint, (Ptr{Cvoid}, Cint, Int64), Î·.h.ptr, 2, solver))
     return Î·

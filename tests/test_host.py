@@ -121,3 +121,36 @@ def test_exp_neg_arithmetic():
     got = np.ldexp(s, nf.astype(int))
     ref = np.exp(t)
     assert np.all(np.abs(got - ref) <= 2.5 * np.spacing(ref))
+
+
+def test_exp_neg_tab_arithmetic():
+    """The row-panel pair kernel's inline exp (pmk_query_rowp.cuh exp_neg_tab: 64-entry table of 2^(j/64), the integer
+    64k + j read from the low word of t*64/ln2 + 1.5*2^52, degree-5 polynomial) restated in numpy: <= 1.5 ulp from the
+    correctly rounded value on the argument range the squared-exponential cross-covariance produces."""
+    from decimal import Decimal, getcontext
+    getcontext().prec = 50
+    ln2 = Decimal(2).ln()
+    tab = np.array([float((ln2 * Decimal(j) / 64).exp()) for j in range(64)])
+    # the table compiled into the library is this one, bit for bit
+    import re, os
+    src = open(os.path.join(os.path.dirname(__file__), "..", "patchmixturekriging_b200", "csrc", "pmk_query_rowp.cuh")).read()
+    lits = re.findall(r"0x1\.[0-9a-f]{13}p\+0", src[src.index("c_exp2_64[64]"):src.index("};", src.index("c_exp2_64[64]"))])
+    assert len(lits) == 64 and all(float.fromhex(a) == b for a, b in zip(lits, tab))
+    C, HI, LO = float.fromhex("0x1.71547652b82fep+6"), float.fromhex("0x1.62e42fee00000p-7"), float.fromhex("0x1.a39ef35793c76p-39")
+    MAGIC = float.fromhex("0x1.8p52")
+    rng = np.random.default_rng(7)
+    t = -np.concatenate([rng.uniform(0, 50, 400000), rng.uniform(0, 699, 400000), [0.0, 1e-300, 1e-9, 699.0]])
+    kd = t * C + MAGIC
+    ki = (kd.view(np.int64) & 0xFFFFFFFF).astype(np.int64)
+    ki = np.where(ki >= 2 ** 31, ki - 2 ** 32, ki)
+    kd = kd - MAGIC
+    assert np.array_equal(kd, ki.astype(float))
+    r = (t - kd * HI) - kd * LO
+    assert np.abs(r).max() <= 0.0054152056
+    T = tab[ki & 63]
+    r2 = r * r
+    pr = r + ((0.5 + r / 6) + (1 / 24 + r / 120) * r2) * r2
+    got = np.ldexp(T + T * pr, (ki >> 6).astype(int))
+    ref = np.exp(t.astype(np.longdouble))
+    err = np.abs(got.astype(np.longdouble) - ref) / np.spacing(np.exp(t)).astype(np.longdouble)
+    assert err.max() <= 1.5
