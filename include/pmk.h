@@ -70,7 +70,7 @@ enum {
   PMK_T_FIT_GRAM = 7,      /* per-leaf Gram tiles of the fit (K1)                              */
   PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +4: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=1536, <=2048) */
   PMK_T_Q_MAKE_M = 13,       /* M_IJ = L_IJ inv(L_JJ), built once per fit by the first variance query               */
-  PMK_T_Q_INVERT = 14,       /* P = inv(L) (operand of the explicit-inverse pair kernel), built once per fit        */
+  PMK_T_Q_INVERT = 14,       /* P = inv(L) (operand of the explicit-inverse pair kernels), built once per fit       */
   PMK_T_COUNT = 15
 };
 
@@ -200,7 +200,10 @@ int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d
  *   1           = blocked forward substitution with 32x32 diagonal-block inverses (closest to dtrsv; use it for
  *                 very ill-conditioned leaves, cond(K) >~ 1e6);
  *   2           = s = P kq as a column sweep with the tile of s in registers (round-1 mid kernel, kept for comparison). */
-enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2 };
+/* PMK_OPT_INVERSE_BUILDER: how P = inv(L) is formed (once per fit) for the explicit-inverse solvers:
+ *   0 (default) = recursive doubling on the packed tiles, P21 = -inv(B) C inv(A), every flop a DMMA GEMM (pmk_invert.cu);
+ *   1           = the substitution pair kernel run on identity right-hand sides (round-1 builder). */
+enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2, PMK_OPT_INVERSE_BUILDER = 3 };
 int pmk_set_option(pmk_handle* h, int option, int64_t value);
 
 /* ---- instrumentation --------------------------------------------------------------------- */

@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("PMK_LIB") or os.path.join(_HERE, "libpmk_b200.so")   
 
 PMK_OK, PMK_ERR_CUDA, PMK_ERR_ARG, PMK_ERR_NOT_POSDEF, PMK_ERR_STATE, PMK_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 BUF_L, BUF_LINV, BUF_ALPHA, BUF_M, BUF_P = 0, 1, 2, 3, 4
-OPT_FULL_HYPERPLANE_SCAN, OPT_QUERY_SOLVER = 1, 2
+OPT_FULL_HYPERPLANE_SCAN, OPT_QUERY_SOLVER, OPT_INVERSE_BUILDER = 1, 2, 3
 SOLVER_INVERSE, SOLVER_SUBSTITUTION, SOLVER_INVERSE_COLSWEEP = 0, 1, 2
 T_FIT_PACK, T_FIT_CHOL, T_FIT_SOLVE, T_Q_TREE, T_Q_PAIRS, T_Q_COMBINE, T_GRAM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 15
 T_Q_MAKE_M = 13

@@ -22,6 +22,9 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
 void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_npad, cudaStream_t s);
+InvPlanHost make_inverse_plan(const std::vector<int>& shapes_present);
+void launch_inverse(const LeafTable& lt, const InvPlanHost& plh, const void* d_nodes, const int* d_off, const int* d_cnt,
+                    double* scratch, int first_leaf, int n_leaves, int max_npad, cudaStream_t s, int64_t* launches);
 void launch_unpack_L(const LeafTable& lt, int p, int n, double* d_out, cudaStream_t s, int which = 0);
 void read_chol_cycles(unsigned long long* out, bool reset);
 void read_query_cycles(int D, unsigned long long* out, bool reset);
@@ -99,6 +102,9 @@ struct pmk_handle {
   int solver = 0;          // PMK_OPT_QUERY_SOLVER: 0 = explicit inverse, row-panel product; 1 = blocked substitution (TRSM);
                            // 2 = explicit inverse, column-sweep product (round-1 kernel, kept for comparison)
   int class_max_npad[5] = {};
+  int inverse_builder = 0; // PMK_OPT_INVERSE_BUILDER: 0 = recursive doubling (pmk_invert.cu), 1 = substitution kernel on identity columns
+  InvPlanHost inv_plan;    // recursion plan of the shapes of the current model
+  DBuf d_inv_nodes, d_inv_off, d_inv_cnt;
   int D = 0;
   int64_t n_leaves = 0, total_leaves = 0;
   int64_t fit_first = 0, fit_count = -1;   // leaves factorised by this handle (multi-GPU: leaf -> rank map)
@@ -254,7 +260,13 @@ void pmk_destroy(pmk_handle* h) {
     h->d_class_leaves[c].release();
     h->d_class_tiles[c].release();
     h->d_tile_off[c].release();
+    h->d_inv_leaves[c].release();
+    h->d_inv_tile_off[c].release();
   }
+  h->d_P.release();
+  h->d_inv_nodes.release();
+  h->d_inv_off.release();
+  h->d_inv_cnt.release();
   for (int i = 0; i < 2 * PMK_T_COUNT; ++i)
     if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   cudaStreamDestroy(h->stream);
@@ -279,6 +291,11 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
       if (value < 0 || value > 2)
         return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: 0 (explicit inverse), 1 (substitution) or 2 (explicit inverse, column sweep)");
       h->solver = (int)value;
+      return PMK_OK;
+    case PMK_OPT_INVERSE_BUILDER:
+      if (value != 0 && value != 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_INVERSE_BUILDER: 0 (recursive doubling) or 1 (substitution)");
+      h->inverse_builder = (int)value;
+      h->p_ready = false;
       return PMK_OK;
     default: return fail(h, PMK_ERR_ARG, "unknown option %d", option);
   }
@@ -396,38 +413,55 @@ int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_lea
   return PMK_OK;
 }
 
-// M (and P = inv(L) when want_P) for the leaves of the fit range.  P comes from the substitution pair kernel itself,
-// run on identity right-hand sides (tile = MQ columns of the inverse, starting at the column's own block).
-static int build_operands(pmk_handle* h, bool want_P) {
+// The pair kernels' operands for the leaves of the fit range: P = inv(L) (explicit-inverse solvers) and/or
+// M_IJ = L_IJ inv(L_JJ) (substitution solver).  P comes from recursive doubling on the packed tiles (pmk_invert.cu; the M
+// buffer doubles as its scratch, so M is rebuilt afterwards if it is wanted too) or, with PMK_OPT_INVERSE_BUILDER = 1, from the
+// substitution pair kernel run on identity right-hand sides (tile = MQ columns of the inverse).
+static int build_operands(pmk_handle* h, bool want_M, bool want_P) {
   const int64_t f0 = std::min<int64_t>(h->fit_first, h->n_leaves);
   const int64_t f1 = h->fit_count < 0 ? h->n_leaves : std::min<int64_t>(h->n_leaves, f0 + h->fit_count);
   const bool all = (f0 == 0 && f1 == h->n_leaves);
-  if (!h->m_ready) {
+  auto make_M = [&]() -> int {
     Timer tm(h, PMK_T_Q_MAKE_M);
     CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
     h->lt.M = h->d_M.as<double>();
     launch_make_M(h->lt, (int)f0, (int)(f1 - f0), h->max_npad, h->stream);
     KCHECK(h, "k_make_M");
     h->m_ready = all;
-  }
+    return PMK_OK;
+  };
   if (want_P && !h->p_ready) {
-    Timer tm(h, PMK_T_Q_INVERT);
     CU(h, h->d_P.ensure(sizeof(double) * (size_t)h->L_doubles));
     h->lt.P = h->d_P.as<double>();
-    h->lt.M = h->d_M.as<double>();
-    for (int c = 0; c < kNumClasses; ++c) {
-      if (h->n_inv_class[c] == 0) continue;
-      PairWork w{};
-      w.class_leaves = h->d_inv_leaves[c].as<int>();
-      w.n_class_leaves = h->n_inv_class[c];
-      w.tile_off = h->d_inv_tile_off[c].as<int64_t>();
-      w.leaf_base = 0;
-      QueryPlan q{};
-      launch_query_pairs(h->D, c, (unsigned)h->inv_tiles[c], h->lt, w, q, h->kp, 4, nullptr, nullptr, h->stream);
-      KCHECK(h, "k_query_pairs (inversion)");
+    if (h->inverse_builder == 0) {
+      Timer tm(h, PMK_T_Q_INVERT);
+      CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));       // scratch for T = C inv(A)
+      h->lt.M = h->d_M.as<double>();
+      h->m_ready = false;
+      launch_inverse(h->lt, h->inv_plan, h->d_inv_nodes.p, h->d_inv_off.as<int>(), h->d_inv_cnt.as<int>(), h->d_M.as<double>(),
+                     (int)f0, (int)(f1 - f0), h->max_npad, h->stream, &h->launches);
+      --h->launches;
+      KCHECK(h, "k_inv_* (recursive inverse)");
+    } else {
+      if (!h->m_ready)
+        if (int rc = make_M()) return rc;
+      Timer tm(h, PMK_T_Q_INVERT);
+      for (int c = 0; c < kNumClasses; ++c) {
+        if (h->n_inv_class[c] == 0) continue;
+        PairWork w{};
+        w.class_leaves = h->d_inv_leaves[c].as<int>();
+        w.n_class_leaves = h->n_inv_class[c];
+        w.tile_off = h->d_inv_tile_off[c].as<int64_t>();
+        w.leaf_base = 0;
+        QueryPlan q{};
+        launch_query_pairs(h->D, c, (unsigned)h->inv_tiles[c], h->lt, w, q, h->kp, 4, nullptr, nullptr, h->stream);
+        KCHECK(h, "k_query_pairs (inversion)");
+      }
     }
     h->p_ready = all;
   }
+  if (want_M && !h->m_ready)
+    if (int rc = make_M()) return rc;
   return PMK_OK;
 }
 
@@ -437,7 +471,7 @@ int pmk_build_M(pmk_handle* h) {
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->m_ready = false;
   h->p_ready = false;
-  return build_operands(h, h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP);
+  return build_operands(h, true, h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP);
 }
 
 int pmk_mark_fitted(pmk_handle* h, int exchanged) {
@@ -493,6 +527,25 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   h->Linv_doubles = io;
   h->x_points = xo;
   h->max_npad = max_npad;
+  {   // recursion plan of the explicit inverse for the shapes (numbers of 32-row blocks) of this model
+    std::vector<int> shapes;
+    std::vector<char> seen(kInvMaxBlocks + 1, 0);
+    for (int64_t p = 0; p < n_leaves; ++p) {
+      const int nb = h->h_npad[p] / 32;
+      if (nb >= 1 && nb <= kInvMaxBlocks && !seen[nb]) {
+        seen[nb] = 1;
+        shapes.push_back(nb);
+      }
+    }
+    h->inv_plan = make_inverse_plan(shapes);
+    CU(h, h->d_inv_nodes.ensure(sizeof(InvNode) * std::max<size_t>(1, h->inv_plan.nodes.size())));
+    CU(h, h->d_inv_off.ensure(sizeof(int) * h->inv_plan.off.size()));
+    CU(h, h->d_inv_cnt.ensure(sizeof(int) * h->inv_plan.cnt.size()));
+    if (!h->inv_plan.nodes.empty())
+      CU(h, cudaMemcpyAsync(h->d_inv_nodes.p, h->inv_plan.nodes.data(), sizeof(InvNode) * h->inv_plan.nodes.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_inv_off.p, h->inv_plan.off.data(), sizeof(int) * h->inv_plan.off.size(), cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaMemcpyAsync(h->d_inv_cnt.p, h->inv_plan.cnt.data(), sizeof(int) * h->inv_plan.cnt.size(), cudaMemcpyHostToDevice, h->stream));
+  }
   h->D = D;
   h->n_leaves = n_leaves;
   h->total_leaves = n_leaves;
@@ -692,7 +745,7 @@ int pmk_get_Linv(pmk_handle* h, int64_t leaf, double* out) {
   if (int rc = check_leaf(h, leaf, &p)) return rc;
   if (!out) return fail(h, PMK_ERR_ARG, "NULL pointer");
   if (int rc = set_device(h)) return rc;
-  if (int rc = build_operands(h, true)) return rc;
+  if (int rc = build_operands(h, false, true)) return rc;
   const int n = h->h_n[p];
   CU(h, h->d_scratch.ensure(sizeof(double) * (size_t)n * n));
   launch_unpack_L(h->lt, (int)p, n, h->d_scratch.as<double>(), h->stream, 1);
@@ -992,7 +1045,8 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
   h->last_flags = flags;
   if (!(flags & 1)) {     // variance wanted: the pair kernel streams M (substitution) or P = inv(L), built once per fit
-    if (int rc = build_operands(h, h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP)) return rc;
+    const bool use_P = h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP;
+    if (int rc = build_operands(h, !use_P, use_P)) return rc;
   }
   if (h->lt.M == nullptr) h->lt.M = h->lt.L;   // mean-only queries never touch the factor
   Timer tt(h, PMK_T_Q_PAIRS);

@@ -1,5 +1,6 @@
 // Internal device-side descriptors shared by the kernels and the C-ABI layer.
 #pragma once
+#include <vector>
 #include "pmk_common.cuh"
 
 namespace pmk {
@@ -60,6 +61,21 @@ struct PairWork {
   const int64_t* leaf_pair_start;   // total_leaves + 1, start of each GLOBAL leaf's run in sorted_pair
   const int32_t* sorted_pair;       // pair ids sorted (stably) by leaf
   int64_t leaf_base;                // global id (0-based) of local leaf 0
+};
+
+// Recursion plan of the explicit inverse P = inv(L) by recursive doubling (pmk_invert.cu): for every shape (number of 32-row
+// blocks) present and every height of the recursion tree, that shape's nodes of that height.
+static constexpr int kInvMaxBlocks = PMK_MAX_LEAF_POINTS / 32;      // 64
+static constexpr int kInvMaxHeight = 8;
+struct InvNode {
+  short lo, mid, hi, pad;       // block ranges: A = [lo, mid), B = [mid, hi), C = rows [mid, hi) x columns [lo, mid)
+};
+struct InvPlanHost {
+  std::vector<InvNode> nodes;
+  std::vector<int> off, cnt;    // [kInvMaxBlocks + 1][kInvMaxHeight + 1]
+  int max_height = 0;
+  int max_cnt[kInvMaxHeight + 1] = {};      // nodes of that height, largest over the shapes
+  int max_blocks[kInvMaxHeight + 1] = {};   // 32x32 output blocks of a node of that height, largest over the shapes
 };
 
 }  // namespace pmk

@@ -145,6 +145,12 @@ def set_query_solver(η: MixtureGPType, solver: int):
     η._h.check(lib().pmk_set_option(η._h.raw, _lib.OPT_QUERY_SOLVER, solver))
 
 
+def set_inverse_builder(η: MixtureGPType, builder: int):
+    """How P = inv(L) is formed: 0 (default) recursive doubling on the packed tiles, 1 the substitution kernel on identity
+    right-hand sides.  PMK_OPT_INVERSE_BUILDER of include/pmk.h."""
+    η._h.check(lib().pmk_set_option(η._h.raw, _lib.OPT_INVERSE_BUILDER, builder))
+
+
 def build_M(η: MixtureGPType):
     """The pair kernel's operands (M_IJ = L_IJ inv(L_JJ), and P = inv(L) for the default solver) for the leaves this
     handle factorised -- what a sharded run exchanges instead of L."""

@@ -121,12 +121,16 @@ def test_fit_factor_and_weights(built_lib, name):
     assert worst_res < 1e-14    # backward-stable solve
 
 
+@pytest.mark.parametrize("builder", [0, 1])
 @pytest.mark.parametrize("name", list(CASES))
-def test_explicit_inverse_operand(built_lib, name):
-    """P = inv(L), the operand of the default (explicit-inverse) query solver: formed on the device by blocked
-    substitution on identity right-hand sides.  Checked as a residual, P L = I, and for exact triangularity."""
+def test_explicit_inverse_operand(built_lib, name, builder):
+    """P = inv(L), the operand of the default (explicit-inverse) query solver: formed on the device by recursive doubling
+    on the packed tiles (builder 0, default) or by blocked substitution on identity right-hand sides (builder 1).
+    Checked as a residual, P L = I, and for exact triangularity."""
+    from patchmixturekriging_b200 import mixturegp
     from patchmixturekriging_b200.mixturegp import _LazyLeafList
     case, m, root, eta, pk = _setup(name)
+    mixturegp.set_inverse_builder(eta, builder)
     P_set = _LazyLeafList(eta, "Linv")
     n_leaves = len(eta.X_parts)
     worst = 0.0
@@ -136,7 +140,8 @@ def test_explicit_inverse_operand(built_lib, name):
         assert np.array_equal(np.triu(Pm, 1), np.zeros_like(Pm))
         R = Pm @ L - np.eye(L.shape[0])
         worst = max(worst, np.abs(R).max() / (np.abs(Pm) @ np.abs(L)).max())
-    print(f"{name}: |P L - I| / (|P||L|) = {worst:.3e}")
+    mixturegp.set_inverse_builder(eta, 0)
+    print(f"{name} builder {builder}: |P L - I| / (|P||L|) = {worst:.3e}")
     assert worst < 1e-14
 
 
