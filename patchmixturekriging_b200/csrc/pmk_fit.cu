@@ -140,6 +140,9 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
 template <int D>
 __global__ void __launch_bounds__(256)
 k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
+  __shared__ double s_exp[64];
+  if (threadIdx.x < 64) s_exp[threadIdx.x] = c_exp2_64[threadIdx.x];
+  __syncthreads();
   const int p = order[blockIdx.x];
   const int n = lt.n[p], ntl = lt.npad[p] >> 3;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -153,28 +156,46 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
   double xr[D];
 #pragma unroll
   for (int d = 0; d < D; ++d) xr[d] = xs[d * xstride + row];
-#pragma unroll 4
-  for (int c = 0; c <= t; ++c) {
-    double kv[2];
+  // one entry, every case: lower triangle of K + sigma2*I, identity on the padding
+  auto entry = [&](int col) {
+    double v = 0.0;
+    if (col <= row) {
+      if (row < n) {          // col <= row < n
+        double xc[D];
 #pragma unroll
-    for (int e = 0; e < 2; ++e) {
-      const int col = 8 * c + 2 * l + e;
-      double v = 0.0;
-      if (col <= row) {
-        if (row < n) {          // col <= row < n
-          double xc[D];
-#pragma unroll
-          for (int d = 0; d < D; ++d) xc[d] = xs[d * xstride + col];
-          v = eval_kernel<D>(kp, xr, xc);               // evalkernel(X[i], X[j]), i >= j  (RKHS.jl:21-25)
-          if (row == col) v = __dadd_rn(v, sigma2);     // mixtureGP.jl:102-104
-        } else {
-          v = (row == col) ? 1.0 : 0.0;                 // identity padding
-        }
+        for (int d = 0; d < D; ++d) xc[d] = xs[d * xstride + col];
+        v = eval_kernel<D>(kp, xr, xc);               // evalkernel(X[i], X[j]), i >= j  (RKHS.jl:21-25)
+        if (row == col) v = __dadd_rn(v, sigma2);     // mixtureGP.jl:102-104
+      } else {
+        v = (row == col) ? 1.0 : 0.0;                 // identity padding
       }
-      kv[e] = v;
     }
-    Lp[c * 32] = make_double2(kv[0], kv[1]);
+    return v;
+  };
+  // Squared exponential, tiles strictly below the diagonal, real rows: no case distinctions, exp(-a |x - z|^2) with the
+  // same table-driven exp as the pair kernel's cross-covariance (<= 2 ulp from the sqrt / re-square / libm-exp form of
+  // kernel.jl:350-357), four column tiles = eight independent evaluations per thread in flight.
+  int c = 0;
+  if (kp.kind == PMK_KERNEL_SQEXP && 8 * t + 7 < n) {
+    for (; c + 4 <= t; c += 4) {
+      double arg[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int col = 8 * (c + (k >> 1)) + 2 * l + (k & 1);
+        double s2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const double dd = xr[d] - xs[d * xstride + col];
+          s2 = fma(dd, dd, s2);
+        }
+        arg[k] = -kp.p * s2;
+      }
+#pragma unroll
+      for (int k = 0; k < 8; k += 2)
+        Lp[(c + (k >> 1)) * 32] = make_double2(exp_neg_tab(arg[k], s_exp), exp_neg_tab(arg[k + 1], s_exp));
+    }
   }
+  for (; c <= t; ++c) Lp[c * 32] = make_double2(entry(8 * c + 2 * l), entry(8 * c + 2 * l + 1));
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -124,7 +124,7 @@ def test_exp_neg_arithmetic():
 
 
 def test_exp_neg_tab_arithmetic():
-    """The row-panel pair kernel's inline exp (pmk_query_rowp.cuh exp_neg_tab: 64-entry table of 2^(j/64), the integer
+    """The row-panel pair kernel's inline exp (pmk_common.cuh exp_neg_tab: 64-entry table of 2^(j/64), the integer
     64k + j read from the low word of t*64/ln2 + 1.5*2^52, degree-5 polynomial) restated in numpy: <= 1.5 ulp from the
     correctly rounded value on the argument range the squared-exponential cross-covariance produces."""
     from decimal import Decimal, getcontext
@@ -133,7 +133,7 @@ def test_exp_neg_tab_arithmetic():
     tab = np.array([float((ln2 * Decimal(j) / 64).exp()) for j in range(64)])
     # the table compiled into the library is this one, bit for bit
     import re, os
-    src = open(os.path.join(os.path.dirname(__file__), "..", "patchmixturekriging_b200", "csrc", "pmk_query_rowp.cuh")).read()
+    src = open(os.path.join(os.path.dirname(__file__), "..", "patchmixturekriging_b200", "csrc", "pmk_common.cuh")).read()
     lits = re.findall(r"0x1\.[0-9a-f]{13}p\+0", src[src.index("c_exp2_64[64]"):src.index("};", src.index("c_exp2_64[64]"))])
     assert len(lits) == 64 and all(float.fromhex(a) == b for a, b in zip(lits, tab))
     C, HI, LO = float.fromhex("0x1.71547652b82fep+6"), float.fromhex("0x1.62e42fee00000p-7"), float.fromhex("0x1.a39ef35793c76p-39")
