@@ -205,6 +205,12 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
 //      row-tile groups off a shared counter, compute C = K[t,J] - L[t,0:J] L[J,0:J]^T on DMMA and park the raw
 //      C tiles in their L slots
 //   C. all warps: L[t,J] = C inv(L_JJ)^T on DMMA, final A-fragment-major tiles.
+// Lookahead of the diagonal block (measured on C3: k_chol 11.68 -> 11.41 ms; with the diagonal block's update removed
+// altogether -- wrong results, timing only -- 10.13 ms: the kernel is bound by the left-looking re-reads of the finished
+// columns, 34 GB per C3 fit, not by the length of the per-panel critical path).
+#ifndef PMK_CHOL_LOOKAHEAD
+#define PMK_CHOL_LOOKAHEAD 1
+#endif
 #ifndef PMK_CHOL_MINB
 #define PMK_CHOL_MINB 3      // resident leaves per SM the register allocation targets (4 forces 64 registers: measured below)
 #endif
@@ -251,7 +257,18 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
         acc[0][b][0] = -kt.x;
         acc[0][b][1] = -kt.y;
       }
-      chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+      // Only the newest panel's four column tiles are left to subtract: the contributions of panels 0 .. J-2 were folded
+      // into the parked tiles during panel J-1's phase B (lookahead below), off the critical path.
+      if (!PMK_CHOL_LOOKAHEAD) {
+        chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+      } else if (J > 0) {
+        int bo2[4], ao2[R];
+#pragma unroll
+        for (int b = 0; b < 4; ++b) bo2[b] = bo[b] + (t0 - 4) * 32;
+#pragma unroll
+        for (int r = 0; r < R; ++r) ao2[r] = ao[r] + (t0 - 4) * 32;
+        chol_kloop<R, 1>(acc, Lp, bo2, ao2, 4, ring_u32, ring);
+      }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
         Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 0] = -acc[0][b][0];
@@ -280,6 +297,32 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
         }
         PMK_CYC({ long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; })
       }
+    }
+    // ---- lookahead: the NEXT panel's diagonal block minus the contributions of the finished panels 0 .. J-1, by two of
+    // the warps that have no part in phase A; parked in the block's own tile slots (C-fragment-major, like K)
+    if (PMK_CHOL_LOOKAHEAD && J > 0 && J + 1 < nblk && (warp == 4 || warp == 5)) {
+      static_assert(R == 2, "the lookahead deals the next diagonal block as two pairs of row tiles");
+      const int tb = t0 + 4 + 2 * (warp - 4);
+      int bo2[4], ao[R];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bo2[b] = (int)tri(t0 + 4 + b) * 32 + lane;
+      double acc[R][4][2];
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        ao[r] = (int)tri(tb + r) * 32 + lane;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) {
+          const double2 kt = (t0 + 4 + b <= tb + r) ? Lp[ao[r] + (t0 + 4 + b) * 32] : make_double2(0.0, 0.0);
+          acc[r][b][0] = -kt.x;
+          acc[r][b][1] = -kt.y;
+        }
+      }
+      chol_kloop<R, R>(acc, Lp, bo2, ao, 4 * J, ring_u32, ring);
+#pragma unroll
+      for (int r = 0; r < R; ++r)
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          if (t0 + 4 + b <= tb + r) Lp[ao[r] + (t0 + 4 + b) * 32] = make_double2(-acc[r][b][0], -acc[r][b][1]);
     }
     // ---- B: off-diagonal row tiles, dynamically dealt; raw C parked in the tile slots -------------
     for (;;) {
