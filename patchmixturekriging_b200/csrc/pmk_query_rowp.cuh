@@ -72,8 +72,8 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
   extern __shared__ __align__(128) unsigned char pmk_dyn_smem[];
   const int ucap = (npmax / 8 + R - 1) / R;                                          // units of the largest leaf
   unsigned char* Kf = pmk_dyn_smem + RING_BYTES;                                    // [column tile][nt][lane] double2
-  double* vpart = reinterpret_cast<double*>(Kf + (size_t)npmax * MQ * 8);           // [2][ucap][MQ]
-  double* s_X = vpart + (size_t)2 * ucap * MQ;                                      // [D+1][npmax]
+  double* vpart = reinterpret_cast<double*>(Kf + (size_t)npmax * MQ * 8);           // [ucap][MQ]
+  double* s_X = vpart + (size_t)ucap * MQ;                                          // [D+1][npmax]
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int64_t n_tiles = w.tile_off[w.n_class_leaves];
@@ -157,7 +157,7 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
       q_mbar_wait(q_smem_u32(&tile_done[vb]), (uint32_t)((kf >> 1) & 1));
       if (lane < MQ) {
         const int n_units = s_desc[sb].n_units;
-        const double* vp = vpart + (size_t)vb * ucap * MQ + lane;
+        const double* vp = vpart + lane;
         double vs = 0.0, u = 0.0;
         for (int m = 0; m < n_units; ++m) vs += vp[m * MQ];        // unit order: independent of which warp took which unit
 #pragma unroll
@@ -200,7 +200,7 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
     q_mbar_wait(q_smem_u32(&stage_full[sb]), (uint32_t)((kt / kRSB) & 1));
     const int p = s_desc[sb].p, n = s_desc[sb].n, ntl = s_desc[sb].ntl, n_units = s_desc[sb].n_units;
     const char* Pp = reinterpret_cast<const char*>(lt.P + lt.loff[p]);
-    double* vp = vpart + (size_t)vb * ucap * MQ;
+    double* vp = vpart;
 
     // chunk ch of unit m: column tiles [ch CW, ch CW + CW) of the unit's R row tiles (row tile t has columns 0..t)
     auto unit_chunks = [&](int m) {
@@ -277,7 +277,7 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
 #pragma unroll
     for (int s = 0; s < DEPTH; ++s) issue_next(s);
 
-    if (kt >= 2) q_mbar_wait(q_smem_u32(&fin_done[vb]), (uint32_t)(((kt >> 1) - 1) & 1));   // vpart/ured[vb] are free again
+    if (kt >= 2) q_mbar_wait(q_smem_u32(&fin_done[vb]), (uint32_t)(((kt >> 1) - 1) & 1));   // ured[vb] is free again
     if (STAGE_X) q_mbar_wait(q_smem_u32(&x_full), (uint32_t)(kt & 1));
     PMK_CYC(const long long c_e0 = clock64();)
 
@@ -344,6 +344,8 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
     }
     PMK_CYC(const long long c_e1 = clock64();)
     rowp_bar();                       // K is complete
+    // the unit partials are single-buffered: the previous tile must have been finalised (long ago: a whole phase E)
+    if (kt >= 1) q_mbar_wait(q_smem_u32(&fin_done[vb ^ 1]), (uint32_t)(((kt - 1) >> 1) & 1));
     PMK_CYC(const long long c_m0 = clock64();)
 
     // ---- phase M: this warp's units of S = P K, each squared and summed per query ----------------------------------
@@ -502,7 +504,7 @@ static bool launch_rowp_one(const LeafTable& lt, const PairWork& w, const QueryP
                             double* pu, double* pv, cudaStream_t s) {
   constexpr size_t ring = (size_t)kRW * DEPTH * R * CW * 512;
   const size_t kbytes = (size_t)npmax * 8 * NQT * 8;
-  const size_t vbytes = (size_t)2 * ((npmax / 8 + R - 1) / R) * 8 * NQT * 8;
+  const size_t vbytes = (size_t)((npmax / 8 + R - 1) / R) * 8 * NQT * 8;
   const size_t xbytes = (size_t)(D + 1) * npmax * 8;
   static int n_sm = 0;              // per process; all devices are B200
   static size_t kMaxDyn = 0;        // 227 KB per CTA minus the kernel's static part
@@ -534,6 +536,9 @@ static bool launch_rowp_one(const LeafTable& lt, const PairWork& w, const QueryP
 #ifndef PMK_ROWP_DEPTH
 #define PMK_ROWP_DEPTH 1
 #endif
+#ifndef PMK_ROWP_CW3          // chunk width of the classes with MQ = 8 (n_pad > 1024)
+#define PMK_ROWP_CW3 3
+#endif
 
 // npmax: largest n_pad among the class's leaves (sizes the K buffer); same size classes / MQ as the other pair kernels.
 // Measured on c3_mini (16 warps): chunks of 2 column tiles x 2 slots 10.71 ms, 3 x 1 10.43, 4 x 1 10.47, 1 x 4 11.51;
@@ -549,8 +554,14 @@ bool launch_rowp_d(int cls, const LeafTable& lt, const PairWork& w, const QueryP
   if (cls == 1)
     return launch_rowp_one<D, 3, 2, PMK_ROWP_CW, PMK_ROWP_DEPTH>(lt, w, q, kp, flags, npmax, pu, pv, s) ||
            launch_rowp_one<D, 3, 2, 2, 1>(lt, w, q, kp, flags, npmax, pu, pv, s);
-  if (cls == 2) return launch_rowp_one<D, 2, 4, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
-  return launch_rowp_one<D, 1, 4, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
+  // large classes, 4 row tiles per unit.  C4 (2 M queries, class <= 1024 / class <= 1536, ms): 1-tile chunks x 2 slots 64.9 / 150.1,
+  // 2 x 1 57.2 / 119.3, 1 x 1 75.9 / 188.4, 3 x 1 (MQ = 8 classes only: K leaves the room) - / 102.5
+  if (cls == 2)
+    return launch_rowp_one<D, 2, 4, 2, 1>(lt, w, q, kp, flags, npmax, pu, pv, s) ||
+           launch_rowp_one<D, 2, 4, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
+  return launch_rowp_one<D, 1, 4, PMK_ROWP_CW3, 1>(lt, w, q, kp, flags, npmax, pu, pv, s) ||
+         launch_rowp_one<D, 1, 4, 2, 1>(lt, w, q, kp, flags, npmax, pu, pv, s) ||
+         launch_rowp_one<D, 1, 4, 1, 2>(lt, w, q, kp, flags, npmax, pu, pv, s);
 }
 
 }  // namespace pmk
