@@ -247,6 +247,8 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
   __shared__ double s_c[kCandCap];
   __shared__ double a_u[D][32];
   __shared__ double a_c[32];
+  __shared__ double a_n[32];                 // |u| of home's ancestors
+  __shared__ double s_n[kCandCap];           // |u| of the candidates
   const int leaf = blockIdx.x;
   const int64_t qa = leaf_qstart[leaf], qb = leaf_qstart[leaf + 1];
   if (qa == qb) return;
@@ -257,28 +259,45 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
   for (int k = threadIdx.x; k < ns; k += blockDim.x) {
     const int i = cand[ca + k];
     s_c[k] = tr.hc[i];
+    double nn = 0.0;
 #pragma unroll
-    for (int d = 0; d < D; ++d) s_u[d][k] = tr.hv[d * tr.n_hp + i];
+    for (int d = 0; d < D; ++d) {
+      const double ud = tr.hv[d * tr.n_hp + i];
+      s_u[d][k] = ud;
+      nn += ud * ud;
+    }
+    s_n[k] = sqrt(nn);
   }
   if (threadIdx.x == 0) {        // home's ancestors: node_0 = 0, node_{d+1} = node_d + (right ? 2^(Lv-1-d) : 1)
     int node = 0;
     for (int d = 0; d < Lv; ++d) {
       a_c[d] = tr.hc[node];
-      for (int dd = 0; dd < D; ++dd) a_u[dd][d] = tr.hv[dd * tr.n_hp + node];
+      double nn = 0.0;
+      for (int dd = 0; dd < D; ++dd) {
+        a_u[dd][d] = tr.hv[dd * tr.n_hp + node];
+        nn += a_u[dd][d] * a_u[dd][d];
+      }
+      a_n[d] = sqrt(nn);
       const int right = (leaf >> (Lv - 1 - d)) & 1;
       node += right ? (1 << (Lv - 1 - d)) : 1;
     }
   }
   __syncthreads();
-  auto in_home = [&](const double* x) -> bool {
+  // findpartition(x1) == home  XOR  findpartition(x2) == home, both descents in one walk over home's ancestors
+  // (same comparisons as partition.jl:254; a point is in home iff it takes home's branch at every ancestor)
+  auto exactly_one_in_home = [&](const double* x1, const double* x2) -> bool {
+    bool in1 = true, in2 = true;
     for (int d = 0; d < Lv; ++d) {
       double v[D];
 #pragma unroll
       for (int dd = 0; dd < D; ++dd) v[dd] = a_u[dd][d];
-      const int right = !(dot_seq<D>(v, x) < a_c[d]);              // partition.jl:254
-      if (right != ((leaf >> (Lv - 1 - d)) & 1)) return false;
+      const double c = a_c[d];
+      const int hb = (leaf >> (Lv - 1 - d)) & 1;
+      in1 = in1 && ((int)!(dot_seq<D>(v, x1) < c) == hb);
+      in2 = in2 && ((int)!(dot_seq<D>(v, x2) < c) == hb);
+      if (!in1 && !in2) return false;
     }
-    return true;
+    return in1 != in2;
   };
   // Every warp walks its queries 32 at a time with ALL lanes in the loop (lanes past the end are masked): the cheap |t| test
   // over the candidate list runs in lock step, the survivors are buffered per lane, and the expensive exact test (square
@@ -297,22 +316,42 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
       pabs += fabs(p[d]);
     }
     const double thr = radius * (1.0 + 1e-9) + 1e-12 * pabs;
+    // distance from the query to the nearest boundary of its home cell (home's ancestors' planes).  A candidate plane that
+    // is closer than that, by more than delta, projects the query to a point whose two probes both lie strictly inside the
+    // home cell: findpartition gives home for both, the reference's xor test fails, the hyperplane is not kept -- no need
+    // to run the two descents.  (Slack 1e-9 * (1 + |p|_1): six orders above the rounding of the dot products, four below
+    // delta; whatever falls inside the slack takes the exact test.)
+    double mrel = 1e300;
+    for (int d = 0; d < Lv; ++d) {
+      double v[D];
+#pragma unroll
+      for (int dd = 0; dd < D; ++dd) v[dd] = a_u[dd][d];
+      mrel = fmin(mrel, fabs(dot_seq<D>(v, p) - a_c[d]) / a_n[d]);
+    }
+    mrel -= 1e-9 * pabs;
     unsigned short surv[64];
     int nsurv = 0, kept = 0;
     unsigned short kl[kKeptMax];
     auto process = [&](int k) {
-      double u[D], c;
+      double u[D], c, un;
       if (k < ns) {
         c = s_c[k];
+        un = s_n[k];
 #pragma unroll
         for (int d = 0; d < D; ++d) u[d] = s_u[d][k];
       } else {
         const int i = cand[ca + k];
         c = tr.hc[i];
+        un = 0.0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) u[d] = tr.hv[d * tr.n_hp + i];
+        for (int d = 0; d < D; ++d) {
+          u[d] = tr.hv[d * tr.n_hp + i];
+          un += u[d] * u[d];
+        }
+        un = sqrt(un);
       }
       const double t = __dadd_rn(-dot_seq<D>(u, p), c);            // mixtureGP.jl:361
+      if (un * (fabs(t) + fabs(delta)) * (1.0 + 1e-9) < mrel) return;   // both probes inside the home cell (see mrel)
       double s = 0.0;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -328,7 +367,7 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
         z1[d] = __dadd_rn(p[d], __dmul_rn(tp, u[d]));              // mixtureGP.jl:370-371
         z2[d] = __dadd_rn(p[d], __dmul_rn(tm, u[d]));
       }
-      if (in_home(z1) != in_home(z2)) {                            // mixtureGP.jl:387 xor
+      if (exactly_one_in_home(z1, z2)) {                           // mixtureGP.jl:387 xor
         if (kept < kKeptMax) kl[kept] = (unsigned short)k;
         ++kept;
       }
