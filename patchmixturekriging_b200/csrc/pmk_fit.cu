@@ -600,8 +600,11 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
   }
 }
 
+#ifndef PMK_CHOL_NW
+#define PMK_CHOL_NW 8
+#endif
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s) {
-  constexpr int NW = 8, R = 2;
+  constexpr int NW = PMK_CHOL_NW, R = 2;
   if (n_order <= 0) return;
   size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings (32 KB)
   // tuning knob: PMK_CHOL_CTAS_PER_SM=1|2 pads the dynamic shared memory so that fewer leaves are resident per SM

@@ -359,6 +359,32 @@ def test_single_gp_variance_query(built_lib):
     assert np.all(np.abs(vv) < 5 * s2)
 
 
+@pytest.mark.parametrize("solver", [_lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION])
+@pytest.mark.parametrize("D,n", [(2, 700), (3, 1000), (1, 1100), (2, 1500), (3, 1700), (2, 2048)])
+def test_large_leaf_size_classes(built_lib, D, n, solver):
+    """One leaf of every large size class (n_pad <= 768, 1024, 1536, 2048; D = 1, 2, 3) through the fit, the inverse
+    builder and the pair kernels (their chunk shapes and shared-memory fallbacks differ per class): posterior mean and
+    latent variance against a dense numpy solve."""
+    from patchmixturekriging_b200 import synth, mixturegp
+    lo, hi = [-1.0] * D, [1.0] * D
+    X = synth.uniform_points(41 + n, n, lo, hi)
+    y = np.sin(3 * X[:, 0]) + (X[:, -1] if D > 1 else 0.0)
+    spacing = (2.0 ** D / n) ** (1.0 / D)
+    ok, pk = helpers.kernels(("SQEXP", 1.0 / (3.0 * spacing) ** 2))
+    s2 = 1e-3
+    A = O.constructkernelmatrix(X, ok) + s2 * np.eye(n)
+    Xq = synth.uniform_points(43, 200, lo, hi)
+    kq = O.kernel_cross(Xq, X, ok)
+    mean_ref = kq @ np.linalg.solve(A, y)
+    var_ref = np.maximum(1.0 - np.einsum("ij,ij->i", kq, np.linalg.solve(A, kq.T).T), 1e-12)
+    eta = P.MixtureGPType([X], (np.zeros((0, D)), np.zeros(0)))
+    P.fitmixtureGP_(eta, [y], pk, s2)
+    mixturegp.set_query_solver(eta, solver)
+    Yq, Vq, _ = P.querymixtureGP(Xq, eta, None, 1, 0.1, 1e-5, pk, s2, P.Spline34KernelType(1.0))
+    assert_close(f"D={D} n={n} mean", Yq, mean_ref, 1e-8)
+    assert_close(f"D={D} n={n} var", Vq, var_ref, 1e-8)
+
+
 @pytest.mark.parametrize("name,eps", [("mixgp_file", 1.5), ("c3_mini", 0.31), ("c4_mini", 0.35), ("c3_mini", 0.0)])
 def test_organizetrainingsets_device_bit_exact(built_lib, name, eps):
     """ε-overlap training sets on the GPU, bit-exact X_set_inds / regions_list_set."""
