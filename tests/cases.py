@@ -48,6 +48,18 @@ def c4_mini(N=12000, levels=5, eps=0.35, nq=8000):
                 kernel=("SQEXP", eps_sq), wkernel=("SPLINE34", 1.0 / eps), Xq=Xq)
 
 
+def c5_mini(G=96, levels=4, eps=0.04):
+    """Scaled-down C5 (dev/image_upscale.jl style): training points = a regular G x G pixel grid scaled to [0,1]^2, values =
+    a smooth synthetic image, Spline34 kernel with a support radius of 5 pixels, sigma2 = 1e-5, ~1400-1800-point leaves
+    (the two largest size classes), query = the 2x upsampled grid."""
+    g = np.linspace(0.0, 1.0, G)
+    X = np.array([[a, b] for b in g for a in g])
+    y = np.sin(7.0 * X[:, 0]) * np.cos(5.0 * X[:, 1]) + 0.5 * np.exp(-8.0 * ((X[:, 0] - 0.6) ** 2 + (X[:, 1] - 0.3) ** 2))
+    a = 0.2 * (G - 1)
+    return dict(name="c5_mini", X=X, y=y, levels=levels, eps=eps, radius=eps, delta=1e-5, sigma2=1e-5,
+                kernel=("SPLINE34", a), wkernel=("SPLINE34", 1.0 / eps), Xq=grid2d(2 * G - 1, 2 * G - 1, (0.0, 0.0), (1.0, 1.0)))
+
+
 def ibb1d(N=15, Nq=100, kind="BB10"):
     """examples/IBB1D.jl: X = LinRange(1e-5, 1-1e-5, N), y = sinc(4x) x^3, sigma2 = 1e-5, query LinRange(0,1,Nq)."""
     x = np.linspace(1e-5, 1.0 - 1e-5, N)

@@ -85,7 +85,8 @@ def _fit_product(case, m):
     return root, eta, pk
 
 
-CASES = {"mixgp_file": cases.mixgp_file, "c3_mini": cases.c3_mini, "c4_mini": cases.c4_mini, "mixgp_driver": cases.mixgp_driver}
+CASES = {"mixgp_file": cases.mixgp_file, "c3_mini": cases.c3_mini, "c4_mini": cases.c4_mini, "mixgp_driver": cases.mixgp_driver,
+         "c5_mini": cases.c5_mini}
 _cache = {}
 
 
