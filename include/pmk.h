@@ -195,11 +195,13 @@ int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d
 /* PMK_OPT_QUERY_SOLVER: how queryinner!'s v = L \ kq (mixtureGP.jl:311) is carried out for a tile of queries:
  *   0 (default) = s = P kq with P = inv(L) formed once per fit by blocked substitution, as a ROW-PANEL product: the
  *                 cross-covariance tile is evaluated once into shared memory, every warp streams its own rows of P and
- *                 keeps only ||s||^2 -- no dependency between warps, so the tensor pipe never waits
- *                 (measured vs dtrsv: <= 3e-11 at sigma2 = 1e-3);
+ *                 keeps only ||s||^2 -- no dependency between warps, so the tensor pipe never waits.  Every kernel
+ *                 function (the squared exponential with an inlined table-driven exp).  Measured vs dtrsv: <= 3e-11 at
+ *                 sigma2 = 1e-3, inside 2e-8 at sigma2 = 1e-5 (Spline34, squared exponential; cond up to 4e6);
  *   1           = blocked forward substitution with 32x32 diagonal-block inverses (closest to dtrsv; use it for
  *                 very ill-conditioned leaves, cond(K) >~ 1e6);
- *   2           = s = P kq as a column sweep with the tile of s in registers (round-1 mid kernel, kept for comparison). */
+ *   2           = s = P kq as a column sweep with the tile of s in registers (round-1 mid kernel, kept for comparison;
+ *                 squared exponential only, other kernel functions fall back to 1). */
 /* PMK_OPT_INVERSE_BUILDER: how P = inv(L) is formed (once per fit) for the explicit-inverse solvers:
  *   0 (default) = recursive doubling on the packed tiles, P21 = -inv(B) C inv(A), every flop a DMMA GEMM (pmk_invert.cu);
  *   1           = the substitution pair kernel run on identity right-hand sides (round-1 builder). */

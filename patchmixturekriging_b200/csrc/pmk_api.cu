@@ -413,6 +413,10 @@ int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_lea
   return PMK_OK;
 }
 
+// Does the variance query stream P = inv(L)?  Solver 0 (row-panel kernel) for every kernel function; solver 2 (column sweep,
+// squared exponential inlined) only for that one -- the others take the substitution kernel there.
+static bool uses_inverse(const pmk_handle* h) { return h->solver == 0 || (h->solver == 2 && h->kp.kind == PMK_KERNEL_SQEXP); }
+
 // The pair kernels' operands for the leaves of the fit range: P = inv(L) (explicit-inverse solvers) and/or
 // M_IJ = L_IJ inv(L_JJ) (substitution solver).  P comes from recursive doubling on the packed tiles (pmk_invert.cu; the M
 // buffer doubles as its scratch, so M is rebuilt afterwards if it is wanted too) or, with PMK_OPT_INVERSE_BUILDER = 1, from the
@@ -471,7 +475,7 @@ int pmk_build_M(pmk_handle* h) {
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->m_ready = false;
   h->p_ready = false;
-  return build_operands(h, true, h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP);
+  return build_operands(h, true, uses_inverse(h));
 }
 
 int pmk_mark_fitted(pmk_handle* h, int exchanged) {
@@ -1045,7 +1049,7 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
   const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
   h->last_flags = flags;
   if (!(flags & 1)) {     // variance wanted: the pair kernel streams M (substitution) or P = inv(L), built once per fit
-    const bool use_P = h->solver != 1 && h->kp.kind == PMK_KERNEL_SQEXP;
+    const bool use_P = uses_inverse(h);
     if (int rc = build_operands(h, !use_P, use_P)) return rc;
   }
   if (h->lt.M == nullptr) h->lt.M = h->lt.L;   // mean-only queries never touch the factor
@@ -1070,7 +1074,7 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     const int64_t ub = q.n_pairs / mq + h->n_class[c];
     {
       Timer tc(h, PMK_T_Q_PAIRS_CLASS0 + c);
-      if (!(mean_only & 1) && h->solver == 0 && h->kp.kind == PMK_KERNEL_SQEXP) {
+      if (!(mean_only & 1) && h->solver == 0) {
         if (!launch_query_rowp(h->D, c, h->lt, w, q, h->kp, mean_only, h->class_max_npad[c], d_pair_u, d_pair_v, h->stream))
           return fail(h, PMK_ERR_UNSUPPORTED, "row-panel pair kernel: no shared-memory configuration for size class %d", c);
       } else if (!(mean_only & 1) && h->solver == 2 && h->kp.kind == PMK_KERNEL_SQEXP)

@@ -177,7 +177,7 @@ def test_query_structure_bit_exact(built_lib, name):
 @pytest.mark.parametrize("name", list(CASES))
 def test_query_mean_variance(built_lib, name, solver):
     """Every query solver against the oracle's dtrsv path: s = inv(L) kq with the explicit inverse (default row-panel
-    kernel and the column-sweep kernel; taken for the squared-exponential kernel) and blocked forward substitution."""
+    kernel, every kernel function; and the column-sweep kernel, squared exponential only) and blocked forward substitution."""
     from patchmixturekriging_b200 import mixturegp
     case, m, root, eta, pk = _setup(name)
     wth, wk = helpers.kernels(case["wkernel"])
