@@ -22,6 +22,7 @@
 // descriptor; the leaf's inputs and weights by TMA) and finalises finished tiles (per-unit partials summed in unit order,
 // whichever warp produced them -> bit-reproducible; k(x*,x*) - ||s||^2, clamp, scatter to the pair arrays).
 #pragma once
+#include <type_traits>
 #include "pmk_query_trmm.cuh"
 
 namespace pmk {
@@ -294,13 +295,15 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
       const double* __restrict__ al = lt.alpha + lt.xoff[p];
       const bool sqexp = kp.kind == PMK_KERNEL_SQEXP;
       double usum = 0.0;
-      for (int c = e_c0; c < ntl; c += 2 * ESTRIDE) {
+      // one step = column tiles c and c + ESTRIDE.  FULL: both hold real rows only -- no row clamps, no selects.
+      auto eval_step = [&](int c, auto full_tag) {
+        constexpr bool FULL = decltype(full_tag)::value;
         double xr[4][D], av[4], kv[4];
         bool ok[4];
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int row = 8 * (c + (e >> 1) * ESTRIDE) + 4 * (e & 1) + l;
-          ok[e] = row < n;
+          ok[e] = FULL || row < n;
           const int rc = ok[e] ? row : n - 1;
 #pragma unroll
           for (int d = 0; d < D; ++d) xr[e][d] = STAGE_X ? s_X[d * npmax + rc] : xs[d * lt.xstride + rc];
@@ -328,12 +331,16 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
         }
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
-          kv[e] = ok[e] ? kv[e] : 0.0;
+          if (!FULL) kv[e] = ok[e] ? kv[e] : 0.0;
           usum = fma(kv[e], av[e], usum);                                          // dot(kq, c)    mixtureGP.jl:308
         }
         reinterpret_cast<double2*>(Kf)[(c * NQT + e_nt) * 32 + lane] = make_double2(kv[0], kv[1]);
-        if (c + ESTRIDE < ntl) reinterpret_cast<double2*>(Kf)[((c + ESTRIDE) * NQT + e_nt) * 32 + lane] = make_double2(kv[2], kv[3]);
-      }
+        if (FULL || c + ESTRIDE < ntl) reinterpret_cast<double2*>(Kf)[((c + ESTRIDE) * NQT + e_nt) * 32 + lane] = make_double2(kv[2], kv[3]);
+      };
+      const int nfull = n >> 3;           // column tiles without padding rows
+      int c = e_c0;
+      for (; c + ESTRIDE < nfull; c += 2 * ESTRIDE) eval_step(c, std::true_type{});
+      for (; c < ntl; c += 2 * ESTRIDE) eval_step(c, std::false_type{});
       usum += __shfl_xor_sync(kFullQ, usum, 1);
       usum += __shfl_xor_sync(kFullQ, usum, 2);
       if (l == 0) ured[vb][warp * 8 + g] = usum;
