@@ -214,6 +214,10 @@ int pmk_get_timings(pmk_handle* h, double* ms /* PMK_T_COUNT entries */);
  * panel solve, barrier wait, #CTAs, reserved.  flags: bit0 = zero them after reading; bit1 = read the pair kernel's
  * counters instead (total, cross-covariance init, publish+barrier, diagonal solve+barrier, update, #CTAs). */
 int pmk_debug_counters(pmk_handle* h, uint64_t* out8, int flags);
+/* The recursion plan pmk_invert.cu uses to form P = inv(L) for a leaf of n_blocks 32-row blocks (host only, no GPU needed):
+ * nodes4[4k .. 4k+3] = {lo, mid, hi, height} of node k, in launch order (ascending height).  A node inverts the block range
+ * [lo, hi) from its children [lo, mid) and [mid, hi): P[mid:hi, lo:mid] = -P[mid:hi, mid:hi] L[mid:hi, lo:mid] P[lo:mid, lo:mid]. */
+int pmk_inverse_plan(int n_blocks, int max_nodes, int16_t* nodes4, int* n_nodes);
 /* number of kernel launches issued by this handle since creation */
 int64_t pmk_launch_count(const pmk_handle* h);
 /* stream the handle launches on, as a cudaStream_t cast to void* (for event timing by the caller) */

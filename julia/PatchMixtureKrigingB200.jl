@@ -130,6 +130,12 @@ function setsolver!(η::MixtureGPType, solver::Integer)
     return η
 end
 
+"""How `P = inv(L)` is formed for the explicit-inverse solvers: 0 = recursive doubling on the packed tiles (default),
+1 = the substitution kernel on identity right-hand sides.  `PMK_OPT_INVERSE_BUILDER` of include/pmk.h."""
+function setinversebuilder!(η::MixtureGPType, builder::Integer)
+    check(η.h, ccall((:pmk_set_option, libpmk), Cint, (Ptr{Cvoid}, Cint, Int64), η.h.ptr, 3, builder))
+end
+
 # flatten the reference's BinaryNode tree for the device: hyperplanes in fetchhyperplanes order (mixtureGP.jl:322-334)
 function settree!(η::MixtureGPType, levels::Integer)
     D = length(η.X_parts[1][1]); hps = η.hps

@@ -22,7 +22,7 @@ T_FIT_GRAM = 7
 
 # every symbol include/pmk.h declares
 SYMBOLS = [
-    "pmk_create", "pmk_destroy", "pmk_last_error", "pmk_version", "pmk_gram", "pmk_cross_gram", "pmk_fit", "pmk_fit_dev",
+    "pmk_create", "pmk_destroy", "pmk_last_error", "pmk_version", "pmk_inverse_plan", "pmk_gram", "pmk_cross_gram", "pmk_fit", "pmk_fit_dev",
     "pmk_leaf_size", "pmk_get_alpha", "pmk_set_alpha", "pmk_get_L", "pmk_get_Linv", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_organize_training_sets", "pmk_organize_fetch", "pmk_query",
     "pmk_query_dev", "pmk_last_query_pairs", "pmk_last_query_debug", "pmk_set_fit_range", "pmk_model_buffer", "pmk_build_M", "pmk_mark_fitted", "pmk_query_plan_dev",
     "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_option", "pmk_get_timings", "pmk_debug_counters", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
     L.pmk_last_error.argtypes = [vp]
     L.pmk_last_error.restype = C.c_char_p
     L.pmk_version.argtypes = []
+    L.pmk_inverse_plan.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     L.pmk_gram.argtypes = [vp, i32, i64, dp, i32, dp, i32, dbl, dp]
     L.pmk_cross_gram.argtypes = [vp, i32, i64, dp, i64, dp, i32, dp, i32, dp]
     L.pmk_fit.argtypes = [vp, i32, i64, dp, dp, dp, i32, dp, i32, dbl, C.POINTER(i64), C.POINTER(i32)]

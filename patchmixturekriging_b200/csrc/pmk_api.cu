@@ -212,6 +212,27 @@ extern "C" {
 
 int pmk_version(void) { return 100; }
 
+// host only (no CUDA call): the recursion plan of the explicit inverse for a leaf of n_blocks 32-row blocks
+int pmk_inverse_plan(int n_blocks, int max_nodes, int16_t* nodes4, int* n_nodes) {
+  if (n_blocks < 1 || n_blocks > kInvMaxBlocks || !n_nodes) return PMK_ERR_ARG;
+  const InvPlanHost pl = make_inverse_plan(std::vector<int>{n_blocks});
+  int k = 0;
+  for (int h = 1; h <= pl.max_height; ++h) {
+    const int idx = n_blocks * (kInvMaxHeight + 1) + h;
+    for (int i = 0; i < pl.cnt[idx]; ++i, ++k) {
+      if (nodes4 && k < max_nodes) {
+        const InvNode& nd = pl.nodes[pl.off[idx] + i];
+        nodes4[4 * k + 0] = nd.lo;
+        nodes4[4 * k + 1] = nd.mid;
+        nodes4[4 * k + 2] = nd.hi;
+        nodes4[4 * k + 3] = (int16_t)h;
+      }
+    }
+  }
+  *n_nodes = k;
+  return PMK_OK;
+}
+
 const char* pmk_last_error(const pmk_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
 
 int pmk_create(pmk_handle** out, int device) {

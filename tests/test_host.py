@@ -154,3 +154,28 @@ def test_exp_neg_tab_arithmetic():
     ref = np.exp(t.astype(np.longdouble))
     err = np.abs(got.astype(np.longdouble) - ref) / np.spacing(np.exp(t)).astype(np.longdouble)
     assert err.max() <= 1.5
+
+
+def test_inverse_plan_covers_every_block_once(built_lib):
+    """The recursive-doubling plan of P = inv(L) (pmk_invert.cu, host side): for every leaf shape the nodes' off-diagonal
+    rectangles tile the strictly-lower block triangle exactly once, and a node's children are finished at a lower height."""
+    import ctypes as C
+    L = _lib.lib()
+    for nb in list(range(1, 25)) + [31, 32, 33, 47, 48, 63, 64]:
+        n = C.c_int(0)
+        assert L.pmk_inverse_plan(nb, 0, None, C.byref(n)) == 0
+        nodes = np.zeros((max(n.value, 1), 4), dtype=np.int16)
+        assert L.pmk_inverse_plan(nb, n.value, nodes.ctypes.data_as(C.c_void_p), C.byref(n)) == 0
+        nodes = nodes[:n.value]
+        assert n.value == nb - 1                                    # a binary tree over nb blocks
+        cover = np.zeros((nb, nb), dtype=int)
+        done_at = {(b, b + 1): 0 for b in range(nb)}                # single blocks: the diagonal inverses exist (height 0)
+        assert np.all(np.diff(nodes[:, 3]) >= 0)                    # launch order = ascending height
+        for lo, mid, hi, h in nodes:
+            assert 0 <= lo < mid < hi <= nb
+            cover[mid:hi, lo:mid] += 1
+            assert done_at[(lo, mid)] < h and done_at[(mid, hi)] < h
+            done_at[(lo, hi)] = h
+        assert np.array_equal(cover, np.tril(np.ones((nb, nb), dtype=int), -1))
+        assert (0, nb) in done_at
+    assert L.pmk_inverse_plan(0, 0, None, C.byref(n)) != 0 and L.pmk_inverse_plan(65, 0, None, C.byref(n)) != 0
