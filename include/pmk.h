@@ -208,6 +208,53 @@ int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d
 enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2, PMK_OPT_INVERSE_BUILDER = 3 };
 int pmk_set_option(pmk_handle* h, int option, int64_t value);
 
+/* ---- setuppartition on the device ------------------------------------------ */
+/* setuppartition(X, levels) (reference src/patchwork/partition.jl:106-129; gethyperplane :86-100, splitpoints :64-83,
+ * createchildren :166-217) with every O(N) step on the GPU, one tree level per call pair:
+ *
+ *   pmk_partition_begin(h, D, N, X, levels)            X: N x D point-major host array (array2matrix(X), utilities.jl:25-36)
+ *   for depth = 0 .. levels-2:
+ *     pmk_partition_level_z(h, depth, z)                z[j*D..] = X_j[1] - mean(X_j) for the 2^depth nodes of this depth,
+ *                                                       left to right (partition.jl:89-90; Base's pairwise summation order)
+ *     v_j = V[:,1] of svd(z_j')                         ON THE HOST, by the caller's own LinearAlgebra (partition.jl:93-94):
+ *                                                       the bits of v are LAPACK dgesdd's and no restatement can promise
+ *                                                       them, so the reference's own call stays where it is
+ *     pmk_partition_level_split(h, depth, v, c)         f = dot(v_j, x), c_j = median(f) (returned), left iff f < c_j; every
+ *                                                       node's points are split in place, order kept (partition.jl:64-83)
+ *   pmk_partition_fetch(h, leaf_off, inds)              leaves in AbstractTrees.Leaves order (= labelleafnodes' numbering,
+ *                                                       partition.jl:131-159): leaf p owns inds[leaf_off[p] .. leaf_off[p+1]),
+ *                                                       ascending 1-based global ids = X_parts_inds; 2^(levels-1)+1 offsets
+ *
+ * The node at depth d with left-to-right index j has pre-order (fetchhyperplanes) index sum over its path bits b_i
+ * (MSB first) of (b_i ? 2^(levels-2-i) : 1).  Bit-exact contract: z, c, leaf_off, inds equal the oracle's for the same v.
+ * Errors: PMK_ERR_STATE (call order), PMK_ERR_ARG (a child without points: the reference fails in mean() there).
+ * pmk_partition_sum_plan is host-only (no GPU needed): the sequential blocks (start, length, depth in the halving tree)
+ * Base.mapreduce_impl(+, A, 1, n, 1024) sums a range of n elements in -- the order k_part_block_sums / k_part_node_z follow. */
+int pmk_partition_begin(pmk_handle* h, int D, int64_t N, const double* X, int levels);
+int pmk_partition_level_z(pmk_handle* h, int depth, double* z_out);
+int pmk_partition_level_split(pmk_handle* h, int depth, const double* v, double* c_out);
+int pmk_partition_fetch(pmk_handle* h, int64_t* leaf_off_out, int32_t* inds_out);
+int pmk_partition_sum_plan(int64_t n, int64_t max_blocks, int64_t* blk_start, int32_t* blk_len, int32_t* blk_depth, int64_t* n_blocks);
+
+/* ---- checkpoint -------------------------------------------------------------------------- */
+/* The reference keeps a fitted MixtureGPType in memory only (src/RKHS/mixtureGP.jl:38-66; no serialisation anywhere in
+ * src/).  pmk_save_model writes the handle's fitted model -- padded training inputs, y, alpha (c_set), the packed factors L
+ * (L_set) with their diagonal-block inverses, kernel id/parameter, sigma2 and, when set, the flattened tree -- to one flat
+ * binary file in the handle's own HBM layout (little-endian, "PMKB200" magic, version 1).  pmk_load_model lays the same
+ * model out in a handle (any previous model of that handle is replaced, its fit range reset to all leaves) and copies the
+ * buffers back: queries on the loaded handle return bit-identical results to the handle that saved.  The pair-kernel
+ * operand P = inv(L) is not stored; the first variance query rebuilds it, as after pmk_fit.
+ * Errors: PMK_ERR_STATE (save before fit), PMK_ERR_ARG (cannot open / truncated / not a model file),
+ * PMK_ERR_UNSUPPORTED (file version or layout of another library version). */
+/* What a host layer needs to rebuild its view of a loaded model: dimensions and hyper-parameters (any out pointer may be
+ * NULL; *levels = 0 when no tree is set), a leaf's training inputs (n x D point-major = X_parts[leaf], mixtureGP.jl:40),
+ * and the hyperplanes in pmk_set_tree's layout (fetchhyperplanes order, mixtureGP.jl:322-334). */
+int pmk_model_info(pmk_handle* h, int* D, int64_t* n_leaves, int* kernel_id, double* kparam, double* sigma2, int* levels);
+int pmk_get_X(pmk_handle* h, int64_t leaf, double* out);
+int pmk_get_tree(pmk_handle* h, double* hp_v, double* hp_c);
+int pmk_save_model(pmk_handle* h, const char* path);
+int pmk_load_model(pmk_handle* h, const char* path);
+
 /* ---- instrumentation --------------------------------------------------------------------- */
 int pmk_get_timings(pmk_handle* h, double* ms /* PMK_T_COUNT entries */);
 /* cycle counters of the fit kernel, summed over CTAs (warp 0): total, gram-init, update loop, diagonal factor,

@@ -25,7 +25,8 @@ SYMBOLS = [
     "pmk_create", "pmk_destroy", "pmk_last_error", "pmk_version", "pmk_inverse_plan", "pmk_gram", "pmk_cross_gram", "pmk_fit", "pmk_fit_dev",
     "pmk_leaf_size", "pmk_get_alpha", "pmk_set_alpha", "pmk_get_L", "pmk_get_Linv", "pmk_get_K", "pmk_set_tree", "pmk_find_partition", "pmk_organize_training_sets", "pmk_organize_fetch", "pmk_query",
     "pmk_query_dev", "pmk_last_query_pairs", "pmk_last_query_debug", "pmk_set_fit_range", "pmk_model_buffer", "pmk_build_M", "pmk_mark_fitted", "pmk_query_plan_dev",
-    "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_option", "pmk_get_timings", "pmk_debug_counters", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
+    "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_option", "pmk_partition_begin", "pmk_partition_level_z", "pmk_partition_level_split", "pmk_partition_fetch",
+    "pmk_partition_sum_plan", "pmk_save_model", "pmk_load_model", "pmk_model_info", "pmk_get_X", "pmk_get_tree", "pmk_get_timings", "pmk_debug_counters", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
 ]
 
 _lib = None
@@ -91,6 +92,16 @@ def lib() -> C.CDLL:
     L.pmk_query_pairs_dev.argtypes = [vp, i32, dp, dp]
     L.pmk_query_combine_dev.argtypes = [vp, dp, dp, dp, dp]
     L.pmk_set_option.argtypes = [vp, i32, i64]
+    L.pmk_partition_begin.argtypes = [vp, i32, i64, dp, i32]
+    L.pmk_partition_level_z.argtypes = [vp, i32, dp]
+    L.pmk_partition_level_split.argtypes = [vp, i32, dp, dp]
+    L.pmk_partition_fetch.argtypes = [vp, dp, dp]
+    L.pmk_partition_sum_plan.argtypes = [i64, i64, dp, dp, dp, C.POINTER(i64)]
+    L.pmk_save_model.argtypes = [vp, C.c_char_p]
+    L.pmk_load_model.argtypes = [vp, C.c_char_p]
+    L.pmk_model_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i64), C.POINTER(i32), C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i32)]
+    L.pmk_get_X.argtypes = [vp, i64, dp]
+    L.pmk_get_tree.argtypes = [vp, dp, dp]
     L.pmk_get_timings.argtypes = [vp, dp]
     L.pmk_debug_counters.argtypes = [vp, dp, i32]
     L.pmk_launch_count.argtypes = [vp]

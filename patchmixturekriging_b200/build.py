@@ -13,7 +13,7 @@ CSRC = os.path.join(HERE, "csrc")
 VARIANT = os.environ.get("PMK_VARIANT", "")
 LIB = os.path.join(HERE, f"libpmk_b200_{VARIANT}.so" if VARIANT else "libpmk_b200.so")
 BUILD_DIR = os.path.join(HERE, f"build_{VARIANT}" if VARIANT else "build")
-SOURCES = ["pmk_api.cu", "pmk_fit.cu", "pmk_tree.cu", "pmk_query.cu", "pmk_query_d1.cu", "pmk_query_d2.cu", "pmk_query_d3.cu", "pmk_gram.cu", "pmk_invert.cu"]
+SOURCES = ["pmk_api.cu", "pmk_fit.cu", "pmk_tree.cu", "pmk_query.cu", "pmk_query_d1.cu", "pmk_query_d2.cu", "pmk_query_d3.cu", "pmk_gram.cu", "pmk_invert.cu", "pmk_partition.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("PMK_NVCC_EXTRA", "").split()     # e.g. PMK_NVCC_EXTRA=-DPMK_PROFILE_CYCLES for the phase counters
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

@@ -46,6 +46,20 @@ void launch_eps_partitions(int D, bool fill, const TreeDev& tr, int64_t N, const
 void launch_aos_to_soa(int D, const double* dX, int64_t n, int64_t stride, double* xs, cudaStream_t s);
 void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double* xc, int64_t xc_stride, int m, KParams kp,
                  double sigma2, int symmetric, double* dK, cudaStream_t s);
+void partition_sum_plan(int64_t n, int64_t base, std::vector<int64_t>& start, std::vector<int32_t>& len, std::vector<int32_t>& depth);
+void launch_part_iota(int32_t* perm, int64_t N, cudaStream_t s);
+void launch_part_one_based(const int32_t* perm, int64_t N, int32_t* out, cudaStream_t s);
+void launch_part_block_sums(int D, const double* X, const int32_t* perm, const int64_t* blk_start, const int32_t* blk_len, int n_blk,
+                            double* blk_sum, cudaStream_t s);
+void launch_part_node_z(int D, const double* X, const int32_t* perm, const int64_t* seg_off, const int32_t* node_blk_off,
+                        const int32_t* blk_depth, const double* blk_sum, int n_nodes, double* z_out, cudaStream_t s);
+void launch_part_project(int D, const double* X, const int32_t* perm, const int64_t* seg_off, int n_nodes, const double* v, int64_t N,
+                         double* f, int32_t* node_id, cudaStream_t s);
+void launch_part_median(const double* f_sorted, const int64_t* seg_off, int n_nodes, double* c_out, cudaStream_t s);
+void launch_part_flags(const double* f, const int32_t* node_id, const double* c, int64_t N, int32_t* flag, cudaStream_t s);
+void launch_part_scatter(const int32_t* perm, const int32_t* node_id, const int32_t* flag, const int32_t* scan, const int64_t* seg_off,
+                         int64_t N, int32_t* perm_out, cudaStream_t s);
+void launch_part_child_offsets(const int32_t* scan, const int64_t* seg_off, int n_nodes, int64_t N, int64_t* child_off, cudaStream_t s);
 int query_class_of(int npad);
 int query_class_mq(int cls);
 void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
@@ -139,6 +153,13 @@ struct pmk_handle {
   // organizetrainingsets on the device (results of the last call)
   DBuf o_X, o_counts, o_off, o_pl, o_pp, o_sl, o_sp, o_lcount, o_lstart;
   int64_t o_N = 0, o_total = 0, o_leaves = 0;
+  // setuppartition on the device, level by level (pmk_partition.cu): state between the calls
+  DBuf pt_X, pt_perm[2], pt_seg[2], pt_f, pt_f_tmp, pt_f_sorted, pt_node, pt_node_tmp, pt_node_sorted, pt_flag, pt_scan;
+  DBuf pt_blk_start, pt_blk_len, pt_blk_depth, pt_node_blk_off, pt_blk_sum, pt_z, pt_v, pt_c;
+  int pt_D = 0, pt_levels = 0, pt_depth = -1, pt_cur = 0;
+  bool pt_z_done = false;
+  int64_t pt_N = 0;
+  std::vector<int64_t> pt_hseg;   // host copy of the current level's segment offsets (nodes + 1)
   DBuf d_scratch;   // Gram scratch
   QueryPlan plan{};
   bool plan_valid = false;
@@ -284,6 +305,10 @@ void pmk_destroy(pmk_handle* h) {
     h->d_inv_leaves[c].release();
     h->d_inv_tile_off[c].release();
   }
+  DBuf* pbufs[] = {&h->pt_X, &h->pt_perm[0], &h->pt_perm[1], &h->pt_seg[0], &h->pt_seg[1], &h->pt_f, &h->pt_f_tmp, &h->pt_f_sorted,
+                   &h->pt_node, &h->pt_node_tmp, &h->pt_node_sorted, &h->pt_flag, &h->pt_scan, &h->pt_blk_start, &h->pt_blk_len,
+                   &h->pt_blk_depth, &h->pt_node_blk_off, &h->pt_blk_sum, &h->pt_z, &h->pt_v, &h->pt_c};
+  for (DBuf* b : pbufs) b->release();
   h->d_P.release();
   h->d_inv_nodes.release();
   h->d_inv_off.release();
@@ -509,8 +534,11 @@ int pmk_mark_fitted(pmk_handle* h, int exchanged) {
   return PMK_OK;
 }
 
-int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* dX, const double* dy,
-                int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
+// Lays the model out in HBM (padded leaves, packed factor slots, size classes, inversion plan) and, with `compute`, packs the
+// training sets and factorises the leaves of the fit range.  Without `compute` (pmk_load_model) the buffers are left for the
+// caller to fill; dX / dy are not read.
+static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* dX, const double* dy,
+                    int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info, bool compute) {
   if (!h) return PMK_ERR_ARG;
   if (int rc = set_device(h)) return rc;
   h->fitted = false;
@@ -518,7 +546,7 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   if (info) *info = 0;
   if (D < 1 || D > PMK_MAX_DIM) return fail(h, PMK_ERR_UNSUPPORTED, "D=%d unsupported (1..%d)", D, PMK_MAX_DIM);
   if (n_leaves < 1 || n_leaves > (1 << 24)) return fail(h, PMK_ERR_ARG, "n_leaves=%lld out of range", (long long)n_leaves);
-  if (!leaf_off || !dX || !dy) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (!leaf_off || (compute && (!dX || !dy))) return fail(h, PMK_ERR_ARG, "NULL pointer");
   KParams kp;
   if (int rc = parse_kernel(h, kernel_id, kparams, nparams, &kp)) return rc;
   if (leaf_off[0] != 0) return fail(h, PMK_ERR_ARG, "leaf_off[0] must be 0");
@@ -659,6 +687,10 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   lt.P = nullptr;
   lt.Linv = h->d_Linv.as<double>();
   lt.info = h->d_info.as<int>();
+  h->m_ready = false;
+  h->p_ready = false;
+  h->plan_valid = false;
+  if (!compute) return PMK_OK;
 
   {
     Timer t(h, PMK_T_FIT_PACK);
@@ -699,6 +731,11 @@ int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off,
   return PMK_OK;
 }
 
+int pmk_fit_dev(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* dX, const double* dy,
+                int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
+  return fit_impl(h, D, n_leaves, leaf_off, dX, dy, kernel_id, kparams, nparams, sigma2, bad_leaf, info, true);
+}
+
 int pmk_fit(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X, const double* y, int kernel_id,
             const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
   if (!h) return PMK_ERR_ARG;
@@ -713,6 +750,322 @@ int pmk_fit(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_off, con
   CU(h, cudaMemcpyAsync(h->d_yin.p, y, sizeof(double) * total, cudaMemcpyHostToDevice, h->stream));
   return pmk_fit_dev(h, D, n_leaves, leaf_off, h->d_Xin.as<double>(), h->d_yin.as<double>(), kernel_id, kparams, nparams, sigma2,
                      bad_leaf, info);
+}
+
+// ---------------------------------------------------------------------------------------------
+// setuppartition on the device (partition.jl:106-217), one level per call pair; see pmk.h and pmk_partition.cu
+int pmk_partition_sum_plan(int64_t n, int64_t max_blocks, int64_t* blk_start, int32_t* blk_len, int32_t* blk_depth, int64_t* n_blocks) {
+  if (n < 1 || !n_blocks) return PMK_ERR_ARG;
+  std::vector<int64_t> st;
+  std::vector<int32_t> ln, dp;
+  partition_sum_plan(n, 0, st, ln, dp);
+  *n_blocks = (int64_t)st.size();
+  if ((int64_t)st.size() > max_blocks) return PMK_ERR_ARG;
+  for (size_t i = 0; i < st.size(); ++i) {
+    if (blk_start) blk_start[i] = st[i];
+    if (blk_len) blk_len[i] = ln[i];
+    if (blk_depth) blk_depth[i] = dp[i];
+  }
+  return PMK_OK;
+}
+
+int pmk_partition_begin(pmk_handle* h, int D, int64_t N, const double* X, int levels) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  h->pt_depth = -1;
+  if (D < 1 || D > PMK_MAX_DIM) return fail(h, PMK_ERR_UNSUPPORTED, "D=%d unsupported (1..%d)", D, PMK_MAX_DIM);
+  if (levels < 2 || levels > 25) return fail(h, PMK_ERR_ARG, "levels=%d out of range [2,25] (examples/mixGP.jl:108)", levels);
+  if (!X || N < 1 || N > INT32_MAX - 1) return fail(h, PMK_ERR_ARG, "bad N or NULL X");
+  if (N < ((int64_t)1 << (levels - 1))) return fail(h, PMK_ERR_ARG, "fewer points (%lld) than leaves (2^%d)", (long long)N, levels - 1);
+  const int64_t max_nodes = (int64_t)1 << (levels - 1);
+  CU(h, h->pt_X.ensure(sizeof(double) * N * D));
+  for (int k = 0; k < 2; ++k) {
+    CU(h, h->pt_perm[k].ensure(sizeof(int32_t) * N));
+    CU(h, h->pt_seg[k].ensure(sizeof(int64_t) * (max_nodes + 1)));
+  }
+  CU(h, h->pt_f.ensure(sizeof(double) * N));
+  CU(h, h->pt_f_tmp.ensure(sizeof(double) * N));
+  CU(h, h->pt_f_sorted.ensure(sizeof(double) * N));
+  CU(h, h->pt_node.ensure(sizeof(int32_t) * N));
+  CU(h, h->pt_node_tmp.ensure(sizeof(int32_t) * N));
+  CU(h, h->pt_node_sorted.ensure(sizeof(int32_t) * N));
+  CU(h, h->pt_flag.ensure(sizeof(int32_t) * (N + 1)));
+  CU(h, h->pt_scan.ensure(sizeof(int32_t) * (N + 1)));
+  CU(h, h->pt_z.ensure(sizeof(double) * max_nodes * D));
+  CU(h, h->pt_v.ensure(sizeof(double) * max_nodes * D));
+  CU(h, h->pt_c.ensure(sizeof(double) * max_nodes));
+  CU(h, cudaMemcpyAsync(h->pt_X.p, X, sizeof(double) * N * D, cudaMemcpyHostToDevice, h->stream));
+  launch_part_iota(h->pt_perm[0].as<int32_t>(), N, h->stream);
+  KCHECK(h, "k_part_iota");
+  h->pt_hseg.assign({0, N});
+  CU(h, cudaMemcpyAsync(h->pt_seg[0].p, h->pt_hseg.data(), sizeof(int64_t) * 2, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->pt_D = D;
+  h->pt_N = N;
+  h->pt_levels = levels;
+  h->pt_cur = 0;
+  h->pt_depth = 0;
+  h->pt_z_done = false;
+  return PMK_OK;
+}
+
+int pmk_partition_level_z(pmk_handle* h, int depth, double* z_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (h->pt_depth < 0) return fail(h, PMK_ERR_STATE, "pmk_partition_begin has not been called");
+  if (depth != h->pt_depth || depth >= h->pt_levels - 1)
+    return fail(h, PMK_ERR_STATE, "pmk_partition_level_z: depth %d requested, next depth is %d of %d", depth, h->pt_depth, h->pt_levels - 1);
+  if (!z_out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const int nodes = 1 << depth;
+  const int D = h->pt_D;
+  std::vector<int64_t> st;
+  std::vector<int32_t> ln, dp, nbo(nodes + 1, 0);
+  for (int j = 0; j < nodes; ++j) {
+    partition_sum_plan(h->pt_hseg[j + 1] - h->pt_hseg[j], h->pt_hseg[j], st, ln, dp);
+    nbo[j + 1] = (int32_t)st.size();
+  }
+  const int n_blk = (int)st.size();
+  CU(h, h->pt_blk_start.ensure(sizeof(int64_t) * n_blk));
+  CU(h, h->pt_blk_len.ensure(sizeof(int32_t) * n_blk));
+  CU(h, h->pt_blk_depth.ensure(sizeof(int32_t) * n_blk));
+  CU(h, h->pt_node_blk_off.ensure(sizeof(int32_t) * (nodes + 1)));
+  CU(h, h->pt_blk_sum.ensure(sizeof(double) * (size_t)n_blk * D));
+  CU(h, cudaMemcpyAsync(h->pt_blk_start.p, st.data(), sizeof(int64_t) * n_blk, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->pt_blk_len.p, ln.data(), sizeof(int32_t) * n_blk, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->pt_blk_depth.p, dp.data(), sizeof(int32_t) * n_blk, cudaMemcpyHostToDevice, h->stream));
+  CU(h, cudaMemcpyAsync(h->pt_node_blk_off.p, nbo.data(), sizeof(int32_t) * (nodes + 1), cudaMemcpyHostToDevice, h->stream));
+  const int32_t* perm = h->pt_perm[h->pt_cur].as<int32_t>();
+  const int64_t* seg = h->pt_seg[h->pt_cur].as<int64_t>();
+  launch_part_block_sums(D, h->pt_X.as<double>(), perm, h->pt_blk_start.as<int64_t>(), h->pt_blk_len.as<int32_t>(), n_blk,
+                         h->pt_blk_sum.as<double>(), h->stream);
+  KCHECK(h, "k_part_block_sums");
+  launch_part_node_z(D, h->pt_X.as<double>(), perm, seg, h->pt_node_blk_off.as<int32_t>(), h->pt_blk_depth.as<int32_t>(),
+                     h->pt_blk_sum.as<double>(), nodes, h->pt_z.as<double>(), h->stream);
+  KCHECK(h, "k_part_node_z");
+  CU(h, cudaMemcpyAsync(z_out, h->pt_z.p, sizeof(double) * (size_t)nodes * D, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));     // also keeps the pageable plan vectors alive until the copies are staged
+  h->pt_z_done = true;
+  return PMK_OK;
+}
+
+int pmk_partition_level_split(pmk_handle* h, int depth, const double* v, double* c_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (h->pt_depth < 0) return fail(h, PMK_ERR_STATE, "pmk_partition_begin has not been called");
+  if (depth != h->pt_depth || !h->pt_z_done)
+    return fail(h, PMK_ERR_STATE, "pmk_partition_level_split: call pmk_partition_level_z for depth %d first", h->pt_depth);
+  if (!v || !c_out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const int nodes = 1 << depth;
+  const int D = h->pt_D;
+  const int64_t N = h->pt_N;
+  cudaStream_t s = h->stream;
+  const int cur = h->pt_cur, nxt = cur ^ 1;
+  const int32_t* perm = h->pt_perm[cur].as<int32_t>();
+  const int64_t* seg = h->pt_seg[cur].as<int64_t>();
+  CU(h, cudaMemcpyAsync(h->pt_v.p, v, sizeof(double) * (size_t)nodes * D, cudaMemcpyHostToDevice, s));
+  launch_part_project(D, h->pt_X.as<double>(), perm, seg, nodes, h->pt_v.as<double>(), N, h->pt_f.as<double>(),
+                      h->pt_node.as<int32_t>(), s);
+  KCHECK(h, "k_part_project");
+  // f ascending inside every node: sort by f, then stably by node id
+  {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, h->pt_f.as<double>(), h->pt_f_tmp.as<double>(), h->pt_node.as<int32_t>(),
+                                    h->pt_node_tmp.as<int32_t>(), (int)N, 0, 64, s);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->pt_f.as<double>(), h->pt_f_tmp.as<double>(), h->pt_node.as<int32_t>(),
+                                          h->pt_node_tmp.as<int32_t>(), (int)N, 0, 64, s));
+    ++h->launches;
+  }
+  const double* f_sorted = h->pt_f_tmp.as<double>();
+  if (depth > 0) {
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, h->pt_node_tmp.as<int32_t>(), h->pt_node_sorted.as<int32_t>(),
+                                    h->pt_f_tmp.as<double>(), h->pt_f_sorted.as<double>(), (int)N, 0, depth, s);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, h->pt_node_tmp.as<int32_t>(), h->pt_node_sorted.as<int32_t>(),
+                                          h->pt_f_tmp.as<double>(), h->pt_f_sorted.as<double>(), (int)N, 0, depth, s));
+    ++h->launches;
+    f_sorted = h->pt_f_sorted.as<double>();
+  }
+  launch_part_median(f_sorted, seg, nodes, h->pt_c.as<double>(), s);
+  KCHECK(h, "k_part_median");
+  launch_part_flags(h->pt_f.as<double>(), h->pt_node.as<int32_t>(), h->pt_c.as<double>(), N, h->pt_flag.as<int32_t>(), s);
+  KCHECK(h, "k_part_flags");
+  {
+    size_t tb = 0;
+    cub::DeviceScan::ExclusiveSum((void*)nullptr, tb, h->pt_flag.as<int32_t>(), h->pt_scan.as<int32_t>(), (int)(N + 1), s);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceScan::ExclusiveSum(h->d_cub.p, tb, h->pt_flag.as<int32_t>(), h->pt_scan.as<int32_t>(), (int)(N + 1), s));
+    ++h->launches;
+  }
+  launch_part_scatter(perm, h->pt_node.as<int32_t>(), h->pt_flag.as<int32_t>(), h->pt_scan.as<int32_t>(), seg, N,
+                      h->pt_perm[nxt].as<int32_t>(), s);
+  KCHECK(h, "k_part_scatter");
+  launch_part_child_offsets(h->pt_scan.as<int32_t>(), seg, nodes, N, h->pt_seg[nxt].as<int64_t>(), s);
+  KCHECK(h, "k_part_child_offsets");
+  std::vector<int64_t> child(2 * (size_t)nodes + 1);
+  CU(h, cudaMemcpyAsync(child.data(), h->pt_seg[nxt].p, sizeof(int64_t) * child.size(), cudaMemcpyDeviceToHost, s));
+  CU(h, cudaMemcpyAsync(c_out, h->pt_c.p, sizeof(double) * nodes, cudaMemcpyDeviceToHost, s));
+  CU(h, cudaStreamSynchronize(s));
+  for (size_t k = 0; k + 1 < child.size(); ++k)
+    if (child[k + 1] <= child[k]) {
+      h->pt_depth = -1;
+      return fail(h, PMK_ERR_ARG, "the split at depth %d leaves child %lld without points (the reference fails in mean() of an empty set, "
+                  "partition.jl:89)", depth, (long long)k);
+    }
+  h->pt_hseg.swap(child);
+  h->pt_cur = nxt;
+  h->pt_depth = depth + 1;
+  h->pt_z_done = false;
+  return PMK_OK;
+}
+
+int pmk_partition_fetch(pmk_handle* h, int64_t* leaf_off_out, int32_t* inds_out) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (h->pt_depth < 0 || h->pt_depth != h->pt_levels - 1)
+    return fail(h, PMK_ERR_STATE, "pmk_partition_fetch: the tree is not complete (depth %d of %d)", h->pt_depth, h->pt_levels - 1);
+  if (leaf_off_out) memcpy(leaf_off_out, h->pt_hseg.data(), sizeof(int64_t) * h->pt_hseg.size());
+  if (inds_out) {
+    int32_t* one = h->pt_perm[h->pt_cur ^ 1].as<int32_t>();
+    launch_part_one_based(h->pt_perm[h->pt_cur].as<int32_t>(), h->pt_N, one, h->stream);
+    KCHECK(h, "k_part_one_based");
+    CU(h, cudaMemcpyAsync(inds_out, one, sizeof(int32_t) * h->pt_N, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+  }
+  return PMK_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// checkpoint: the fitted model as one flat file (the reference keeps MixtureGPType in memory only)
+namespace {
+struct ModelFileHeader {
+  char magic[8];            // "PMKB200\0"
+  int32_t version, D, kernel_kind, levels, tree_D, n_hp, tree_set, reserved;
+  int64_t n_leaves, xstride, x_points, L_doubles, Linv_doubles;
+  double kernel_p, sigma2;
+};
+const char kModelMagic[8] = {'P', 'M', 'K', 'B', '2', '0', '0', 0};
+
+// device span -> file through a bounded pinned-size staging vector (the factors are GBs)
+int dump_dev(pmk_handle* h, FILE* f, const void* dptr, size_t bytes, std::vector<char>& stage) {
+  const char* src = static_cast<const char*>(dptr);
+  for (size_t done = 0; done < bytes;) {
+    const size_t n = std::min(stage.size(), bytes - done);
+    CU(h, cudaMemcpyAsync(stage.data(), src + done, n, cudaMemcpyDeviceToHost, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    if (fwrite(stage.data(), 1, n, f) != n) return fail(h, PMK_ERR_ARG, "pmk_save_model: short write");
+    done += n;
+  }
+  return PMK_OK;
+}
+int fill_dev(pmk_handle* h, FILE* f, void* dptr, size_t bytes, std::vector<char>& stage) {
+  char* dst = static_cast<char*>(dptr);
+  for (size_t done = 0; done < bytes;) {
+    const size_t n = std::min(stage.size(), bytes - done);
+    if (fread(stage.data(), 1, n, f) != n) return fail(h, PMK_ERR_ARG, "pmk_load_model: file truncated");
+    CU(h, cudaMemcpyAsync(dst + done, stage.data(), n, cudaMemcpyHostToDevice, h->stream));
+    CU(h, cudaStreamSynchronize(h->stream));
+    done += n;
+  }
+  return PMK_OK;
+}
+struct FileCloser {
+  FILE* f;
+  ~FileCloser() { if (f) fclose(f); }
+};
+}  // namespace
+
+int pmk_save_model(pmk_handle* h, const char* path) {
+  if (!h || !path) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->fitted) return fail(h, PMK_ERR_STATE, "pmk_save_model: model is not fitted");
+  FileCloser fc{fopen(path, "wb")};
+  if (!fc.f) return fail(h, PMK_ERR_ARG, "pmk_save_model: cannot open %s for writing", path);
+  ModelFileHeader hd{};
+  memcpy(hd.magic, kModelMagic, 8);
+  hd.version = 1;
+  hd.D = h->D;
+  hd.kernel_kind = h->kp.kind;
+  hd.kernel_p = h->kp.p;
+  hd.sigma2 = h->sigma2;
+  hd.tree_set = h->tree_set ? 1 : 0;
+  hd.levels = h->tree_set ? h->levels : 1;
+  hd.tree_D = h->tree_set ? h->tree_D : 0;
+  hd.n_hp = h->tree_set ? h->n_hp : 0;
+  hd.n_leaves = h->n_leaves;
+  hd.xstride = h->xstride;
+  hd.x_points = h->x_points;
+  hd.L_doubles = h->L_doubles;
+  hd.Linv_doubles = h->Linv_doubles;
+  if (fwrite(&hd, sizeof hd, 1, fc.f) != 1) return fail(h, PMK_ERR_ARG, "pmk_save_model: short write");
+  std::vector<int64_t> off(h->n_leaves + 1, 0);
+  for (int64_t p = 0; p < h->n_leaves; ++p) off[p + 1] = off[p] + h->h_n[p];
+  if (fwrite(off.data(), sizeof(int64_t), off.size(), fc.f) != off.size()) return fail(h, PMK_ERR_ARG, "pmk_save_model: short write");
+  std::vector<char> stage((size_t)64 << 20);
+  if (int rc = dump_dev(h, fc.f, h->d_xs.p, sizeof(double) * h->xstride * h->D, stage)) return rc;
+  if (int rc = dump_dev(h, fc.f, h->d_y.p, sizeof(double) * h->xstride, stage)) return rc;
+  if (int rc = dump_dev(h, fc.f, h->d_alpha.p, sizeof(double) * h->xstride, stage)) return rc;
+  if (int rc = dump_dev(h, fc.f, h->d_L.p, sizeof(double) * (size_t)h->L_doubles, stage)) return rc;
+  if (int rc = dump_dev(h, fc.f, h->d_Linv.p, sizeof(double) * (size_t)h->Linv_doubles, stage)) return rc;
+  if (hd.n_hp > 0) {
+    if (int rc = dump_dev(h, fc.f, h->d_hv.p, sizeof(double) * (size_t)hd.tree_D * hd.n_hp, stage)) return rc;
+    if (int rc = dump_dev(h, fc.f, h->d_hc.p, sizeof(double) * (size_t)hd.n_hp, stage)) return rc;
+  }
+  FILE* f = fc.f;
+  fc.f = nullptr;
+  if (fclose(f) != 0) return fail(h, PMK_ERR_ARG, "pmk_save_model: close of %s failed", path);
+  return PMK_OK;
+}
+
+int pmk_load_model(pmk_handle* h, const char* path) {
+  if (!h || !path) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  FileCloser fc{fopen(path, "rb")};
+  if (!fc.f) return fail(h, PMK_ERR_ARG, "pmk_load_model: cannot open %s", path);
+  ModelFileHeader hd{};
+  if (fread(&hd, sizeof hd, 1, fc.f) != 1 || memcmp(hd.magic, kModelMagic, 8) != 0)
+    return fail(h, PMK_ERR_ARG, "pmk_load_model: %s is not a libpmk_b200 model file", path);
+  if (hd.version != 1) return fail(h, PMK_ERR_UNSUPPORTED, "pmk_load_model: file version %d", hd.version);
+  if (hd.n_leaves < 1 || hd.n_leaves > (1 << 24)) return fail(h, PMK_ERR_ARG, "pmk_load_model: corrupt header");
+  std::vector<int64_t> off(hd.n_leaves + 1);
+  if (fread(off.data(), sizeof(int64_t), off.size(), fc.f) != off.size()) return fail(h, PMK_ERR_ARG, "pmk_load_model: file truncated");
+  h->fit_first = 0;     // a loaded model is complete: every leaf's factor is in the file
+  h->fit_count = -1;
+  const double kparam = hd.kernel_p;
+  if (int rc = fit_impl(h, hd.D, hd.n_leaves, off.data(), nullptr, nullptr, hd.kernel_kind, &kparam, 1, hd.sigma2, nullptr, nullptr, false))
+    return rc;
+  if (h->xstride != hd.xstride || h->x_points != hd.x_points || h->L_doubles != hd.L_doubles || h->Linv_doubles != hd.Linv_doubles)
+    return fail(h, PMK_ERR_UNSUPPORTED, "pmk_load_model: %s was written with a different memory layout", path);
+  std::vector<char> stage((size_t)64 << 20);
+  if (int rc = fill_dev(h, fc.f, h->d_xs.p, sizeof(double) * h->xstride * h->D, stage)) return rc;
+  if (int rc = fill_dev(h, fc.f, h->d_y.p, sizeof(double) * h->xstride, stage)) return rc;
+  if (int rc = fill_dev(h, fc.f, h->d_alpha.p, sizeof(double) * h->xstride, stage)) return rc;
+  if (int rc = fill_dev(h, fc.f, h->d_L.p, sizeof(double) * (size_t)h->L_doubles, stage)) return rc;
+  if (int rc = fill_dev(h, fc.f, h->d_Linv.p, sizeof(double) * (size_t)h->Linv_doubles, stage)) return rc;
+  if (hd.tree_set) {
+    if (hd.tree_D < 1 || hd.tree_D > PMK_MAX_DIM || hd.levels < 1 || hd.levels > 25 || hd.n_hp != (1 << (hd.levels - 1)) - 1)
+      return fail(h, PMK_ERR_ARG, "pmk_load_model: corrupt tree header");
+    h->tree_D = hd.tree_D;
+    h->levels = hd.levels;
+    h->n_hp = hd.n_hp;
+    if (hd.n_hp > 0) {
+      CU(h, h->d_hv.ensure(sizeof(double) * (size_t)hd.tree_D * hd.n_hp));
+      CU(h, h->d_hc.ensure(sizeof(double) * (size_t)hd.n_hp));
+      if (int rc = fill_dev(h, fc.f, h->d_hv.p, sizeof(double) * (size_t)hd.tree_D * hd.n_hp, stage)) return rc;
+      if (int rc = fill_dev(h, fc.f, h->d_hc.p, sizeof(double) * (size_t)hd.n_hp, stage)) return rc;
+    }
+    h->tree.levels = hd.levels;
+    h->tree.n_hp = hd.n_hp;
+    h->tree.hv = h->d_hv.as<double>();
+    h->tree.hc = h->d_hc.as<double>();
+    h->tree_set = true;
+  }
+  CU(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * h->n_leaves, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  h->fitted = true;
+  h->plan_valid = false;
+  return PMK_OK;
 }
 
 static int check_leaf(pmk_handle* h, int64_t leaf, int64_t* local) {
@@ -738,6 +1091,49 @@ int pmk_get_alpha(pmk_handle* h, int64_t leaf, double* out) {
   if (int rc = set_device(h)) return rc;
   CU(h, cudaMemcpyAsync(out, h->d_alpha.as<double>() + h->h_xoff[p], sizeof(double) * h->h_n[p], cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_get_X(pmk_handle* h, int64_t leaf, double* out) {
+  int64_t p;
+  if (int rc = check_leaf(h, leaf, &p)) return rc;
+  if (!out) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (int rc = set_device(h)) return rc;
+  const int n = h->h_n[p];
+  std::vector<double> soa((size_t)n * h->D);
+  for (int d = 0; d < h->D; ++d)
+    CU(h, cudaMemcpyAsync(soa.data() + (size_t)d * n, h->d_xs.as<double>() + (size_t)d * h->xstride + h->h_xoff[p], sizeof(double) * n,
+                          cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int i = 0; i < n; ++i)
+    for (int d = 0; d < h->D; ++d) out[(size_t)i * h->D + d] = soa[(size_t)d * n + i];
+  return PMK_OK;
+}
+
+int pmk_model_info(pmk_handle* h, int* D, int64_t* n_leaves, int* kernel_id, double* kparam, double* sigma2, int* levels) {
+  if (!h) return PMK_ERR_ARG;
+  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit or pmk_load_model first)");
+  if (D) *D = h->D;
+  if (n_leaves) *n_leaves = h->n_leaves;
+  if (kernel_id) *kernel_id = h->kp.kind;
+  if (kparam) *kparam = h->kp.p;
+  if (sigma2) *sigma2 = h->sigma2;
+  if (levels) *levels = h->tree_set ? h->levels : 0;
+  return PMK_OK;
+}
+
+int pmk_get_tree(pmk_handle* h, double* hp_v, double* hp_c) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->tree_set) return fail(h, PMK_ERR_STATE, "no tree set (pmk_set_tree / pmk_load_model)");
+  if (h->n_hp == 0) return PMK_OK;
+  if (!hp_v || !hp_c) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  std::vector<double> soa((size_t)h->tree_D * h->n_hp);
+  CU(h, cudaMemcpyAsync(soa.data(), h->d_hv.p, sizeof(double) * soa.size(), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(hp_c, h->d_hc.p, sizeof(double) * h->n_hp, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int k = 0; k < h->n_hp; ++k)
+    for (int d = 0; d < h->tree_D; ++d) hp_v[(size_t)k * h->tree_D + d] = soa[(size_t)d * h->n_hp + k];
   return PMK_OK;
 }
 

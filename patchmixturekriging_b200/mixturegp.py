@@ -131,6 +131,54 @@ def fitmixtureGP_(η: MixtureGPType, y_parts: Sequence[np.ndarray], θ, σ2: flo
     return η
 
 
+def savemixtureGP(η: MixtureGPType, path: str, root: Optional[BSPTree] = None, levels: Optional[int] = None) -> None:
+    """Checkpoint of a fitted model (pmk_save_model): X_parts, c_set, L_set, kernel, σ² and the tree (`root`, or the one
+    the last query used) in one flat file.  The reference has no serialisation; this is the §8f-4 row."""
+    if not η._fitted:
+        raise PMKError(_lib.PMK_ERR_STATE, "savemixtureGP before fitmixtureGP_")
+    if root is not None:
+        _set_tree(η, root, root.levels if levels is None else levels)
+    η._h.check(lib().pmk_save_model(η._h.raw, str(path).encode()))
+
+
+def loadmixtureGP(path: str, device: int = 0):
+    """Inverse of savemixtureGP: returns (η, root, levels).  η queries bit-identically to the model that was saved;
+    root is the flattened tree stored in the file (None, levels 1 when the model was saved without one)."""
+    from . import kernels as K
+    η = MixtureGPType.__new__(MixtureGPType)
+    η._h = Handle(device)
+    L = lib()
+    η._h.check(L.pmk_load_model(η._h.raw, str(path).encode()))
+    D, nl, kid, lv = C.c_int(0), C.c_int64(0), C.c_int(0), C.c_int(0)
+    kpar, s2 = C.c_double(0), C.c_double(0)
+    η._h.check(L.pmk_model_info(η._h.raw, C.byref(D), C.byref(nl), C.byref(kid), C.byref(kpar), C.byref(s2), C.byref(lv)))
+    η.X_parts = []
+    for p in range(nl.value):
+        n = C.c_int64(0)
+        η._h.check(L.pmk_leaf_size(η._h.raw, p + 1, C.byref(n)))
+        X = np.empty((n.value, D.value))
+        η._h.check(L.pmk_get_X(η._h.raw, p + 1, ptr(X)))
+        η.X_parts.append(X)
+    by_id = {c.kernel_id: c for c in vars(K).values() if isinstance(c, type) and issubclass(c, K._Kernel) and c is not K._Kernel}
+    η.θ = by_id[kid.value](kpar.value)
+    η.σ2_set = [s2.value] * nl.value
+    η.c_set = _LazyLeafList(η, "c")
+    η.L_set = _LazyLeafList(η, "L")
+    η.U_set = _LazyLeafList(η, "K")
+    η._fitted = True
+    η._fit_range = None
+    η._tree_key = None
+    root, levels = None, 1
+    if lv.value > 1:
+        n_hp = (1 << (lv.value - 1)) - 1
+        hv, hc = np.empty((n_hp, D.value)), np.empty(n_hp)
+        η._h.check(L.pmk_get_tree(η._h.raw, ptr(hv), ptr(hc)))
+        root, levels = BSPTree(levels=lv.value, hps_v=hv, hps_c=hc), lv.value
+        η._tree_key = (id(root), levels)      # the handle already holds this tree
+    η.hps = (root.hps_v, root.hps_c) if root is not None else (np.zeros((0, D.value)), np.zeros(0))
+    return η, root, levels
+
+
 def model_buffer(η: MixtureGPType, which: int, first_leaf: int, n_leaves: int):
     """(device address, bytes) of the contiguous span holding leaves [first_leaf, first_leaf+n_leaves) of
     buffer `which` (_lib.BUF_L / BUF_LINV / BUF_ALPHA) -- what the ranks exchange after a sharded fit."""

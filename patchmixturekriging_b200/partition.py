@@ -205,3 +205,57 @@ def organizetrainingsets_device(root: BSPTree, levels: int, X0, ε: float, handl
     X_set_inds = [inds64[leaf_off[r]:leaf_off[r + 1]] for r in range(root.n_leaves)]
     X_set = [X0[i - 1] for i in X_set_inds]
     return X_set, X_set_inds, _RaggedView(pleaves.astype(np.int64), poff), []
+
+
+def _split_direction(z: np.ndarray, svd_form: str) -> np.ndarray:
+    """v = V[:,1] of svd((array2matrix([z]))') (partition.jl:90-94), by the host LAPACK exactly as gethyperplane does it."""
+    if svd_form == "column":
+        U, _, _ = np.linalg.svd(z.reshape(-1, 1), full_matrices=False)
+        return np.ascontiguousarray(U[:, 0])
+    _, _, Vt = np.linalg.svd(z.reshape(1, -1), full_matrices=False)
+    return np.ascontiguousarray(Vt[0, :])
+
+
+def preorder_index(depth: int, j: int, levels: int) -> int:
+    """Pre-order (fetchhyperplanes) index of the node at `depth` with left-to-right index j in a complete tree."""
+    Lv = levels - 1
+    k = 0
+    for i in range(depth):
+        k += (1 << (Lv - 1 - i)) if (j >> (depth - 1 - i)) & 1 else 1
+    return k
+
+
+def setuppartition_device(X, levels: int, svd_form: str = "column", handle=None):
+    """setuppartition(X, levels) (partition.jl:106-129) with the O(N) work of every level on the GPU
+    (pmk_partition_begin / _level_z / _level_split / _fetch): node means in Base's pairwise order, projections, medians and
+    the stable splits.  The 1 x D svd of each node stays on the host (LAPACK, as in gethyperplane), so root, X_parts and
+    X_parts_inds are bit-identical to setuppartition's.  Same return values."""
+    from ._lib import Handle, lib, ptr
+    X = np.ascontiguousarray(np.asarray(X, dtype=np.float64))
+    if X.ndim == 1:
+        X = X[:, None]
+    if levels < 2:
+        raise ValueError("levels must be larger than 1 (examples/mixGP.jl:108)")
+    N, D = X.shape
+    h = handle or Handle(0)
+    L = lib()
+    h.check(L.pmk_partition_begin(h.raw, D, N, ptr(X), levels))
+    n_hp = (1 << (levels - 1)) - 1
+    hv, hc = np.empty((n_hp, D)), np.empty(n_hp)
+    for depth in range(levels - 1):
+        nodes = 1 << depth
+        z = np.empty((nodes, D))
+        h.check(L.pmk_partition_level_z(h.raw, depth, ptr(z)))
+        v = np.ascontiguousarray(np.stack([_split_direction(z[j], svd_form) for j in range(nodes)]))
+        c = np.empty(nodes)
+        h.check(L.pmk_partition_level_split(h.raw, depth, ptr(v), ptr(c)))
+        ks = [preorder_index(depth, j, levels) for j in range(nodes)]
+        hv[ks], hc[ks] = v, c
+    n_leaves = 1 << (levels - 1)
+    leaf_off = np.empty(n_leaves + 1, dtype=np.int64)
+    inds = np.empty(N, dtype=np.int32)
+    h.check(L.pmk_partition_fetch(h.raw, ptr(leaf_off), ptr(inds)))
+    inds64 = inds.astype(np.int64)
+    leaf_inds = [inds64[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
+    root = BSPTree(levels=levels, hps_v=hv, hps_c=hc, leaf_inds=leaf_inds)
+    return root, [X[i - 1] for i in leaf_inds], leaf_inds

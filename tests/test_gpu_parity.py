@@ -399,3 +399,96 @@ def test_organizetrainingsets_device_bit_exact(built_lib, name, eps):
         assert np.array_equal(a, b) and np.array_equal(xa, X[b - 1])
     for i in range(0, len(X), 53):
         assert list(rl_d[i]) == list(rl_h[i])
+
+
+@pytest.mark.parametrize("name", ["mixgp_file", "c3_mini"])
+def test_checkpoint_round_trip(built_lib, name, tmp_path):
+    """savemixtureGP -> loadmixtureGP into a fresh handle: X_parts, c_set, L_set, hyperplanes and the query results
+    (mean, variance, debug structure) are bit-identical to the handle that fitted; error paths keep their codes."""
+    case, m, root, eta, pk = _setup(name)
+    _, wk = helpers.kernels(case["wkernel"])
+    path = tmp_path / "model.pmk"
+    P.savemixtureGP(eta, path, root, case["levels"])
+    eta2, root2, levels2 = P.loadmixtureGP(path)
+    assert levels2 == case["levels"]
+    assert np.array_equal(root2.hps_v, root.hps_v) and np.array_equal(root2.hps_c, root.hps_c)
+    assert len(eta2.X_parts) == len(eta.X_parts)
+    assert eta2.θ == pk and eta2.σ2_set[0] == case["sigma2"]
+    for leaf in sorted({0, len(eta.X_parts) // 2, len(eta.X_parts) - 1}):
+        assert np.array_equal(eta2.X_parts[leaf], eta.X_parts[leaf])
+        assert np.array_equal(eta2.c_set[leaf], eta.c_set[leaf])
+        assert np.array_equal(eta2.L_set[leaf], eta.L_set[leaf])
+    Xq = case["Xq"][:4000]
+    args = (case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
+    Y0, V0, d0 = P.querymixtureGP(Xq, eta, root, *args, debug_flag=True)
+    Y1, V1, d1 = P.querymixtureGP(Xq, eta2, root2, *args, debug_flag=True)
+    assert np.array_equal(Y0, Y1) and np.array_equal(V0, V1)
+    for key in ("home", "pair_off", "pair_leaf", "pair_hp", "pair_t", "pair_w", "pair_u", "pair_v"):
+        assert np.array_equal(d0._flat[key], d1._flat[key]), key
+    eta2.close()
+    # error behaviour: not a model file / truncated file / save before fit
+    bad = tmp_path / "bad.pmk"
+    bad.write_bytes(b"not a model")
+    with pytest.raises(P.PMKError) as e:
+        P.loadmixtureGP(bad)
+    assert e.value.code == _lib.PMK_ERR_ARG
+    trunc = tmp_path / "trunc.pmk"
+    trunc.write_bytes(path.read_bytes()[:4096])
+    with pytest.raises(P.PMKError) as e:
+        P.loadmixtureGP(trunc)
+    assert e.value.code == _lib.PMK_ERR_ARG
+    h = P.Handle(0)
+    assert _lib.lib().pmk_save_model(h.raw, str(tmp_path / "x.pmk").encode()) == _lib.PMK_ERR_STATE
+    h.close()
+
+
+@pytest.mark.parametrize("N,levels,D", [(850, 3, 2), (5000, 6, 2), (4097, 4, 3), (3000, 2, 1), (16384, 7, 2), (12000, 5, 3),
+                                        (300001, 10, 2)])
+def test_setuppartition_device_bit_exact(built_lib, N, levels, D):
+    """setuppartition with the per-level O(N) work on the GPU (pmk_partition_*): hyperplanes, X_parts_inds and X_parts are
+    bit-identical to the oracle's (and the host mirror's) for every node, including the pairwise-summed means of nodes
+    larger than 1024 points and the even/odd median rule."""
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(25, N, [-5.0, -10.0, -5.0][:D], [5.0, 10.0, 5.0][:D])
+    root, X_parts, X_parts_inds = P.setuppartition_device(X, levels)
+    if N <= 20000:
+        oroot, _, oinds = O.setuppartition(X, levels)
+        hv, hc = O.fetchhyperplanes(oroot)
+    else:                                   # the oracle's recursion is slow here; the host mirror is pinned to it on CPU
+        hroot, _, oinds = P.setuppartition(X, levels)
+        hv, hc = hroot.hps_v, hroot.hps_c
+    assert np.array_equal(root.hps_v, hv) and np.array_equal(root.hps_c, hc)
+    assert len(X_parts_inds) == len(oinds) == 2 ** (levels - 1)
+    for a, b, Xa in zip(X_parts_inds, oinds, X_parts):
+        assert np.array_equal(a, b) and np.array_equal(Xa, X[b - 1])
+
+
+def test_setuppartition_device_ties_and_errors(built_lib):
+    """Regular grids give many equal projections (ties go right: f < c is strict, partition.jl:75); call-order and size
+    errors keep their codes."""
+    case = cases.c5_mini()
+    X = case["X"]
+    root, _, inds = P.setuppartition_device(X, case["levels"])
+    oroot, _, oinds = O.setuppartition(X, case["levels"])
+    hv, hc = O.fetchhyperplanes(oroot)
+    assert np.array_equal(root.hps_v, hv) and np.array_equal(root.hps_c, hc)
+    assert all(np.array_equal(a, b) for a, b in zip(inds, oinds))
+    L = _lib.lib()
+    h = P.Handle(0)
+    z = np.empty((4, 2))
+    assert L.pmk_partition_level_z(h.raw, 0, _lib.ptr(z)) == _lib.PMK_ERR_STATE
+    Xs = np.ascontiguousarray(X[:3])
+    assert L.pmk_partition_begin(h.raw, 2, 3, _lib.ptr(Xs), 4) == _lib.PMK_ERR_ARG          # fewer points than leaves
+    assert L.pmk_partition_begin(h.raw, 2, 3, _lib.ptr(Xs), 1) == _lib.PMK_ERR_ARG          # levels must be > 1
+    assert L.pmk_partition_begin(h.raw, 2, X.shape[0], _lib.ptr(X), 3) == _lib.PMK_OK
+    c = np.empty(4)
+    assert L.pmk_partition_level_split(h.raw, 0, _lib.ptr(z), _lib.ptr(c)) == _lib.PMK_ERR_STATE   # z of depth 0 not taken yet
+    assert L.pmk_partition_level_z(h.raw, 1, _lib.ptr(z)) == _lib.PMK_ERR_STATE
+    assert L.pmk_partition_fetch(h.raw, None, None) == _lib.PMK_ERR_STATE
+    # identical points: every projection equals the median, the left child stays empty -> the reference fails in mean()
+    Xc = np.ones((64, 2))
+    assert L.pmk_partition_begin(h.raw, 2, 64, _lib.ptr(Xc), 3) == _lib.PMK_OK
+    assert L.pmk_partition_level_z(h.raw, 0, _lib.ptr(z)) == _lib.PMK_OK
+    v = np.array([[1.0, 0.0]])
+    assert L.pmk_partition_level_split(h.raw, 0, _lib.ptr(v), _lib.ptr(c)) == _lib.PMK_ERR_ARG
+    h.close()

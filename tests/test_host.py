@@ -179,3 +179,86 @@ def test_inverse_plan_covers_every_block_once(built_lib):
         assert np.array_equal(cover, np.tril(np.ones((nb, nb), dtype=int), -1))
         assert (0, nb) in done_at
     assert L.pmk_inverse_plan(0, 0, None, C.byref(n)) != 0 and L.pmk_inverse_plan(65, 0, None, C.byref(n)) != 0
+
+
+def _sum_plan(n):
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    L.pmk_partition_sum_plan.argtypes = [ctypes.c_int64, ctypes.c_int64, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.POINTER(ctypes.c_int64)]
+    cap = n // 512 + 2
+    st, ln, dp = np.zeros(cap, np.int64), np.zeros(cap, np.int32), np.zeros(cap, np.int32)
+    nb = ctypes.c_int64(0)
+    assert L.pmk_partition_sum_plan(n, cap, st.ctypes.data, ln.ctypes.data, dp.ctypes.data, ctypes.byref(nb)) == 0
+    return st[:nb.value], ln[:nb.value], dp[:nb.value]
+
+
+def _planned_sum(X):
+    """What k_part_block_sums + k_part_node_z do (csrc/pmk_partition.cu), in numpy: sequential block sums, then the stack
+    combination by depth."""
+    st, ln, dp = _sum_plan(X.shape[0])
+    assert st[0] == 0 and np.array_equal(st[1:], np.cumsum(ln)[:-1]) and ln.sum() == X.shape[0] and ln.max() <= 1024
+    stack = []
+    for s, l, d in zip(st, ln, dp):
+        stack.append([int(d), np.add.accumulate(X[s:s + l], axis=0)[-1]])
+        while len(stack) >= 2 and stack[-1][0] == stack[-2][0]:
+            b = stack.pop()
+            stack[-1] = [stack[-1][0] - 1, stack[-1][1] + b[1]]
+    assert len(stack) == 1 and stack[0][0] == 0
+    return stack[0][1]
+
+
+@pytest.mark.parametrize("n", [1, 2, 15, 16, 1023, 1024, 1025, 2048, 2049, 3071, 4097, 10000, 65537, 300001])
+def test_partition_sum_plan_is_base_pairwise_order(built_lib, n):
+    """pmk_partition_sum_plan (host-only export) + the device's combination rule reproduce Statistics.mean's summation
+    order (oracle mean_pairwise; partition.jl:89) bit for bit."""
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(3, n, [-5.0, -10.0, 1e3], [5.0, 10.0, 1e3 + 1.0])
+    got = _planned_sum(X) / n
+    # the oracle's recursion (forced: its short-cut for n <= 1024 is the same order)
+    assert np.array_equal(got, O.mean_pairwise(X))
+
+
+def test_partition_level_algorithm_in_numpy():
+    """The level-by-level formulation of setuppartition the device follows (stable in-place splits of contiguous segments,
+    left-to-right node order, preorder_index) yields the reference's tree: restated in numpy and compared with the oracle."""
+    from patchmixturekriging_b200 import synth
+    from patchmixturekriging_b200.partition import _split_direction, preorder_index
+    for N, levels, D in [(850, 3, 2), (6000, 6, 3), (3000, 4, 1)]:
+        X = synth.uniform_points(25, N, [-5.0, -10.0, -5.0][:D], [5.0, 10.0, 5.0][:D])
+        perm = np.arange(N)
+        seg = np.array([0, N])
+        n_hp = (1 << (levels - 1)) - 1
+        hv, hc = np.empty((n_hp, D)), np.empty(n_hp)
+        for depth in range(levels - 1):
+            nodes = 1 << depth
+            node_id = np.searchsorted(seg, np.arange(N), side="right") - 1
+            v = np.empty((nodes, D)); c = np.empty(nodes)
+            f = np.empty(N)
+            for j in range(nodes):
+                Xj = X[perm[seg[j]:seg[j + 1]]]
+                z = Xj[0] - _planned_sum(Xj) / Xj.shape[0]
+                v[j] = _split_direction(z, "column")
+                fj = O.dot_seq(v[j][None, :], Xj)
+                f[seg[j]:seg[j + 1]] = fj
+                fs = np.sort(fj)
+                n = len(fj)
+                c[j] = fs[(n - 1) // 2] if n & 1 else fs[n // 2 - 1] / 2.0 + fs[n // 2] / 2.0
+                k = preorder_index(depth, j, levels)
+                hv[k], hc[k] = v[j], c[j]
+            flag = np.concatenate([(f < c[node_id]).astype(np.int64), [0]])
+            scan = np.concatenate([[0], np.cumsum(flag)[:-1]])
+            s, e = seg[node_id], seg[node_id + 1]
+            lt, lb = scan[e] - scan[s], scan[:N] - scan[s]
+            dst = np.where(flag[:N] == 1, s + lb, s + lt + (np.arange(N) - s) - lb)
+            new = np.empty(N, dtype=np.int64)
+            new[dst] = perm
+            child = np.empty(2 * nodes + 1, dtype=np.int64)
+            child[0:2 * nodes:2] = seg[:-1]
+            child[1:2 * nodes:2] = seg[:-1] + (scan[seg[1:]] - scan[seg[:-1]])
+            child[-1] = N
+            perm, seg = new, child
+        oroot, _, oinds = O.setuppartition(X, levels)
+        ohv, ohc = O.fetchhyperplanes(oroot)
+        assert np.array_equal(hv, ohv) and np.array_equal(hc, ohc)
+        for p, b in enumerate(oinds):
+            assert np.array_equal(perm[seg[p]:seg[p + 1]] + 1, b)
