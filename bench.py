@@ -155,6 +155,13 @@ def fp64_peak():
         return FP64_PEAK_FALLBACK_TFLOPS, "fallback constant (profiles/fp64_peaks_r01.json missing)"
 
 
+def hbm_peak_gbs():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json (driver-written copy bandwidth)"
+    except Exception:
+        return 6650.0, "fallback of B200_PROFILING.md (MEASURED_PEAKS.json missing)"
+
+
 # --------------------------------------------------------------------------------------------
 def cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=1, warmup=0, sample_leaves=512, sample_queries=200000, threads=0):
     """The reference's algorithm (C restatement, oracle/pmk_oracle.c) on the host cores, bounded sample:
@@ -417,12 +424,13 @@ def main():
         ach = flops_pairs / (kt[_lib.T_Q_PAIRS] * 1e-3) / 1e12
         try:      # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch, leaf class <=512)
             tr_ = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic_r01.json")))
-            traffic = {"bytes": tr_["dram_bytes_read"] + tr_["dram_bytes_write"], "of": tr_["kernel"], "source": tr_["source"]}
+            traffic = float(tr_["dram_bytes_read"] + tr_["dram_bytes_write"])
+            traffic_of = {"kernel": tr_["kernel"], "source": tr_["source"]}
         except Exception:
-            traffic = None
+            traffic, traffic_of = None, None
         roofline = {"kernel": "k_query_rowp (fused cross-covariance + mean + variance, s = inv(L) kq as a row-panel product on DMMA, per (query, leaf) pair)", "bound": "tensor",
                     "pipe": "FP64 DMMA.8x8x4 (mma.sync.m8n8k4.f64); tcgen05 has no f64 kind", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic,
+                    "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic, "traffic_of": traffic_of,
                     "algorithmic_flops_per_launch": flops_pairs, "ms_per_launch": float(kt[_lib.T_Q_PAIRS]),
                     "pairs_per_launch": int(npairs.value)}
         fit_ach = flops_fit / ((kt[_lib.T_FIT_CHOL] + kt[_lib.T_FIT_GRAM]) * 1e-3) / 1e12
@@ -432,6 +440,28 @@ def main():
                   "query_make_M_ms": float(kt[_lib.T_Q_MAKE_M]), "query_invert_ms": float(kt[_lib.T_Q_INVERT]), "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]),
                   "query_combine_ms": float(kt[_lib.T_Q_COMBINE]),
                   "fit_gram_chol_tflops": fit_ach, "fit_gram_chol_frac_of_fp64_peak": fit_ach / peak}
+        # HBM side (north star: "achieved HBM GB/s for Gram build"): the fit's Gram tiles write the lower tiles of every leaf
+        # once (8 B x packed factor doubles); the standalone Gram kernel (constructkernelmatrix) writes 8 n^2 B.
+        hbm_peak, hbm_src = hbm_peak_gbs()
+        try:
+            _, l_bytes = mixturegp.model_buffer(η, _lib.BUF_L, l0, l1 - l0)
+            gt = l_bytes / (kt[_lib.T_FIT_GRAM] * 1e-3) / 1e9
+            ng = 8192
+            Xg = np.ascontiguousarray(w["X"][:ng])
+            hg = _lib.Handle(dev)
+            Kg = np.empty((ng, ng), order="F")
+            tg = []
+            for _ in range(3):
+                hg.check(L.pmk_gram(hg.raw, w["D"], ng, _lib.ptr(Xg), θ.kernel_id, _lib.ptr(kp), kp.shape[0], 0.0, _lib.ptr(Kg)))
+                tg.append(float(hg.timings()[_lib.T_GRAM]))
+            hg.close()
+            g_ms = float(np.mean(tg[1:]))
+            phases["hbm"] = {"peak_gbs": hbm_peak, "peak_source": hbm_src,
+                             "k_gram_tiles": {"bytes_written": int(l_bytes), "ms": float(kt[_lib.T_FIT_GRAM]), "gbs": gt, "frac": gt / hbm_peak},
+                             "k_gram": {"what": f"constructkernelmatrix, n={ng} (8 n^2 = {8 * ng * ng >> 20} MiB written, > L2)", "ms": g_ms,
+                                        "gbs": 8.0 * ng * ng / (g_ms * 1e-3) / 1e9, "frac": 8.0 * ng * ng / (g_ms * 1e-3) / 1e9 / hbm_peak}}
+        except Exception as exc:      # an instrumentation extra: never lose the bench line to it
+            phases["hbm"] = {"error": repr(exc)}
         # per leaf-size class of the pair kernel: ms and achieved TFLOP/s
         npad_ = (sizes + 31) // 32 * 32
         cls_ = np.where(npad_ <= 512, 0, np.where(npad_ <= 768, 1, np.where(npad_ <= 1024, 2, np.where(npad_ <= 1536, 3, 4))))
