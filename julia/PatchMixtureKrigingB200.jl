@@ -4,7 +4,8 @@
 # reference's names, argument order and return values (reference file:line in each docstring) and
 # replace only the BODIES with `ccall`s.  Everything the north star keeps on the host stays the
 # reference's own Julia code: `setuppartition`, `organizetrainingsets`, `fetchhyperplanes`,
-# `findpartition`, `findneighbourpartitions`, the kernel parameter structs and `array2matrix`.
+# `findpartition`, `findneighbourpartitions`, the kernel parameter structs and `array2matrix`
+# (an optional `setuppartition` with the per-level O(N) work on the GPU is at the end of this file).
 #
 # NOTE: this image has no Julia toolchain, so this file is written against the C ABI but has not been
 # executed here; the same ABI is exercised call-for-call by the Python mirror
@@ -224,6 +225,79 @@ function query!(Yq::Vector{Float64}, Xq::Vector{Vector{Float64}}, η::PMK.RKHSPr
         (Ptr{Cvoid}, Int64, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
         h.ptr, length(Xq), Xm, 0.0, 0.0, 1, wp, 1, 1, Yq, C_NULL))
     return nothing
+end
+
+# ---- setuppartition(X, levels) on the device, one level per round trip  (src/patchwork/partition.jl:106-217) -------
+# The O(N) work of every level -- mean(X) in Base's pairwise order, the projections dot(v, X[n]), median(f) and the
+# order-preserving split X[left_indicators] / X[.!left_indicators] -- runs on the GPU (pmk_partition_*); the 1 x D svd of
+# gethyperplane (partition.jl:90-94) is the reference's own LinearAlgebra call on z = X[1] - mean(X), so hp.v carries
+# exactly the bits gethyperplane would have produced.  Returns (root, X_parts, X_parts_inds) like the reference.
+function setuppartition(X::Vector{Vector{T}}, levels::Integer; h::Handle = sharedhandle()) where T
+    D = length(X[1]); N = length(X); Xm = pack(X)
+    GC.@preserve Xm check(h, ccall((:pmk_partition_begin, libpmk), Cint, (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Cint),
+                                   h.ptr, D, N, Xm, levels))
+    hps_by_depth = Vector{Vector{PMK.HyperplaneType{T}}}()
+    for depth in 0:levels-2
+        nodes = 1 << depth
+        z = Matrix{Float64}(undef, D, nodes); v = similar(z); c = Vector{Float64}(undef, nodes)
+        GC.@preserve z check(h, ccall((:pmk_partition_level_z, libpmk), Cint, (Ptr{Cvoid}, Cint, Ptr{Float64}), h.ptr, depth, z))
+        for j in 1:nodes
+            Z_mat = (PMK.array2matrix([z[:, j]]))'            # partition.jl:91-92, same object the reference hands to svd
+            v[:, j] = svd(Z_mat).V[:, 1]                      # partition.jl:93-94
+        end
+        GC.@preserve v c check(h, ccall((:pmk_partition_level_split, libpmk), Cint,
+                                        (Ptr{Cvoid}, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, depth, v, c))
+        push!(hps_by_depth, [PMK.HyperplaneType{T}(v[:, j], c[j]) for j in 1:nodes])
+    end
+    n_leaves = 1 << (levels - 1)
+    leaf_off = Vector{Int64}(undef, n_leaves + 1); inds = Vector{Int32}(undef, N)
+    GC.@preserve leaf_off inds check(h, ccall((:pmk_partition_fetch, libpmk), Cint, (Ptr{Cvoid}, Ptr{Int64}, Ptr{Int32}),
+                                              h.ptr, leaf_off, inds))
+    X_parts_inds = [Int.(inds[leaf_off[p]+1:leaf_off[p+1]]) for p in 1:n_leaves]
+    # rebuild the reference's BinaryNode tree (partition.jl:3-29, 166-217): node (depth, j) has children (depth+1, 2j-1 / 2j)
+    emptyX() = Vector{Vector{T}}(undef, 0)
+    root = PMK.BinaryNode(PMK.PartitionDataType(hps_by_depth[1][1], emptyX(), Int[], 0))
+    function grow!(parent, depth, j)          # children of node j (1-based) at `depth`
+        for (side, jc) in ((PMK.leftchild!, 2j - 1), (PMK.rightchild!, 2j))
+            if depth + 1 == levels - 1        # kid is a leaf: keeps its global indices, gets its label (labelleafnodes :131-159)
+                side(parent, PMK.PartitionDataType(PMK.HyperplaneType{T}(), emptyX(), X_parts_inds[jc], jc))
+            else
+                kid = side(parent, PMK.PartitionDataType(hps_by_depth[depth+2][jc], emptyX(), Int[], 0))
+                grow!(kid, depth + 1, jc)
+            end
+        end
+    end
+    grow!(root, 0, 1)
+    return root, [X[i] for i in X_parts_inds], X_parts_inds
+end
+
+# ---- checkpoint (no counterpart in the reference: MixtureGPType lives in memory only) -------------------------------------
+"savemixtureGP(η, path, levels): X_parts, c_set, L_set, kernel, σ² and the tree in one file (pmk_save_model)"
+function savemixtureGP(η::MixtureGPType, path::AbstractString, levels::Integer)
+    settree!(η, levels)
+    check(η.h, ccall((:pmk_save_model, libpmk), Cint, (Ptr{Cvoid}, Cstring), η.h.ptr, path))
+end
+
+"loadmixtureGP(path; device) -> η with X_parts and hps read back from the file (pmk_load_model, pmk_get_X, pmk_get_tree)"
+function loadmixtureGP(path::AbstractString; device = 0)
+    h = Handle(device)
+    check(h, ccall((:pmk_load_model, libpmk), Cint, (Ptr{Cvoid}, Cstring), h.ptr, path))
+    D = Ref{Cint}(0); nl = Ref{Int64}(0); kid = Ref{Cint}(0); kp = Ref{Float64}(0); s2 = Ref{Float64}(0); lv = Ref{Cint}(0)
+    check(h, ccall((:pmk_model_info, libpmk), Cint, (Ptr{Cvoid}, Ref{Cint}, Ref{Int64}, Ref{Cint}, Ref{Float64}, Ref{Float64}, Ref{Cint}),
+                   h.ptr, D, nl, kid, kp, s2, lv))
+    X_parts = Vector{Vector{Vector{Float64}}}(undef, nl[])
+    for p in 1:nl[]
+        n = Ref{Int64}(0)
+        check(h, ccall((:pmk_leaf_size, libpmk), Cint, (Ptr{Cvoid}, Int64, Ref{Int64}), h.ptr, p, n))
+        Xm = Matrix{Float64}(undef, D[], n[])
+        GC.@preserve Xm check(h, ccall((:pmk_get_X, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), h.ptr, p, Xm))
+        X_parts[p] = [Xm[:, i] for i in 1:n[]]
+    end
+    n_hp = lv[] > 1 ? (1 << (lv[] - 1)) - 1 : 0
+    hv = Matrix{Float64}(undef, D[], n_hp); hc = Vector{Float64}(undef, n_hp)
+    n_hp > 0 && GC.@preserve hv hc check(h, ccall((:pmk_get_tree, libpmk), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, hv, hc))
+    hps = [PMK.HyperplaneType{Float64}(hv[:, i], hc[i]) for i in 1:n_hp]
+    return MixtureGPType{Float64}(X_parts, hps, h, fill(s2[], nl[]), true), Int(lv[])
 end
 
 end # module
