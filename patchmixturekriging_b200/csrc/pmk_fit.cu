@@ -88,7 +88,22 @@ __device__ __noinline__ int factor_block32(double* Dbuf, double* Ibuf, int lane)
 // The warp's own operand tiles L[t_r, ct] stream through a per-warp cp.async ring kDepth-1 column tiles ahead
 // (register-free prefetch: without it every iteration exposed an L2 round trip and a leaf took ~3.5 M cycles);
 // the panel's row tiles L[J, ct] are shared by all warps of the CTA and come through L1.
-static constexpr int kCholDepth = 4;
+#ifndef PMK_CHOL_DEPTH
+#define PMK_CHOL_DEPTH 3
+#endif
+static constexpr int kCholDepth = PMK_CHOL_DEPTH;
+// Register prefetch of the panel-row fragments one column tile ahead costs 16 registers at a cap of 80: with it ptxas spills
+// 484 B (some of it inside the update loop), without it 280 B -- and the other five warps of the sub-partition hide the
+// L1 / L2 latency anyway (C3 k_chol, same box: 11.55 -> 10.82 ms).
+#ifndef PMK_CHOL_BPREFETCH
+#define PMK_CHOL_BPREFETCH 0
+#endif
+#ifndef PMK_CHOL_FUSED_SOLVE
+#define PMK_CHOL_FUSED_SOLVE 1
+#endif
+#ifndef PMK_CHOL_CPREFETCH
+#define PMK_CHOL_CPREFETCH 1
+#endif
 template <int R, int NV>
 __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2* __restrict__ Lp, const int (&bo)[4],
                                            const int (&ao)[R], int nct, uint32_t ring_u32, const double2* ring) {
@@ -102,17 +117,24 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
 #pragma unroll
   for (int s = 0; s < kCholDepth - 1; ++s) issue(s, s);
   int cslot = 0, fslot = kCholDepth - 1;
+#if PMK_CHOL_BPREFETCH
   double2 bn[4];                                   // panel-row fragments, loaded one column tile ahead
 #pragma unroll
   for (int b = 0; b < 4; ++b) bn[b] = nct > 0 ? Lp[bo[b]] : make_double2(0.0, 0.0);
+#endif
   for (int ct = 0; ct < nct; ++ct) {
     double2 bf[4];
+#if PMK_CHOL_BPREFETCH
 #pragma unroll
     for (int b = 0; b < 4; ++b) bf[b] = bn[b];
     if (ct + 1 < nct) {
 #pragma unroll
       for (int b = 0; b < 4; ++b) bn[b] = Lp[bo[b] + (ct + 1) * 32];
     }
+#else
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bf[b] = Lp[bo[b] + ct * 32];
+#endif
     cp_async_wait<kCholDepth - 2>();
     const double2* rs = ring + cslot * (R * 32);
     issue(ct + kCholDepth - 1, fslot);      // refill the slot consumed one iteration ago
@@ -137,8 +159,11 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
 // A-fragment-major).  Full-occupancy elementwise kernel: the evaluations (sqrt + exp chains) run at FP64
 // pipe throughput here instead of stalling the low-occupancy factorisation (measured: evaluating them
 // inside k_chol took 31 % of its cycles).  One warp per row tile.
+#ifndef PMK_GRAMT_MINB
+#define PMK_GRAMT_MINB 4      // 64 registers instead of 110: 2 -> 4 resident CTAs per SM (C3: 1.80 -> 1.19 ms; 5: 1.17 with more spills)
+#endif
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, PMK_GRAMT_MINB)
 k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
   __shared__ double s_exp[64];
   if (threadIdx.x < 64) s_exp[threadIdx.x] = c_exp2_64[threadIdx.x];
@@ -194,6 +219,23 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
       for (int k = 0; k < 8; k += 2)
         Lp[(c + (k >> 1)) * 32] = make_double2(exp_neg_tab(arg[k], s_exp), exp_neg_tab(arg[k + 1], s_exp));
     }
+#ifndef PMK_GRAMT_NO_TAIL
+    for (; c < t; ++c) {          // the up to three remaining tiles strictly below the diagonal, same arithmetic
+      double arg[2];
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const int col = 8 * c + 2 * l + k;
+        double s2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const double dd = xr[d] - xs[d * xstride + col];
+          s2 = fma(dd, dd, s2);
+        }
+        arg[k] = -kp.p * s2;
+      }
+      Lp[c * 32] = make_double2(exp_neg_tab(arg[0], s_exp), exp_neg_tab(arg[1], s_exp));
+    }
+#endif
   }
   for (; c <= t; ++c) Lp[c * 32] = make_double2(entry(8 * c + 2 * l), entry(8 * c + 2 * l + 1));
 }
@@ -208,6 +250,18 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
 // Lookahead of the diagonal block (measured on C3: k_chol 11.68 -> 11.41 ms; with the diagonal block's update removed
 // altogether -- wrong results, timing only -- 10.13 ms: the kernel is bound by the left-looking re-reads of the finished
 // columns, 34 GB per C3 fit, not by the length of the per-panel critical path).
+// Loads of tiles that are read once per panel (the parked K / C tiles): L2 only, so they do not evict the panel's row tiles
+// L[J, 0:J] -- shared by all warps of the CTA and re-read for every unit -- from L1.
+#ifndef PMK_CHOL_LDCG
+#define PMK_CHOL_LDCG 1
+#endif
+__device__ __forceinline__ double2 ld_once(const double2* p) {
+#if PMK_CHOL_LDCG
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
 #ifndef PMK_CHOL_LOOKAHEAD
 #define PMK_CHOL_LOOKAHEAD 1
 #endif
@@ -219,7 +273,7 @@ __global__ void __launch_bounds__(NW * 32, PMK_CHOL_MINB)
 k_chol(LeafTable lt, const int* __restrict__ order) {
   __shared__ double Dbuf[32 * LDD];
   __shared__ double Ibuf[32 * LD];
-  __shared__ int s_fail, s_next;
+  __shared__ int s_fail, s_next, s_next2[2], s_ready;
   const int p = order[blockIdx.x];
   const int npad = lt.npad[p];
   const int nblk = npad >> 5, ntl = npad >> 3;
@@ -230,6 +284,9 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
   if (threadIdx.x == 0) {
     s_fail = 0;
     s_next = 4;
+    s_next2[0] = 4;
+    s_next2[1] = 8;
+    s_ready = 0;
   }
   __syncthreads();
   extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
@@ -237,6 +294,40 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
   const int src_lo = (lane & ~3) | (l >> 1);
   const int src_hi = (lane & ~3) | (2 + (l >> 1));
+
+  // L[t, J] = C inv(L_JJ)^T for one row tile: cf = the raw block C in C-fragment order (four column tiles), trow = the
+  // row tile's slots of panel J; inv(L_JJ) is read from Ibuf.  Final tiles are stored A-fragment-major.
+  auto solve_store = [&](const double2 (&cf)[4], double2* trow) {
+    double alo[4], ahi[4];
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {     // C-fragment (cols 2l, 2l+1) -> A-fragment (cols l, l+4) inside the quad
+      const double v0 = __shfl_sync(kFull, cf[kb].x, src_lo);
+      const double v1 = __shfl_sync(kFull, cf[kb].y, src_lo);
+      const double w0 = __shfl_sync(kFull, cf[kb].x, src_hi);
+      const double w1 = __shfl_sync(kFull, cf[kb].y, src_hi);
+      alo[kb] = (l & 1) ? v1 : v0;
+      ahi[kb] = (l & 1) ? w1 : w0;
+    }
+    double* tile_row = reinterpret_cast<double*>(trow);
+    double o0[4], o1[4], p0[4], p1[4];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) o0[cb] = o1[cb] = p0[cb] = p1[cb] = 0.0;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {     // kb outermost: the four output tiles advance in lock step
+#pragma unroll
+      for (int cb = kb; cb < 4; ++cb) dmma884(o0[cb], o1[cb], alo[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + l]);
+#pragma unroll
+      for (int cb = kb; cb < 4; ++cb) dmma884(p0[cb], p1[cb], ahi[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + 4 + l]);
+    }
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      // C-fragment (row g, cols 2l, 2l+1) -> packed A-fragment-major tile
+      double* tile = tile_row + cb * 64;
+      const int q0 = 2 * l, q1 = 2 * l + 1;
+      tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0[cb] + p0[cb];
+      tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1[cb] + p1[cb];
+    }
+  };
 
   PMK_CYC(long long c_total = clock64(), c_diag = 0, c_work = 0, c_factor = 0, c_solve = 0, c_wait = 0;)
   for (int J = 0; J < nblk; ++J) {
@@ -253,7 +344,7 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
       for (int r = 0; r < R; ++r) ao[r] = (int)tri(t0 + warp) * 32 + lane;
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const double2 kt = (b <= warp) ? Lp[ao[0] + (t0 + b) * 32] : make_double2(0.0, 0.0);
+        const double2 kt = (b <= warp) ? ld_once(Lp + ao[0] + (t0 + b) * 32) : make_double2(0.0, 0.0);
         acc[0][b][0] = -kt.x;
         acc[0][b][1] = -kt.y;
       }
@@ -295,6 +386,11 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
             }
           }
         }
+#if PMK_CHOL_FUSED_SOLVE
+        __syncwarp();
+        __threadfence_block();
+        if (lane == 0) *(volatile int*)&s_ready = J + 1;     // inv(L_JJ) is in Ibuf (or s_fail is set): the units' epilogues may run
+#endif
         PMK_CYC({ long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; })
       }
     }
@@ -312,7 +408,7 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
         ao[r] = (int)tri(tb + r) * 32 + lane;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const double2 kt = (t0 + 4 + b <= tb + r) ? Lp[ao[r] + (t0 + 4 + b) * 32] : make_double2(0.0, 0.0);
+          const double2 kt = (t0 + 4 + b <= tb + r) ? ld_once(Lp + ao[r] + (t0 + 4 + b) * 32) : make_double2(0.0, 0.0);
           acc[r][b][0] = -kt.x;
           acc[r][b][1] = -kt.y;
         }
@@ -327,7 +423,11 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
     // ---- B: off-diagonal row tiles, dynamically dealt; raw C parked in the tile slots -------------
     for (;;) {
       int tb = 0;
+#if PMK_CHOL_FUSED_SOLVE
+      if (lane == 0) tb = atomicAdd(&s_next2[J & 1], R);
+#else
       if (lane == 0) tb = atomicAdd(&s_next, R);
+#endif
       tb = __shfl_sync(kFull, tb, 0);
       if (tb >= ntl) break;
       double acc[R][4][2];
@@ -340,13 +440,32 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
         ao[r] = (int)tri(tv ? tb + r : tb) * 32 + lane;
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
-          const double2 kt = tv ? Lp[ao[r] + (t0 + b) * 32] : make_double2(0.0, 0.0);
+          const double2 kt = tv ? ld_once(Lp + ao[r] + (t0 + b) * 32) : make_double2(0.0, 0.0);
           acc[r][b][0] = -kt.x;
           acc[r][b][1] = -kt.y;
         }
       }
       if (nv == R) chol_kloop<R, R>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
       else chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);     // R == 2: one valid tile
+#if PMK_CHOL_FUSED_SOLVE
+      // The raw block never leaves the registers: as soon as warp 0 has published inv(L_JJ) -- long before a unit's update loop
+      // ends, except in the first panels -- the unit multiplies it in and stores the FINAL tiles (no parked C: one write and
+      // one read of the whole factor less per fit, and one CTA barrier per panel instead of two).
+      if (lane == 0)
+        while (*(volatile int*)&s_ready <= J) __nanosleep(40);
+      __syncwarp();
+      __threadfence_block();
+      if (*(volatile int*)&s_fail) break;
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        if (r < nv) {
+          double2 cf[4];
+#pragma unroll
+          for (int b = 0; b < 4; ++b) cf[b] = make_double2(-acc[r][b][0], -acc[r][b][1]);
+          solve_store(cf, Lp + (tri(tb + r) + t0) * 32);
+        }
+      }
+#else
 #pragma unroll
       for (int r = 0; r < R; ++r) {
         if (r < nv) {
@@ -354,56 +473,46 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
           for (int b = 0; b < 4; ++b) Lp[ao[r] + (t0 + b) * 32] = make_double2(-acc[r][b][0], -acc[r][b][1]);
         }
       }
+#endif
     }
     PMK_CYC({ long long c1 = clock64(); c_work += c1 - c0; c0 = c1; })
+#if PMK_CHOL_FUSED_SOLVE
+    if (threadIdx.x == 0) s_next2[(J + 1) & 1] = t0 + 8;      // panel J+1's first off-diagonal row tile (that counter is idle during panel J)
+    __syncthreads();     // panel J complete and visible before panel J+1 reads it; Ibuf free for the next factor
+    PMK_CYC({ long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; })
+    if (s_fail) return;
+    continue;
+#endif
     __syncthreads();     // inverse block ready, every C tile parked
     PMK_CYC({ long long c1 = clock64(); c_wait += c1 - c0; c0 = c1; })
     if (s_fail) return;
     // ---- C: L[t, J] = C * inv(L_JJ)^T -----------------------------------------------------------
     {
       int t = t0 + 4 + warp;
-      double2 cf[4], cn[4];
+      double2 cf[4];
+#if PMK_CHOL_CPREFETCH
+      double2 cn[4];
       if (t < ntl) {
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) cf[kb] = Lp[(tri(t) + t0 + kb) * 32 + lane];
+        for (int kb = 0; kb < 4; ++kb) cf[kb] = ld_once(Lp + (tri(t) + t0 + kb) * 32 + lane);
       }
+#endif
       for (; t < ntl; t += NW) {
         double2* trow = Lp + (tri(t) + t0) * 32;
+#if PMK_CHOL_CPREFETCH
         if (t + NW < ntl) {               // next row tile's parked block, one iteration ahead
 #pragma unroll
-          for (int kb = 0; kb < 4; ++kb) cn[kb] = Lp[(tri(t + NW) + t0 + kb) * 32 + lane];
+          for (int kb = 0; kb < 4; ++kb) cn[kb] = ld_once(Lp + (tri(t + NW) + t0 + kb) * 32 + lane);
         }
-        double alo[4], ahi[4];
+#else
 #pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {     // C-fragment (cols 2l, 2l+1) -> A-fragment (cols l, l+4) inside the quad
-          const double v0 = __shfl_sync(kFull, cf[kb].x, src_lo);
-          const double v1 = __shfl_sync(kFull, cf[kb].y, src_lo);
-          const double w0 = __shfl_sync(kFull, cf[kb].x, src_hi);
-          const double w1 = __shfl_sync(kFull, cf[kb].y, src_hi);
-          alo[kb] = (l & 1) ? v1 : v0;
-          ahi[kb] = (l & 1) ? w1 : w0;
-        }
-        double* tile_row = reinterpret_cast<double*>(trow);
-        double o0[4], o1[4], p0[4], p1[4];
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) o0[cb] = o1[cb] = p0[cb] = p1[cb] = 0.0;
-#pragma unroll
-        for (int kb = 0; kb < 4; ++kb) {     // kb outermost: the four output tiles advance in lock step
-#pragma unroll
-          for (int cb = kb; cb < 4; ++cb) dmma884(o0[cb], o1[cb], alo[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + l]);
-#pragma unroll
-          for (int cb = kb; cb < 4; ++cb) dmma884(p0[cb], p1[cb], ahi[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + 4 + l]);
-        }
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) {
-          // C-fragment (row g, cols 2l, 2l+1) -> packed A-fragment-major tile
-          double* tile = tile_row + cb * 64;
-          const int q0 = 2 * l, q1 = 2 * l + 1;
-          tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0[cb] + p0[cb];
-          tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1[cb] + p1[cb];
-        }
+        for (int kb = 0; kb < 4; ++kb) cf[kb] = ld_once(trow + kb * 32 + lane);
+#endif
+        solve_store(cf, trow);
+#if PMK_CHOL_CPREFETCH
 #pragma unroll
         for (int kb = 0; kb < 4; ++kb) cf[kb] = cn[kb];
+#endif
       }
     }
     if (threadIdx.x == 0) s_next = t0 + 8;     // first off-diagonal row tile of the next panel
@@ -475,8 +584,11 @@ __device__ __forceinline__ double linv_elem(const double* __restrict__ Iblk, int
   return Iblk[((a * (a + 1) / 2 + b) * 32 + (i & 7) * 4 + (k & 3)) * 2 + ((k & 7) >> 2)];
 }
 
+#ifndef PMK_SOLVE_MINB
+#define PMK_SOLVE_MINB 6      // 40 registers, 6 resident leaves per SM: the solves are latency-bound (C3: 1.96 -> 1.70 ms; 5: 1.76)
+#endif
 template <int NW>
-__global__ void __launch_bounds__(NW * 32)
+__global__ void __launch_bounds__(NW * 32, PMK_SOLVE_MINB)
 k_solve_alpha(LeafTable lt, const int* __restrict__ order) {
   extern __shared__ double sm[];
   const int p = order[blockIdx.x];
