@@ -6,6 +6,8 @@
 // column-major with 16-byte stores, 1 KB contiguous per column segment.
 // (The fit path does NOT use this kernel: k_chol evaluates the Gram entries straight into its
 //  accumulators; this one serves the public constructkernelmatrix / U_set surface.)
+#include <cstdlib>
+
 #include "pmk_internal.cuh"
 
 namespace pmk {
@@ -47,15 +49,25 @@ __global__ void k_aos_to_soa(const double* __restrict__ X, int64_t n, int64_t st
 
 static constexpr int TM = 128, TN = 64;
 
+static constexpr int TMP = TM + 1;     // padded row length of the mirror tile: transposed reads are bank-conflict-free
+
+// symmetric: 0 = cross-Gram; 1 = Gram, every entry evaluated by its own tile (the lower triangle as evalkernel(X[i], X[j]), the
+// upper one with the arguments swapped = the mirrored value, RKHS.jl:27-31); 2 = Gram, tiles strictly above the diagonal are
+// skipped and written by the tile below it instead: that tile keeps its 128 x 64 values in shared memory and stores them a
+// second time transposed (512-byte column segments), so every kernel value is evaluated once -- half the FP64 work of a
+// kernel that is bound by the sqrt + exp chains, not by its 8 n^2 bytes.
 template <int D>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 k_gram(const double* __restrict__ xr, int64_t xr_stride, int n, const double* __restrict__ xc, int64_t xc_stride, int m,
        KParams kp, double sigma2, int symmetric, double* __restrict__ K) {
   __shared__ __align__(16) double s_r[D][TM];
   __shared__ __align__(16) double s_c[D][TN];
   __shared__ __align__(8) uint64_t bar;
+  extern __shared__ __align__(16) double s_t[];     // symmetric == 2: [TN][TMP] mirror tile
   const int tid = threadIdx.x;
   const int i0 = blockIdx.x * TM, j0 = blockIdx.y * TN;
+  if (symmetric == 2 && j0 >= i0 + TM) return;       // strictly above the diagonal: the mirrored tile writes it
+  const bool mirror = symmetric == 2 && i0 >= j0 + TN;   // strictly below: evaluate once, store twice
   if (tid == 0) mbar_init(&bar, 1);
   __syncthreads();
   if (tid == 0) {
@@ -70,35 +82,59 @@ k_gram(const double* __restrict__ xr, int64_t xr_stride, int n, const double* __
 
   const int r2 = (tid & 63) * 2;
   const int i = i0 + r2;
-  if (i >= n) return;
-  double xa[D], xb[D];
+  if (i < n) {
+    double xa[D], xb[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) {
-    xa[d] = s_r[d][r2];
-    xb[d] = s_r[d][r2 + 1];
-  }
-  const bool two = (i + 1 < n);
-  const bool vec = two && ((n & 1) == 0);
-  for (int jj = tid >> 6; jj < TN; jj += 4) {
-    const int j = j0 + jj;
-    if (j >= m) break;
-    double xz[D];
-#pragma unroll
-    for (int d = 0; d < D; ++d) xz[d] = s_c[d][jj];
-    // reference evaluates the lower triangle as evalkernel(X[i], X[j]) (i >= j) and mirrors it
-    double k0 = (symmetric && i < j) ? eval_kernel<D>(kp, xz, xa) : eval_kernel<D>(kp, xa, xz);
-    if (symmetric && i == j) k0 = __dadd_rn(k0, sigma2);
-    double k1 = 0.0;
-    if (two) {
-      k1 = (symmetric && i + 1 < j) ? eval_kernel<D>(kp, xz, xb) : eval_kernel<D>(kp, xb, xz);
-      if (symmetric && i + 1 == j) k1 = __dadd_rn(k1, sigma2);
+    for (int d = 0; d < D; ++d) {
+      xa[d] = s_r[d][r2];
+      xb[d] = s_r[d][r2 + 1];
     }
-    double* dst = K + (int64_t)j * n + i;
-    if (vec) {
-      *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
+    const bool two = (i + 1 < n);
+    const bool vec = two && ((n & 1) == 0);
+    for (int jj = tid >> 6; jj < TN; jj += 4) {
+      const int j = j0 + jj;
+      if (j >= m) break;
+      double xz[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) xz[d] = s_c[d][jj];
+      // reference evaluates the lower triangle as evalkernel(X[i], X[j]) (i >= j) and mirrors it
+      double k0 = (symmetric && i < j) ? eval_kernel<D>(kp, xz, xa) : eval_kernel<D>(kp, xa, xz);
+      if (symmetric && i == j) k0 = __dadd_rn(k0, sigma2);
+      double k1 = 0.0;
+      if (two) {
+        k1 = (symmetric && i + 1 < j) ? eval_kernel<D>(kp, xz, xb) : eval_kernel<D>(kp, xb, xz);
+        if (symmetric && i + 1 == j) k1 = __dadd_rn(k1, sigma2);
+      }
+      double* dst = K + (int64_t)j * n + i;
+      if (vec) {
+        *reinterpret_cast<double2*>(dst) = make_double2(k0, k1);
+      } else {
+        dst[0] = k0;
+        if (two) dst[1] = k1;
+      }
+      if (mirror) {
+        s_t[jj * TMP + r2] = k0;
+        s_t[jj * TMP + r2 + 1] = k1;
+      }
+    }
+  }
+  if (!mirror) return;
+  __syncthreads();
+  // K[j, i] = K[i, j]: column i of the mirrored block is 64 consecutive doubles; a warp stores one column per step
+  const int warp = tid >> 5, lane = tid & 31;
+  const int j = j0 + 2 * lane;
+  const bool vec = (n & 1) == 0;
+  for (int ii = warp; ii < TM; ii += 8) {
+    const int ic = i0 + ii;
+    if (ic >= n) break;
+    if (j >= m) continue;
+    const double v0 = s_t[(2 * lane) * TMP + ii], v1 = s_t[(2 * lane + 1) * TMP + ii];
+    double* dst = K + (int64_t)ic * n + j;
+    if (vec && j + 1 < m) {
+      *reinterpret_cast<double2*>(dst) = make_double2(v0, v1);
     } else {
-      dst[0] = k0;
-      if (two) dst[1] = k1;
+      dst[0] = v0;
+      if (j + 1 < m) dst[1] = v1;
     }
   }
 }
@@ -118,10 +154,22 @@ void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double
                  double sigma2, int symmetric, double* dK, cudaStream_t s) {
   if (n <= 0 || m <= 0) return;
   dim3 grid((n + TM - 1) / TM, (m + TN - 1) / TN);
+  // Gram matrices of more than a few tiles: evaluate the lower tiles only and mirror them (mode 2); PMK_GRAM_NO_MIRROR=1
+  // keeps every tile evaluating its own entries (the round-1 kernel) for A/B timing.
+  static const bool no_mirror = [] { const char* e = getenv("PMK_GRAM_NO_MIRROR"); return e && atoi(e) != 0; }();
+  const int mode = (symmetric && n == m && n > 2 * TM && !no_mirror) ? 2 : (symmetric ? 1 : 0);
+  const size_t dyn = mode == 2 ? (size_t)TN * TMP * sizeof(double) : 0;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(k_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TN * TMP * sizeof(double)));
+    cudaFuncSetAttribute(k_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TN * TMP * sizeof(double)));
+    cudaFuncSetAttribute(k_gram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TN * TMP * sizeof(double)));
+    configured = true;
+  }
   switch (D) {
-    case 1: k_gram<1><<<grid, 256, 0, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, symmetric, dK); break;
-    case 2: k_gram<2><<<grid, 256, 0, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, symmetric, dK); break;
-    case 3: k_gram<3><<<grid, 256, 0, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, symmetric, dK); break;
+    case 1: k_gram<1><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
+    case 2: k_gram<2><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
+    case 3: k_gram<3><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
     default: break;
   }
 }

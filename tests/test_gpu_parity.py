@@ -492,3 +492,17 @@ def test_setuppartition_device_ties_and_errors(built_lib):
     v = np.array([[1.0, 0.0]])
     assert L.pmk_partition_level_split(h.raw, 0, _lib.ptr(v), _lib.ptr(c)) == _lib.PMK_ERR_ARG
     h.close()
+
+
+@pytest.mark.parametrize("kname,param,D,n", [("SQEXP", 3.0, 2, 1000), ("SPLINE34", 0.4, 3, 777), ("BB20", 1.0, 1, 1300), ("RQ", 1.7, 2, 2049)])
+def test_gram_mirrored_large(built_lib, kname, param, D, n):
+    """constructkernelmatrix beyond a few tiles: the tiles above the diagonal are written by the tiles below them (each kernel
+    value evaluated once, RKHS.jl:27-31 mirrors the lower triangle the same way) -- exact symmetry, oracle values, odd and even n."""
+    from patchmixturekriging_b200 import synth
+    lo, hi = ([0.0] * D, [1.0] * D) if kname == "BB20" else ([-1.0] * D, [1.0] * D)
+    X = synth.uniform_points(4, n, lo, hi)
+    ok, pk = helpers.kernels((kname, param))
+    K = P.constructkernelmatrix(X, pk)
+    assert np.array_equal(K, K.T)
+    ref = O.constructkernelmatrix(X, ok)
+    np.testing.assert_allclose(K, ref, rtol=5e-15, atol=1e-300)
