@@ -266,6 +266,9 @@ def main():
     dev = local_rank if world > 1 else 0
     torch.cuda.set_device(dev)
     if world > 1:
+        # NCCL_DEBUG=VERSION (set in some images) makes NCCL print its version to STDOUT, next to the one JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
 
     root, sizes, leaf_off, Xp, yp = partition(w, device=True)
