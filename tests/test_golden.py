@@ -57,6 +57,8 @@ def test_gpu_matches_golden(built_lib, name):
     _, wθ = helpers.kernels(case["wkernel"])
     root, _, _ = P.setuppartition(case["X"], case["levels"])
     assert np.array_equal(root.hps_v, g["hps_v"]) and np.array_equal(root.hps_c, g["hps_c"])
+    droot, _, _ = P.setuppartition_device(case["X"], case["levels"])          # the level-stepped device build, same golden tree
+    assert np.array_equal(droot.hps_v, g["hps_v"]) and np.array_equal(droot.hps_c, g["hps_c"])
     X_set, X_set_inds, _, _ = P.organizetrainingsets_device(root, case["levels"], case["X"], case["eps"])
     assert np.array_equal([len(i) for i in X_set_inds], g["set_sizes"])
     assert np.array_equal([int(i.sum()) for i in X_set_inds], g["set_inds_sum"])
