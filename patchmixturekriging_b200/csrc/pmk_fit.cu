@@ -4,11 +4,11 @@
 //     U = constructkernelmatrix(X, θ); U[i,i] += σ²; c = U\y; L = cholesky(U).L
 // One CTA per BSP leaf.  Left-looking blocked Cholesky with 32-column panels:
 //   panel J:  C = K[J:, J] - L[J:, 0:J] * L[J, 0:J]^T
-//             (K evaluated on the fly straight into the accumulators -- the Gram matrix is never
-//              written to HBM; the trailing update runs on DMMA.8x8x4 with both operands read as
-//              packed fragment tiles, 512 B coalesced per warp load)
+//             (k_gram_tiles has written the lower tiles of K + sigma2*I into the leaf's L tile slots, in the order the
+//              accumulators want them; the update runs on DMMA.8x8x4 with both operands read as packed fragment
+//              tiles, 512 B coalesced per warp load)
 //             diagonal block: Cholesky + explicit 32x32 inverse by warp 0 (registers + shuffles)
-//             L[J+1:, J] = C * inv(L_JJ)^T on DMMA, stored once in packed-tile form.
+//             L[J+1:, J] = C * inv(L_JJ)^T on DMMA, straight from the accumulators, stored once in packed-tile form.
 // Several CTAs are resident per SM so that one leaf's serial diagonal-block phase overlaps the
 // other leaves' DMMA phases.
 #include <cstdlib>
@@ -243,10 +243,11 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
 // ---------------------------------------------------------------------------------------------
 // K2: blocked left-looking Cholesky of one leaf per CTA (see the file header).  Per 32-column panel J:
 //   A. warps 0-3: diagonal block  D = K_JJ - L[J,0:J] L[J,0:J]^T  -> shared memory (named barrier of 4 warps)
-//   B. warp 0 factors + inverts D (serial, latency-bound) WHILE all other warps (and warp 0 afterwards) pull
-//      row-tile groups off a shared counter, compute C = K[t,J] - L[t,0:J] L[J,0:J]^T on DMMA and park the raw
-//      C tiles in their L slots
-//   C. all warps: L[t,J] = C inv(L_JJ)^T on DMMA, final A-fragment-major tiles.
+//   B. warp 0 factors + inverts D (serial, latency-bound) and raises a shared-memory flag WHILE all other warps (and
+//      warp 0 afterwards) pull row-tile groups off a shared counter and compute C = K[t,J] - L[t,0:J] L[J,0:J]^T on DMMA;
+//      a group keeps C in its accumulators, waits for the flag and stores L[t,J] = C inv(L_JJ)^T (DMMA), final
+//      A-fragment-major tiles (PMK_CHOL_FUSED_SOLVE; with 0 the raw C tiles are parked in their L slots and
+//   C. after a CTA barrier all warps compute L[t,J] = C inv(L_JJ)^T from the parked tiles -- the round-1 kernel).
 // Lookahead of the diagonal block (measured on C3: k_chol 11.68 -> 11.41 ms; with the diagonal block's update removed
 // altogether -- wrong results, timing only -- 10.13 ms: the kernel is bound by the left-looking re-reads of the finished
 // columns, 34 GB per C3 fit, not by the length of the per-panel critical path).
