@@ -262,3 +262,22 @@ def test_partition_level_algorithm_in_numpy():
         assert np.array_equal(hv, ohv) and np.array_equal(hc, ohc)
         for p, b in enumerate(oinds):
             assert np.array_equal(perm[seg[p]:seg[p + 1]] + 1, b)
+
+
+def test_bench_reference_arm_contract():
+    """`bench.py --impl reference` (the CPU restatement timed on the host cores) prints ONE JSON line with the keys the driver
+    reads, on the product arm's metric / unit / config; small workload so that the CPU suite stays short."""
+    import json
+    import subprocess
+    import sys
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--steps", "1", "--warmup", "0"],
+                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "pts/s" and d["higher_is_better"] is True and d["dtype"] == "f64"
+    assert d["value"] > 0 and d["fit_leaves_per_s"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert d["config"]["workload"].startswith("c2:")
