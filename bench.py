@@ -146,6 +146,14 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
+def host_threads() -> int:
+    """Host threads the CPU arm may use: the cores this process may run on, whatever OMP_NUM_THREADS says."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def fp64_peak():
     p = os.path.join(ROOT, "profiles", "fp64_peaks_r01.json")
     try:
@@ -170,7 +178,8 @@ def cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=1, warmup=0, sample_lea
     findneighbourpartitions runs over the full tree, as in the reference)."""
     from oracle import c_oracle
     SQEXP, SPLINE34 = 0, 1
-    threads = threads or c_oracle.max_threads()
+    # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 into every rank, which omp_get_max_threads() obeys
+    threads = threads or host_threads()
     nl = min(sample_leaves, len(sizes))
     off_s = leaf_off.copy()
     off_s[nl + 1:] = off_s[nl]                      # leaves >= nl absent
@@ -233,6 +242,8 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    if args.impl == "reference" and rank != 0:
+        return                      # the CPU arm runs on rank 0 alone; the other ranks exit 0 without work
     w = workload(args.workload, args.nq)
     cfg = {"workload": f"{w['name']}: {w['D']}-D mixture-GP, N={len(w['X'])}, {1 << (w['levels'] - 1)} BSP leaves, eps={w['eps']}, "
                        f"radius={w['radius']}, delta={w['delta']}, SqExp eps_sq={w['eps_sq']}, sigma2={w['sigma2']}, Nq={w['nq']}",
@@ -240,13 +251,14 @@ def main():
 
     # ---------------- reference arm: CPU restatement on the host cores -----------------------
     if args.impl == "reference":
-        if rank != 0:
-            return
         root, sizes, leaf_off, Xp, yp = partition(w)
-        cb = cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=args.steps, warmup=min(args.warmup, 1))
+        # a bounded run whatever --steps says: one step of the sample is seconds of CPU work, three give a stable mean
+        ref_steps, ref_warmup = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        cb = cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=ref_steps, warmup=ref_warmup)
         line = {"impl": "reference", "metric": "query_pts_per_s (mixture-GP query; fit throughput in fit_leaves_per_s)",
                 "value": cb["query_pts_per_s"], "unit": "pts/s", "fit_leaves_per_s": cb["fit_leaves_per_s"], "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": 1e3 * (cb["fit_s"] + cb["query_s"]),
+                "steps": ref_steps, "warmup": ref_warmup, "steps_requested": args.steps,
+                "ms_per_step": 1e3 * (cb["fit_s"] + cb["query_s"]),
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": cfg,
                 "cpu_baseline": {"value": cb["query_pts_per_s"], "unit": "pts/s", "fit_leaves_per_s": cb["fit_leaves_per_s"],

@@ -266,18 +266,26 @@ def test_partition_level_algorithm_in_numpy():
 
 def test_bench_reference_arm_contract():
     """`bench.py --impl reference` (the CPU restatement timed on the host cores) prints ONE JSON line with the keys the driver
-    reads, on the product arm's metric / unit / config; small workload so that the CPU suite stays short."""
+    reads, on the product arm's metric / unit / config; small workload so that the CPU suite stays short.  Run the way torchrun
+    runs it: OMP_NUM_THREADS=1 injected, WORLD_SIZE=2 -- rank 0 must still use every host core and cap the step count, rank 1
+    must exit 0 without output."""
     import json
     import subprocess
     import sys
-    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "c2", "--steps", "1", "--warmup", "0"],
-                       capture_output=True, text=True, timeout=600, cwd=ROOT)
+    env = dict(os.environ, OMP_NUM_THREADS="1", WORLD_SIZE="2", RANK="0", LOCAL_RANK="0")
+    cmd = [sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--workload", "c2", "--steps", "20", "--warmup", "3"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, cwd=ROOT, env=env)
     assert r.returncode == 0, r.stderr[-2000:]
     lines = [l for l in r.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["unit"] == "pts/s" and d["higher_is_better"] is True and d["dtype"] == "f64"
-    assert d["value"] > 0 and d["fit_leaves_per_s"] > 0 and d["n_gpus"] == 1 and d["steps"] == 1
-    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["value"] > 0 and d["fit_leaves_per_s"] > 0 and d["n_gpus"] == 2
+    assert d["steps"] == 3 and d["steps_requested"] == 20 and d["warmup"] == 1          # bounded whatever was asked
+    ncores = len(os.sched_getaffinity(0))
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] == ncores   # not the injected OMP_NUM_THREADS=1
+    assert d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "pts/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["config"]["workload"].startswith("c2:")
+    r1 = subprocess.run(cmd, capture_output=True, text=True, timeout=120, cwd=ROOT, env=dict(env, RANK="1", LOCAL_RANK="1"))
+    assert r1.returncode == 0 and r1.stdout.strip() == ""
