@@ -40,7 +40,10 @@ def eval_flops(D):                 # one SqExp evaluation: differences/squares/s
 
 # --------------------------------------------------------------------------------------------
 def workload(name: str, nq_override: int | None = None):
+    import patchmixturekriging_b200 as P
     from patchmixturekriging_b200 import synth
+    if name in ("c5", "c5_mini"):
+        return workload_image(name, nq_override)
     lo, hi = [-5.0, -10.0], [5.0, 10.0]
     if name == "c3":          # BASELINE configs[2]: 2-D, N = 1M, 4096 leaves of ~512 points with overlap, 10M queries
         N, levels, eps, nq = 1_000_000, 13, 0.043, 10_000_000
@@ -70,15 +73,47 @@ def workload(name: str, nq_override: int | None = None):
     else:
         eps_sq = round(1.0 / (2.0 * spacing) ** 2)      # 3-D: length-scale ~2 spacings
     radius = 0.3 if name == "c2" else eps
-    return dict(name=name, X=X, y=y, levels=levels, eps=eps, radius=radius, delta=1e-5, sigma2=1e-3, eps_sq=float(eps_sq),
-                nq=nq, lo=lo, hi=hi, D=D)
+    eps_sq = float(eps_sq)
+    return dict(name=name, X=X, y=y, levels=levels, eps=eps, radius=radius, delta=1e-5, sigma2=1e-3, eps_sq=eps_sq,
+                kernel_desc=f"SqExp eps_sq={eps_sq}", kernel_oracle=(0, eps_sq), theta=lambda: P.GaussianKernel1DType(eps_sq),
+                nq=nq, lo=lo, hi=hi, D=D, queries="uniform")
+
+
+def workload_image(name: str, nq_override: int | None = None):
+    """BASELINE configs[4]: dev/image_upscale.jl-style image kriging (reference dev/image_upscale.jl:147-158,179-180,217-219):
+    training inputs = a regular G x G pixel grid scaled to [0,1]^2, values = a smooth synthetic image, Spline34 kernel with a
+    support radius of 5 pixels, sigma2 = 1e-5; queries = the 2x upsampled grid (4096^2 for c5).  levels = 13 with eps = 0.0015
+    gives 4096 leaves of 1235 .. 2040 points (mean 1562): every leaf inside PMK_MAX_LEAF_POINTS = 2048, the two largest size
+    classes of the pair kernel."""
+    import patchmixturekriging_b200 as P
+    if name == "c5":
+        G, levels, eps = 2048, 13, 0.0015
+    else:                     # 1/16 of it, same pixels per leaf
+        G, levels, eps = 512, 9, 0.0015 * 4
+    g = np.linspace(0.0, 1.0, G)
+    X = np.empty((G * G, 2))
+    X[:, 0] = np.tile(g, G)                 # x1 fastest, like vec(X_nD) in examples/mixGP.jl:55-63
+    X[:, 1] = np.repeat(g, G)
+    y = np.sin(7.0 * X[:, 0]) * np.cos(5.0 * X[:, 1]) + 0.5 * np.exp(-8.0 * ((X[:, 0] - 0.6) ** 2 + (X[:, 1] - 0.3) ** 2))
+    a = 0.2 * (G - 1)
+    Gq = 2 * G
+    nq = nq_override or Gq * Gq
+    return dict(name=name, X=X, y=y, levels=levels, eps=eps, radius=eps, delta=1e-5, sigma2=1e-5, eps_sq=None,
+                kernel_desc=f"Spline34 a={a}", kernel_oracle=(1, a), theta=lambda: P.Spline34KernelType(a),
+                nq=nq, lo=[0.0, 0.0], hi=[1.0, 1.0], D=2, queries=f"{Gq}x{Gq} grid", Gq=Gq)
 
 
 def gen_queries(w, first: int, count: int) -> np.ndarray:
-    """queries [first, first+count) of the workload's stream (uniform on the domain)."""
+    """queries [first, first+count) of the workload's stream (uniform on the domain; the upsampled grid, x1 fastest, for the
+    image workloads)."""
     from patchmixturekriging_b200 import synth
     lo, hi = np.asarray(w["lo"]), np.asarray(w["hi"])
     D = len(lo)
+    if w["queries"] != "uniform":
+        Gq = w["Gq"]
+        g = np.linspace(lo[0], hi[0], Gq)
+        idx = np.arange(first, first + count, dtype=np.int64)
+        return np.ascontiguousarray(np.column_stack([g[idx % Gq], g[(idx // Gq) % Gq]]))
     Xq = np.empty((count, D))
     for d in range(D):
         u = synth.uniform01(1234567, count, d * w["nq"] + first)
@@ -177,7 +212,8 @@ def cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=1, warmup=0, sample_lea
     query stream among those whose home and neighbour leaves are all in that set (the all-hyperplanes scan of
     findneighbourpartitions runs over the full tree, as in the reference)."""
     from oracle import c_oracle
-    SQEXP, SPLINE34 = 0, 1
+    SPLINE34 = 1
+    KIND, KPAR = w["kernel_oracle"]
     # all host cores, explicitly: torchrun exports OMP_NUM_THREADS=1 into every rank, which omp_get_max_threads() obeys
     threads = threads or host_threads()
     nl = min(sample_leaves, len(sizes))
@@ -199,15 +235,15 @@ def cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=1, warmup=0, sample_lea
         cand.append(Xq[home <= nl])
         first += cnt
     cand = np.concatenate(cand) if cand else np.zeros((0, w["D"]))
-    _, _, _, _, absent = c_oracle.query(hv, hc, w["levels"], off_s, Xs, np.zeros(len(Xs)), np.zeros(1), SQEXP, w["eps_sq"], cand,
+    _, _, _, _, absent = c_oracle.query(hv, hc, w["levels"], off_s, Xs, np.zeros(len(Xs)), np.zeros(1), KIND, KPAR, cand,
                                         w["radius"], w["delta"], SPLINE34, 1.0 / w["radius"], threads, structure_only=True)
     Xq_s = np.ascontiguousarray(cand[absent == 0][:sample_queries])
     fit_t, q_t = [], []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        alpha, L, off2, Xpk = c_oracle.fit(X_set, y_set, SQEXP, w["eps_sq"], w["sigma2"], threads)
+        alpha, L, off2, Xpk = c_oracle.fit(X_set, y_set, KIND, KPAR, w["sigma2"], threads)
         t1 = time.perf_counter()
-        Yq, Vq, _, npairs, ab = c_oracle.query(hv, hc, w["levels"], off_s, Xpk, alpha, L, SQEXP, w["eps_sq"], Xq_s, w["radius"],
+        Yq, Vq, _, npairs, ab = c_oracle.query(hv, hc, w["levels"], off_s, Xpk, alpha, L, KIND, KPAR, Xq_s, w["radius"],
                                                w["delta"], SPLINE34, 1.0 / w["radius"], threads)
         t2 = time.perf_counter()
         if it >= warmup:
@@ -221,11 +257,6 @@ def cpu_baseline(w, root, sizes, leaf_off, Xp, yp, steps=1, warmup=0, sample_lea
 
 
 # --------------------------------------------------------------------------------------------
-class _CudaSpan:
-    def __init__(self, ptr, nbytes):
-        self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -236,6 +267,7 @@ def main():
     ap.add_argument("--nq", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-setup", action="store_true")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -246,7 +278,7 @@ def main():
         return                      # the CPU arm runs on rank 0 alone; the other ranks exit 0 without work
     w = workload(args.workload, args.nq)
     cfg = {"workload": f"{w['name']}: {w['D']}-D mixture-GP, N={len(w['X'])}, {1 << (w['levels'] - 1)} BSP leaves, eps={w['eps']}, "
-                       f"radius={w['radius']}, delta={w['delta']}, SqExp eps_sq={w['eps_sq']}, sigma2={w['sigma2']}, Nq={w['nq']}",
+                       f"radius={w['radius']}, delta={w['delta']}, {w['kernel_desc']}, sigma2={w['sigma2']}, Nq={w['nq']} ({w['queries']})",
            "l2": "inputs larger than L2 (packed factors + queries + pair arrays are GBs per step vs 126 MB L2)"}
 
     # ---------------- reference arm: CPU restatement on the host cores -----------------------
@@ -268,248 +300,264 @@ def main():
         return
 
     # ---------------- B200 arm ---------------------------------------------------------------
+    # One model over the N GPUs of the box by sub-tree ownership, through the library's own multi-GPU entry points
+    # (pmk_multi_*: one host thread + stream set per GPU, CUDA peer copies over NVLink) -- the path a caller of
+    # fitmixtureGP! / querymixtureGP! reaches.  Under torchrun every rank joins the NCCL process group (launch barrier, final
+    # reduction of the timings); rank 0's process drives all N GPUs through the library, the other ranks wait on the host.
     import torch
-    import torch.distributed as dist
     import patchmixturekriging_b200 as P
-    from patchmixturekriging_b200 import _lib, mixturegp, sharding
+    from patchmixturekriging_b200 import _lib
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback")
-    dev = local_rank if world > 1 else 0
-    torch.cuda.set_device(dev)
+    dist = None
+    host_group = None
     if world > 1:
+        import torch.distributed as dist
         # NCCL_DEBUG=VERSION (set in some images) makes NCCL print its version to STDOUT, next to the one JSON line
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
-        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{dev}"))
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
+        host_group = dist.new_group(backend="gloo")     # long waits happen on the host: no NCCL kernel spins on a GPU rank 0 is using
+        one = torch.ones(1, device="cuda")
+        dist.all_reduce(one)                            # every rank's GPU is up and NCCL connects the N of them
+        torch.cuda.synchronize()
+        assert int(one.item()) == world
+    n_gpus = world if world > 1 else max(1, args.gpus)
+    result = None
+    if rank == 0:
+        if torch.cuda.device_count() < n_gpus:
+            raise SystemExit(f"bench.py: {n_gpus} GPUs asked, {torch.cuda.device_count()} visible to rank 0")
+        result = run_b200(args, w, cfg, n_gpus)
+    if world > 1:
+        dist.barrier(group=host_group)                  # ranks > 0 wait here (gloo: on the host) while rank 0 measures
+        t = torch.tensor([result["ms_per_step"] if result else 0.0], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)        # the contract's max over ranks (rank 0 timed all N GPUs)
+        if result:
+            result["ms_per_step"] = float(t.item())
+    if rank == 0:
+        print(json.dumps(result))
+    if world > 1:
+        dist.barrier(group=host_group)
+        dist.destroy_process_group()
 
+
+def measure_setup(w):
+    """setuppartition + organizetrainingsets with the O(N) work on the GPU (what a caller pays once per data set, outside the
+    timed fit + query step): milliseconds, second of two runs."""
+    import patchmixturekriging_b200 as P
+    ms = None
+    for _ in range(2):
+        t0 = time.perf_counter()
+        root, _, _ = P.setuppartition_device(w["X"], w["levels"])
+        t1 = time.perf_counter()
+        P.organizetrainingsets_device(root, w["levels"], w["X"], w["eps"])
+        t2 = time.perf_counter()
+        ms = {"setuppartition_device_ms": 1e3 * (t1 - t0), "organizetrainingsets_device_ms": 1e3 * (t2 - t1)}
+    return ms
+
+
+def run_b200(args, w, cfg, n_gpus):
+    import torch
+    import patchmixturekriging_b200 as P
+    from patchmixturekriging_b200 import _lib
+    L = _lib.lib()
+    D = w["D"]
     root, sizes, leaf_off, Xp, yp = partition(w, device=True)
     n_leaves = len(sizes)
     Nq = w["nq"]
-    q0, q1 = sharding.query_slice(rank, world, Nq)
-    Xq_h = gen_queries(w, q0, q1 - q0)
-    nq_loc = q1 - q0
-    l0, lc = sharding.leaf_range(rank, world, n_leaves)
-    l1 = l0 + lc
-
-    θ = P.GaussianKernel1DType(w["eps_sq"])
+    Xq_h = gen_queries(w, 0, Nq)
+    θ = w["theta"]()
     wθ = P.Spline34KernelType(1.0 / w["radius"])
-    X_set = [Xp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
-    y_set = [yp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
-    η = P.MixtureGPType(X_set, P.fetchhyperplanes(root), device=dev, fit_range=(l0, l1 - l0) if world > 1 else None)
-    h = η.handle
-    L = _lib.lib()
-    hv = np.ascontiguousarray(root.hps_v); hc = np.ascontiguousarray(root.hps_c)
-    h.check(L.pmk_set_tree(h.raw, w["D"], w["levels"], _lib.ptr(hv), _lib.ptr(hc)))
-    if world > 1:
-        h.check(L.pmk_set_fit_range(h.raw, l0, l1 - l0))
+    kp, wp = θ.params, wθ.params
+    hv, hc = np.ascontiguousarray(root.hps_v), np.ascontiguousarray(root.hps_c)
+    # pinned host buffers: what the reference-side caller hands over (packed leaves, queries) and gets back
+    pin = lambda a: torch.from_numpy(a).pin_memory().numpy()
+    hXp, hyp, hXq = pin(Xp), pin(yp), pin(Xq_h)
+    hYq, hVq = pin(np.empty(Nq)), pin(np.empty(Nq))
 
-    dX = torch.from_numpy(Xp).cuda(); dy = torch.from_numpy(yp).cuda(); dXq = torch.from_numpy(Xq_h).cuda()
-    dYq = torch.empty(nq_loc, dtype=torch.float64, device="cuda"); dVq = torch.empty_like(dYq)
-    gathered = [None, None]
-    kp = θ.params; wp = wθ.params
-    stream = torch.cuda.ExternalStream(int(L.pmk_stream(h.raw)), device=dev)
+    m = _lib.MultiHandle(list(range(n_gpus)))
+    m.check(L.pmk_multi_set_tree(m.raw, D, w["levels"], _lib.ptr(hv), _lib.ptr(hc)))
     bad, info = C.c_int64(0), C.c_int(0)
 
-    def span_of(which, first, count):
-        ptr, nb = mixturegp.model_buffer(η, which, first, count)
-        return torch.as_tensor(_CudaSpan(ptr, nb), device=f"cuda:{dev}") if nb else torch.empty(0, dtype=torch.float64, device="cuda")
+    def sync_all():
+        for d in range(n_gpus):
+            torch.cuda.synchronize(d)
 
-    def exchange_factors():
-        """leaf -> rank map: every rank broadcasts the spans it factorised (NCCL over NVLink)."""
-        mixturegp.build_M(η)          # pair-kernel operands of the leaves this rank factorised; only P = inv(L) travels
-        h.synchronize()
-        sharding.exchange_spans(span_of, n_leaves, (_lib.BUF_P, _lib.BUF_ALPHA))
-        torch.cuda.current_stream().synchronize()
-        mixturegp.mark_fitted(η, p_exchanged=True)
+    # ---- value: inputs resident in HBM (staged once), K timed steps of fit + query ------------------------------------
+    m.check(L.pmk_multi_stage_training(m.raw, D, n_leaves, _lib.ptr(leaf_off), _lib.ptr(hXp), _lib.ptr(hyp)))
+    m.check(L.pmk_multi_stage_queries(m.raw, Nq, _lib.ptr(hXq)))
 
     def step_device():
-        """fit + query with inputs resident in HBM; returns (fit_ms, exchange_ms, query_ms) from CUDA events on the
-        handle's stream (the NCCL work is bracketed by stream synchronisation, so the events see it)."""
-        e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-        e[0].record(stream)
-        h.check(L.pmk_fit_dev(h.raw, w["D"], n_leaves, _lib.ptr(leaf_off), dX.data_ptr(), dy.data_ptr(), θ.kernel_id, _lib.ptr(kp), 1,
-                              w["sigma2"], C.byref(bad), C.byref(info)))
-        e[1].record(stream)
-        if world > 1:
-            h.synchronize()
-            exchange_factors()
-        e[2].record(stream)
-        h.check(L.pmk_query_dev(h.raw, nq_loc, dXq.data_ptr(), w["radius"], w["delta"], wθ.kernel_id, _lib.ptr(wp), 1, 0,
-                                dYq.data_ptr(), dVq.data_ptr()))
-        if world > 1:
-            h.synchronize()
-            gathered[0] = sharding.gather_slices(dYq, Nq)
-            gathered[1] = sharding.gather_slices(dVq, Nq)
-            torch.cuda.current_stream().synchronize()
-        e[3].record(stream)
-        e[3].synchronize()
-        return e[0].elapsed_time(e[1]), e[1].elapsed_time(e[2]), e[2].elapsed_time(e[3])
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+        m.check(L.pmk_multi_fit_staged(m.raw, θ.kernel_id, _lib.ptr(kp), kp.shape[0], w["sigma2"], C.byref(bad), C.byref(info)))
+        m.check(L.pmk_multi_query_staged(m.raw, w["radius"], w["delta"], wθ.kernel_id, _lib.ptr(wp), wp.shape[0], 0))
+        return m.timings()
 
     for _ in range(args.warmup):
         step_device()
-    barrier()
-    launches0 = h.launch_count()
-    sampler = ClockSampler(dev)
-    if rank == 0:
-        sampler.start()
+    sync_all()
+    launches0 = m.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
     t_wall0 = time.perf_counter()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record(stream)
-    fit_ms, exch_ms, query_ms, kt = [], [], [], []
+    fit_ms, query_ms, mt_all, kt_all = [], [], [], []
     for _ in range(args.steps):
-        f, x, q = step_device()
-        fit_ms.append(f + x); exch_ms.append(x); query_ms.append(q)
-        kt.append(h.timings().copy())
-    ev1.record(stream)
-    barrier()
-    ev1.synchronize()
-    total_ms = ev0.elapsed_time(ev1)
+        mt, per = step_device()          # device times: CUDA events on every rank's stream, max over the ranks
+        fit_ms.append(mt[_lib.MT_FIT]); query_ms.append(mt[_lib.MT_QUERY]); mt_all.append(mt.copy()); kt_all.append(per.copy())
+    sync_all()
     wall_ms = 1e3 * (time.perf_counter() - t_wall0)
-    clocks = sampler.stop() if rank == 0 else None
-    launches = h.launch_count() - launches0
+    clocks = sampler.stop()
+    launches = m.launch_count() - launches0
+    fit_ms_m, query_ms_m = float(np.mean(fit_ms)), float(np.mean(query_ms))
+    mt = np.mean(np.array(mt_all), axis=0)
+    kt = np.mean(np.array(kt_all), axis=0)            # (n_gpus, T_COUNT) per-kernel times of every rank
+    ktmax = kt.max(axis=0)
+    pairs_per_leaf = np.empty(n_leaves, dtype=np.int64)
+    m.check(L.pmk_multi_leaf_pairs(m.raw, _lib.ptr(pairs_per_leaf)))
 
-    t = torch.tensor([total_ms, float(np.mean(fit_ms)), float(np.mean(query_ms)), float(np.mean(exch_ms))], dtype=torch.float64,
-                     device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms, fit_ms_m, query_ms_m, exch_ms_m = (float(x) for x in t.cpu())
-    kt = np.mean(np.array(kt), axis=0)
-
-    # ---------------- e2e through the public host API, pinned host buffers --------------------
+    # ---- e2e: the caller's path, host buffers in, all Nq results in the caller's host arrays ----------------------------
     e2e = None
     if not args.no_e2e:
-        hXq = torch.from_numpy(Xq_h).pin_memory().numpy()
-        hYq = torch.empty(nq_loc, dtype=torch.float64).pin_memory().numpy()
-        hVq = torch.empty(nq_loc, dtype=torch.float64).pin_memory().numpy()
-        hXp = torch.from_numpy(Xp).pin_memory().numpy()
-        hyp = torch.from_numpy(yp).pin_memory().numpy()
-        η.X_parts = [hXp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
-        y_set_p = [hyp[leaf_off[p]:leaf_off[p + 1]] for p in range(n_leaves)]
-
         def step_host():
             t0 = time.perf_counter()
-            # fitmixtureGP_ packs the leaf list; the packed arrays are what crosses the ABI
-            h.check(L.pmk_fit(h.raw, w["D"], n_leaves, _lib.ptr(leaf_off), _lib.ptr(hXp), _lib.ptr(hyp), θ.kernel_id, _lib.ptr(kp), 1,
-                              w["sigma2"], C.byref(bad), C.byref(info)))
-            if world > 1:
-                exchange_factors()
-            η._fitted, η.θ = True, θ
+            m.check(L.pmk_multi_fit(m.raw, D, n_leaves, _lib.ptr(leaf_off), _lib.ptr(hXp), _lib.ptr(hyp), θ.kernel_id, _lib.ptr(kp),
+                                    kp.shape[0], w["sigma2"], C.byref(bad), C.byref(info)))
             t1 = time.perf_counter()
-            P.querymixtureGP_(hYq, hVq, hXq, η, root, w["levels"], w["radius"], w["delta"], θ, w["sigma2"], wθ)
-            if world > 1:
-                gathered[0] = sharding.gather_slices(torch.from_numpy(hYq).cuda(), Nq)
-                gathered[1] = sharding.gather_slices(torch.from_numpy(hVq).cuda(), Nq)
-                torch.cuda.synchronize()
+            m.check(L.pmk_multi_query(m.raw, Nq, _lib.ptr(hXq), w["radius"], w["delta"], wθ.kernel_id, _lib.ptr(wp), wp.shape[0], 0,
+                                      _lib.ptr(hYq), _lib.ptr(hVq)))
             t2 = time.perf_counter()
             return 1e3 * (t1 - t0), 1e3 * (t2 - t1)
 
         step_host()
-        barrier()
-        ef, eq = [], []
-        for _ in range(max(1, min(args.steps, 3))):
-            a, b = step_host()
-            ef.append(a); eq.append(b)
-        te = torch.tensor([float(np.mean(ef)), float(np.mean(eq))], dtype=torch.float64, device="cuda")
-        if world > 1:
-            dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        ef_m, eq_m = (float(x) for x in te.cpu())
+        ef, eq = zip(*[step_host() for _ in range(max(1, min(args.steps, 3)))])
+        ef_m, eq_m = float(np.mean(ef)), float(np.mean(eq))
+        assert np.isfinite(hYq).all() and np.all(hVq >= 1e-12)
         e2e = {"value": Nq / (eq_m * 1e-3), "unit": "pts/s", "fit_leaves_per_s": n_leaves / (ef_m * 1e-3),
-               "h2d_bytes_per_step": int(Xq_h.nbytes + Xp.nbytes + yp.nbytes), "d2h_bytes_per_step": int(2 * 8 * nq_loc),
+               "h2d_bytes_per_step": int(Xq_h.nbytes + Xp.nbytes + yp.nbytes), "d2h_bytes_per_step": int(2 * 8 * Nq),
                "ms_fit": ef_m, "ms_query": eq_m,
-               "api": "pmk_fit(host X,y) + patchmixturekriging_b200.querymixtureGP_(Yq, Vq, Xq, ...) with pinned host arrays"}
+               "api": "pmk_multi_fit(host X, y) + pmk_multi_query(host Xq -> host Yq, Vq) on pinned host arrays; all Nq results end "
+                      "in the calling process's host buffers"}
 
-    # ---------------- roofline of the dominant kernel (K3, k_query_pairs) ---------------------
-    if rank == 0:
-        npairs = C.c_int64(0)
-        h.check(L.pmk_last_query_pairs(h.raw, C.byref(npairs)))
-        pl = np.empty(npairs.value, dtype=np.int32)
-        h.check(L.pmk_last_query_debug(h.raw, None, None, _lib.ptr(pl), None, None, None, None, None))
-        per_leaf = np.bincount(pl - 1, minlength=n_leaves).astype(np.float64)
-        nn = sizes.astype(np.float64)
-        flops_pairs = float((per_leaf * (nn * nn + nn * (eval_flops(w["D"]) + 4))).sum())      # TRSM n^2 + n*(eval + mean 2 + ||s||^2 2)
-        flops_fit = float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * eval_flops(w["D"])).sum()) * (l1 - l0) / n_leaves if world > 1 else \
-            float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * eval_flops(w["D"])).sum())
+    # ---- rooflines ----------------------------------------------------------------------------------------------------
+    nn = sizes.astype(np.float64)
+    per_leaf = pairs_per_leaf.astype(np.float64)
+    flops_pairs = float((per_leaf * (nn * nn + nn * (eval_flops(D) + 4))).sum())      # TRSM n^2 + n*(eval + mean 2 + ||s||^2 2)
+    flops_chol = float((nn ** 3 / 3).sum())
+    flops_fit = float((nn ** 3 / 3 + 2 * nn * nn + nn * (nn + 1) / 2 * eval_flops(D)).sum())
+    h0 = m.rank_handle(0)
+    peak_run = C.c_double(0.0)
+    try:
+        h0.check(L.pmk_measure_fp64_peak(h0.raw, C.byref(peak_run)))
+        peak, peak_src = float(peak_run.value), ("measured in this run: register-resident mma.sync.m8n8k4.f64 (DMMA.8x8x4) loop on GPU 0, "
+                                                 "best of 3 (pmk_measure_fp64_peak); MEASURED_PEAKS.json has no FP64 entry")
+    except Exception:
         peak, peak_src = fp64_peak()
-        ach = flops_pairs / (kt[_lib.T_Q_PAIRS] * 1e-3) / 1e12
-        try:      # DRAM bytes of the dominant kernel from the committed ncu --set full capture (per launch, leaf class <=512)
-            tr_ = json.load(open(os.path.join(ROOT, "profiles", "k3_traffic_r01.json")))
-            traffic = float(tr_["dram_bytes_read"] + tr_["dram_bytes_write"])
-            traffic_of = {"kernel": tr_["kernel"], "source": tr_["source"]}
-        except Exception:
-            traffic, traffic_of = None, None
-        roofline = {"kernel": "k_query_rowp (fused cross-covariance + mean + variance, s = inv(L) kq as a row-panel product on DMMA, per (query, leaf) pair)", "bound": "tensor",
-                    "pipe": "FP64 DMMA.8x8x4 (mma.sync.m8n8k4.f64); tcgen05 has no f64 kind", "achieved": ach, "peak": peak,
-                    "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic, "traffic_of": traffic_of,
-                    "algorithmic_flops_per_launch": flops_pairs, "ms_per_launch": float(kt[_lib.T_Q_PAIRS]),
-                    "pairs_per_launch": int(npairs.value)}
-        fit_ach = flops_fit / ((kt[_lib.T_FIT_CHOL] + kt[_lib.T_FIT_GRAM]) * 1e-3) / 1e12
-        phases = {"fit_pack_ms": float(kt[_lib.T_FIT_PACK]), "fit_gram_ms": float(kt[_lib.T_FIT_GRAM]),
-                  "fit_chol_ms": float(kt[_lib.T_FIT_CHOL]),
-                  "fit_solve_ms": float(kt[_lib.T_FIT_SOLVE]), "query_tree_ms": float(kt[_lib.T_Q_TREE]),
-                  "query_make_M_ms": float(kt[_lib.T_Q_MAKE_M]), "query_invert_ms": float(kt[_lib.T_Q_INVERT]), "query_pairs_ms": float(kt[_lib.T_Q_PAIRS]),
-                  "query_combine_ms": float(kt[_lib.T_Q_COMBINE]),
-                  "fit_gram_chol_tflops": fit_ach, "fit_gram_chol_frac_of_fp64_peak": fit_ach / peak}
-        # HBM side (north star: "achieved HBM GB/s for Gram build"): the fit's Gram tiles write the lower tiles of every leaf
-        # once (8 B x packed factor doubles); the standalone Gram kernel (constructkernelmatrix) writes 8 n^2 B.
-        hbm_peak, hbm_src = hbm_peak_gbs()
-        try:
-            _, l_bytes = mixturegp.model_buffer(η, _lib.BUF_L, l0, l1 - l0)
-            gt = l_bytes / (kt[_lib.T_FIT_GRAM] * 1e-3) / 1e9
-            ng = 8192
-            Xg = np.ascontiguousarray(w["X"][:ng])
-            hg = _lib.Handle(dev)
-            Kg = np.empty((ng, ng), order="F")
-            tg = []
-            for _ in range(3):
-                hg.check(L.pmk_gram(hg.raw, w["D"], ng, _lib.ptr(Xg), θ.kernel_id, _lib.ptr(kp), kp.shape[0], 0.0, _lib.ptr(Kg)))
-                tg.append(float(hg.timings()[_lib.T_GRAM]))
-            hg.close()
-            g_ms = float(np.mean(tg[1:]))
-            phases["hbm"] = {"peak_gbs": hbm_peak, "peak_source": hbm_src,
-                             "k_gram_tiles": {"bytes_written": int(l_bytes), "ms": float(kt[_lib.T_FIT_GRAM]), "gbs": gt, "frac": gt / hbm_peak},
-                             "k_gram": {"what": f"constructkernelmatrix, n={ng} (8 n^2 = {8 * ng * ng >> 20} MiB written, > L2)", "ms": g_ms,
-                                        "gbs": 8.0 * ng * ng / (g_ms * 1e-3) / 1e9, "frac": 8.0 * ng * ng / (g_ms * 1e-3) / 1e9 / hbm_peak}}
-        except Exception as exc:      # an instrumentation extra: never lose the bench line to it
-            phases["hbm"] = {"error": repr(exc)}
-        # per leaf-size class of the pair kernel: ms and achieved TFLOP/s
-        npad_ = (sizes + 31) // 32 * 32
-        cls_ = np.where(npad_ <= 512, 0, np.where(npad_ <= 768, 1, np.where(npad_ <= 1024, 2, np.where(npad_ <= 1536, 3, 4))))
-        phases["leaf_points_min_mean_max"] = [int(sizes.min()), float(sizes.mean()), int(sizes.max())]
-        fl_leaf = per_leaf * (nn * nn + nn * (eval_flops(w["D"]) + 4))
-        phases["pairs_by_class"] = [
-            {"class": c, "leaves": int((cls_ == c).sum()), "pairs": int(per_leaf[cls_ == c].sum()),
-             "ms": float(kt[_lib.T_Q_PAIRS_CLASS0 + c]),
-             "tflops": float(fl_leaf[cls_ == c].sum() / max(kt[_lib.T_Q_PAIRS_CLASS0 + c], 1e-9) / 1e9)}
-            for c in range(5) if (cls_ == c).any()]
+    hbm_peak, hbm_src = hbm_peak_gbs()
+    # per-GPU rate of the dominant kernel: all pairs' flops over the GPU-seconds the pair kernel ran on all ranks
+    pair_gpu_s = float(kt[:, _lib.T_Q_PAIRS].sum()) * 1e-3
+    ach = flops_pairs / pair_gpu_s / 1e12
+    npairs_total = int(pairs_per_leaf.sum())
 
-        line = {"metric": "query_pts_per_s (mixture-GP query; fit throughput in fit_leaves_per_s)", "value": Nq / (query_ms_m * 1e-3),
-                "unit": "pts/s", "fit_leaves_per_s": n_leaves / (fit_ms_m * 1e-3), "n_gpus": world, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "ms_fit": fit_ms_m, "ms_query": query_ms_m,
-                "ms_factor_exchange": exch_ms_m, "fit_compute_leaves_per_s": n_leaves / max((fit_ms_m - exch_ms_m) * 1e-3, 1e-9),
-                "wall_ms_per_step": wall_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-                "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
-                "roofline": roofline, "phases": phases}
-        if e2e:
-            line["e2e"] = e2e
-        if world == 1 and not args.no_cpu_baseline:
-            cb = cpu_baseline(w, root, sizes, leaf_off, Xp, yp)
-            # parity spot check of the sample against the GPU through the public API
-            Yg, Vg, _ = P.querymixtureGP(cb["sample_xq"], η, root, w["levels"], w["radius"], w["delta"], θ, w["sigma2"], wθ)
-            sc_y, sc_v = np.sqrt(np.mean(cb["sample_y"] ** 2)), np.sqrt(np.mean(cb["sample_v"] ** 2))
-            line["cpu_baseline"] = {"value": cb["query_pts_per_s"], "unit": "pts/s", "fit_leaves_per_s": cb["fit_leaves_per_s"],
-                                    "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
-                                    "parity_vs_gpu": {"mean_max_err_over_rms": float(np.abs(Yg - cb["sample_y"]).max() / sc_y),
-                                                      "var_max_err_over_rms": float(np.abs(Vg - cb["sample_v"]).max() / sc_v)}}
-        print(json.dumps(line))
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+    def committed_traffic(fname):
+        """DRAM bytes per launch from a committed `ncu --set full` capture (ncu cannot run inside the bench): only quoted for
+        the configuration it was captured on (c3, one GPU); otherwise null."""
+        if n_gpus != 1 or w["name"] != "c3":
+            return None, None
+        try:
+            tr_ = json.load(open(os.path.join(ROOT, "profiles", fname)))
+            return float(tr_["dram_bytes_read"] + tr_["dram_bytes_write"]), {"kernel": tr_["kernel"], "source": tr_["source"]}
+        except Exception:
+            return None, None
+
+    traffic, traffic_of = committed_traffic("k3_traffic_r02.json")
+    if traffic is None:
+        traffic, traffic_of = committed_traffic("k3_traffic_r01.json")
+    roofline = {"kernel": "k_query_rowp (fused cross-covariance + mean + variance, s = inv(L) kq as a row-panel product on DMMA, per (query, leaf) pair)",
+                "bound": "tensor", "pipe": "FP64 DMMA.8x8x4 (mma.sync.m8n8k4.f64); tcgen05 has no f64 kind", "achieved": ach, "peak": peak,
+                "unit": "TFLOP/s", "frac": ach / peak, "peak_source": peak_src, "traffic": traffic, "traffic_of": traffic_of,
+                "algorithmic_flops_per_step": flops_pairs, "ms_per_launch_set_max_over_ranks": float(ktmax[_lib.T_Q_PAIRS]),
+                "gpu_ms_all_ranks": pair_gpu_s * 1e3, "pairs_per_step": npairs_total,
+                "note": "achieved = algorithmic flops of all (query, leaf) pairs / GPU-seconds of the pair kernel summed over the ranks = per-GPU rate"}
+    chol_gpu_s = float(kt[:, _lib.T_FIT_CHOL].sum()) * 1e-3
+    gram_gpu_s = float(kt[:, _lib.T_FIT_GRAM].sum()) * 1e-3
+    chol_traffic, chol_traffic_of = committed_traffic("k_chol_traffic_r02.json")
+    l_bytes = float((np.square((sizes + 31) // 32 * 32 // 8) + (sizes + 31) // 32 * 32 // 8).sum() / 2 * 512)      # packed lower tiles
+    roofline_fit = {"kernel": "k_chol (batched blocked Cholesky, one leaf per CTA, DMMA trailing updates)", "bound": "tensor",
+                    "achieved": flops_chol / chol_gpu_s / 1e12, "peak": peak, "unit": "TFLOP/s", "frac": flops_chol / chol_gpu_s / 1e12 / peak,
+                    "algorithmic_flops_per_step": flops_chol, "algorithmic_bytes_per_step": 2.0 * l_bytes,
+                    "traffic": chol_traffic, "traffic_of": chol_traffic_of, "gpu_ms_all_ranks": chol_gpu_s * 1e3,
+                    "with_gram_tiles": {"achieved": flops_fit / (chol_gpu_s + gram_gpu_s) / 1e12,
+                                        "frac": flops_fit / (chol_gpu_s + gram_gpu_s) / 1e12 / peak}}
+    phases = {"ranks": n_gpus,
+              "max_over_ranks_ms": {"fit_pack": float(ktmax[_lib.T_FIT_PACK]), "fit_gram": float(ktmax[_lib.T_FIT_GRAM]),
+                                    "fit_chol": float(ktmax[_lib.T_FIT_CHOL]), "fit_solve": float(ktmax[_lib.T_FIT_SOLVE]),
+                                    "fit_refine": float(ktmax[_lib.T_FIT_REFINE]), "fit_operand_invert": float(ktmax[_lib.T_Q_INVERT]),
+                                    "fit_operand_make_M": float(ktmax[_lib.T_Q_MAKE_M]), "query_tree": float(ktmax[_lib.T_Q_TREE]),
+                                    "query_route_sort": float(ktmax[_lib.T_Q_ROUTE_SORT]), "query_pairs": float(ktmax[_lib.T_Q_PAIRS]),
+                                    "query_combine": float(ktmax[_lib.T_Q_COMBINE])},
+              "query_stages_ms": {"plan": float(mt[_lib.MT_Q_PLAN]), "route": float(mt[_lib.MT_Q_ROUTE]), "pairs": float(mt[_lib.MT_Q_PAIRS]),
+                                  "return_combine": float(mt[_lib.MT_Q_RETURN])},
+              "per_rank_query_pairs_ms": [float(x) for x in kt[:, _lib.T_Q_PAIRS]],
+              "per_rank_fit_chol_ms": [float(x) for x in kt[:, _lib.T_FIT_CHOL]],
+              "setup_ms": measure_setup(w) if not args.no_setup else None}
+    # HBM side (north star: "achieved HBM GB/s for Gram build")
+    try:
+        gt = l_bytes / gram_gpu_s / 1e9
+        ng = 8192
+        Xg = np.ascontiguousarray(w["X"][:ng])
+        Kg = np.empty((ng, ng), order="F")
+        tg = []
+        for _ in range(3):
+            h0.check(L.pmk_gram(h0.raw, D, ng, _lib.ptr(Xg), θ.kernel_id, _lib.ptr(kp), kp.shape[0], 0.0, _lib.ptr(Kg)))
+            tg.append(float(h0.timings()[_lib.T_GRAM]))
+        g_ms = float(np.mean(tg[1:]))
+        phases["hbm"] = {"peak_gbs": hbm_peak, "peak_source": hbm_src,
+                         "k_gram_tiles": {"bytes_written": int(l_bytes), "gpu_ms_all_ranks": gram_gpu_s * 1e3, "gbs": gt, "frac": gt / hbm_peak},
+                         "k_gram": {"what": f"constructkernelmatrix, n={ng} (8 n^2 = {8 * ng * ng >> 20} MiB written, > L2)", "ms": g_ms,
+                                    "gbs": 8.0 * ng * ng / (g_ms * 1e-3) / 1e9, "frac": 8.0 * ng * ng / (g_ms * 1e-3) / 1e9 / hbm_peak}}
+    except Exception as exc:      # an instrumentation extra: never lose the bench line to it
+        phases["hbm"] = {"error": repr(exc)}
+    npad_ = (sizes + 31) // 32 * 32
+    cls_ = np.where(npad_ <= 512, 0, np.where(npad_ <= 768, 1, np.where(npad_ <= 1024, 2, np.where(npad_ <= 1536, 3, 4))))
+    phases["leaf_points_min_mean_max"] = [int(sizes.min()), float(sizes.mean()), int(sizes.max())]
+    fl_leaf = per_leaf * (nn * nn + nn * (eval_flops(D) + 4))
+    phases["pairs_by_class"] = [
+        {"class": c, "leaves": int((cls_ == c).sum()), "pairs": int(per_leaf[cls_ == c].sum()),
+         "gpu_ms_all_ranks": float(kt[:, _lib.T_Q_PAIRS_CLASS0 + c].sum()),
+         "tflops_per_gpu": float(fl_leaf[cls_ == c].sum() / max(kt[:, _lib.T_Q_PAIRS_CLASS0 + c].sum(), 1e-9) / 1e9)}
+        for c in range(5) if (cls_ == c).any()]
+    cond = C.c_double(0.0); sv = C.c_int(0)
+    h0.check(L.pmk_condition_estimate(h0.raw, C.byref(cond), C.byref(sv)))
+    phases["query_solver"] = {"in_use": int(sv.value), "cond_lower_bound_rank0": float(cond.value)}
+
+    line = {"metric": "query_pts_per_s (mixture-GP query; fit throughput in fit_leaves_per_s)", "value": Nq / (query_ms_m * 1e-3),
+            "unit": "pts/s", "fit_leaves_per_s": n_leaves / (fit_ms_m * 1e-3), "n_gpus": n_gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": wall_ms / args.steps, "ms_fit": fit_ms_m, "ms_query": query_ms_m,
+            "ms_fit_plus_query_device": fit_ms_m + query_ms_m,
+            "timing": "ms_fit / ms_query: CUDA events on every rank's stream inside the library, max over the ranks, mean over the steps "
+                      "(the query operand P = inv(L) is built inside the fit at every rank count); ms_per_step: host clock around the K "
+                      "steps, bracketed by a synchronize of all GPUs",
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": cfg, "clocks": clocks, "gpu_launches": int(launches),
+            "roofline": roofline, "roofline_fit": roofline_fit, "phases": phases}
+    if e2e:
+        line["e2e"] = e2e
+    if n_gpus == 1 and not args.no_cpu_baseline:
+        cb = cpu_baseline(w, root, sizes, leaf_off, Xp, yp)
+        # parity spot check of the sample against the GPU through the multi-GPU entry point
+        ns = len(cb["sample_xq"])
+        Yg, Vg = np.empty(ns), np.empty(ns)
+        Xs = np.ascontiguousarray(cb["sample_xq"])
+        m.check(L.pmk_multi_query(m.raw, ns, _lib.ptr(Xs), w["radius"], w["delta"], wθ.kernel_id, _lib.ptr(wp), wp.shape[0], 0,
+                                  _lib.ptr(Yg), _lib.ptr(Vg)))
+        sc_y, sc_v = np.sqrt(np.mean(cb["sample_y"] ** 2)), np.sqrt(np.mean(cb["sample_v"] ** 2))
+        line["cpu_baseline"] = {"value": cb["query_pts_per_s"], "unit": "pts/s", "fit_leaves_per_s": cb["fit_leaves_per_s"],
+                                "cores": cb["cores"], "kind": "port", "sample": cb["sample"],
+                                "parity_vs_gpu": {"mean_max_err_over_rms": float(np.abs(Yg - cb["sample_y"]).max() / sc_y),
+                                                  "var_max_err_over_rms": float(np.abs(Vg - cb["sample_v"]).max() / sc_v)}}
+    m.close()
+    return line
 
 
 if __name__ == "__main__":

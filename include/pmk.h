@@ -16,7 +16,8 @@
  *  - return value: PMK_OK or a negative pmk_status; pmk_last_error() gives the text.
  *    No C++ exception crosses this boundary.  There is NO CPU fallback: without a CUDA
  *    device pmk_create fails with PMK_ERR_CUDA.
- *  - one handle = one fitted model on one GPU; calls on one handle must be serialised.
+ *  - one pmk_handle = one fitted model (or one rank's sub-tree of it) on one GPU; one pmk_multi = one model sharded over the
+ *    GPUs of a box by sub-tree ownership (below).  Calls on one handle must be serialised.
  *  - *_dev variants take DEVICE pointers (same layouts) and run on the handle's stream
  *    without host synchronisation beyond what is documented.
  */
@@ -71,7 +72,9 @@ enum {
   PMK_T_Q_PAIRS_CLASS0 = 8,  /* .. +4: the fused pair kernel per leaf-size class (<=512, <=768, <=1024, <=1536, <=2048) */
   PMK_T_Q_MAKE_M = 13,       /* M_IJ = L_IJ inv(L_JJ), built once per fit by the first variance query               */
   PMK_T_Q_INVERT = 14,       /* P = inv(L) (operand of the explicit-inverse pair kernels), built once per fit       */
-  PMK_T_COUNT = 15
+  PMK_T_FIT_REFINE = 15,     /* one step of iterative refinement of alpha (ill-conditioned models only)              */
+  PMK_T_Q_ROUTE_SORT = 16,   /* owner side of routed pairs: binning the received pairs by leaf                       */
+  PMK_T_COUNT = 17
 };
 
 /* ---- lifetime ---------------------------------------------------------------------------- */
@@ -162,25 +165,16 @@ int pmk_last_query_pairs(pmk_handle* h, int64_t* n_pairs);
 int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_t* pair_leaf, int32_t* pair_hp,
                          double* pair_t, double* pair_w, double* pair_u, double* pair_v);
 
-/* ---- multi-GPU (leaf -> rank map) --------------------------------------------------------- */
-/* Leaves are independent (reference: one GP per leaf, mixtureGP.jl:92-115), so a rank factorises only
- * the leaves the leaf->rank map gives it: pmk_set_fit_range(first_leaf 0-based, n) BEFORE pmk_fit (which
- * still receives ALL leaves' inputs, so every rank lays the model out identically).  After the fit each
- * rank's L / inv-diagonal-block / alpha ranges are contiguous device spans (pmk_model_buffer) that the
- * host layer exchanges with NCCL over NVLink (PMK_BUF_M, after pmk_build_M, in place of PMK_BUF_L when only queries
- * follow); pmk_mark_fitted then declares the replicated model
- * complete.  Queries are sliced across ranks with no data-path collective; results are gathered once. */
-enum { PMK_BUF_L = 0, PMK_BUF_LINV = 1, PMK_BUF_ALPHA = 2, PMK_BUF_M = 3, PMK_BUF_P = 4 };
-int pmk_set_fit_range(pmk_handle* h, int64_t first_leaf, int64_t n_leaves /* -1 = to the end */);
-int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_leaves, void** dptr, int64_t* bytes);
-/* The pair kernel's operands for the leaves of the fit range: M_IJ = L_IJ inv(L_JJ) (substitution solver) and
- * P = inv(L) (explicit-inverse solver, the default; packed like L).  Single-GPU queries build them lazily. */
-int pmk_build_M(pmk_handle* h);
-/* exchanged: bit0 = the peers' M spans were copied in (PMK_BUF_M), bit1 = the peers' P spans (PMK_BUF_P); an operand
- * that was not exchanged cannot be rebuilt for foreign leaves unless their L and Linv spans were exchanged too */
-int pmk_mark_fitted(pmk_handle* h, int exchanged);
+/* debug_flag=true outputs that are dense over the hyperplanes (mixtureGP.jl:17-19,256-258: hps_keep_flags_set, zs_set, ts_set)
+ * for queries [first_query, first_query + n_queries) of the LAST query: for every hyperplane i (fetchhyperplanes order)
+ *   ts[j*n_hp + i] = t_i = -dot(u_i, p_j) + c_i,  zs[(j*n_hp + i)*D + d] = p_j + t_i u_i,  keep_flags[j*n_hp + i] = 0 / 1
+ * (findneighbourpartitions, mixtureGP.jl:347-352,361-365,389).  n_queries * n_hp <= 2^28 per call; any pointer may be NULL. */
+int pmk_last_query_debug_dense(pmk_handle* h, int64_t first_query, int64_t n_queries, uint8_t* keep_flags, double* ts, double* zs);
+/* number of (query, leaf) pairs of the last plan per leaf (n_leaves of the whole model entries) */
+int pmk_last_query_leaf_pairs(pmk_handle* h, int64_t* pairs_per_leaf);
 
-/* The query in three stages on DEVICE buffers (pmk_query_dev = the three in sequence):
+/* ---- query in stages on DEVICE buffers ---------------------------------------------------- */
+/* pmk_query_dev = the three in sequence:
  *   pmk_query_plan_dev   : home leaves, neighbours, weights, pair list binned by leaf; returns n_pairs
  *   pmk_query_pairs_dev  : fused pair kernel; writes u,v of every pair into n_pairs-long device arrays
  *   pmk_query_combine_dev: convex combination -> Yq, Vq. */
@@ -188,12 +182,90 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
                        int wkernel_id, const double* wparams, int nw, int64_t* n_pairs);
 int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pair_v);
 int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d_pair_v, double* dYq, double* dVq);
+/* The pair kernel's operands (P = inv(L) for the explicit-inverse solver, M_IJ = L_IJ inv(L_JJ) for substitution) are built by
+ * the first variance query after a fit; pmk_build_M builds them now (so that the cost is the fit's, not the first query's). */
+int pmk_build_M(pmk_handle* h);
+
+/* ---- sub-tree ownership: building blocks (pmk_multi below is the ready-made single-box form) ------------------------------- */
+/* Leaves are independent (reference: one GP per leaf, mixtureGP.jl:92-115).  A handle may own a contiguous range of a larger
+ * model's leaves -- a sub-tree of the BSP: pmk_set_leaf_base(h, first leaf 0-based, leaves of the whole model) BEFORE pmk_fit,
+ * which then receives only the owned leaves' inputs.  Leaf ids stay global everywhere (pmk_get_alpha(h, leaf) ...).  Every
+ * handle holds the (tiny) whole tree, so any of them can PLAN any slice of the queries; the (query, leaf) pairs of a plan are
+ * then answered by the owners of their leaves:
+ *   pmk_query_plan_segments   : the plan's pairs sorted by leaf form one contiguous segment per owner; seg_off[o] .. seg_off[o+1]
+ *                               (n_owners + 1 entries out) for owners holding leaves owner_first_leaf[o] .. owner_first_leaf[o+1]
+ *   pmk_query_plan_pack_dev   : the sorted pairs as what travels: query point (D doubles, point-major) and 1-based leaf id
+ *   pmk_query_pairs_routed_dev: OWNER side -- R pairs (points + leaf ids, any order, own leaves only) -> u, v in the same order
+ *   pmk_query_plan_unpack_dev : the owners' answers, concatenated in sorted order, back to the plan's pair order
+ *   pmk_query_set_flags + pmk_query_combine_dev finish the query on the planning handle.
+ * Results are bit-identical to a single handle owning every leaf: a pair's u, v depend on its leaf and point only. */
+int pmk_set_leaf_base(pmk_handle* h, int64_t leaf_base, int64_t total_leaves);
+int pmk_query_plan_segments(pmk_handle* h, int n_owners, const int64_t* owner_first_leaf, int64_t* seg_off);
+int pmk_query_plan_pack_dev(pmk_handle* h, double* d_X_sorted, int32_t* d_leaf_sorted);
+int pmk_query_pairs_routed_dev(pmk_handle* h, int64_t R, const double* d_X, const int32_t* d_leaf, int flags, double* d_u, double* d_v);
+int pmk_query_plan_unpack_dev(pmk_handle* h, const double* d_u_sorted, const double* d_v_sorted, double* d_pair_u, double* d_pair_v);
+int pmk_query_set_flags(pmk_handle* h, int flags);
+
+/* ---- multi-GPU: one model over the GPUs of one box (north star: "patches are partitioned across the 8 GPUs ... by a
+ * BSP-leaf-to-rank map") ---------------------------------------------------------------------------------------------------- */
+/* One process, one host thread and one stream set per GPU, CUDA peer copies over NVLink between them.  Rank r OWNS the
+ * contiguous leaf range pmk_multi_leaf_range gives it (the top log2(n) levels of the BSP = n sub-trees) and keeps X, alpha, L and
+ * the query operand for those leaves only; nothing is replicated but the tree.  fitmixtureGP! (mixtureGP.jl:70) = every rank
+ * fits its leaves, no exchange.  querymixtureGP! (mixtureGP.jl:159) = every rank plans a contiguous slice of the queries
+ * (pmk_multi_query_range), the pairs travel to the owners of their leaves (D doubles + 4 bytes each), the owners run the fused
+ * pair kernel, u and v travel back (16 bytes per pair), the planning rank combines in the reference's order and its slice of
+ * Yq, Vq goes straight into the caller's host arrays.  Results are bit-identical to one GPU.
+ * device_ids: n_devices CUDA ordinals (NULL = 0 .. n_devices-1); an ordinal may repeat (several ranks on one GPU: tests).
+ * The *_staged forms keep inputs and results resident in HBM between calls (timing without host copies):
+ *   pmk_multi_stage_training + pmk_multi_fit_staged = pmk_multi_fit;
+ *   pmk_multi_stage_queries + pmk_multi_query_staged + pmk_multi_fetch_results = pmk_multi_query. */
+typedef struct pmk_multi pmk_multi;
+int pmk_multi_create(pmk_multi** out, int n_devices, const int* device_ids);
+void pmk_multi_destroy(pmk_multi* m);
+const char* pmk_multi_last_error(const pmk_multi* m);     /* m may be NULL: error of a failed pmk_multi_create */
+int pmk_multi_size(const pmk_multi* m);
+/* the leaf -> rank map and the query slices (host only, no GPU needed): [first, first + count) */
+int pmk_multi_leaf_range(int n_ranks, int64_t n_leaves, int rank, int64_t* first, int64_t* count);
+int pmk_multi_query_range(int n_ranks, int64_t Nq, int rank, int64_t* first, int64_t* count);
+/* rank's own handle, for inspection of the leaves it owns (pmk_get_L, pmk_get_alpha, pmk_condition_estimate ...) */
+int pmk_multi_handle(pmk_multi* m, int rank, pmk_handle** h);
+int pmk_multi_set_option(pmk_multi* m, int option, int64_t value);
+int pmk_multi_fit(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X_packed, const double* y_packed,
+                  int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info);
+int pmk_multi_set_tree(pmk_multi* m, int D, int levels, const double* hp_v, const double* hp_c);
+int pmk_multi_query(pmk_multi* m, int64_t Nq, const double* Xq, double radius, double delta, int wkernel_id, const double* wparams,
+                    int nw, int flags, double* Yq, double* Vq);
+int pmk_multi_stage_training(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X_packed,
+                             const double* y_packed);
+int pmk_multi_fit_staged(pmk_multi* m, int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info);
+int pmk_multi_stage_queries(pmk_multi* m, int64_t Nq, const double* Xq);
+int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkernel_id, const double* wparams, int nw, int flags);
+int pmk_multi_fetch_results(pmk_multi* m, double* Yq, double* Vq);
+/* (query, leaf) pairs of the last query per leaf, summed over the ranks (n_leaves entries) */
+int pmk_multi_leaf_pairs(pmk_multi* m, int64_t* pairs_per_leaf);
+/* Device times of the last staged fit / query in milliseconds, CUDA events on each rank's stream, MAXIMUM over the ranks:
+ * a phase's time on a rank runs from the rank's first event of the call to the end of the phase, waits for peers included. */
+enum {
+  PMK_MT_FIT = 0,          /* whole fit: pack + Gram + Cholesky + alpha + the query operand                  */
+  PMK_MT_QUERY = 1,        /* whole query: plan .. combine                                                   */
+  PMK_MT_Q_PLAN = 2,       /* home leaves, neighbours, pair list (per-rank duration, max over ranks)         */
+  PMK_MT_Q_ROUTE = 3,      /* pack + peer copies of the pairs to their owners                                */
+  PMK_MT_Q_PAIRS = 4,      /* owners: binning + fused pair kernel                                            */
+  PMK_MT_Q_RETURN = 5,     /* peer copies of u, v back + unpack + combine                                    */
+  PMK_MT_COUNT = 8
+};
+int pmk_multi_get_timings(pmk_multi* m, double* ms /* PMK_MT_COUNT */, double* per_rank_ms /* n x PMK_T_COUNT, or NULL */);
+int64_t pmk_multi_launch_count(const pmk_multi* m);
 
 /* ---- options ----------------------------------------------------------------------------- */
 /* PMK_OPT_FULL_HYPERPLANE_SCAN: 1 = findneighbourpartitions scans ALL hyperplanes per query exactly as the
  * reference loop does (mixtureGP.jl:354); 0 (default) = exact per-leaf candidate lists (same result). */
 /* PMK_OPT_QUERY_SOLVER: how queryinner!'s v = L \ kq (mixtureGP.jl:311) is carried out for a tile of queries:
- *   0 (default) = s = P kq with P = inv(L) formed once per fit by blocked substitution, as a ROW-PANEL product: the
+ *  -1 (default) = by conditioning: 0 unless the fit's lower bound of cond(K + sigma2 I), (max diag L / min diag L)^2 over the
+ *                 leaves (pmk_condition_estimate), reaches 1e4 -- then 1.  Measured against the reference's dtrsv
+ *                 (profiles/parity_r02.json): the explicit inverse stays below 1e-9 of the variance up to cond ~ 1e5 and
+ *                 reaches 3e-9 at cond 3e6, substitution stays at the level at which dtrsv and dtrsm differ from each other;
+ *   0           = s = P kq with P = inv(L) formed once per fit by blocked substitution, as a ROW-PANEL product: the
  *                 cross-covariance tile is evaluated once into shared memory, every warp streams its own rows of P and
  *                 keeps only ||s||^2 -- no dependency between warps, so the tensor pipe never waits.  Every kernel
  *                 function (the squared exponential with an inlined table-driven exp).  Measured vs dtrsv: <= 3e-11 at
@@ -205,8 +277,13 @@ int pmk_query_combine_dev(pmk_handle* h, const double* d_pair_u, const double* d
 /* PMK_OPT_INVERSE_BUILDER: how P = inv(L) is formed (once per fit) for the explicit-inverse solvers:
  *   0 (default) = recursive doubling on the packed tiles, P21 = -inv(B) C inv(A), every flop a DMMA GEMM (pmk_invert.cu);
  *   1           = the substitution pair kernel run on identity right-hand sides (round-1 builder). */
-enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2, PMK_OPT_INVERSE_BUILDER = 3 };
+/* PMK_OPT_ALPHA_REFINE: one step of iterative refinement of alpha = (K + sigma2 I)^-1 y after the Cholesky solve (the reference
+ * solves U\y by LU, mixtureGP.jl:106): -1 (default) = for models flagged by the same conditioning estimate, 0 = never,
+ * 1 = always.  Set before pmk_fit. */
+enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2, PMK_OPT_INVERSE_BUILDER = 3, PMK_OPT_ALPHA_REFINE = 4 };
 int pmk_set_option(pmk_handle* h, int option, int64_t value);
+/* lower bound of the worst leaf's cond(K + sigma2 I) from the last fit, and the query solver PMK_OPT_QUERY_SOLVER = -1 resolves to */
+int pmk_condition_estimate(pmk_handle* h, double* cond_lower_bound, int* solver_in_use);
 
 /* ---- setuppartition on the device ------------------------------------------ */
 /* setuppartition(X, levels) (reference src/patchwork/partition.jl:106-129; gethyperplane :86-100, splitpoints :64-83,
@@ -265,6 +342,10 @@ int pmk_debug_counters(pmk_handle* h, uint64_t* out8, int flags);
  * nodes4[4k .. 4k+3] = {lo, mid, hi, height} of node k, in launch order (ascending height).  A node inverts the block range
  * [lo, hi) from its children [lo, mid) and [mid, hi): P[mid:hi, lo:mid] = -P[mid:hi, mid:hi] L[mid:hi, lo:mid] P[lo:mid, lo:mid]. */
 int pmk_inverse_plan(int n_blocks, int max_nodes, int16_t* nodes4, int* n_nodes);
+/* The FP64 tensor-pipe rate of the handle's GPU, measured now: a register-resident loop of independent mma.sync.m8n8k4.f64
+ * (SASS DMMA.8x8x4) chains on every SM, best of three ~2 ms launches, in TFLOP/s.  bench.py quotes every FP64 fraction
+ * against this number (MEASURED_PEAKS.json carries no FP64 entry). */
+int pmk_measure_fp64_peak(pmk_handle* h, double* dmma_tflops);
 /* number of kernel launches issued by this handle since creation */
 int64_t pmk_launch_count(const pmk_handle* h);
 /* stream the handle launches on, as a cudaStream_t cast to void* (for event timing by the caller) */

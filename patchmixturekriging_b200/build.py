@@ -13,11 +13,11 @@ CSRC = os.path.join(HERE, "csrc")
 VARIANT = os.environ.get("PMK_VARIANT", "")
 LIB = os.path.join(HERE, f"libpmk_b200_{VARIANT}.so" if VARIANT else "libpmk_b200.so")
 BUILD_DIR = os.path.join(HERE, f"build_{VARIANT}" if VARIANT else "build")
-SOURCES = ["pmk_api.cu", "pmk_fit.cu", "pmk_tree.cu", "pmk_query.cu", "pmk_query_d1.cu", "pmk_query_d2.cu", "pmk_query_d3.cu", "pmk_gram.cu", "pmk_invert.cu", "pmk_partition.cu"]
+SOURCES = ["pmk_api.cu", "pmk_fit.cu", "pmk_tree.cu", "pmk_query.cu", "pmk_query_d1.cu", "pmk_query_d2.cu", "pmk_query_d3.cu", "pmk_gram.cu", "pmk_invert.cu", "pmk_partition.cu", "pmk_multi.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 EXTRA = os.environ.get("PMK_NVCC_EXTRA", "").split()     # e.g. PMK_NVCC_EXTRA=-DPMK_PROFILE_CYCLES for the phase counters
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
-         "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-pthread", "-Xptxas", "-v"]
 
 
 def _stale(target: str, deps: list[str]) -> bool:
@@ -58,7 +58,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if r.returncode != 0:
                 raise RuntimeError(f"nvcc failed: {' '.join(cmd)}")
     if force or jobs or _stale(LIB, objs):
-        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB, *objs]
+        cmd = [NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-pthread", "-o", LIB, *objs]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             sys.stderr.write(r.stdout + r.stderr)

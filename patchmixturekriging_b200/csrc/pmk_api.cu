@@ -3,6 +3,7 @@
 // failures to status codes.  No CPU compute path exists here: every numerical result comes
 // from the sm_100a kernels in pmk_fit.cu / pmk_tree.cu / pmk_query.cu / pmk_gram.cu.
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -20,7 +21,8 @@ void launch_pack(int D, const LeafTable& lt, const int64_t* d_leaf_off, const do
 void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_order, int max_npad, KParams kp, double sigma2,
                        cudaStream_t s);
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s);
-void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s);
+void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s, const double* rhs = nullptr,
+                  double* out = nullptr);
 void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_npad, cudaStream_t s);
 InvPlanHost make_inverse_plan(const std::vector<int>& shapes_present);
 void launch_inverse(const LeafTable& lt, const InvPlanHost& plh, const void* d_nodes, const int* d_off, const int* d_cnt,
@@ -60,6 +62,15 @@ void launch_part_flags(const double* f, const int32_t* node_id, const double* c,
 void launch_part_scatter(const int32_t* perm, const int32_t* node_id, const int32_t* flag, const int32_t* scan, const int64_t* seg_off,
                          int64_t N, int32_t* perm_out, cudaStream_t s);
 void launch_part_child_offsets(const int32_t* scan, const int64_t* seg_off, int n_nodes, int64_t N, int64_t* child_off, cudaStream_t s);
+void launch_pack_sorted_pairs(int D, const QueryPlan& q, const int32_t* sorted_pair, double* X_sorted, int32_t* leaf_sorted, cudaStream_t s);
+void launch_unpack_sorted_pairs(int64_t n, const int32_t* sorted_pair, const double* us, const double* vs, double* pu, double* pv, cudaStream_t s);
+void launch_run_starts(const int32_t* keys, int64_t R, int64_t TL, int64_t leaf_base, int64_t n_own, int64_t* start, int* foreign, cudaStream_t s);
+void launch_diag_range(const LeafTable& lt, double* out2, cudaStream_t s);
+void launch_alpha_residual(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, double* r, cudaStream_t s);
+void launch_alpha_add(const LeafTable& lt, const double* d, int64_t n, cudaStream_t s);
+void launch_dense_debug(int D, const TreeDev& tr, const QueryPlan& q, double radius, double delta, uint8_t* keep, double* ts, double* zs,
+                        cudaStream_t s);
+double launch_dmma_peak(double* d_out, int iters, cudaStream_t s);
 int query_class_of(int npad);
 int query_class_mq(int cls);
 void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp,
@@ -113,15 +124,16 @@ struct pmk_handle {
   bool fitted = false;
   bool m_ready = false;    // M (operand of the substitution pair kernel) built for the current factors
   bool p_ready = false;    // P = inv(L) (operand of the explicit-inverse pair kernel) built for the current factors
-  int solver = 0;          // PMK_OPT_QUERY_SOLVER: 0 = explicit inverse, row-panel product; 1 = blocked substitution (TRSM);
-                           // 2 = explicit inverse, column-sweep product (round-1 kernel, kept for comparison)
+  int solver = -1;         // PMK_OPT_QUERY_SOLVER: -1 = by conditioning (default); 0 = explicit inverse, row-panel product;
+                           // 1 = blocked substitution (TRSM); 2 = explicit inverse, column-sweep product (round-1 kernel)
   int class_max_npad[5] = {};
   int inverse_builder = 0; // PMK_OPT_INVERSE_BUILDER: 0 = recursive doubling (pmk_invert.cu), 1 = substitution kernel on identity columns
   InvPlanHost inv_plan;    // recursion plan of the shapes of the current model
   DBuf d_inv_nodes, d_inv_off, d_inv_cnt;
   int D = 0;
   int64_t n_leaves = 0, total_leaves = 0;
-  int64_t fit_first = 0, fit_count = -1;   // leaves factorised by this handle (multi-GPU: leaf -> rank map)
+  int64_t leaf_base = 0;                   // global 0-based id of this handle's leaf 0 (pmk_set_leaf_base: sub-tree ownership)
+  int64_t total_opt = 0;                   // leaves of the whole model when this handle owns a part of it (0 = all of them)
   KParams kp{0, 1.0};
   double sigma2 = 0.0;
   int max_npad = 0;
@@ -133,7 +145,7 @@ struct pmk_handle {
   DBuf d_class_leaves[kNumClasses], d_class_tiles[kNumClasses], d_tile_off[kNumClasses];
   int n_class[kNumClasses] = {};
   // inversion work lists (leaves of the fit range, per size class): tile = MQ columns of inv(L)
-  DBuf d_P, d_inv_leaves[kNumClasses], d_inv_tile_off[kNumClasses];
+  DBuf d_P, d_T, d_inv_leaves[kNumClasses], d_inv_tile_off[kNumClasses];
   int n_inv_class[kNumClasses] = {};
   int64_t inv_tiles[kNumClasses] = {};
   LeafTable lt{};
@@ -150,6 +162,13 @@ struct pmk_handle {
   DBuf d_leaf_count, d_leaf_pair_start, d_cub;
   DBuf d_leaf_qcount, d_leaf_qstart, d_qperm, d_qkeys, d_bbox, d_cand_count, d_cand_start, d_cand, d_kept;
   bool full_scan = false;   // PMK_OPT_FULL_HYPERPLANE_SCAN
+  bool force_full_scan = false;   // the tree's normals are not unit vectors, or it has more hyperplanes than the pruned search's 16-bit slots
+  // routed pairs (this handle as the OWNER of leaves other handles' queries touch): sort scratch, separate from its own plan
+  DBuf r_keys, r_sorted, r_leaf_start, d_info2;
+  // conditioning: (max diag(L) / min diag(L))^2 over the leaves of the last fit, a lower bound of cond(K + sigma2 I)
+  DBuf d_diag_range;
+  double cond_est = 0.0;
+  int alpha_refine = -1;    // PMK_OPT_ALPHA_REFINE: -1 auto (flagged models), 0 never, 1 always
   // organizetrainingsets on the device (results of the last call)
   DBuf o_X, o_counts, o_off, o_pl, o_pp, o_sl, o_sp, o_lcount, o_lstart;
   int64_t o_N = 0, o_total = 0, o_leaves = 0;
@@ -164,6 +183,7 @@ struct pmk_handle {
   QueryPlan plan{};
   bool plan_valid = false;
   int last_flags = 0;
+  double last_radius = 0.0, last_delta = 0.0;
 
   // timings
   cudaEvent_t ev[2 * PMK_T_COUNT] = {};
@@ -282,6 +302,10 @@ int pmk_create(pmk_handle** out, int device) {
     return fail(nullptr, PMK_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
   for (int i = 0; i < 2 * PMK_T_COUNT; ++i) cudaEventCreate(&h->ev[i]);
+  if (h->d_info2.ensure(sizeof(int)) != cudaSuccess) {
+    pmk_destroy(h);
+    return fail(nullptr, PMK_ERR_CUDA, "cudaMalloc failed");
+  }
   *out = h;
   return PMK_OK;
 }
@@ -310,6 +334,12 @@ void pmk_destroy(pmk_handle* h) {
                    &h->pt_blk_depth, &h->pt_node_blk_off, &h->pt_blk_sum, &h->pt_z, &h->pt_v, &h->pt_c};
   for (DBuf* b : pbufs) b->release();
   h->d_P.release();
+  h->d_T.release();
+  h->r_keys.release();
+  h->r_sorted.release();
+  h->r_leaf_start.release();
+  h->d_info2.release();
+  h->d_diag_range.release();
   h->d_inv_nodes.release();
   h->d_inv_off.release();
   h->d_inv_cnt.release();
@@ -334,9 +364,13 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
   switch (option) {
     case PMK_OPT_FULL_HYPERPLANE_SCAN: h->full_scan = value != 0; h->plan_valid = false; return PMK_OK;
     case PMK_OPT_QUERY_SOLVER:
-      if (value < 0 || value > 2)
-        return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: 0 (explicit inverse), 1 (substitution) or 2 (explicit inverse, column sweep)");
+      if (value < -1 || value > 2)
+        return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: -1 (by conditioning), 0 (explicit inverse), 1 (substitution) or 2 (explicit inverse, column sweep)");
       h->solver = (int)value;
+      return PMK_OK;
+    case PMK_OPT_ALPHA_REFINE:
+      if (value < -1 || value > 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_ALPHA_REFINE: -1 (by conditioning), 0 (never) or 1 (always)");
+      h->alpha_refine = (int)value;
       return PMK_OK;
     case PMK_OPT_INVERSE_BUILDER:
       if (value != 0 && value != 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_INVERSE_BUILDER: 0 (recursive doubling) or 1 (substitution)");
@@ -424,53 +458,40 @@ int pmk_cross_gram(pmk_handle* h, int D, int64_t n, const double* X, int64_t m, 
 
 // ---------------------------------------------------------------------------------------------
 // fit
-int pmk_set_fit_range(pmk_handle* h, int64_t first_leaf, int64_t n_leaves) {
-  if (!h) return PMK_ERR_ARG;
-  if (first_leaf < 0 || n_leaves < -1) return fail(h, PMK_ERR_ARG, "bad fit range");
-  h->fit_first = first_leaf;
-  h->fit_count = n_leaves;
-  return PMK_OK;
+// PMK_OPT_QUERY_SOLVER = -1 (default): by the conditioning of the fitted leaves.  s = inv(L) kq through the explicit inverse
+// carries an error of order cond(L) eps |inv(L)||kq| -- measured against the reference's dtrsv: 2e-11 of the variance at
+// cond(K + sigma2 I) ~ 3e4, 3e-9 at 3e6 (profiles/parity_floor_r02.json) -- while blocked substitution stays at the level at
+// which dtrsv and dtrsm differ from each other.  A model whose worst leaf has (max diag L / min diag L)^2 above the
+// threshold is therefore queried by substitution; the estimate is a lower bound of cond(K + sigma2 I), a by-product of the fit.
+static constexpr double kCondFlag = 1e4;
+static constexpr int64_t kInvScratchDoubles = (int64_t)1 << 30;     // 8 GB of scratch for the recursive inverse (per chunk of leaves)
+static int effective_solver(const pmk_handle* h) {
+  if (h->solver >= 0) return h->solver;
+  return h->cond_est >= kCondFlag ? 1 : 0;
+}
+// Does the variance query stream P = inv(L)?  Solver 0 (row-panel kernel) for every kernel function; solver 2 (column sweep,
+// squared exponential inlined) only for that one -- the others take the substitution kernel there.
+static bool uses_inverse(const pmk_handle* h) {
+  const int sv = effective_solver(h);
+  return sv == 0 || (sv == 2 && h->kp.kind == PMK_KERNEL_SQEXP);
 }
 
-int pmk_model_buffer(pmk_handle* h, int which, int64_t first_leaf, int64_t n_leaves, void** dptr, int64_t* bytes) {
-  if (!h || !dptr || !bytes) return PMK_ERR_ARG;
-  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
-  if (first_leaf < 0 || n_leaves < 0 || first_leaf + n_leaves > h->n_leaves) return fail(h, PMK_ERR_ARG, "leaf range out of bounds");
-  auto span = [&](const std::vector<int64_t>& off, int64_t end_total, double* base) {
-    const int64_t a0 = first_leaf < h->n_leaves ? off[first_leaf] : end_total;
-    const int64_t a1 = first_leaf + n_leaves < h->n_leaves ? off[first_leaf + n_leaves] : end_total;
-    *dptr = (void*)(base + a0);
-    *bytes = (a1 - a0) * (int64_t)sizeof(double);
-  };
-  switch (which) {
-    case PMK_BUF_L: span(h->h_loff, h->L_doubles, h->d_L.as<double>()); break;
-    case PMK_BUF_LINV: span(h->h_ioff, h->Linv_doubles, h->d_Linv.as<double>()); break;
-    case PMK_BUF_ALPHA: span(h->h_xoff, h->x_points, h->d_alpha.as<double>()); break;
-    case PMK_BUF_M:
-      if (!h->d_M.p) return fail(h, PMK_ERR_STATE, "M has not been built (pmk_build_M)");
-      span(h->h_loff, h->L_doubles, h->d_M.as<double>());
-      break;
-    case PMK_BUF_P:
-      if (!h->d_P.p) return fail(h, PMK_ERR_STATE, "P has not been built (pmk_build_M)");
-      span(h->h_loff, h->L_doubles, h->d_P.as<double>());
-      break;
-    default: return fail(h, PMK_ERR_ARG, "unknown buffer id %d", which);
+// 0, 1, 2, ... on the device (pair / query ids for the radix sorts), grown on demand
+static int ensure_iota(pmk_handle* h, int64_t n) {
+  if (h->d_iota.cap < sizeof(int32_t) * (size_t)n) {
+    CU(h, h->d_iota.ensure(sizeof(int32_t) * n));
+    launch_part_iota(h->d_iota.as<int32_t>(), (int64_t)(h->d_iota.cap / sizeof(int32_t)), h->stream);
+    KCHECK(h, "k_part_iota");
   }
   return PMK_OK;
 }
 
-// Does the variance query stream P = inv(L)?  Solver 0 (row-panel kernel) for every kernel function; solver 2 (column sweep,
-// squared exponential inlined) only for that one -- the others take the substitution kernel there.
-static bool uses_inverse(const pmk_handle* h) { return h->solver == 0 || (h->solver == 2 && h->kp.kind == PMK_KERNEL_SQEXP); }
-
-// The pair kernels' operands for the leaves of the fit range: P = inv(L) (explicit-inverse solvers) and/or
-// M_IJ = L_IJ inv(L_JJ) (substitution solver).  P comes from recursive doubling on the packed tiles (pmk_invert.cu; the M
-// buffer doubles as its scratch, so M is rebuilt afterwards if it is wanted too) or, with PMK_OPT_INVERSE_BUILDER = 1, from the
-// substitution pair kernel run on identity right-hand sides (tile = MQ columns of the inverse).
+// The pair kernels' operands: P = inv(L) (explicit-inverse solvers) and/or M_IJ = L_IJ inv(L_JJ) (substitution solver).
+// P comes from recursive doubling on the packed tiles (pmk_invert.cu, with a bounded scratch buffer) or, with
+// PMK_OPT_INVERSE_BUILDER = 1, from the substitution pair kernel run on identity right-hand sides (tile = MQ columns of the inverse).
 static int build_operands(pmk_handle* h, bool want_M, bool want_P) {
-  const int64_t f0 = std::min<int64_t>(h->fit_first, h->n_leaves);
-  const int64_t f1 = h->fit_count < 0 ? h->n_leaves : std::min<int64_t>(h->n_leaves, f0 + h->fit_count);
-  const bool all = (f0 == 0 && f1 == h->n_leaves);
+  const int64_t f0 = 0, f1 = h->n_leaves;
+  const bool all = true;
   auto make_M = [&]() -> int {
     Timer tm(h, PMK_T_Q_MAKE_M);
     CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));
@@ -485,11 +506,24 @@ static int build_operands(pmk_handle* h, bool want_M, bool want_P) {
     h->lt.P = h->d_P.as<double>();
     if (h->inverse_builder == 0) {
       Timer tm(h, PMK_T_Q_INVERT);
-      CU(h, h->d_M.ensure(sizeof(double) * (size_t)h->L_doubles));       // scratch for T = C inv(A)
-      h->lt.M = h->d_M.as<double>();
-      h->m_ready = false;
-      launch_inverse(h->lt, h->inv_plan, h->d_inv_nodes.p, h->d_inv_off.as<int>(), h->d_inv_cnt.as<int>(), h->d_M.as<double>(),
-                     (int)f0, (int)(f1 - f0), h->max_npad, h->stream, &h->launches);
+      // scratch for T = C inv(A), addressed like the factor (scratch + loff[p]): leaves go through in chunks of at most
+      // kInvScratchDoubles so that a large model (C5: 68 GB of factors) does not need a third buffer of its size
+      std::vector<std::pair<int64_t, int64_t>> chunks;       // [first leaf, count)
+      int64_t need = 0;
+      for (int64_t a = f0; a < f1;) {
+        int64_t b = a;
+        const int64_t base = h->h_loff[a];
+        auto end_of = [&](int64_t p) { return p + 1 < h->n_leaves ? h->h_loff[p + 1] : h->L_doubles; };
+        while (b < f1 && (b == a || end_of(b) - base <= kInvScratchDoubles)) ++b;
+        need = std::max(need, end_of(b - 1) - base);
+        chunks.emplace_back(a, b - a);
+        a = b;
+      }
+      CU(h, h->d_T.ensure(sizeof(double) * (size_t)need));
+      for (const auto& ck : chunks) {
+        launch_inverse(h->lt, h->inv_plan, h->d_inv_nodes.p, h->d_inv_off.as<int>(), h->d_inv_cnt.as<int>(),
+                       h->d_T.as<double>() - h->h_loff[ck.first], (int)ck.first, (int)ck.second, h->max_npad, h->stream, &h->launches);
+      }
       --h->launches;
       KCHECK(h, "k_inv_* (recursive inverse)");
     } else {
@@ -521,17 +555,8 @@ int pmk_build_M(pmk_handle* h) {
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
   h->m_ready = false;
   h->p_ready = false;
-  return build_operands(h, true, uses_inverse(h));
-}
-
-int pmk_mark_fitted(pmk_handle* h, int exchanged) {
-  if (!h) return PMK_ERR_ARG;
-  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
-  h->fitted = true;
-  h->m_ready = (exchanged & 1) != 0 && h->d_M.p != nullptr;
-  h->p_ready = (exchanged & 2) != 0 && h->d_P.p != nullptr;
-  h->plan_valid = false;
-  return PMK_OK;
+  const bool use_P = uses_inverse(h);
+  return build_operands(h, !use_P, use_P);
 }
 
 // Lays the model out in HBM (padded leaves, packed factor slots, size classes, inversion plan) and, with `compute`, packs the
@@ -601,7 +626,10 @@ static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_
   }
   h->D = D;
   h->n_leaves = n_leaves;
-  h->total_leaves = n_leaves;
+  h->total_leaves = h->total_opt > 0 ? h->total_opt : n_leaves;
+  if (h->total_opt > 0 && h->leaf_base + n_leaves > h->total_opt)
+    return fail(h, PMK_ERR_ARG, "leaves [%lld, %lld) do not fit a model of %lld leaves (pmk_set_leaf_base)", (long long)h->leaf_base,
+                (long long)(h->leaf_base + n_leaves), (long long)h->total_opt);
   h->kp = kp;
   h->sigma2 = sigma2;
 
@@ -620,9 +648,8 @@ static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_
   CU(h, h->d_Linv.ensure(sizeof(double) * (size_t)io));
   (void)total_pts;
 
-  // leaves this handle factorises (all of them unless pmk_set_fit_range narrowed it), LPT order
-  const int64_t f0 = std::min<int64_t>(h->fit_first, n_leaves);
-  const int64_t f1 = h->fit_count < 0 ? n_leaves : std::min<int64_t>(n_leaves, f0 + h->fit_count);
+  // every leaf is factorised, largest first (LPT order)
+  const int64_t f0 = 0, f1 = n_leaves;
   std::vector<int> order;
   for (int64_t p = f0; p < f1; ++p) order.push_back((int)p);
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return h->h_npad[a] > h->h_npad[b]; });
@@ -712,21 +739,42 @@ static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_
     launch_solve(lt, h->d_order.as<int>(), n_order, max_npad, h->stream);
   }
   KCHECK(h, "k_solve_alpha");
-  // status: first failing leaf
+  // conditioning estimate (by-product of the factor) and status: first failing leaf
+  CU(h, h->d_diag_range.ensure(sizeof(double)));
+  CU(h, cudaMemsetAsync(h->d_diag_range.p, 0, sizeof(double), h->stream));
+  launch_diag_range(lt, h->d_diag_range.as<double>(), h->stream);
+  KCHECK(h, "k_diag_range");
   std::vector<int> h_info(n_leaves);
+  double cond_est = 0.0;
   CU(h, cudaMemcpyAsync(h_info.data(), h->d_info.p, sizeof(int) * n_leaves, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaMemcpyAsync(&cond_est, h->d_diag_range.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  h->cond_est = cond_est;
   for (int64_t p = 0; p < n_leaves; ++p) {
     if (h_info[p] != 0) {
-      if (bad_leaf) *bad_leaf = p + 1;
+      if (bad_leaf) *bad_leaf = h->leaf_base + p + 1;
       if (info) *info = h_info[p];
       return fail(h, PMK_ERR_NOT_POSDEF, "leaf %lld: K + sigma2*I is not positive definite (info=%d)",
-                  (long long)(p + 1), h_info[p]);
+                  (long long)(h->leaf_base + p + 1), h_info[p]);
     }
+  }
+  if (h->alpha_refine == 1 || (h->alpha_refine < 0 && cond_est >= kCondFlag)) {
+    // alpha <- alpha + (L L^T)^-1 (y - (K + sigma2 I) alpha): the reference's c = U\y is an LU solve (mixtureGP.jl:106); one step
+    // of refinement in working precision makes the Cholesky solution componentwise backward-stable like it
+    Timer t(h, PMK_T_FIT_REFINE);
+    CU(h, h->d_scratch.ensure(sizeof(double) * 2 * (size_t)h->xstride));
+    double* r = h->d_scratch.as<double>();
+    double* d = r + h->xstride;
+    launch_alpha_residual(D, lt, h->d_order.as<int>(), n_order, kp, sigma2, r, h->stream);
+    KCHECK(h, "k_alpha_residual");
+    launch_solve(lt, h->d_order.as<int>(), n_order, max_npad, h->stream, r, d);
+    KCHECK(h, "k_solve_alpha");
+    launch_alpha_add(lt, d, h->x_points, h->stream);
+    KCHECK(h, "k_alpha_add");
   }
   h->m_ready = false;
   h->p_ready = false;
-  h->fitted = (n_order == n_leaves);   // a partial fit becomes usable after the peers' factors arrive (pmk_mark_fitted)
+  h->fitted = true;
   h->plan_valid = false;
   return PMK_OK;
 }
@@ -980,6 +1028,9 @@ int pmk_save_model(pmk_handle* h, const char* path) {
   if (!h || !path) return PMK_ERR_ARG;
   if (int rc = set_device(h)) return rc;
   if (!h->fitted) return fail(h, PMK_ERR_STATE, "pmk_save_model: model is not fitted");
+  if (h->leaf_base != 0 || h->n_leaves != h->total_leaves)
+    return fail(h, PMK_ERR_STATE, "pmk_save_model: this handle owns leaves [%lld, %lld) of a %lld-leaf model; a model file holds a whole model",
+                (long long)h->leaf_base, (long long)(h->leaf_base + h->n_leaves), (long long)h->total_leaves);
   FileCloser fc{fopen(path, "wb")};
   if (!fc.f) return fail(h, PMK_ERR_ARG, "pmk_save_model: cannot open %s for writing", path);
   ModelFileHeader hd{};
@@ -1030,8 +1081,8 @@ int pmk_load_model(pmk_handle* h, const char* path) {
   if (hd.n_leaves < 1 || hd.n_leaves > (1 << 24)) return fail(h, PMK_ERR_ARG, "pmk_load_model: corrupt header");
   std::vector<int64_t> off(hd.n_leaves + 1);
   if (fread(off.data(), sizeof(int64_t), off.size(), fc.f) != off.size()) return fail(h, PMK_ERR_ARG, "pmk_load_model: file truncated");
-  h->fit_first = 0;     // a loaded model is complete: every leaf's factor is in the file
-  h->fit_count = -1;
+  h->leaf_base = 0;     // a model file holds a whole model
+  h->total_opt = 0;
   const double kparam = hd.kernel_p;
   if (int rc = fit_impl(h, hd.D, hd.n_leaves, off.data(), nullptr, nullptr, hd.kernel_kind, &kparam, 1, hd.sigma2, nullptr, nullptr, false))
     return rc;
@@ -1060,6 +1111,17 @@ int pmk_load_model(pmk_handle* h, const char* path) {
     h->tree.hv = h->d_hv.as<double>();
     h->tree.hc = h->d_hc.as<double>();
     h->tree_set = true;
+    h->force_full_scan = hd.n_hp > 65535;
+    if (hd.n_hp > 0 && !h->force_full_scan) {
+      std::vector<double> soa((size_t)hd.tree_D * hd.n_hp);
+      CU(h, cudaMemcpyAsync(soa.data(), h->d_hv.p, sizeof(double) * soa.size(), cudaMemcpyDeviceToHost, h->stream));
+      CU(h, cudaStreamSynchronize(h->stream));
+      for (int k = 0; k < hd.n_hp; ++k) {
+        double nn = 0.0;
+        for (int d = 0; d < hd.tree_D; ++d) nn += soa[(size_t)d * hd.n_hp + k] * soa[(size_t)d * hd.n_hp + k];
+        if (!(std::fabs(std::sqrt(nn) - 1.0) <= 1e-9)) h->force_full_scan = true;
+      }
+    }
   }
   CU(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * h->n_leaves, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
@@ -1071,7 +1133,7 @@ int pmk_load_model(pmk_handle* h, const char* path) {
 static int check_leaf(pmk_handle* h, int64_t leaf, int64_t* local) {
   if (!h) return PMK_ERR_ARG;
   if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "model is not fitted");
-  const int64_t p = leaf - 1;
+  const int64_t p = leaf - 1 - h->leaf_base;
   if (p < 0 || p >= h->n_leaves) return fail(h, PMK_ERR_ARG, "leaf %lld not owned by this handle", (long long)leaf);
   *local = p;
   return PMK_OK;
@@ -1206,6 +1268,15 @@ int pmk_set_tree(pmk_handle* h, int D, int levels, const double* hp_v, const dou
   h->tree_D = D;
   h->levels = levels;
   h->n_hp = n_hp;
+  // The pruned neighbour search compares |t| = |c - u.p| with the radius, which is the reference's norm(z - p) = |t| |u| only
+  // for unit normals (setuppartition's are: V[:,1] of an svd), and keeps candidate slots in 16 bits.  Anything else takes the
+  // reference's own scan over all hyperplanes.
+  h->force_full_scan = n_hp > 65535;
+  for (int k = 0; k < n_hp && !h->force_full_scan; ++k) {
+    double nn = 0.0;
+    for (int d = 0; d < D; ++d) nn += hp_v[(size_t)k * D + d] * hp_v[(size_t)k * D + d];
+    if (!(std::fabs(std::sqrt(nn) - 1.0) <= 1e-9)) h->force_full_scan = true;
+  }
   if (n_hp > 0) {
     std::vector<double> soa((size_t)D * n_hp);
     for (int k = 0; k < n_hp; ++k)
@@ -1353,18 +1424,7 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
   q.pair_off = h->d_pair_off.as<int64_t>();
 
   Timer tt(h, PMK_T_Q_TREE);
-  const bool pruned = !h->full_scan && h->n_hp > 0;
-  // iota (pair / query ids for the radix sorts)
-  auto ensure_iota = [&](int64_t n) -> int {
-    if (h->d_iota.cap < sizeof(int32_t) * (size_t)n) {
-      CU(h, h->d_iota.ensure(sizeof(int32_t) * n));
-      std::vector<int32_t> iota((size_t)(h->d_iota.cap / sizeof(int32_t)));
-      std::iota(iota.begin(), iota.end(), 0);
-      CU(h, cudaMemcpyAsync(h->d_iota.p, iota.data(), sizeof(int32_t) * iota.size(), cudaMemcpyHostToDevice, h->stream));
-      CU(h, cudaStreamSynchronize(h->stream));
-    }
-    return PMK_OK;
-  };
+  const bool pruned = !h->full_scan && !h->force_full_scan && h->n_hp > 0;
   int end_bit = 1;
   while ((1ll << end_bit) <= TL) ++end_bit;
   CU(h, cudaMemsetAsync(h->d_npairs.as<int32_t>() + Nq, 0, sizeof(int32_t), h->stream));
@@ -1378,7 +1438,7 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
     CU(h, h->d_cand_count.ensure(sizeof(int32_t) * TL));
     CU(h, h->d_cand_start.ensure(sizeof(int64_t) * (TL + 1)));
     CU(h, h->d_kept.ensure(sizeof(uint16_t) * 8 * Nq));
-    if (int rc = ensure_iota(Nq)) return rc;
+    if (int rc = ensure_iota(h, Nq)) return rc;
     CU(h, cudaMemsetAsync(h->d_leaf_qcount.p, 0, sizeof(int32_t) * TL, h->stream));
   }
   launch_home(D, h->tree, Nq, dXq, q.home, pruned ? h->d_leaf_qcount.as<int32_t>() : nullptr, h->stream);
@@ -1444,7 +1504,7 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
   KCHECK(h, "k_scan_small");
   // stable sort of pair ids by leaf
   {
-    if (int rc = ensure_iota(n_pairs)) return rc;
+    if (int rc = ensure_iota(h, n_pairs)) return rc;
     size_t tb = 0;
     cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, q.pair_leaf, h->d_keys_out.as<int32_t>(), h->d_iota.as<int32_t>(),
                                     h->d_sorted_pair.as<int32_t>(), (int)n_pairs, 0, end_bit, h->stream);
@@ -1453,18 +1513,19 @@ int pmk_query_plan_dev(pmk_handle* h, int64_t Nq, const double* dXq, double radi
                                           h->d_sorted_pair.as<int32_t>(), (int)n_pairs, 0, end_bit, h->stream));
   }
   if (n_pairs_out) *n_pairs_out = n_pairs;
+  h->last_radius = radius;
+  h->last_delta = delta;
   h->plan_valid = true;
   return PMK_OK;
 }
 
-int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pair_v) {
-  if (!h) return PMK_ERR_ARG;
-  if (int rc = set_device(h)) return rc;
-  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
-  if (!d_pair_u || !d_pair_v) return fail(h, PMK_ERR_ARG, "NULL pointer");
-  const QueryPlan& q = h->plan;
+// The fused pair kernel over a pair list binned by leaf: q.Xq / q.pair_q give every pair's query point, sorted_pair the pair
+// ids sorted by (global) leaf, leaf_pair_start the start of every global leaf's run.  Only this handle's leaves
+// [leaf_base, leaf_base + n_leaves) may occur.  Writes u, v of pair id i to pu[i], pv[i].
+static int run_pair_kernels(pmk_handle* h, const QueryPlan& q, const int64_t* leaf_pair_start, const int32_t* sorted_pair, int flags,
+                            double* pu, double* pv) {
   const int mean_only = flags & 3;   // bit0: mean only; bit1: variance without the 1e-12 clamp
-  h->last_flags = flags;
+  const int solver = effective_solver(h);
   if (!(flags & 1)) {     // variance wanted: the pair kernel streams M (substitution) or P = inv(L), built once per fit
     const bool use_P = uses_inverse(h);
     if (int rc = build_operands(h, !use_P, use_P)) return rc;
@@ -1479,9 +1540,9 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     w.class_leaves = h->d_class_leaves[c].as<int>();
     w.n_class_leaves = h->n_class[c];
     w.tile_off = h->d_tile_off[c].as<int64_t>();
-    w.leaf_pair_start = h->d_leaf_pair_start.as<int64_t>();
-    w.sorted_pair = h->d_sorted_pair.as<int32_t>();
-    w.leaf_base = 0;
+    w.leaf_pair_start = leaf_pair_start;
+    w.sorted_pair = sorted_pair;
+    w.leaf_base = h->leaf_base;
     const int mq = query_class_mq(c);
     launch_class_tiles(w, mq, h->d_class_tiles[c].as<int32_t>(), h->stream);
     KCHECK(h, "k_class_tiles");
@@ -1491,16 +1552,128 @@ int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pa
     const int64_t ub = q.n_pairs / mq + h->n_class[c];
     {
       Timer tc(h, PMK_T_Q_PAIRS_CLASS0 + c);
-      if (!(mean_only & 1) && h->solver == 0) {
-        if (!launch_query_rowp(h->D, c, h->lt, w, q, h->kp, mean_only, h->class_max_npad[c], d_pair_u, d_pair_v, h->stream))
+      if (!(mean_only & 1) && solver == 0) {
+        if (!launch_query_rowp(h->D, c, h->lt, w, q, h->kp, mean_only, h->class_max_npad[c], pu, pv, h->stream))
           return fail(h, PMK_ERR_UNSUPPORTED, "row-panel pair kernel: no shared-memory configuration for size class %d", c);
-      } else if (!(mean_only & 1) && h->solver == 2 && h->kp.kind == PMK_KERNEL_SQEXP)
-        launch_query_trmm(h->D, c, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
+      } else if (!(mean_only & 1) && solver == 2 && h->kp.kind == PMK_KERNEL_SQEXP)
+        launch_query_trmm(h->D, c, h->lt, w, q, h->kp, mean_only, pu, pv, h->stream);
       else
-        launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, d_pair_u, d_pair_v, h->stream);
+        launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, pu, pv, h->stream);
     }
     KCHECK(h, "k_query_pairs");
   }
+  return PMK_OK;
+}
+
+int pmk_query_pairs_dev(pmk_handle* h, int flags, double* d_pair_u, double* d_pair_v) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
+  if (!d_pair_u || !d_pair_v) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  if (h->leaf_base != 0 || h->n_leaves != h->total_leaves)
+    return fail(h, PMK_ERR_STATE, "this handle owns leaves [%lld, %lld) of %lld: route the pairs to their owners (pmk_query_plan_segments / "
+                "pmk_query_pairs_routed_dev, or pmk_multi_query)", (long long)h->leaf_base, (long long)(h->leaf_base + h->n_leaves),
+                (long long)h->total_leaves);
+  h->last_flags = flags;
+  return run_pair_kernels(h, h->plan, h->d_leaf_pair_start.as<int64_t>(), h->d_sorted_pair.as<int32_t>(), flags, d_pair_u, d_pair_v);
+}
+
+// ---- sub-tree ownership: the pairs of a plan travel to the handles that own their leaves ------------------------------------
+int pmk_set_leaf_base(pmk_handle* h, int64_t leaf_base, int64_t total_leaves) {
+  if (!h) return PMK_ERR_ARG;
+  if (leaf_base < 0 || total_leaves < 0 || (total_leaves > 0 && leaf_base >= total_leaves)) return fail(h, PMK_ERR_ARG, "bad leaf base");
+  h->leaf_base = leaf_base;
+  h->total_opt = total_leaves;
+  h->fitted = false;
+  h->plan_valid = false;
+  return PMK_OK;
+}
+
+int pmk_query_plan_segments(pmk_handle* h, int n_owners, const int64_t* owner_first_leaf, int64_t* seg_off) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
+  if (n_owners < 1 || !owner_first_leaf || !seg_off) return fail(h, PMK_ERR_ARG, "NULL pointer or n_owners < 1");
+  const int64_t TL = h->total_leaves;
+  for (int o = 0; o <= n_owners; ++o) {
+    const int64_t f = owner_first_leaf[o];
+    if (f < 0 || f > TL || (o > 0 && f < owner_first_leaf[o - 1]) || (o == 0 && f != 0) || (o == n_owners && f != TL))
+      return fail(h, PMK_ERR_ARG, "owner_first_leaf must ascend from 0 to the number of leaves (%lld)", (long long)TL);
+  }
+  // leaf_pair_start has TL + 1 entries: the start of every leaf's run in the leaf-sorted pair list
+  for (int o = 0; o <= n_owners; ++o)
+    CU(h, cudaMemcpyAsync(seg_off + o, h->d_leaf_pair_start.as<int64_t>() + owner_first_leaf[o], sizeof(int64_t), cudaMemcpyDeviceToHost,
+                          h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_query_plan_pack_dev(pmk_handle* h, double* d_X_sorted, int32_t* d_leaf_sorted) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
+  if (!d_X_sorted || !d_leaf_sorted) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const QueryPlan& q = h->plan;
+  launch_pack_sorted_pairs(h->D, q, h->d_sorted_pair.as<int32_t>(), d_X_sorted, d_leaf_sorted, h->stream);
+  KCHECK(h, "k_pack_sorted_pairs");
+  return PMK_OK;
+}
+
+int pmk_query_plan_unpack_dev(pmk_handle* h, const double* d_u_sorted, const double* d_v_sorted, double* d_pair_u, double* d_pair_v) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "pmk_query_plan_dev has not been called");
+  if (!d_u_sorted || !d_pair_u) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  launch_unpack_sorted_pairs(h->plan.n_pairs, h->d_sorted_pair.as<int32_t>(), d_u_sorted, d_v_sorted, d_pair_u, d_pair_v, h->stream);
+  KCHECK(h, "k_unpack_sorted_pairs");
+  return PMK_OK;
+}
+
+int pmk_query_set_flags(pmk_handle* h, int flags) {
+  if (!h) return PMK_ERR_ARG;
+  h->last_flags = flags;
+  return PMK_OK;
+}
+
+int pmk_query_pairs_routed_dev(pmk_handle* h, int64_t R, const double* d_X, const int32_t* d_leaf, int flags, double* d_u, double* d_v) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->fitted) return fail(h, PMK_ERR_STATE, "query before fit");
+  if (R < 0 || R > INT32_MAX) return fail(h, PMK_ERR_ARG, "R=%lld out of range", (long long)R);
+  if (R == 0) return PMK_OK;
+  if (!d_X || !d_leaf || !d_u || (!(flags & 1) && !d_v)) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const int64_t TL = h->total_leaves;
+  CU(h, h->r_keys.ensure(sizeof(int32_t) * R));
+  CU(h, h->r_sorted.ensure(sizeof(int32_t) * R));
+  CU(h, h->r_leaf_start.ensure(sizeof(int64_t) * (TL + 1)));
+  if (int rc = ensure_iota(h, R)) return rc;
+  int end_bit = 1;
+  while ((1ll << end_bit) <= TL) ++end_bit;
+  {
+    Timer tt(h, PMK_T_Q_ROUTE_SORT);
+    size_t tb = 0;
+    cub::DeviceRadixSort::SortPairs((void*)nullptr, tb, d_leaf, h->r_keys.as<int32_t>(), h->d_iota.as<int32_t>(), h->r_sorted.as<int32_t>(),
+                                    (int)R, 0, end_bit, h->stream);
+    CU(h, h->d_cub.ensure(tb));
+    CU(h, cub::DeviceRadixSort::SortPairs(h->d_cub.p, tb, d_leaf, h->r_keys.as<int32_t>(), h->d_iota.as<int32_t>(), h->r_sorted.as<int32_t>(),
+                                          (int)R, 0, end_bit, h->stream));
+    ++h->launches;
+    // start of every global leaf's run in the sorted keys; flags any leaf outside [leaf_base, leaf_base + n_leaves)
+    CU(h, cudaMemsetAsync(h->d_info2.p, 0, sizeof(int), h->stream));
+    launch_run_starts(h->r_keys.as<int32_t>(), R, TL, h->leaf_base, h->n_leaves, h->r_leaf_start.as<int64_t>(), h->d_info2.as<int>(), h->stream);
+    KCHECK(h, "k_run_starts");
+  }
+  QueryPlan q{};
+  q.Nq = R;
+  q.Xq = d_X;
+  q.n_pairs = R;
+  q.pair_q = h->d_iota.as<int32_t>();
+  if (int rc = run_pair_kernels(h, q, h->r_leaf_start.as<int64_t>(), h->r_sorted.as<int32_t>(), flags, d_u, d_v)) return rc;
+  int foreign = 0;
+  CU(h, cudaMemcpyAsync(&foreign, h->d_info2.p, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  if (foreign) return fail(h, PMK_ERR_ARG, "routed pairs name leaves this handle does not own ([%lld, %lld) of %lld)", (long long)h->leaf_base + 1,
+                           (long long)(h->leaf_base + h->n_leaves + 1), (long long)TL);
   return PMK_OK;
 }
 
@@ -1580,6 +1753,86 @@ int pmk_last_query_debug(pmk_handle* h, int32_t* home, int64_t* pair_off, int32_
     CU(h, cudaMemcpyAsync(pair_v, h->d_pair_v.p, sizeof(double) * np, cudaMemcpyDeviceToHost, s));
   }
   CU(h, cudaStreamSynchronize(s));
+  return PMK_OK;
+}
+
+int pmk_last_query_debug_dense(pmk_handle* h, int64_t first_query, int64_t n_queries, uint8_t* keep_flags, double* ts, double* zs) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "no query plan");
+  const QueryPlan& q = h->plan;
+  if (first_query < 0 || n_queries < 0 || first_query + n_queries > q.Nq) return fail(h, PMK_ERR_ARG, "query range out of bounds");
+  const int64_t total = n_queries * (int64_t)h->n_hp;
+  if (total == 0) return PMK_OK;
+  if (total > ((int64_t)1 << 28))
+    return fail(h, PMK_ERR_UNSUPPORTED, "dense debug arrays of %lld queries x %d hyperplanes: ask for at most 2^28 entries per call",
+                (long long)n_queries, h->n_hp);
+  const int D = h->D;
+  const size_t bt = (size_t)total * sizeof(double), bz = bt * D, bk = ((size_t)total + 7) / 8 * 8;
+  CU(h, h->d_scratch.ensure(bt + bz + bk));
+  double* dts = h->d_scratch.as<double>();
+  double* dzs = dts + total;
+  uint8_t* dk = reinterpret_cast<uint8_t*>(dzs + (size_t)total * D);
+  QueryPlan sub = q;
+  sub.Nq = n_queries;
+  sub.Xq = q.Xq + first_query * D;
+  sub.home = q.home + first_query;
+  launch_dense_debug(D, h->tree, sub, h->last_radius, h->last_delta, keep_flags ? dk : nullptr, ts ? dts : nullptr, zs ? dzs : nullptr,
+                     h->stream);
+  KCHECK(h, "k_dense_debug");
+  if (ts) CU(h, cudaMemcpyAsync(ts, dts, bt, cudaMemcpyDeviceToHost, h->stream));
+  if (zs) CU(h, cudaMemcpyAsync(zs, dzs, bz, cudaMemcpyDeviceToHost, h->stream));
+  if (keep_flags) CU(h, cudaMemcpyAsync(keep_flags, dk, (size_t)total, cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  return PMK_OK;
+}
+
+int pmk_measure_fp64_peak(pmk_handle* h, double* dmma_tflops) {
+  if (!h || !dmma_tflops) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  CU(h, h->d_scratch.ensure(1024));
+  cudaEvent_t e0, e1;
+  CU(h, cudaEventCreate(&e0));
+  CU(h, cudaEventCreate(&e1));
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {      // first launch warms up; best of the other three
+    cudaEventRecord(e0, h->stream);
+    const double flops = launch_dmma_peak(h->d_scratch.as<double>(), 4000, h->stream);
+    cudaEventRecord(e1, h->stream);
+    if (cudaGetLastError() != cudaSuccess || cudaEventSynchronize(e1) != cudaSuccess) {
+      cudaEventDestroy(e0);
+      cudaEventDestroy(e1);
+      return fail(h, PMK_ERR_CUDA, "k_dmma_peak failed");
+    }
+    ++h->launches;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms > 0.f) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *dmma_tflops = best;
+  return PMK_OK;
+}
+
+int pmk_condition_estimate(pmk_handle* h, double* cond_lower_bound, int* solver_in_use) {
+  if (!h) return PMK_ERR_ARG;
+  if (h->n_leaves == 0) return fail(h, PMK_ERR_STATE, "no model laid out (call pmk_fit first)");
+  if (cond_lower_bound) *cond_lower_bound = h->cond_est;
+  if (solver_in_use) *solver_in_use = effective_solver(h);
+  return PMK_OK;
+}
+
+int pmk_last_query_leaf_pairs(pmk_handle* h, int64_t* pairs_per_leaf) {
+  if (!h) return PMK_ERR_ARG;
+  if (int rc = set_device(h)) return rc;
+  if (!h->plan_valid) return fail(h, PMK_ERR_STATE, "no query plan");
+  if (!pairs_per_leaf) return fail(h, PMK_ERR_ARG, "NULL pointer");
+  const int64_t TL = h->total_leaves;
+  std::vector<int64_t> st((size_t)TL + 1);
+  CU(h, cudaMemcpyAsync(st.data(), h->d_leaf_pair_start.p, sizeof(int64_t) * (TL + 1), cudaMemcpyDeviceToHost, h->stream));
+  CU(h, cudaStreamSynchronize(h->stream));
+  for (int64_t g = 0; g < TL; ++g) pairs_per_leaf[g] = st[g + 1] - st[g];
   return PMK_OK;
 }
 

@@ -5,6 +5,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include "../../include/pmk.h"
 
 // Per-phase cycle counters (tools/chol_phases.py, tools/query_phases.py) are compiled in only with
@@ -16,6 +17,29 @@
 #endif
 
 namespace pmk {
+
+// Host side: run a launcher's one-time setup once per DEVICE.  cudaFuncSetAttribute is per device, and pmk_multi drives several
+// devices from several host threads of one process, so "static bool configured" is neither enough nor safe.
+struct DeviceOnce {
+  std::mutex mu;
+  unsigned long long done = 0;      // one bit per device ordinal
+  template <class F>
+  void run(F&& f) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> g(mu);
+    if (!((done >> (dev & 63)) & 1ull)) {
+      f();
+      done |= 1ull << (dev & 63);
+    }
+  }
+};
+inline int device_sm_count() {
+  int dev = 0, n = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+  return n;
+}
 
 struct KParams {
   int kind;     // pmk_kernel_id

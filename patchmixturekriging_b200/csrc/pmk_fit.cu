@@ -590,7 +590,7 @@ __device__ __forceinline__ double linv_elem(const double* __restrict__ Iblk, int
 #endif
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, PMK_SOLVE_MINB)
-k_solve_alpha(LeafTable lt, const int* __restrict__ order) {
+k_solve_alpha(LeafTable lt, const int* __restrict__ order, const double* __restrict__ rhs_in, double* __restrict__ out) {
   extern __shared__ double sm[];
   const int p = order[blockIdx.x];
   if (lt.info[p] != 0) return;
@@ -604,7 +604,7 @@ k_solve_alpha(LeafTable lt, const int* __restrict__ order) {
   const double2* __restrict__ Lp = reinterpret_cast<const double2*>(lt.L + lt.loff[p]);
   const double* __restrict__ Ib = lt.Linv + lt.ioff[p];
   const int64_t xo = lt.xoff[p];
-  for (int i = threadIdx.x; i < npad; i += NW * 32) z[i] = lt.y[xo + i];
+  for (int i = threadIdx.x; i < npad; i += NW * 32) z[i] = rhs_in[xo + i];
   __syncthreads();
   // ---- forward: z <- L^-1 y
   for (int J = 0; J < nblk; ++J) {
@@ -676,7 +676,76 @@ k_solve_alpha(LeafTable lt, const int* __restrict__ order) {
     }
     __syncthreads();
   }
-  for (int i = threadIdx.x; i < npad; i += NW * 32) lt.alpha[xo + i] = i < n ? z[i] : 0.0;
+  for (int i = threadIdx.x; i < npad; i += NW * 32) out[xo + i] = i < n ? z[i] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// One step of iterative refinement of alpha: r = y - (K + sigma2 I) alpha with the Gram entries re-evaluated
+// (the factor only knows L L^T, whose distance to K + sigma2 I is the backward error refinement is meant to remove),
+// d = L^-T L^-1 r by k_solve_alpha, alpha += d.  One warp per row; FP64 residual.
+template <int D>
+__global__ void __launch_bounds__(256)
+k_alpha_residual(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2, double* __restrict__ r) {
+  const int p = order[blockIdx.x];
+  const int n = lt.n[p], npad = lt.npad[p];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t xo = lt.xoff[p];
+  const double* __restrict__ xs = lt.xs + xo;
+  const double* __restrict__ al = lt.alpha + xo;
+  for (int i = blockIdx.y * 8 + warp; i < npad; i += gridDim.y * 8) {
+    double acc = 0.0;
+    if (i < n) {
+      double xi[D];
+#pragma unroll
+      for (int d = 0; d < D; ++d) xi[d] = xs[d * lt.xstride + i];
+      for (int j = lane; j < n; j += 32) {
+        double xj[D];
+#pragma unroll
+        for (int d = 0; d < D; ++d) xj[d] = xs[d * lt.xstride + j];
+        double k = (i >= j) ? eval_kernel<D>(kp, xi, xj) : eval_kernel<D>(kp, xj, xi);   // the lower-triangle entry, mirrored (RKHS.jl:21-31)
+        if (i == j) k = __dadd_rn(k, sigma2);
+        acc = fma(k, al[j], acc);
+      }
+    }
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) acc += __shfl_xor_sync(kFull, acc, m);
+    if (lane == 0) r[xo + i] = i < n ? lt.y[xo + i] - acc : 0.0;
+  }
+}
+
+__global__ void k_alpha_add(double* __restrict__ alpha, const double* __restrict__ d, int64_t n) {
+  const int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (i < n) alpha[i] += d[i];
+}
+
+// (max diag(L) / min diag(L))^2 over the real rows of every leaf, maximum over the leaves: a lower bound of
+// cond(K + sigma2 I), free with the factor.  out[0] is raised with an atomic max on the bit pattern (positive doubles order like
+// their bit patterns).
+__global__ void k_diag_range(LeafTable lt, double* __restrict__ out) {
+  const int p = blockIdx.x;
+  const int n = lt.n[p];
+  const double* __restrict__ Lp = lt.L + lt.loff[p];
+  double lo = INFINITY, hi = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const double d = Lp[ltile_elem(i, i)];
+    lo = fmin(lo, d);
+    hi = fmax(hi, d);
+  }
+  __shared__ double slo[8], shi[8];
+#pragma unroll
+  for (int m = 16; m >= 1; m >>= 1) {
+    lo = fmin(lo, __shfl_xor_sync(kFull, lo, m));
+    hi = fmax(hi, __shfl_xor_sync(kFull, hi, m));
+  }
+  if ((threadIdx.x & 31) == 0) { slo[threadIdx.x >> 5] = lo; shi[threadIdx.x >> 5] = hi; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { lo = fmin(lo, slo[w]); hi = fmax(hi, shi[w]); }
+    if (lt.info[p] == 0 && lo > 0.0) {
+      const double ratio = hi / lo;
+      atomicMax(reinterpret_cast<unsigned long long*>(out), (unsigned long long)__double_as_longlong(ratio * ratio));
+    }
+  }
 }
 
 // dense column-major n x n lower-triangular copy of leaf p's factor (pmk_get_L)
@@ -725,11 +794,8 @@ void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStrea
   static int ctas_per_sm = [] { const char* e = getenv("PMK_CHOL_CTAS_PER_SM"); return e ? atoi(e) : 3; }();
   if (ctas_per_sm == 2) dyn = 100 * 1024;
   else if (ctas_per_sm == 1) dyn = 150 * 1024;
-  static bool configured = false;   // static + dynamic shared memory exceeds the 48 KB default
-  if (!configured) {
-    cudaFuncSetAttribute(k_chol<NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-    configured = true;
-  }
+  static DeviceOnce once;           // static + dynamic shared memory exceeds the 48 KB default
+  once.run([&] { cudaFuncSetAttribute(k_chol<NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); });
   k_chol<NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order);
 }
 
@@ -739,11 +805,33 @@ void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_np
   k_make_M<<<grid, 256, 0, s>>>(lt, first_leaf);
 }
 
-void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s) {
+// rhs / out: padded per-leaf vectors laid out like lt.y (nullptr = lt.y -> lt.alpha, the fit itself)
+void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s, const double* rhs, double* out) {
   constexpr int NW = 8;
   if (n_order <= 0) return;
   const size_t smem = (size_t)(max_npad + NW * 32 + 32) * sizeof(double);
-  k_solve_alpha<NW><<<n_order, NW * 32, smem, s>>>(lt, d_order);
+  k_solve_alpha<NW><<<n_order, NW * 32, smem, s>>>(lt, d_order, rhs ? rhs : lt.y, out ? out : lt.alpha);
+}
+
+void launch_alpha_residual(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, double* r, cudaStream_t s) {
+  if (n_order <= 0) return;
+  dim3 grid(n_order, 8);
+  switch (D) {
+    case 1: k_alpha_residual<1><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2, r); break;
+    case 2: k_alpha_residual<2><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2, r); break;
+    case 3: k_alpha_residual<3><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2, r); break;
+    default: break;
+  }
+}
+
+void launch_alpha_add(const LeafTable& lt, const double* d, int64_t n, cudaStream_t s) {
+  if (n <= 0) return;
+  k_alpha_add<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(lt.alpha, d, n);
+}
+
+void launch_diag_range(const LeafTable& lt, double* out, cudaStream_t s) {
+  if (lt.n_leaves <= 0) return;
+  k_diag_range<<<lt.n_leaves, 256, 0, s>>>(lt, out);
 }
 
 void read_chol_cycles(unsigned long long* out, bool reset) {

@@ -159,19 +159,49 @@ void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double
   static const bool no_mirror = [] { const char* e = getenv("PMK_GRAM_NO_MIRROR"); return e && atoi(e) != 0; }();
   const int mode = (symmetric && n == m && n > 2 * TM && !no_mirror) ? 2 : (symmetric ? 1 : 0);
   const size_t dyn = mode == 2 ? (size_t)TN * TMP * sizeof(double) : 0;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce once;
+  once.run([&] {
     cudaFuncSetAttribute(k_gram<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TN * TMP * sizeof(double)));
     cudaFuncSetAttribute(k_gram<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TN * TMP * sizeof(double)));
     cudaFuncSetAttribute(k_gram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TN * TMP * sizeof(double)));
-    configured = true;
-  }
+  });
   switch (D) {
     case 1: k_gram<1><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
     case 2: k_gram<2><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
     case 3: k_gram<3><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
     default: break;
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The FP64 roofline denominator, measured where the bench runs (pmk_measure_fp64_peak): a register-resident loop of
+// independent mma.sync.m8n8k4.f64 (-> DMMA.8x8x4) chains, 32 warps per SM x 8 accumulator pairs each -- nothing but the tensor
+// pipe is exercised.  512 flops per warp-level DMMA.
+__global__ void __launch_bounds__(1024) k_dmma_peak(double* __restrict__ out, int iters, double a, double b) {
+  double c0[8], c1[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    c0[i] = threadIdx.x * 1e-9;
+    c1[i] = i;
+  }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                   : "+d"(c0[i]), "+d"(c1[i])
+                   : "d"(a), "d"(b));
+  }
+  double s = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) s += c0[i] + c1[i];
+  if (s == 123.456) out[0] = s;      // never true: keeps the loop alive
+}
+
+// returns the flops one launch performs
+double launch_dmma_peak(double* d_out, int iters, cudaStream_t s) {
+  const int n_sm = device_sm_count();
+  k_dmma_peak<<<n_sm, 1024, 0, s>>>(d_out, iters, 1.0000001, 0.9999999);
+  return (double)n_sm * 32.0 * (double)iters * 8.0 * 512.0;
 }
 
 }  // namespace pmk

@@ -513,20 +513,17 @@ static bool launch_rowp_one(const LeafTable& lt, const PairWork& w, const QueryP
   const size_t kbytes = (size_t)npmax * 8 * NQT * 8;
   const size_t vbytes = (size_t)((npmax / 8 + R - 1) / R) * 8 * NQT * 8;
   const size_t xbytes = (size_t)(D + 1) * npmax * 8;
-  static int n_sm = 0;              // per process; all devices are B200
-  static size_t kMaxDyn = 0;        // 227 KB per CTA minus the kernel's static part
   auto k_staged = k_query_rowp<D, NQT, R, CW, DEPTH, true>;
   auto k_plain = k_query_rowp<D, NQT, R, CW, DEPTH, false>;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncAttributes fa{};
-    cudaFuncGetAttributes(&fa, k_staged);
-    kMaxDyn = (size_t)232448 - fa.sharedSizeBytes - 64;
+  const int n_sm = device_sm_count();
+  cudaFuncAttributes fa{};
+  cudaFuncGetAttributes(&fa, k_staged);
+  const size_t kMaxDyn = (size_t)232448 - fa.sharedSizeBytes - 64;   // 227 KB per CTA minus the kernel's static part
+  static DeviceOnce once;
+  once.run([&] {
     cudaFuncSetAttribute(k_staged, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn);
     cudaFuncSetAttribute(k_plain, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kMaxDyn);
-  }
+  });
   // persistent: tiles are strided over the CTAs
   if (ring + kbytes + vbytes + xbytes <= kMaxDyn)
     k_staged<<<n_sm, kRowpThreads, ring + kbytes + vbytes + xbytes, s>>>(lt, w, q, kp, flags, npmax, pu, pv);

@@ -506,14 +506,10 @@ static void launch_trmm_one(const LeafTable& lt, const PairWork& w, const QueryP
                             double* pu, double* pv, cudaStream_t s) {
   constexpr size_t dyn = (size_t)kUW * DEPTH * GI * CG * 512 + (size_t)kSB * (D + 1) * NPMAX * 8 + (size_t)3 * 32 * (8 * NQT + 4) * 8;
   static_assert(dyn <= 214 * 1024, "rings, staged inputs and the K ring do not fit in shared memory");
-  static int n_sm = 0;              // per process; all devices are B200
   auto kern = k_query_trmm<D, NT, NQT, CG, GI, DEPTH, NPMAX>;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  }
+  const int n_sm = device_sm_count();
+  static DeviceOnce once;
+  once.run([&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); });
   kern<<<n_sm, kTrmmThreads, dyn, s>>>(lt, w, q, kp, flags, pu, pv);   // persistent: tiles are strided over the CTAs
 }
 

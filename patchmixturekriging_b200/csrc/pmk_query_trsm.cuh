@@ -465,14 +465,10 @@ static void launch_one(unsigned grid, const LeafTable& lt, const PairWork& w, co
                        double* pu, double* pv, cudaStream_t s) {
   constexpr size_t dyn = (size_t)kCW * DEPTH * GI * CG * 512;
   static_assert(dyn <= 200 * 1024, "rings do not fit in shared memory");
-  static int n_sm = 0;              // per process; all devices are B200
   auto kern = k_query_pairs<D, NT, NQT, CG, GI, DEPTH>;
-  if (n_sm == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
-  }
+  const int n_sm = device_sm_count();
+  static DeviceOnce once;
+  once.run([&] { cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); });
   const unsigned ctas = grid < (unsigned)n_sm ? grid : (unsigned)n_sm;   // persistent: tiles are strided over the CTAs
   kern<<<ctas, kK3Threads, dyn, s>>>(lt, w, q, kp, mean_only, pu, pv);
 }

@@ -552,6 +552,80 @@ __global__ void k_scan_small(const int32_t* __restrict__ in, int64_t* __restrict
   if (threadIdx.x == 0) out[n] = carry;
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Sub-tree ownership: the pairs of a plan, in leaf-sorted order, as what travels to the owners of the leaves --
+// every pair's query point (D doubles) and its global leaf id.  Leaf-sorted order makes each owner's share one contiguous
+// segment (owners hold contiguous leaf ranges).
+template <int D>
+__global__ void k_pack_sorted_pairs(QueryPlan q, const int32_t* __restrict__ sorted_pair, double* __restrict__ Xs,
+                                    int32_t* __restrict__ leaf_s) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= q.n_pairs) return;
+  const int32_t id = sorted_pair[j];
+  const int64_t qi = q.pair_q[id];
+#pragma unroll
+  for (int d = 0; d < D; ++d) Xs[j * D + d] = q.Xq[qi * D + d];
+  leaf_s[j] = q.pair_leaf[id];
+}
+
+// the owners' answers, received in leaf-sorted order, back to pair-id order
+__global__ void k_unpack_sorted_pairs(int64_t n, const int32_t* __restrict__ sorted_pair, const double* __restrict__ us,
+                                      const double* __restrict__ vs, double* __restrict__ pu, double* __restrict__ pv) {
+  const int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (j >= n) return;
+  const int32_t id = sorted_pair[j];
+  pu[id] = us[j];
+  if (vs && pv) pv[id] = vs[j];
+}
+
+// start of every global leaf's run in an ascending key list (keys = 1-based leaf ids): start[g] = first index with key > g,
+// g = 0 .. TL (binary search, one thread per leaf); *foreign is raised when a key lies outside the owned leaf range.
+__global__ void k_run_starts(const int32_t* __restrict__ keys, int64_t R, int64_t TL, int64_t leaf_base, int64_t n_own,
+                             int64_t* __restrict__ start, int* __restrict__ foreign) {
+  const int64_t g = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (g > TL) return;
+  int64_t lo = 0, hi = R;               // first index whose key >= g + 1
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if ((int64_t)keys[mid] < g + 1) lo = mid + 1;
+    else hi = mid;
+  }
+  start[g] = lo;
+  if (g == 0 && R > 0) {
+    const int64_t first = (int64_t)keys[0] - 1, last = (int64_t)keys[R - 1] - 1;
+    if (first < leaf_base || last >= leaf_base + n_own) *foreign = 1;
+  }
+}
+
+// debug_flag outputs of findneighbourpartitions for EVERY hyperplane (mixtureGP.jl:347-352,364-365,389 -> debug_vars.ts_set,
+// zs_set, hps_keep_flags_set, :256-258): t_i, z_i = p + t_i u_i and the keep flag, dense Nq x n_hp.  One thread per (query,
+// hyperplane); same arithmetic as the search itself (neighbour_test).  Small Nq only: the caller bounds Nq * n_hp.
+template <int D>
+__global__ void k_dense_debug(TreeDev tr, QueryPlan q, double radius, double delta, uint8_t* __restrict__ keep,
+                              double* __restrict__ ts, double* __restrict__ zs) {
+  const int64_t idx = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+  if (idx >= q.Nq * tr.n_hp) return;
+  const int64_t j = idx / tr.n_hp;
+  const int i = (int)(idx % tr.n_hp);
+  double p[D], u[D];
+#pragma unroll
+  for (int d = 0; d < D; ++d) {
+    p[d] = q.Xq[j * D + d];
+    u[d] = tr.hv[d * tr.n_hp + i];
+  }
+  const double t = __dadd_rn(-dot_seq<D>(u, p), tr.hc[i]);       // mixtureGP.jl:361
+  if (ts) ts[idx] = t;
+  if (zs) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) zs[idx * D + d] = __dadd_rn(p[d], __dmul_rn(t, u[d]));   // mixtureGP.jl:362
+  }
+  if (keep) {
+    double t2;
+    keep[idx] = neighbour_test<D>(tr, p, q.home[j], i, radius, delta, &t2) != 0 ? 1 : 0;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 void launch_home(int D, const TreeDev& tr, int64_t Nq, const double* dXq, int32_t* d_home, int32_t* d_leaf_qcount,
                  cudaStream_t s) {
@@ -663,6 +737,47 @@ void launch_combine(int64_t Nq, const int64_t* pair_off, const double* pw, const
 
 void launch_scan_small(const int32_t* in, int64_t* out, int n, cudaStream_t s) {
   k_scan_small<<<1, 1024, 0, s>>>(in, out, n);
+}
+
+void launch_pack_sorted_pairs(int D, const QueryPlan& q, const int32_t* sorted_pair, double* X_sorted, int32_t* leaf_sorted,
+                              cudaStream_t s) {
+  const int T = 256;
+  const unsigned B = (unsigned)((q.n_pairs + T - 1) / T);
+  if (B == 0) return;
+  switch (D) {
+    case 1: k_pack_sorted_pairs<1><<<B, T, 0, s>>>(q, sorted_pair, X_sorted, leaf_sorted); break;
+    case 2: k_pack_sorted_pairs<2><<<B, T, 0, s>>>(q, sorted_pair, X_sorted, leaf_sorted); break;
+    case 3: k_pack_sorted_pairs<3><<<B, T, 0, s>>>(q, sorted_pair, X_sorted, leaf_sorted); break;
+    default: break;
+  }
+}
+
+void launch_unpack_sorted_pairs(int64_t n, const int32_t* sorted_pair, const double* us, const double* vs, double* pu, double* pv,
+                                cudaStream_t s) {
+  const int T = 256;
+  const unsigned B = (unsigned)((n + T - 1) / T);
+  if (B == 0) return;
+  k_unpack_sorted_pairs<<<B, T, 0, s>>>(n, sorted_pair, us, vs, pu, pv);
+}
+
+void launch_run_starts(const int32_t* keys, int64_t R, int64_t TL, int64_t leaf_base, int64_t n_own, int64_t* start, int* foreign,
+                       cudaStream_t s) {
+  const int T = 256;
+  k_run_starts<<<(unsigned)((TL + 1 + T - 1) / T), T, 0, s>>>(keys, R, TL, leaf_base, n_own, start, foreign);
+}
+
+void launch_dense_debug(int D, const TreeDev& tr, const QueryPlan& q, double radius, double delta, uint8_t* keep, double* ts,
+                        double* zs, cudaStream_t s) {
+  const int T = 128;
+  const int64_t total = q.Nq * (int64_t)tr.n_hp;
+  const unsigned B = (unsigned)((total + T - 1) / T);
+  if (B == 0) return;
+  switch (D) {
+    case 1: k_dense_debug<1><<<B, T, 0, s>>>(tr, q, radius, delta, keep, ts, zs); break;
+    case 2: k_dense_debug<2><<<B, T, 0, s>>>(tr, q, radius, delta, keep, ts, zs); break;
+    case 3: k_dense_debug<3><<<B, T, 0, s>>>(tr, q, radius, delta, keep, ts, zs); break;
+    default: break;
+  }
 }
 
 }  // namespace pmk

@@ -20,7 +20,7 @@ from typing import List, Optional, Sequence
 import numpy as np
 
 from . import _lib
-from ._lib import Handle, PMKError, PosDefException, lib, ptr
+from ._lib import Handle, MultiHandle, PMKError, PosDefException, lib, ptr
 from .partition import BSPTree
 
 
@@ -39,12 +39,20 @@ class MixtureGPDebugType:
     v_set: List[np.ndarray] = field(default_factory=list)
     region_inds_set: List[np.ndarray] = field(default_factory=list)
     p_region_ind_set: np.ndarray = field(default_factory=lambda: np.zeros(0, dtype=np.int32))
-    # hyperplane bookkeeping: instead of Nq x n_hp dense ts/zs/keep_flags arrays (4095 per query in
-    # the 1M-point configuration) the kept hyperplane ids and their t are returned per query
+    # hyperplane bookkeeping, compact: the kept hyperplane ids and their t per query ...
     kept_hp_set: List[np.ndarray] = field(default_factory=list)
     t_kept_set: List[np.ndarray] = field(default_factory=list)
+    # ... and the reference's dense arrays over ALL hyperplanes (mixtureGP.jl:17-19,256-258), filled when
+    # Nq * n_hp <= DENSE_DEBUG_LIMIT (4095 values per query in the 1M-point configuration): per query j,
+    # hps_keep_flags_set[j] (bool, n_hp), zs_set[j] (n_hp x D), ts_set[j] (n_hp)
+    hps_keep_flags_set: List[np.ndarray] = field(default_factory=list)
+    zs_set: List[np.ndarray] = field(default_factory=list)
+    ts_set: List[np.ndarray] = field(default_factory=list)
     # flat CSR form of the same data
     pair_off: Optional[np.ndarray] = None
+
+
+DENSE_DEBUG_LIMIT = 1 << 26     # Nq * n_hp entries up to which debug_flag also fills the dense per-hyperplane arrays
 
 
 class _LazyLeafList:
@@ -63,13 +71,14 @@ class _LazyLeafList:
         n = eta.X_parts[i].shape[0]
         leaf = i + 1
         L = lib()
+        h = eta._leaf_handle(i)          # the handle (rank) that owns the leaf; leaf ids stay global
         if self._what == "c":
             out = np.empty(n)
-            eta._h.check(L.pmk_get_alpha(eta._h.raw, leaf, ptr(out)))
+            h.check(L.pmk_get_alpha(h.raw, leaf, ptr(out)))
             return out
         out = np.empty((n, n), order="F")
         fn = {"L": L.pmk_get_L, "Linv": L.pmk_get_Linv}.get(self._what, L.pmk_get_K)
-        eta._h.check(fn(eta._h.raw, leaf, ptr(out)))
+        h.check(fn(h.raw, leaf, ptr(out)))
         return out
 
 
@@ -78,16 +87,18 @@ class MixtureGPType:
     The fitted state lives in HBM; c_set / L_set / U_set materialise a leaf on the host on demand
     (U_set is the Gram matrix WITHOUT σ², mixtureGP.jl:99)."""
 
-    def __init__(self, X_parts: Sequence[np.ndarray], hps, device: int = 0, fit_range: Optional[tuple] = None):
+    def __init__(self, X_parts: Sequence[np.ndarray], hps, device: int = 0, devices=None):
+        """devices: a list of CUDA ordinals (or their number) shards the model over several GPUs of the box by sub-tree
+        ownership (pmk_multi): rank r owns a contiguous range of the leaves; fit and query keep their signatures."""
         self.X_parts = [_as_points(X) for X in X_parts]
         self.hps = hps                     # (hps_v, hps_c) as returned by fetchhyperplanes
         self.σ2_set: List[float] = []
         self.c_set = _LazyLeafList(self, "c")
         self.L_set = _LazyLeafList(self, "L")
         self.U_set = _LazyLeafList(self, "K")
-        self._h = Handle(device)
+        self._multi = MultiHandle(devices) if devices is not None else None
+        self._h = Handle(device) if self._multi is None else None
         self._fitted = False
-        self._fit_range = fit_range        # (first_leaf 0-based, n_leaves): leaf -> rank map slice, None = all
         self._tree_key = None
         self.θ = None
 
@@ -96,8 +107,20 @@ class MixtureGPType:
     def handle(self) -> Handle:
         return self._h
 
+    @property
+    def multi(self) -> Optional[MultiHandle]:
+        return self._multi
+
+    def _leaf_handle(self, i: int) -> Handle:
+        if self._multi is None:
+            return self._h
+        return self._multi.rank_handle(self._multi.owner_of_leaf(i, len(self.X_parts)))
+
     def close(self):
-        self._h.close()
+        if self._multi is not None:
+            self._multi.close()
+        if self._h is not None:
+            self._h.close()
 
 
 def fitmixtureGP_(η: MixtureGPType, y_parts: Sequence[np.ndarray], θ, σ2: float) -> MixtureGPType:
@@ -115,17 +138,22 @@ def fitmixtureGP_(η: MixtureGPType, y_parts: Sequence[np.ndarray], θ, σ2: flo
     X_packed = np.ascontiguousarray(np.concatenate(η.X_parts, axis=0))
     y_packed = np.ascontiguousarray(np.concatenate([np.asarray(y, dtype=np.float64) for y in y_parts]))
     L = lib()
-    if η._fit_range is not None:
-        η._h.check(L.pmk_set_fit_range(η._h.raw, int(η._fit_range[0]), int(η._fit_range[1])))
     bad, info = C.c_int64(0), C.c_int(0)
     kp = θ.params
     η._fitted = False
-    rc = L.pmk_fit(η._h.raw, D, N_parts, ptr(leaf_off), ptr(X_packed), ptr(y_packed), θ.kernel_id, ptr(kp), kp.shape[0],
-                   float(σ2), C.byref(bad), C.byref(info))
-    if rc == _lib.PMK_ERR_NOT_POSDEF:
-        raise PosDefException(info.value, bad.value, L.pmk_last_error(η._h.raw).decode())
-    η._h.check(rc)
-    η._fitted = η._fit_range is None or (η._fit_range[0] == 0 and η._fit_range[1] >= N_parts)
+    if η._multi is not None:
+        rc = L.pmk_multi_fit(η._multi.raw, D, N_parts, ptr(leaf_off), ptr(X_packed), ptr(y_packed), θ.kernel_id, ptr(kp), kp.shape[0],
+                             float(σ2), C.byref(bad), C.byref(info))
+        if rc == _lib.PMK_ERR_NOT_POSDEF:
+            raise PosDefException(info.value, bad.value, L.pmk_multi_last_error(η._multi.raw).decode())
+        η._multi.check(rc)
+    else:
+        rc = L.pmk_fit(η._h.raw, D, N_parts, ptr(leaf_off), ptr(X_packed), ptr(y_packed), θ.kernel_id, ptr(kp), kp.shape[0],
+                       float(σ2), C.byref(bad), C.byref(info))
+        if rc == _lib.PMK_ERR_NOT_POSDEF:
+            raise PosDefException(info.value, bad.value, L.pmk_last_error(η._h.raw).decode())
+        η._h.check(rc)
+    η._fitted = True
     η.θ = θ
     η.σ2_set = [float(σ2)] * N_parts
     return η
@@ -136,6 +164,8 @@ def savemixtureGP(η: MixtureGPType, path: str, root: Optional[BSPTree] = None, 
     the last query used) in one flat file.  The reference has no serialisation; this is the §8f-4 row."""
     if not η._fitted:
         raise PMKError(_lib.PMK_ERR_STATE, "savemixtureGP before fitmixtureGP_")
+    if η._multi is not None:
+        raise PMKError(_lib.PMK_ERR_UNSUPPORTED, "savemixtureGP of a model sharded over several GPUs: a model file holds a whole model")
     if root is not None:
         _set_tree(η, root, root.levels if levels is None else levels)
     η._h.check(lib().pmk_save_model(η._h.raw, str(path).encode()))
@@ -146,6 +176,7 @@ def loadmixtureGP(path: str, device: int = 0):
     root is the flattened tree stored in the file (None, levels 1 when the model was saved without one)."""
     from . import kernels as K
     η = MixtureGPType.__new__(MixtureGPType)
+    η._multi = None
     η._h = Handle(device)
     L = lib()
     η._h.check(L.pmk_load_model(η._h.raw, str(path).encode()))
@@ -166,7 +197,6 @@ def loadmixtureGP(path: str, device: int = 0):
     η.L_set = _LazyLeafList(η, "L")
     η.U_set = _LazyLeafList(η, "K")
     η._fitted = True
-    η._fit_range = None
     η._tree_key = None
     root, levels = None, 1
     if lv.value > 1:
@@ -174,23 +204,18 @@ def loadmixtureGP(path: str, device: int = 0):
         hv, hc = np.empty((n_hp, D.value)), np.empty(n_hp)
         η._h.check(L.pmk_get_tree(η._h.raw, ptr(hv), ptr(hc)))
         root, levels = BSPTree(levels=lv.value, hps_v=hv, hps_c=hc), lv.value
-        η._tree_key = (id(root), levels)      # the handle already holds this tree
+        η._tree_key = _tree_fingerprint(root, levels)      # the handle already holds this tree
     η.hps = (root.hps_v, root.hps_c) if root is not None else (np.zeros((0, D.value)), np.zeros(0))
     return η, root, levels
 
 
-def model_buffer(η: MixtureGPType, which: int, first_leaf: int, n_leaves: int):
-    """(device address, bytes) of the contiguous span holding leaves [first_leaf, first_leaf+n_leaves) of
-    buffer `which` (_lib.BUF_L / BUF_LINV / BUF_ALPHA) -- what the ranks exchange after a sharded fit."""
-    dptr, nbytes = C.c_void_p(), C.c_int64(0)
-    η._h.check(lib().pmk_model_buffer(η._h.raw, which, first_leaf, n_leaves, C.byref(dptr), C.byref(nbytes)))
-    return int(dptr.value or 0), int(nbytes.value)
-
-
 def set_query_solver(η: MixtureGPType, solver: int):
-    """_lib.SOLVER_INVERSE (default: s = inv(L) kq, inverse formed once per fit) or _lib.SOLVER_SUBSTITUTION
-    (blocked forward substitution, closest to the reference's dtrsv)."""
-    η._h.check(lib().pmk_set_option(η._h.raw, _lib.OPT_QUERY_SOLVER, solver))
+    """_lib.SOLVER_AUTO (default: by the fit's conditioning estimate), _lib.SOLVER_INVERSE (s = inv(L) kq, inverse formed once
+    per fit) or _lib.SOLVER_SUBSTITUTION (blocked forward substitution, closest to the reference's dtrsv)."""
+    if η._multi is not None:
+        η._multi.check(lib().pmk_multi_set_option(η._multi.raw, _lib.OPT_QUERY_SOLVER, solver))
+    else:
+        η._h.check(lib().pmk_set_option(η._h.raw, _lib.OPT_QUERY_SOLVER, solver))
 
 
 def set_inverse_builder(η: MixtureGPType, builder: int):
@@ -200,34 +225,53 @@ def set_inverse_builder(η: MixtureGPType, builder: int):
 
 
 def build_M(η: MixtureGPType):
-    """The pair kernel's operands (M_IJ = L_IJ inv(L_JJ), and P = inv(L) for the default solver) for the leaves this
-    handle factorised -- what a sharded run exchanges instead of L."""
+    """Build the pair kernel's operand (P = inv(L), or M_IJ = L_IJ inv(L_JJ) for the substitution solver) now instead of in
+    the first variance query (pmk_build_M)."""
     η._h.check(lib().pmk_build_M(η._h.raw))
 
 
-def mark_fitted(η: MixtureGPType, m_exchanged: bool = False, p_exchanged: bool = False):
-    """Declare the replicated model complete after the peers' factors have been copied in (m/p_exchanged: the
-    peers' pair-kernel operands M / P = inv(L) came along, so nothing is rebuilt for foreign leaves)."""
-    η._h.check(lib().pmk_mark_fitted(η._h.raw, (1 if m_exchanged else 0) | (2 if p_exchanged else 0)))
-    η._fitted = True
+def condition_estimate(η: MixtureGPType):
+    """(lower bound of the worst leaf's cond(K + σ²I), query solver SOLVER_AUTO resolves to) of the fitted model."""
+    cond, sv = C.c_double(0), C.c_int(0)
+    hs = [η._h] if η._multi is None else [η._multi.rank_handle(r) for r in range(η._multi.size)]
+    worst, solver = 0.0, 0
+    for h in hs:
+        h.check(lib().pmk_condition_estimate(h.raw, C.byref(cond), C.byref(sv)))
+        worst, solver = max(worst, cond.value), max(solver, sv.value)
+    return worst, solver
+
+
+def _tree_fingerprint(root: BSPTree, levels: int):
+    """Content key of the tree a handle holds: in-place edits of root.hps_v / hps_c and a recycled id() both change it."""
+    import hashlib
+    hv = np.ascontiguousarray(root.hps_v, dtype=np.float64)
+    hc = np.ascontiguousarray(root.hps_c, dtype=np.float64)
+    return (levels, hv.shape, hashlib.blake2b(hv.tobytes() + hc.tobytes(), digest_size=16).digest())
 
 
 def _set_tree(η: MixtureGPType, root: Optional[BSPTree], levels: int):
     L = lib()
     D = η.X_parts[0].shape[1]
+
+    def upload(lv, hv, hc):
+        if η._multi is not None:
+            η._multi.check(L.pmk_multi_set_tree(η._multi.raw, D, lv, ptr(hv), ptr(hc)))
+        else:
+            η._h.check(L.pmk_set_tree(η._h.raw, D, lv, ptr(hv), ptr(hc)))
+
     if root is None or levels == 1:
         key = ("none",)
         if η._tree_key != key:
-            η._h.check(L.pmk_set_tree(η._h.raw, D, 1, None, None))
+            upload(1, None, None)
             η._tree_key = key
         return
     if levels != root.levels:
         raise PMKError(_lib.PMK_ERR_ARG, "levels does not match the tree")
-    key = (id(root), levels)
+    key = _tree_fingerprint(root, levels)       # content, not id(root): edits in place and recycled ids must re-upload
     if η._tree_key != key:
         hv = np.ascontiguousarray(root.hps_v, dtype=np.float64)
         hc = np.ascontiguousarray(root.hps_c, dtype=np.float64)
-        η._h.check(L.pmk_set_tree(η._h.raw, D, levels, ptr(hv), ptr(hc)))
+        upload(levels, hv, hc)
         η._tree_key = key
 
 
@@ -251,6 +295,17 @@ def _fetch_debug(η: MixtureGPType, Nq: int, debug_vars: MixtureGPDebugType):
     debug_vars.kept_hp_set = [hp[off[j]:off[j + 1] - 1] for j in range(Nq)]
     debug_vars.t_kept_set = [t[off[j]:off[j + 1] - 1] for j in range(Nq)]
     debug_vars._flat = dict(home=home, pair_off=off, pair_leaf=leaf, pair_hp=hp, pair_t=t, pair_w=w, pair_u=u, pair_v=v)
+    # the reference's dense per-hyperplane arrays (mixtureGP.jl:256-258), when they are small enough to be wanted
+    n_hp = int(np.asarray(η.hps[1]).shape[0]) if η.hps is not None else 0
+    D = η.X_parts[0].shape[1]
+    if n_hp > 0 and Nq * n_hp <= DENSE_DEBUG_LIMIT:
+        keep = np.empty((Nq, n_hp), dtype=np.uint8)
+        ts = np.empty((Nq, n_hp))
+        zs = np.empty((Nq, n_hp, D))
+        η._h.check(L.pmk_last_query_debug_dense(η._h.raw, 0, Nq, ptr(keep), ptr(ts), ptr(zs)))
+        debug_vars.hps_keep_flags_set = list(keep.astype(bool))
+        debug_vars.ts_set = list(ts)
+        debug_vars.zs_set = list(zs)
 
 
 def querymixtureGP_(Yq: np.ndarray, Vq: np.ndarray, Xq, η: MixtureGPType, root: Optional[BSPTree], levels: int,
@@ -269,6 +324,12 @@ def querymixtureGP_(Yq: np.ndarray, Vq: np.ndarray, Xq, η: MixtureGPType, root:
         raise PMKError(_lib.PMK_ERR_ARG, "θ differs from the kernel the model was fitted with")
     _set_tree(η, root, levels)
     wp = weight_θ.params
+    if η._multi is not None:
+        if debug_flag:
+            raise PMKError(_lib.PMK_ERR_UNSUPPORTED, "debug_flag on a model sharded over several GPUs: query a single-GPU model for the debug outputs")
+        η._multi.check(lib().pmk_multi_query(η._multi.raw, Nq, ptr(Xq), float(radius), float(δ), weight_θ.kernel_id, ptr(wp), wp.shape[0], 0,
+                                             ptr(Yq), ptr(Vq)))
+        return None
     η._h.check(lib().pmk_query(η._h.raw, Nq, ptr(Xq), float(radius), float(δ), weight_θ.kernel_id, ptr(wp), wp.shape[0], 0,
                                ptr(Yq), ptr(Vq)))
     if debug_flag and debug_vars is not None:

@@ -132,7 +132,8 @@ def setupGPquery(c, X, θ, σ2: float):
     leaf_off = np.array([0, n], dtype=np.int64)
     kp = θ.params
     bad, info = C.c_int64(0), C.c_int(0)
-    rc = L.pmk_fit(h.raw, D, 1, ptr(leaf_off), ptr(X), ptr(np.zeros(n)), θ.kernel_id, ptr(kp), kp.shape[0], float(σ2),
+    y0 = np.zeros(n)          # bound to a name: ptr() hands out a bare address
+    rc = L.pmk_fit(h.raw, D, 1, ptr(leaf_off), ptr(X), ptr(y0), θ.kernel_id, ptr(kp), kp.shape[0], float(σ2),
                    C.byref(bad), C.byref(info))
     if rc == _lib.PMK_ERR_NOT_POSDEF:
         raise PosDefException(info.value, bad.value, L.pmk_last_error(h.raw).decode())

@@ -1,23 +1,32 @@
-"""Leaf -> rank map and query slicing for one-process-per-GPU runs.
+"""Sub-tree ownership: the leaf -> rank map, the query slices and the routing bookkeeping of a sharded query.
 
-The fit shards by leaves (contiguous ranges = contiguous sub-trees of the BSP, so every rank's factor spans are
-contiguous in the packed buffers); the query shards by query index with no data-path collective; results are
-gathered once at the end.  Pure index arithmetic + torch.distributed calls, backend-agnostic (NCCL on GPUs,
-gloo in the CPU tests)."""
+Inside one box this is done by the library itself (pmk_multi_*, csrc/pmk_multi.cu: host threads + CUDA peer copies).  This
+module restates the same index arithmetic in Python -- pinned to the library's host-only exports by tests/test_multi.py --
+and carries the SAME flow over torch.distributed point-to-point operations (NCCL between boxes, gloo in the CPU tests) for a
+host layer that runs one process per GPU on top of the single-GPU building blocks (pmk_set_leaf_base,
+pmk_query_plan_segments / _pack_dev, pmk_query_pairs_routed_dev, pmk_query_plan_unpack_dev):
+
+  fit   : rank r fits leaves leaf_range(r); no exchange.
+  query : rank r plans queries query_slice(r); its (query, leaf) pairs, sorted by leaf, form one contiguous segment per
+          owner (segments); the segments travel to the owners (exchange_segments), the owners answer them in the order
+          received, the answers travel back (return_segments), the planner combines in the reference's slot order.
+"""
 from __future__ import annotations
 
-from typing import List, Tuple
+from typing import List, Sequence, Tuple
+
+import numpy as np
 
 
 def leaf_range(rank: int, world: int, n_leaves: int) -> Tuple[int, int]:
-    """(first_leaf 0-based, count) factorised by `rank`."""
+    """(first_leaf 0-based, count) owned by `rank` -- pmk_multi_leaf_range."""
     a = (n_leaves * rank) // world
     b = (n_leaves * (rank + 1)) // world
     return a, b - a
 
 
 def query_slice(rank: int, world: int, nq: int) -> Tuple[int, int]:
-    """[first, last) of the queries answered by `rank`."""
+    """[first, last) of the queries planned by `rank` -- pmk_multi_query_range."""
     return (nq * rank) // world, (nq * (rank + 1)) // world
 
 
@@ -25,51 +34,82 @@ def all_ranges(world: int, n: int, fn) -> List[Tuple[int, int]]:
     return [fn(r, world, n) for r in range(world)]
 
 
-def gather_slices(local, nq: int, group=None):
-    """all-gather the ranks' result slices (possibly of unequal length) into the full length-nq tensor."""
+def owner_first_leaf(world: int, n_leaves: int) -> np.ndarray:
+    """world + 1 ascending 0-based leaf ids: owner o holds leaves [f[o], f[o+1])."""
+    return np.array([leaf_range(r, world, n_leaves)[0] for r in range(world)] + [n_leaves], dtype=np.int64)
+
+
+def segments(sorted_leaf: np.ndarray, first_leaf: Sequence[int]) -> np.ndarray:
+    """Offsets (len(first_leaf) entries) of every owner's segment in a pair list sorted by 1-based leaf id --
+    pmk_query_plan_segments."""
+    return np.searchsorted(np.asarray(sorted_leaf), np.asarray(first_leaf) + 1, side="left").astype(np.int64)
+
+
+def rx_offsets(seg_all: np.ndarray, owner: int) -> np.ndarray:
+    """seg_all[s] = segments of planner s.  Offsets (world + 1) at which `owner` stores what each planner sends it."""
+    seg_all = np.asarray(seg_all)
+    counts = seg_all[:, owner + 1] - seg_all[:, owner]
+    return np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
+
+
+# --- the same flow over torch.distributed (one process per rank) ------------------------------------------------------------
+def _all_gather_rows(row, group=None):
     import torch
     import torch.distributed as dist
     world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    a, b = query_slice(rank, world, nq)
-    assert local.shape[0] == b - a
-    if nq % world == 0:
-        out = torch.empty(nq, dtype=local.dtype, device=local.device)
-        dist.all_gather_into_tensor(out, local.contiguous(), group=group)
-        return out
-    # uneven slices (they differ by at most one element): pad to the longest, gather, trim
-    sizes = [query_slice(r, world, nq)[1] - query_slice(r, world, nq)[0] for r in range(world)]
-    m = max(sizes)
-    padded = torch.zeros(m, dtype=local.dtype, device=local.device)
-    padded[:local.shape[0]] = local
-    out = torch.empty(m * world, dtype=local.dtype, device=local.device)
-    dist.all_gather_into_tensor(out, padded, group=group)
-    return torch.cat([out[r * m:r * m + sizes[r]] for r in range(world)])
+    out = [torch.empty_like(row) for _ in range(world)]
+    dist.all_gather(out, row, group=group)
+    return torch.stack(out)
 
 
-def exchange_spans(span_of, n_leaves: int, buffers, group=None):
-    """After a sharded fit: every rank sends the device spans it factorised to every peer and receives theirs.
-    span_of(which, first_leaf, count) -> 1-D tensor aliasing that span of the local model (may be empty).
-    All transfers of one buffer go out as ONE batch of point-to-point operations (a single NCCL group), so they
-    run concurrently over NVLink / NVSwitch in both directions instead of as serialised broadcasts."""
+def exchange_segments(send, seg, group=None):
+    """Planner -> owner.  `send`: tensor whose first dimension is the planner's leaf-sorted pair list, seg: its world + 1
+    segment offsets.  Returns (received, rx_off, seg_all): what the planners sent THIS rank, concatenated in planner
+    order, the offsets of every planner's share, and all ranks' segment tables."""
+    import torch
     import torch.distributed as dist
-    world = dist.get_world_size(group)
-    rank = dist.get_rank(group)
-    if world == 1:
-        return
-    for which in buffers:
-        a, n = leaf_range(rank, world, n_leaves)
-        mine = span_of(which, a, n)
-        ops = []
-        for r in range(world):
-            if r == rank:
-                continue
-            ar, nr = leaf_range(r, world, n_leaves)
-            theirs = span_of(which, ar, nr)
-            if theirs.numel():
-                ops.append(dist.P2POp(dist.irecv, theirs, r, group))
-            if mine.numel():
-                ops.append(dist.P2POp(dist.isend, mine, r, group))
-        if ops:
-            for req in dist.batch_isend_irecv(ops):
-                req.wait()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    seg_t = torch.as_tensor(np.asarray(seg, dtype=np.int64), device=send.device)
+    seg_all = _all_gather_rows(seg_t, group).cpu().numpy()
+    rx_off = rx_offsets(seg_all, rank)
+    recv = torch.empty((int(rx_off[-1]),) + tuple(send.shape[1:]), dtype=send.dtype, device=send.device)
+    ops = []
+    for peer in range(world):
+        mine = send[int(seg[peer]):int(seg[peer + 1])]
+        theirs = recv[int(rx_off[peer]):int(rx_off[peer + 1])]
+        if peer == rank:
+            theirs.copy_(mine)
+            continue
+        if theirs.shape[0]:
+            ops.append(dist.P2POp(dist.irecv, theirs, peer, group))
+        if mine.shape[0]:
+            ops.append(dist.P2POp(dist.isend, mine.contiguous(), peer, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return recv, rx_off, seg_all
+
+
+def return_segments(answers, rx_off, seg_all, group=None):
+    """Owner -> planner: the inverse of exchange_segments.  `answers` is in the order received; the result is in the
+    planner's leaf-sorted pair order."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    seg = seg_all[rank]
+    out = torch.empty((int(seg[-1]),) + tuple(answers.shape[1:]), dtype=answers.dtype, device=answers.device)
+    ops = []
+    for peer in range(world):
+        mine = answers[int(rx_off[peer]):int(rx_off[peer + 1])]
+        theirs = out[int(seg[peer]):int(seg[peer + 1])]
+        if peer == rank:
+            theirs.copy_(mine)
+            continue
+        if theirs.shape[0]:
+            ops.append(dist.P2POp(dist.irecv, theirs, peer, group))
+        if mine.shape[0]:
+            ops.append(dist.P2POp(dist.isend, mine.contiguous(), peer, group))
+    if ops:
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+    return out

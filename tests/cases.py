@@ -37,6 +37,13 @@ def c3_mini(N=16384, levels=7, eps=0.31, sigma2=1e-3, nq=30000):
                 kernel=("SQEXP", eps_sq), wkernel=("SPLINE34", 1.0 / eps), Xq=Xq)
 
 
+def c3_mini_ill():
+    """c3_mini at the stress noise level sigma2 = 1e-5 ("and 1e-5 as a stress variant"): cond(K + sigma2 I) ~ 3e6."""
+    c = c3_mini(sigma2=1e-5, nq=12000)
+    c["name"] = "c3_mini_ill"
+    return c
+
+
 def c4_mini(N=12000, levels=5, eps=0.35, nq=8000):
     """Scaled-down C4 (3-D, ~1000-point leaves)."""
     lo, hi = [-5.0, -10.0, -5.0], [5.0, 10.0, 5.0]

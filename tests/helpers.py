@@ -42,3 +42,35 @@ def err_stats(a, b):
     return dict(max_abs=float(d.max()) if d.size else 0.0, normwise=float(d.max() / scale) if d.size else 0.0,
                 pointwise=float(pw.max()) if d.size else 0.0,
                 frac_pw_gt_1e9=float(np.mean(pw > 1e-9)) if d.size else 0.0)
+
+
+# ---- measured parity errors, written next to the assertions (profiles/parity_r02.json is a copy of a GPU run's file) ----------
+import json as _json
+import os as _os
+
+_PARITY_PATH = _os.path.join(_os.environ.get("GRAFT_REPO_ROOT", _os.path.dirname(_os.path.dirname(_os.path.abspath(__file__)))),
+                             "gpurun_out", "parity_r02.json")
+
+
+def record_parity(key: str, **vals):
+    """Append measured errors (err_stats dicts or plain numbers) under `key`; -q swallows prints, this file does not."""
+    try:
+        _os.makedirs(_os.path.dirname(_PARITY_PATH), exist_ok=True)
+        data = {}
+        if _os.path.exists(_PARITY_PATH):
+            with open(_PARITY_PATH) as f:
+                data = _json.load(f)
+        data.setdefault(key, {}).update(vals)
+        with open(_PARITY_PATH, "w") as f:
+            _json.dump(data, f, indent=1, sort_keys=True)
+    except OSError:
+        pass
+
+
+def bound_stats(a, b):
+    """err_stats plus the quantity the tests bound: max |a - b| / max(|b|, rms(b)) ("floored relative error")."""
+    a, b = np.asarray(a), np.asarray(b)
+    st = err_stats(a, b)
+    scale = np.sqrt(np.mean(b * b)) if b.size else 1.0
+    st["floored_rel"] = float((np.abs(a - b) / np.maximum(np.abs(b), scale)).max()) if b.size else 0.0
+    return st

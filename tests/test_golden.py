@@ -70,8 +70,9 @@ def test_gpu_matches_golden(built_lib, name):
     assert np.array_equal(dv.p_region_ind_set, g["home"])
     assert np.array_equal(np.diff(dv.pair_off), g["npairs"])
     assert np.array_equal(np.concatenate([r for r in dv.region_inds_set] + [np.zeros(0, np.int32)]), g["region_inds"])
-    tol = 1e-9 if case["sigma2"] >= 1e-4 else 2e-8
+    tol = 1e-9          # every golden case, sigma2 = 1e-5 included: the default solver is chosen by conditioning
     sy, sv = np.sqrt(np.mean(g["Yq"] ** 2)), np.sqrt(np.mean(g["Vq"] ** 2))
+    helpers.record_parity(f"golden/{name}", Yq=helpers.bound_stats(Yq, g["Yq"]), Vq=helpers.bound_stats(Vq, g["Vq"]), tol=tol)
     assert np.all(np.abs(Yq - g["Yq"]) <= tol * np.maximum(np.abs(g["Yq"]), sy))
     assert np.all(np.abs(Vq - g["Vq"]) <= tol * np.maximum(np.abs(g["Vq"]), sv))
     np.testing.assert_allclose(np.diag(η.L_set[0]), g["L0_diag"], rtol=1e-10)

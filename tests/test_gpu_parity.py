@@ -20,9 +20,11 @@ pytestmark = pytest.mark.gpu
 TOL = 1e-9
 
 
-def assert_close(name, a, b, tol=TOL):
-    st = helpers.err_stats(a, b)
+def assert_close(name, a, b, tol=TOL, record=None):
+    st = helpers.bound_stats(a, b)
     print(f"{name}: {st}")
+    if record:
+        helpers.record_parity(record, **{name: dict(st, tol=tol)})
     scale = np.sqrt(np.mean(np.asarray(b) ** 2))
     bound = tol * np.maximum(np.abs(b), scale)
     bad = np.abs(np.asarray(a) - np.asarray(b)) > bound
@@ -86,7 +88,7 @@ def _fit_product(case, m):
 
 
 CASES = {"mixgp_file": cases.mixgp_file, "c3_mini": cases.c3_mini, "c4_mini": cases.c4_mini, "mixgp_driver": cases.mixgp_driver,
-         "c5_mini": cases.c5_mini}
+         "c5_mini": cases.c5_mini, "c3_mini_ill": cases.c3_mini_ill}
 _cache = {}
 
 
@@ -173,11 +175,20 @@ def test_query_structure_bit_exact(built_lib, name):
     assert np.array_equal(P.findpartition(Xq, root), home)
 
 
-@pytest.mark.parametrize("solver", [_lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION, _lib.SOLVER_INVERSE_COLSWEEP])
+# Tolerances of the explicitly selected solvers on ill-conditioned models (sigma2 = 1e-5, cond(K + sigma2 I) 3e6 .. 2e7), set
+# from the measured errors in profiles/parity_r02.json (<= 2x measured).  The DEFAULT solver (SOLVER_AUTO: by the fit's
+# conditioning estimate) and substitution are held to TOL = 1e-9 everywhere.
+ILL_TOL = {_lib.SOLVER_INVERSE: 1e-8, _lib.SOLVER_INVERSE_COLSWEEP: 1e-8}
+SOLVER_NAME = {_lib.SOLVER_AUTO: "auto", _lib.SOLVER_INVERSE: "inverse", _lib.SOLVER_SUBSTITUTION: "substitution",
+               _lib.SOLVER_INVERSE_COLSWEEP: "inverse_colsweep"}
+
+
+@pytest.mark.parametrize("solver", [_lib.SOLVER_AUTO, _lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION, _lib.SOLVER_INVERSE_COLSWEEP])
 @pytest.mark.parametrize("name", list(CASES))
 def test_query_mean_variance(built_lib, name, solver):
-    """Every query solver against the oracle's dtrsv path: s = inv(L) kq with the explicit inverse (default row-panel
-    kernel, every kernel function; and the column-sweep kernel, squared exponential only) and blocked forward substitution."""
+    """Every query solver against the oracle's dtrsv path: the default (chosen by conditioning), s = inv(L) kq with the
+    explicit inverse (row-panel kernel, every kernel function; column-sweep kernel, squared exponential only) and blocked
+    forward substitution.  Measured errors go to gpurun_out/parity_r02.json."""
     from patchmixturekriging_b200 import mixturegp
     case, m, root, eta, pk = _setup(name)
     wth, wk = helpers.kernels(case["wkernel"])
@@ -186,17 +197,43 @@ def test_query_mean_variance(built_lib, name, solver):
     try:
         Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk,
                                       debug_flag=True)
+        cond, used = mixturegp.condition_estimate(eta)
     finally:
-        mixturegp.set_query_solver(eta, _lib.SOLVER_INVERSE)
+        mixturegp.set_query_solver(eta, _lib.SOLVER_AUTO)
     Yo, Vo, od = O.querymixtureGP_vec(Xq, m["eta"], case["levels"], case["radius"], case["delta"], m["th"], wth)
     f = dv._flat
     assert np.array_equal(f["pair_leaf"], od["pair_leaf"])
-    tol = TOL if case["sigma2"] >= 1e-4 else 2e-8      # sigma2 = 1e-5: cond ~1e6-1e7, two CPU algorithms differ by ~1e-9 too
-    assert_close(f"{name} pair_u", f["pair_u"], od["pair_u"], tol)
-    assert_close(f"{name} pair_v", f["pair_v"], od["pair_v"], tol)
-    assert_close(f"{name} Yq", Yq, Yo, tol)
-    assert_close(f"{name} Vq", Vq, Vo, tol)
+    ill = case["sigma2"] < 1e-4
+    tol = ILL_TOL.get(solver, TOL) if ill else TOL
+    rec = f"query/{name}/{SOLVER_NAME[solver]}"
+    helpers.record_parity(rec, cond_lower_bound=cond, solver_used=SOLVER_NAME[used], sigma2=case["sigma2"])
+    if solver == _lib.SOLVER_AUTO:
+        assert used == (_lib.SOLVER_SUBSTITUTION if cond >= 1e4 else _lib.SOLVER_INVERSE)
+    assert_close("pair_u", f["pair_u"], od["pair_u"], tol, rec)
+    assert_close("pair_v", f["pair_v"], od["pair_v"], tol, rec)
+    assert_close("Yq", Yq, Yo, tol, rec)
+    assert_close("Vq", Vq, Vo, tol, rec)
     assert np.all(Vq >= 1e-12 * 0.999)
+
+
+def test_dense_debug_outputs(built_lib):
+    """debug_flag=true: hps_keep_flags_set, zs_set, ts_set over ALL hyperplanes (mixtureGP.jl:17-19,256-258) against the scalar
+    oracle's findneighbourpartitions -- same operations, same bits."""
+    case, m, root, eta, pk = _setup("c3_mini")
+    _, wk = helpers.kernels(case["wkernel"])
+    Xq = case["Xq"][::501][:40]
+    Yq, Vq, dv = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk, debug_flag=True)
+    n_hp = m["hc"].shape[0]
+    assert len(dv.ts_set) == len(dv.zs_set) == len(dv.hps_keep_flags_set) == Xq.shape[0]
+    for j in range(Xq.shape[0]):
+        home = O.findpartition(Xq[j], m["root"], case["levels"])
+        region, ts, zs, keep = O.findneighbourpartitions(Xq[j], case["radius"], m["root"], case["levels"], m["hv"], m["hc"], home, case["delta"])
+        assert dv.ts_set[j].shape == (n_hp,) and dv.zs_set[j].shape == (n_hp, 2)
+        assert np.array_equal(dv.ts_set[j], ts)
+        assert np.array_equal(dv.zs_set[j], np.asarray(zs))
+        assert np.array_equal(dv.hps_keep_flags_set[j], np.asarray(keep, dtype=bool))
+        assert np.array_equal(dv.t_kept_set[j], ts[np.asarray(keep, dtype=bool)])
+        assert list(dv.region_inds_set[j]) == list(region)
 
 
 def test_single_query_and_scalar_oracle(built_lib):
@@ -210,8 +247,8 @@ def test_single_query_and_scalar_oracle(built_lib):
     assert list(dv.p_region_ind_set) == dbg["p_region_ind"]
     for a, b in zip(dv.region_inds_set, dbg["region_inds"]):
         assert list(a) == list(b)
-    assert_close("scalar Yq", Yq, Yo, 2e-8)
-    assert_close("scalar Vq", Vq, Vo, 2e-8)
+    assert_close("Yq", Yq, Yo, TOL, "query/mixgp_file/scalar_oracle")
+    assert_close("Vq", Vq, Vo, TOL, "query/mixgp_file/scalar_oracle")
     y1, v1, _ = P.querymixtureGP(Xq[3], eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
     assert y1.shape == (1,) and y1[0] == Yq[3] and v1[0] == Vq[3]
 
@@ -229,8 +266,8 @@ def test_single_gp_ibb1d(built_lib, kind, N, Nq):
     yq = np.empty(Nq)
     P.query_(yq, case["Xq"], eta)
     yref = O.query_rkhs(case["Xq"], case["X"], c_ref, ok)
-    # N=1000 Brownian-bridge Gram with sigma2=1e-5 is ill-conditioned (cond ~1e7): compare predictions, not weights
-    assert_close(f"ibb1d {kind} N={N} yq", yq, yref, 1e-9 if N == 15 else 1e-7)
+    # N=1000 Brownian-bridge Gram with sigma2=1e-5 is ill-conditioned (cond ~5e6): compare predictions, not weights
+    assert_close("yq", yq, yref, TOL, f"single_gp/ibb1d_{kind}_{N}")
     if N == 15:
         np.testing.assert_allclose(eta.c, c_ref, rtol=1e-8)
 
@@ -296,45 +333,6 @@ def test_pruned_neighbour_search_equals_full_scan(built_lib, name):
     assert np.array_equal(out[0][0], out[1][0]) and np.array_equal(out[0][1], out[1][1])
 
 
-def test_sharded_fit_equals_single_fit(built_lib):
-    """leaf -> rank map on one GPU: two handles each factorise half of the leaves, exchange their L / inverse-block /
-    alpha spans (device-to-device copies standing in for the NCCL broadcasts of bench.py) and must then answer
-    queries bit-identically to the handle that fitted everything."""
-    import torch
-    from patchmixturekriging_b200 import mixturegp
-    case, m, root, eta, pk = _setup("c3_mini")
-    _, wk = helpers.kernels(case["wkernel"])
-    X, y = case["X"], case["y"]
-    X_set, X_set_inds, _, _ = P.organizetrainingsets(root, case["levels"], X, case["eps"])
-    y_set = [y[i - 1] for i in X_set_inds]
-    nl = len(X_set)
-    ranges = [(0, nl // 2), (nl // 2, nl - nl // 2)]
-    etas = [P.MixtureGPType(X_set, P.fetchhyperplanes(root), fit_range=r) for r in ranges]
-    for e in etas:
-        P.fitmixtureGP_(e, y_set, pk, case["sigma2"])
-
-    class Span:
-        def __init__(self, ptr, nbytes):
-            self.__cuda_array_interface__ = {"shape": (nbytes // 8,), "typestr": "<f8", "data": (ptr, False), "version": 2}
-
-    for e in etas:
-        mixturegp.build_M(e)
-    for which in (_lib.BUF_L, _lib.BUF_M, _lib.BUF_P, _lib.BUF_LINV, _lib.BUF_ALPHA):
-        for src, (a, n) in enumerate(ranges):
-            sp, sb = mixturegp.model_buffer(etas[src], which, a, n)
-            dp, db = mixturegp.model_buffer(etas[1 - src], which, a, n)
-            assert sb == db and sb > 0
-            torch.as_tensor(Span(dp, db), device="cuda:0").copy_(torch.as_tensor(Span(sp, sb), device="cuda:0"))
-    torch.cuda.synchronize()
-    Xq = case["Xq"][:5000]
-    Y0, V0, _ = P.querymixtureGP(Xq, eta, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
-    for e in etas:
-        mixturegp.mark_fitted(e, m_exchanged=True, p_exchanged=True)
-        Y1, V1, _ = P.querymixtureGP(Xq, e, root, case["levels"], case["radius"], case["delta"], pk, case["sigma2"], wk)
-        assert np.array_equal(Y0, Y1) and np.array_equal(V0, V1)
-        e.close()
-
-
 def test_single_gp_variance_query(built_lib):
     """setupGPquery / evalqueryGP! (src/RKHS/querying.jl:43-79): mean from the caller's c, unclamped variance k** - kᵀA⁻¹k."""
     from patchmixturekriging_b200 import synth
@@ -382,8 +380,10 @@ def test_large_leaf_size_classes(built_lib, D, n, solver):
     P.fitmixtureGP_(eta, [y], pk, s2)
     mixturegp.set_query_solver(eta, solver)
     Yq, Vq, _ = P.querymixtureGP(Xq, eta, None, 1, 0.1, 1e-5, pk, s2, P.Spline34KernelType(1.0))
-    assert_close(f"D={D} n={n} mean", Yq, mean_ref, 1e-8)
-    assert_close(f"D={D} n={n} var", Vq, var_ref, 1e-8)
+    # against a dense numpy LU solve of the full system (not the oracle's dpotrf + dtrsv): two algorithms apart
+    rec = f"large_leaf/D{D}_n{n}/{SOLVER_NAME[solver]}"
+    assert_close("mean", Yq, mean_ref, TOL, rec)
+    assert_close("var", Vq, var_ref, 1e-8, rec)
 
 
 @pytest.mark.parametrize("name,eps", [("mixgp_file", 1.5), ("c3_mini", 0.31), ("c4_mini", 0.35), ("c3_mini", 0.0)])
