@@ -1124,7 +1124,16 @@ int pmk_load_model(pmk_handle* h, const char* path) {
     }
   }
   CU(h, cudaMemsetAsync(h->d_info.p, 0, sizeof(int) * h->n_leaves, h->stream));
+  // the conditioning estimate is a function of the stored factors: recompute it, so that PMK_OPT_QUERY_SOLVER = -1 resolves
+  // to the solver the saving handle used (bit-identical queries)
+  CU(h, h->d_diag_range.ensure(sizeof(double)));
+  CU(h, cudaMemsetAsync(h->d_diag_range.p, 0, sizeof(double), h->stream));
+  launch_diag_range(h->lt, h->d_diag_range.as<double>(), h->stream);
+  KCHECK(h, "k_diag_range");
+  double cond_est = 0.0;
+  CU(h, cudaMemcpyAsync(&cond_est, h->d_diag_range.p, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
   CU(h, cudaStreamSynchronize(h->stream));
+  h->cond_est = cond_est;
   h->fitted = true;
   h->plan_valid = false;
   return PMK_OK;

@@ -218,6 +218,7 @@ int pmk_multi_size(const pmk_multi* m) { return m ? m->n : 0; }
 void pmk_multi_destroy(pmk_multi* m) {
   if (!m) return;
   for (Rank& r : m->rk) {
+    if (!r.h) continue;             // a rank that was never created (pmk_multi_create failed on the way) owns nothing
     cudaSetDevice(r.device);
     if (r.stream) cudaStreamSynchronize(r.stream);
     Buf* bufs[] = {&r.dX, &r.dy, &r.dXq, &r.dYq, &r.dVq, &r.tx_X, &r.tx_leaf, &r.tu, &r.tv, &r.pu, &r.pv, &r.rx_X, &r.rx_leaf, &r.rx_u, &r.rx_v};

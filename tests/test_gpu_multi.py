@@ -104,7 +104,13 @@ def test_multi_staged_and_mean_only(built_lib):
     Ym = np.empty(len(Xq))
     m.check(L.pmk_multi_query(m.raw, len(Xq), _lib.ptr(Xq), case["radius"], case["delta"], wk.kernel_id, _lib.ptr(wp), wp.shape[0], 1,
                               _lib.ptr(Ym), None))
-    assert np.array_equal(Ym, Y0)          # mean only (flags bit 0): same means, Vq untouched
+    # mean only (flags bit 0, Vq untouched): the mean-only pair kernel, bit-identical to the single handle's mean-only query
+    Ys = np.empty(len(Xq))
+    h = eta.handle
+    h.check(L.pmk_set_tree(h.raw, 2, case["levels"], _lib.ptr(hv), _lib.ptr(hc)))
+    h.check(L.pmk_query(h.raw, len(Xq), _lib.ptr(Xq), case["radius"], case["delta"], wk.kernel_id, _lib.ptr(wp), wp.shape[0], 1, _lib.ptr(Ys), None))
+    assert np.array_equal(Ym, Ys)
+    np.testing.assert_allclose(Ym, Y0, rtol=0, atol=1e-12 * np.abs(Y0).max())
     assert m.launch_count() > 0
     m.close()
 
