@@ -320,7 +320,8 @@ def main():
         torch.cuda.set_device(local_rank)
         dist.init_process_group("nccl", device_id=torch.device(f"cuda:{local_rank}"))
         host_group = dist.new_group(backend="gloo")     # long waits happen on the host: no NCCL kernel spins on a GPU rank 0 is using
-        one = torch.ones(1, device="cuda")
+        my_dev = torch.device(f"cuda:{local_rank}")
+        one = torch.ones(1, device=my_dev)
         dist.all_reduce(one)                            # every rank's GPU is up and NCCL connects the N of them
         torch.cuda.synchronize()
         assert int(one.item()) == world
@@ -332,7 +333,7 @@ def main():
         result = run_b200(args, w, cfg, n_gpus)
     if world > 1:
         dist.barrier(group=host_group)                  # ranks > 0 wait here (gloo: on the host) while rank 0 measures
-        t = torch.tensor([result["ms_per_step"] if result else 0.0], dtype=torch.float64, device="cuda")
+        t = torch.tensor([result["ms_per_step"] if result else 0.0], dtype=torch.float64, device=my_dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)        # the contract's max over ranks (rank 0 timed all N GPUs)
         if result:
             result["ms_per_step"] = float(t.item())

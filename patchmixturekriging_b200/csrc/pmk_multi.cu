@@ -157,6 +157,17 @@ int rcuda(Rank& r, cudaError_t e, const char* what) {
     if (int rc_ = rcuda(r, (expr), #expr)) return rc_;    \
   } while (0)
 
+// the calling thread's current device is the caller's business (torch tracks it): put it back on the way out
+struct DeviceGuard {
+  int dev = -1;
+  DeviceGuard() {
+    if (cudaGetDevice(&dev) != cudaSuccess) dev = -1;
+  }
+  ~DeviceGuard() {
+    if (dev >= 0) cudaSetDevice(dev);
+  }
+};
+
 // run fn(rank) on one host thread per rank; first failure (lowest rank) becomes the call's status
 template <class F>
 int run_ranks(pmk_multi* m, F&& fn) {
@@ -165,6 +176,7 @@ int run_ranks(pmk_multi* m, F&& fn) {
     r.err.clear();
   }
   m->meet->reset();
+  DeviceGuard guard;
   if (m->n == 1) {
     cudaSetDevice(m->rk[0].device);
     fn(0);
@@ -217,6 +229,7 @@ int pmk_multi_size(const pmk_multi* m) { return m ? m->n : 0; }
 
 void pmk_multi_destroy(pmk_multi* m) {
   if (!m) return;
+  DeviceGuard guard;
   for (Rank& r : m->rk) {
     if (!r.h) continue;             // a rank that was never created (pmk_multi_create failed on the way) owns nothing
     cudaSetDevice(r.device);
@@ -240,6 +253,7 @@ int pmk_multi_create(pmk_multi** out, int n_devices, const int* device_ids) {
   if (e != cudaSuccess || ndev == 0)
     return mfail(nullptr, PMK_ERR_CUDA, "pmk_multi_create: no CUDA device (%s); libpmk_b200 has no CPU fallback",
                  e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  DeviceGuard guard;
   pmk_multi* m = new (std::nothrow) pmk_multi();
   if (!m) return mfail(nullptr, PMK_ERR_CUDA, "out of host memory");
   m->n = n_devices;
@@ -375,6 +389,7 @@ int pmk_multi_fit(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_off
 
 int pmk_multi_set_tree(pmk_multi* m, int D, int levels, const double* hp_v, const double* hp_c) {
   if (!m) return PMK_ERR_ARG;
+  DeviceGuard guard;
   m->tree_set = false;
   for (Rank& r : m->rk) {
     const int rc = pmk_set_tree(r.h, D, levels, hp_v, hp_c);
@@ -550,6 +565,7 @@ int pmk_multi_query(pmk_multi* m, int64_t Nq, const double* Xq, double radius, d
 int pmk_multi_leaf_pairs(pmk_multi* m, int64_t* pairs_per_leaf) {
   if (!m || !pairs_per_leaf) return PMK_ERR_ARG;
   if (!m->results_ready) return mfail(m, PMK_ERR_STATE, "no query results (pmk_multi_query_staged)");
+  DeviceGuard guard;
   std::vector<int64_t> one((size_t)m->n_leaves);
   std::fill(pairs_per_leaf, pairs_per_leaf + m->n_leaves, (int64_t)0);
   for (Rank& r : m->rk) {
@@ -562,6 +578,7 @@ int pmk_multi_leaf_pairs(pmk_multi* m, int64_t* pairs_per_leaf) {
 
 int pmk_multi_get_timings(pmk_multi* m, double* ms, double* per_rank_ms) {
   if (!m || !ms) return PMK_ERR_ARG;
+  DeviceGuard guard;
   for (int k = 0; k < PMK_MT_COUNT; ++k) ms[k] = m->ms[k];
   if (per_rank_ms)
     for (int i = 0; i < m->n; ++i) {
