@@ -280,7 +280,11 @@ int64_t pmk_multi_launch_count(const pmk_multi* m);
 /* PMK_OPT_ALPHA_REFINE: one step of iterative refinement of alpha = (K + sigma2 I)^-1 y after the Cholesky solve (the reference
  * solves U\y by LU, mixtureGP.jl:106): -1 (default) = for models flagged by the same conditioning estimate, 0 = never,
  * 1 = always.  Set before pmk_fit. */
-enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2, PMK_OPT_INVERSE_BUILDER = 3, PMK_OPT_ALPHA_REFINE = 4 };
+/* PMK_OPT_CHOL_VARIANT: the batched Cholesky of the fit: 0 (default) = level-synchronous -- all leaves advance panel by panel,
+ * the serial 32x32 diagonal factorisations in one launch (k_chol_diag), the DMMA panel updates in the next (k_chol_panel);
+ * 1 = one CTA per leaf running its panels to the end (round-1 kernel, kept for A/B timing; same L to rounding). */
+enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2, PMK_OPT_INVERSE_BUILDER = 3, PMK_OPT_ALPHA_REFINE = 4,
+       PMK_OPT_CHOL_VARIANT = 5 };
 int pmk_set_option(pmk_handle* h, int option, int64_t value);
 /* lower bound of the worst leaf's cond(K + sigma2 I) from the last fit, and the query solver PMK_OPT_QUERY_SOLVER = -1 resolves to */
 int pmk_condition_estimate(pmk_handle* h, double* cond_lower_bound, int* solver_in_use);

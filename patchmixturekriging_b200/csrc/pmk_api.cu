@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -22,7 +23,9 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
                        cudaStream_t s);
 void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s);
 void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s, const double* rhs = nullptr,
-                  double* out = nullptr);
+                  double* out = nullptr, int backward_only = 0);
+int launch_chol_levels(const LeafTable& lt, const int* d_order, const std::vector<int>& leaves_per_panel, int max_npad, int with_z,
+                       cudaStream_t s);
 void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_npad, cudaStream_t s);
 InvPlanHost make_inverse_plan(const std::vector<int>& shapes_present);
 void launch_inverse(const LeafTable& lt, const InvPlanHost& plh, const void* d_nodes, const int* d_off, const int* d_cnt,
@@ -169,6 +172,7 @@ struct pmk_handle {
   DBuf d_diag_range;
   double cond_est = 0.0;
   int alpha_refine = -1;    // PMK_OPT_ALPHA_REFINE: -1 auto (flagged models), 0 never, 1 always
+  int chol_variant = 1;     // PMK_OPT_CHOL_VARIANT: 1 = one CTA per leaf (default: faster on C3 / C4), 0 = level-synchronous kernels
   // organizetrainingsets on the device (results of the last call)
   DBuf o_X, o_counts, o_off, o_pl, o_pp, o_sl, o_sp, o_lcount, o_lstart;
   int64_t o_N = 0, o_total = 0, o_leaves = 0;
@@ -296,6 +300,7 @@ int pmk_create(pmk_handle** out, int device) {
   pmk_handle* h = new (std::nothrow) pmk_handle();
   if (!h) return fail(nullptr, PMK_ERR_CUDA, "out of host memory");
   h->device = device;
+  if (const char* ev = getenv("PMK_CHOL_VARIANT")) h->chol_variant = atoi(ev) == 0 ? 0 : 1;      // A/B timing of the two factorisations
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete h;
@@ -367,6 +372,10 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
       if (value < -1 || value > 2)
         return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: -1 (by conditioning), 0 (explicit inverse), 1 (substitution) or 2 (explicit inverse, column sweep)");
       h->solver = (int)value;
+      return PMK_OK;
+    case PMK_OPT_CHOL_VARIANT:
+      if (value != 0 && value != 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_CHOL_VARIANT: 0 (level-synchronous) or 1 (one CTA per leaf)");
+      h->chol_variant = (int)value;
       return PMK_OK;
     case PMK_OPT_ALPHA_REFINE:
       if (value < -1 || value > 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_ALPHA_REFINE: -1 (by conditioning), 0 (never) or 1 (always)");
@@ -729,14 +738,23 @@ static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_
     launch_gram_tiles(D, lt, h->d_order.as<int>(), n_order, max_npad, kp, sigma2, h->stream);
   }
   KCHECK(h, "k_gram_tiles");
+  const bool levels = h->chol_variant == 0;
   {
     Timer t(h, PMK_T_FIT_CHOL);
-    launch_chol(lt, h->d_order.as<int>(), n_order, h->stream);
+    if (levels) {
+      // leaves of `order` (largest first) that still have a J-th 32-column panel: a prefix
+      std::vector<int> per_panel(max_npad / 32, 0);
+      for (int k = 0; k < n_order; ++k)
+        for (int J = 0; J < h->h_npad[order[k]] / 32; ++J) ++per_panel[J];
+      h->launches += launch_chol_levels(lt, h->d_order.as<int>(), per_panel, max_npad, 1, h->stream) - 1;
+    } else {
+      launch_chol(lt, h->d_order.as<int>(), n_order, h->stream);
+    }
   }
   KCHECK(h, "k_chol");
   {
     Timer t(h, PMK_T_FIT_SOLVE);
-    launch_solve(lt, h->d_order.as<int>(), n_order, max_npad, h->stream);
+    launch_solve(lt, h->d_order.as<int>(), n_order, max_npad, h->stream, levels ? lt.alpha : nullptr, nullptr, levels ? 1 : 0);
   }
   KCHECK(h, "k_solve_alpha");
   // conditioning estimate (by-product of the factor) and status: first failing leaf

@@ -12,6 +12,7 @@
 // Several CTAs are resident per SM so that one leaf's serial diagonal-block phase overlaps the
 // other leaves' DMMA phases.
 #include <cstdlib>
+#include <vector>
 #include "pmk_internal.cuh"
 
 namespace pmk {
@@ -47,38 +48,58 @@ __global__ void k_pack_leaves(LeafTable lt, const int64_t* __restrict__ leaf_off
 //   Ibuf (stride LD) : out = inv(L_JJ) (upper zeroed)
 // returns 0 or the (block-local, 1-based) order of the first non-positive pivot.
 static constexpr int LDD = 33;
+#ifndef PMK_FACTOR_UNROLLED
+#define PMK_FACTOR_UNROLLED 1      /* measured (tools/factor_bench.cu, k_chol on C3): the rolled loop nest is slower, 40 k vs 26 k cycles alone */
+#endif
 __device__ __noinline__ int factor_block32(double* Dbuf, double* Ibuf, int lane) {
   // Step j does column j of the left-looking (dot-product form) Cholesky -- lane i >= j owns L[i][j] -- and,
   // fused into the same step, row j of X = inv(L) by forward substitution (lane c owns column c of X):
   //     x_jc = (delta_jc - sum_{k<j} L[j][k] x_kc) / L[j][j].
-  // Both need row j of L (k < j), loaded once; the two dependency chains are independent, so they overlap.
-  // Fully unrolled: every shared-memory address is an immediate and the inner products have static trip
-  // counts -- this serial phase is latency-bound on a single warp, instruction count is what matters.
+  // Both need row j of L (k < j), loaded once; the dependency chains are independent, so they overlap.
+  // ROLLED loops, four partial sums per chain: the fully unrolled form of round 1 (4 k instructions of straight-line code,
+  // executed once per call) ran at the speed of the instruction fetch -- 38 k cycles per block measured with the cycle
+  // counters, with or without DMMA warps on the SM -- while this loop nest lives in the instruction cache.
   const double* rowp = Dbuf + lane * LDD;
   const double* xcol = Ibuf + lane;
   int info = 0;
+#if PMK_FACTOR_UNROLLED
 #pragma unroll
+#else
+#pragma unroll 1
+#endif
   for (int j = 0; j < 32; ++j) {
-    double s0 = rowp[j], s1 = 0.0;
-    double t0 = (j == lane) ? 1.0 : 0.0, t1 = 0.0;
+    const double* lj = Dbuf + j * LDD;
+    double s0 = rowp[j], s1 = 0.0, s2 = 0.0, s3 = 0.0;
+    double t0 = (j == lane) ? 1.0 : 0.0, t1 = 0.0, t2 = 0.0, t3 = 0.0;
+    int k = 0;
+#if PMK_FACTOR_UNROLLED
 #pragma unroll
-    for (int k = 0; k < j; ++k) {
-      const double ljk = Dbuf[j * LDD + k];
-      if (k & 1) {
-        s1 = fma(-rowp[k], ljk, s1);
-        t1 = fma(-ljk, xcol[k * LD], t1);
-      } else {
-        s0 = fma(-rowp[k], ljk, s0);
-        t0 = fma(-ljk, xcol[k * LD], t0);
-      }
+#else
+#pragma unroll 1
+#endif
+    for (; k + 4 <= j; k += 4) {
+      const double l0 = lj[k], l1 = lj[k + 1], l2 = lj[k + 2], l3 = lj[k + 3];
+      s0 = fma(-rowp[k], l0, s0);
+      s1 = fma(-rowp[k + 1], l1, s1);
+      s2 = fma(-rowp[k + 2], l2, s2);
+      s3 = fma(-rowp[k + 3], l3, s3);
+      t0 = fma(-l0, xcol[k * LD], t0);
+      t1 = fma(-l1, xcol[(k + 1) * LD], t1);
+      t2 = fma(-l2, xcol[(k + 2) * LD], t2);
+      t3 = fma(-l3, xcol[(k + 3) * LD], t3);
     }
-    const double s = s0 + s1;
+    for (; k < j; ++k) {
+      const double l0 = lj[k];
+      s0 = fma(-rowp[k], l0, s0);
+      t0 = fma(-l0, xcol[k * LD], t0);
+    }
+    const double s = (s0 + s1) + (s2 + s3);
     const double d = __shfl_sync(kFull, s, j);
     if (!(d > 0.0) && info == 0) info = j + 1;    // uniform: d is a broadcast
     const double inv = rsqrt(d);                  // 1/ajj (dpotf2 scales the column by 1/ajj)
     __syncwarp();
     Dbuf[lane * LDD + j] = lane > j ? s * inv : (lane == j ? d * inv : 0.0);
-    Ibuf[j * LD + lane] = (j >= lane) ? (t0 + t1) * inv : 0.0;
+    Ibuf[j * LD + lane] = (j >= lane) ? ((t0 + t1) + (t2 + t3)) * inv : 0.0;
     __syncwarp();
   }
   return info;
@@ -104,9 +125,12 @@ static constexpr int kCholDepth = PMK_CHOL_DEPTH;
 #ifndef PMK_CHOL_CPREFETCH
 #define PMK_CHOL_CPREFETCH 1
 #endif
-template <int R, int NV>
+// zv (optional): the forward-solve vector z = L^-1 y of the finished columns; zacc[r] then collects this lane's share of
+// L[row tile r, 0:nct] z[0:8 nct] (rows g, columns l and 4 + l of every tile) on the way -- the A fragments are in registers anyway.
+template <int R, int NV, bool WITH_Z = false>
 __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2* __restrict__ Lp, const int (&bo)[4],
-                                           const int (&ao)[R], int nct, uint32_t ring_u32, const double2* ring) {
+                                           const int (&ao)[R], int nct, uint32_t ring_u32, const double2* ring,
+                                           const double* __restrict__ zv = nullptr, double* zacc = nullptr) {
   auto issue = [&](int ct, int slot) {
     if (ct < nct) {
 #pragma unroll
@@ -140,6 +164,11 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
     issue(ct + kCholDepth - 1, fslot);      // refill the slot consumed one iteration ago
     fslot = cslot;
     cslot = (cslot + 1 == kCholDepth) ? 0 : cslot + 1;
+    double zl = 0.0, zh = 0.0;
+    if (WITH_Z) {
+      zl = zv[8 * ct + (threadIdx.x & 3)];
+      zh = zv[8 * ct + 4 + (threadIdx.x & 3)];
+    }
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
       const double2 af = rs[r * 32];
@@ -147,6 +176,7 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
       for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af.x, bf[b].x);
 #pragma unroll
       for (int b = 0; b < 4; ++b) dmma884(acc[r][b][0], acc[r][b][1], af.y, bf[b].y);
+      if (WITH_Z) zacc[r] = fma(af.y, zh, fma(af.x, zl, zacc[r]));
     }
   }
   cp_async_wait<0>();
@@ -535,6 +565,177 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// K2, level-synchronous form (the default; PMK_CHOL_VARIANT=1 selects the one-CTA-per-leaf kernel above).
+//
+// What the cycle counters of k_chol showed (tools/chol_phases.py, C3): warp 0 spends 605 k of a leaf's 2.17 M cycles in
+// factor_block32 -- 38 k cycles per 32x32 block, eight times what the routine takes alone -- because its ~1500 scalar FP64
+// instructions queue behind the DMMAs of the 23 other warps of the SM on the one FP64 pipe.  The per-panel chain
+// "diagonal block -> factor -> panel solve" is serial per leaf, so every leaf carries 16 x 43 k cycles the other leaves can only
+// partly cover.  Here the two kinds of work never share an SM at the same time: all leaves advance panel by panel,
+//     k_chol_diag (J)  : D = K_JJ - L[J,0:J] L[J,0:J]^T (DMMA, four warps), then Cholesky + inverse of D by one warp -- every
+//                        CTA of the grid is in the same phase, so the scalar chain runs next to other scalar chains;
+//                        the forward solve z_J = inv(L_JJ) (y_J - L[J,0:J] z[0:J]) of alpha rides on the same operand tiles;
+//     k_chol_panel (J) : L[t, J] = (K[t,J] - L[t,0:J] L[J,0:J]^T) inv(L_JJ)^T for the row tiles below, one warp per pair of
+//                        row tiles, no flag, no barrier, no atomics: pure DMMA work at full occupancy.
+// 2 x (n_pad_max / 32) launches per fit; kernels of one panel are as long as the panel's share of the n^3/3 flops.
+template <int NW>
+__global__ void __launch_bounds__(NW * 32)
+k_chol_diag(LeafTable lt, const int* __restrict__ order, int J, int with_z) {
+  static_assert(NW == 4, "one warp per row tile of the 32x32 diagonal block");
+  __shared__ double Dbuf[32 * LDD];
+  __shared__ double Ibuf[32 * LD];
+  __shared__ double rbuf[32];
+  extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
+  const int p = order[blockIdx.x];
+  const int ntl = lt.npad[p] >> 3;
+  const int t0 = 4 * J;
+  if (t0 >= ntl || lt.info[p] != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, l = lane & 3;
+  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
+  double2* Ip = reinterpret_cast<double2*>(lt.Linv + lt.ioff[p]);
+  const double2* ring = reinterpret_cast<const double2*>(pmk_chol_smem) + (size_t)warp * (kCholDepth * 32) + lane;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int64_t xo = lt.xoff[p];
+  {
+    int bo[4], ao[1];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
+    ao[0] = (int)tri(t0 + warp) * 32 + lane;
+    double acc[1][4][2];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const double2 kt = (b <= warp) ? ld_once(Lp + ao[0] + (t0 + b) * 32) : make_double2(0.0, 0.0);
+      acc[0][b][0] = -kt.x;
+      acc[0][b][1] = -kt.y;
+    }
+    double zacc[1] = {0.0};
+    if (with_z) chol_kloop<1, 1, true>(acc, Lp, bo, ao, t0, ring_u32, ring, lt.alpha + xo, zacc);
+    else chol_kloop<1, 1, false>(acc, Lp, bo, ao, t0, ring_u32, ring);
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 0] = -acc[0][b][0];
+      Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 1] = -acc[0][b][1];
+    }
+    if (with_z) {
+      double zs = zacc[0];
+      zs += __shfl_xor_sync(kFull, zs, 1);
+      zs += __shfl_xor_sync(kFull, zs, 2);
+      if (l == 0) rbuf[8 * warp + g] = lt.y[xo + 32 * J + 8 * warp + g] - zs;      // y_J - L[J, 0:J] z[0:J]
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+  const int info = factor_block32(Dbuf, Ibuf, lane);
+  if (info != 0) {
+    if (lane == 0) lt.info[p] = 32 * J + info;
+    return;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    for (int b = 0; b <= a; ++b) {
+      const int rd = (8 * a + g) * LDD + 8 * b + l;
+      const int ri = (8 * a + g) * LD + 8 * b + l;
+      Lp[(tri(t0 + a) + t0 + b) * 32 + lane] = make_double2(Dbuf[rd], Dbuf[rd + 4]);
+      Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane] = make_double2(Ibuf[ri], Ibuf[ri + 4]);
+    }
+  }
+  if (with_z) {          // z_J = inv(L_JJ) r  (lower triangular: row `lane` uses r[0 .. lane])
+    double zz = 0.0;
+    for (int k = 0; k <= lane; ++k) zz = fma(Ibuf[lane * LD + k], rbuf[k], zz);
+    lt.alpha[xo + 32 * J + lane] = zz;
+  }
+}
+
+template <int NW, int R>
+__global__ void __launch_bounds__(NW * 32, PMK_CHOL_MINB)
+k_chol_panel(LeafTable lt, const int* __restrict__ order, int J) {
+  __shared__ double Ibuf[32 * LD];
+  extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
+  const int p = order[blockIdx.y];
+  const int ntl = lt.npad[p] >> 3;
+  const int t0 = 4 * J;
+  const int tb0 = t0 + 4 + blockIdx.x * (NW * R);           // first row tile of this CTA's NW units
+  if (tb0 >= ntl || lt.info[p] != 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, l = lane & 3;
+  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
+  {   // inv(L_JJ): the block's 10 packed tiles -> dense rows in shared memory (the panel solve's B operand)
+    const double* __restrict__ Ib = lt.Linv + lt.ioff[p] + (size_t)J * kInvDoublesPerBlock;
+    for (int e = threadIdx.x; e < 32 * 32; e += NW * 32) {
+      const int i = e >> 5, k = e & 31;
+      double v = 0.0;
+      if (k <= i) {
+        const int a = i >> 3, b = k >> 3;
+        v = Ib[((a * (a + 1) / 2 + b) * 32 + (i & 7) * 4 + (k & 3)) * 2 + ((k & 7) >> 2)];
+      }
+      Ibuf[i * LD + k] = v;
+    }
+  }
+  __syncthreads();
+  const int tb = tb0 + warp * R;
+  if (tb >= ntl) return;
+  const double2* ring = reinterpret_cast<const double2*>(pmk_chol_smem) + (size_t)warp * (kCholDepth * R * 32) + lane;
+  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
+  const int src_lo = (lane & ~3) | (l >> 1);
+  const int src_hi = (lane & ~3) | (2 + (l >> 1));
+  int bo[4], ao[R];
+#pragma unroll
+  for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
+  double acc[R][4][2];
+  int nv = 0;
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    const bool tv = tb + r < ntl;
+    nv += tv ? 1 : 0;
+    ao[r] = (int)tri(tv ? tb + r : tb) * 32 + lane;
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      const double2 kt = tv ? ld_once(Lp + ao[r] + (t0 + b) * 32) : make_double2(0.0, 0.0);
+      acc[r][b][0] = -kt.x;
+      acc[r][b][1] = -kt.y;
+    }
+  }
+  if (nv == R) chol_kloop<R, R>(acc, Lp, bo, ao, t0, ring_u32, ring);
+  else chol_kloop<R, 1>(acc, Lp, bo, ao, t0, ring_u32, ring);
+  // L[t, J] = C inv(L_JJ)^T: C-fragment -> A-fragment inside the quad, 20 DMMAs per row tile, final tiles stored once
+#pragma unroll
+  for (int r = 0; r < R; ++r) {
+    if (r < nv) {
+      double alo[4], ahi[4];
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+        const double c0 = -acc[r][kb][0], c1 = -acc[r][kb][1];
+        const double v0 = __shfl_sync(kFull, c0, src_lo);
+        const double v1 = __shfl_sync(kFull, c1, src_lo);
+        const double w0 = __shfl_sync(kFull, c0, src_hi);
+        const double w1 = __shfl_sync(kFull, c1, src_hi);
+        alo[kb] = (l & 1) ? v1 : v0;
+        ahi[kb] = (l & 1) ? w1 : w0;
+      }
+      double* tile_row = reinterpret_cast<double*>(Lp + (tri(tb + r) + t0) * 32);
+      double o0[4], o1[4], p0[4], p1[4];
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) o0[cb] = o1[cb] = p0[cb] = p1[cb] = 0.0;
+#pragma unroll
+      for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+        for (int cb = kb; cb < 4; ++cb) dmma884(o0[cb], o1[cb], alo[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + l]);
+#pragma unroll
+        for (int cb = kb; cb < 4; ++cb) dmma884(p0[cb], p1[cb], ahi[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + 4 + l]);
+      }
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) {
+        double* tile = tile_row + cb * 64;
+        const int q0 = 2 * l, q1 = 2 * l + 1;
+        tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0[cb] + p0[cb];
+        tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1[cb] + p1[cb];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
 // M_IJ = L_IJ inv(L_JJ) for every strictly-lower 32x32 block (one warp per row tile; full occupancy, HBM-bound:
 // reads L once, writes M once).  With M the pair kernel's blocked TRSM needs no diagonal solve between its
 // updates:  W_J := L_JJ S_J obeys  W_I = C_I - sum_{J<I} M_IJ W_J.
@@ -590,7 +791,7 @@ __device__ __forceinline__ double linv_elem(const double* __restrict__ Iblk, int
 #endif
 template <int NW>
 __global__ void __launch_bounds__(NW * 32, PMK_SOLVE_MINB)
-k_solve_alpha(LeafTable lt, const int* __restrict__ order, const double* __restrict__ rhs_in, double* __restrict__ out) {
+k_solve_alpha(LeafTable lt, const int* __restrict__ order, const double* rhs_in, double* out, int backward_only) {
   extern __shared__ double sm[];
   const int p = order[blockIdx.x];
   if (lt.info[p] != 0) return;
@@ -606,8 +807,8 @@ k_solve_alpha(LeafTable lt, const int* __restrict__ order, const double* __restr
   const int64_t xo = lt.xoff[p];
   for (int i = threadIdx.x; i < npad; i += NW * 32) z[i] = rhs_in[xo + i];
   __syncthreads();
-  // ---- forward: z <- L^-1 y
-  for (int J = 0; J < nblk; ++J) {
+  // ---- forward: z <- L^-1 y  (backward_only: rhs_in already holds z, computed panel by panel by k_chol_diag)
+  for (int J = backward_only ? nblk : 0; J < nblk; ++J) {
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     for (int ct = warp; ct < 4 * J; ct += NW) {
       const double zlo = z[8 * ct + l], zhi = z[8 * ct + 4 + l];
@@ -806,11 +1007,37 @@ void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_np
 }
 
 // rhs / out: padded per-leaf vectors laid out like lt.y (nullptr = lt.y -> lt.alpha, the fit itself)
-void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s, const double* rhs, double* out) {
+// backward_only: rhs already holds z = L^-1 y (the level-synchronous factorisation leaves it in lt.alpha)
+void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_npad, cudaStream_t s, const double* rhs, double* out,
+                  int backward_only) {
   constexpr int NW = 8;
   if (n_order <= 0) return;
   const size_t smem = (size_t)(max_npad + NW * 32 + 32) * sizeof(double);
-  k_solve_alpha<NW><<<n_order, NW * 32, smem, s>>>(lt, d_order, rhs ? rhs : lt.y, out ? out : lt.alpha);
+  k_solve_alpha<NW><<<n_order, NW * 32, smem, s>>>(lt, d_order, rhs ? rhs : lt.y, out ? out : lt.alpha, backward_only);
+}
+
+// Level-synchronous factorisation: leaves sorted by size (order), leaves_per_panel[J] = how many of them have a J-th 32-column
+// panel (a prefix of `order`).  Returns the number of launches.  with_z: k_chol_diag also forms z = L^-1 y in lt.alpha.
+int launch_chol_levels(const LeafTable& lt, const int* d_order, const std::vector<int>& leaves_per_panel, int max_npad, int with_z,
+                       cudaStream_t s) {
+  constexpr int NW = PMK_CHOL_NW, R = 2;
+  const size_t dyn_panel = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);
+  const size_t dyn_diag = (size_t)4 * kCholDepth * 32 * sizeof(double2);
+  int launches = 0;
+  const int max_ntl = max_npad / 8;
+  for (int J = 0; J < (int)leaves_per_panel.size(); ++J) {
+    const int cnt = leaves_per_panel[J];
+    if (cnt <= 0) break;
+    k_chol_diag<4><<<cnt, 128, dyn_diag, s>>>(lt, d_order, J, with_z);
+    ++launches;
+    const int rows_below = max_ntl - 4 * J - 4;
+    if (rows_below > 0) {
+      dim3 grid((rows_below + NW * R - 1) / (NW * R), cnt);
+      k_chol_panel<NW, R><<<grid, NW * 32, dyn_panel, s>>>(lt, d_order, J);
+      ++launches;
+    }
+  }
+  return launches;
 }
 
 void launch_alpha_residual(int D, const LeafTable& lt, const int* d_order, int n_order, KParams kp, double sigma2, double* r, cudaStream_t s) {
