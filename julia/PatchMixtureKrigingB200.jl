@@ -5,7 +5,10 @@
 # replace only the BODIES with `ccall`s.  Everything the north star keeps on the host stays the
 # reference's own Julia code: `setuppartition`, `organizetrainingsets`, `fetchhyperplanes`,
 # `findpartition`, `findneighbourpartitions`, the kernel parameter structs and `array2matrix`
-# (an optional `setuppartition` with the per-level O(N) work on the GPU is at the end of this file).
+# (optional device forms of `setuppartition` and `organizetrainingsets` are further down).
+# `MixtureGPType(X_set, hps; devices = 0:7)` shards the model over the GPUs of the box by sub-tree ownership
+# (pmk_multi_*: rank r owns a contiguous range of the leaves; nothing but the tree is replicated); `fitmixtureGP!` and
+# `querymixtureGP!` keep their signatures.
 #
 # NOTE: this image has no Julia toolchain, so this file is written against the C ABI but has not been
 # executed here; the same ABI is exercised call-for-call by the Python mirror
@@ -51,6 +54,40 @@ end
 
 lasterror(h::Handle) = unsafe_string(ccall((:pmk_last_error, libpmk), Cstring, (Ptr{Cvoid},), h.ptr))
 
+"One model over several GPUs of the box (pmk_multi, include/pmk.h): `devices` are CUDA ordinals."
+mutable struct MultiHandle
+    ptr::Ptr{Cvoid}
+    devices::Vector{Cint}
+    function MultiHandle(devices)
+        ids = Cint.(collect(devices))
+        out = Ref{Ptr{Cvoid}}(C_NULL)
+        rc = GC.@preserve ids ccall((:pmk_multi_create, libpmk), Cint, (Ref{Ptr{Cvoid}}, Cint, Ptr{Cint}), out, length(ids), ids)
+        rc == PMK_OK || error("pmk_multi_create: ", unsafe_string(ccall((:pmk_multi_last_error, libpmk), Cstring, (Ptr{Cvoid},), C_NULL)))
+        m = new(out[], ids)
+        finalizer(x -> ccall((:pmk_multi_destroy, libpmk), Cvoid, (Ptr{Cvoid},), x.ptr), m)
+        return m
+    end
+end
+lasterror(m::MultiHandle) = unsafe_string(ccall((:pmk_multi_last_error, libpmk), Cstring, (Ptr{Cvoid},), m.ptr))
+function check(m::MultiHandle, rc::Cint)
+    rc == PMK_OK && return nothing
+    rc == Cint(-2) && throw(DimensionMismatch(lasterror(m)))
+    error("libpmk_b200 error $(rc): ", lasterror(m))
+end
+"the single-GPU handle of the rank that owns (1-based) leaf `n` of an `N`-leaf model: leaf ids stay global"
+function ownerhandle(m::MultiHandle, n::Integer, N::Integer)
+    first = Ref{Int64}(0); count = Ref{Int64}(0)
+    for r in 0:length(m.devices)-1
+        ccall((:pmk_multi_leaf_range, libpmk), Cint, (Cint, Int64, Cint, Ref{Int64}, Ref{Int64}), length(m.devices), N, r, first, count)
+        if first[] < n <= first[] + count[]
+            h = Ref{Ptr{Cvoid}}(C_NULL)
+            check(m, ccall((:pmk_multi_handle, libpmk), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), m.ptr, r, h))
+            return h[]
+        end
+    end
+    throw(BoundsError())
+end
+
 function check(h::Handle, rc::Cint)
     rc == PMK_OK && return nothing
     rc == Cint(-2) && throw(DimensionMismatch(lasterror(h)))       # mixtureGP.jl:298, RKHS.jl:18,199-203,225-227
@@ -74,33 +111,83 @@ function constructkernelmatrix(X::Vector{Vector{Float64}}, Î¸)::Matrix{Float64}
     return K
 end
 
+"constructkernelmatrix(X, Z, Î¸): K[i,j] = evalkernel(X[i], Z[j], Î¸)   (src/RKHS/RKHS.jl:95-110)"
+function constructkernelmatrix(X::Vector{Vector{Float64}}, Z::Vector{Vector{Float64}}, Î¸)::Matrix{Float64}
+    h = sharedhandle()
+    Xm = pack(X); Zm = pack(Z); kp = kernelparams(Î¸)
+    K = Matrix{Float64}(undef, length(X), length(Z))
+    GC.@preserve Xm Zm kp K check(h, ccall((:pmk_cross_gram, libpmk), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Float64}, Int64, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Ptr{Float64}),
+        h.ptr, size(Xm, 1), length(X), Xm, length(Z), Zm, kernelid(Î¸), kp, length(kp), K))
+    return K
+end
+
+"evalquery(x, c, X, Î¸) = Î£ c[n] k(x, X[n])   (src/RKHS/querying.jl:2-5)"
+evalquery(x::Vector{Float64}, c::Vector{Float64}, X::Vector{Vector{Float64}}, Î¸)::Float64 =
+    dot(vec(constructkernelmatrix([x], X, Î¸)), c)
+
+"""
+setupGPquery(c, X, Î¸, ÏƒÂ²) -> fq   (src/RKHS/querying.jl:43-58); fq(xq) = evalqueryGP!(...) -> (mean, variance) with
+mean = Î£ c[n] k(xq, X[n]) and variance = k(xq,xq) - káµ€(K + ÏƒÂ²I)â»Â¹k, NOT clamped (querying.jl:60-79).  The reference solves
+A\k by LU per query; here the leaf is factorised once and the fused pair kernel returns â€–Lâ»Â¹kâ€–Â² (flags bit 1 = no clamp).
+"""
+function setupGPquery(c::Vector{Float64}, X::Vector{Vector{Float64}}, Î¸, ÏƒÂ²::Float64)::Function
+    length(c) == length(X) || throw(DimensionMismatch("length(c) != length(X)"))
+    h = Handle(0)
+    Xm = pack(X); kp = kernelparams(Î¸); off = Int64[0, length(X)]; y0 = zeros(length(X))
+    bad = Ref{Int64}(0); info = Ref{Cint}(0)
+    rc = GC.@preserve Xm kp off y0 ccall((:pmk_fit, libpmk), Cint,
+        (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Float64, Ref{Int64}, Ref{Cint}),
+        h.ptr, size(Xm, 1), 1, off, Xm, y0, kernelid(Î¸), kp, length(kp), ÏƒÂ², bad, info)
+    rc == PMK_ERR_NOT_POSDEF && throw(PosDefException(info[]))
+    check(h, rc)
+    GC.@preserve c check(h, ccall((:pmk_set_alpha, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), h.ptr, 1, c))
+    check(h, ccall((:pmk_set_tree, libpmk), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, size(Xm, 1), 1, C_NULL, C_NULL))
+    wp = Float64[1.0]
+    function fq(xq::Vector{Float64})
+        Yq = zeros(1); Vq = zeros(1); Xq = reshape(copy(xq), :, 1)
+        GC.@preserve Xq wp Yq Vq check(h, ccall((:pmk_query, libpmk), Cint,
+            (Ptr{Cvoid}, Int64, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+            h.ptr, 1, Xq, 0.0, 0.0, 1, wp, 1, 2, Yq, Vq))
+        return Yq[1], Vq[1]
+    end
+    return fq
+end
+
 # ---- MixtureGPType: the fitted state lives in HBM behind the handle -----------------------------------
 mutable struct MixtureGPType{T}
     X_parts::Vector{Vector{Vector{T}}}
     hps::Vector{PMK.HyperplaneType{T}}
-    h::Handle
+    h::Union{Handle,Nothing}              # single-GPU model
+    multi::Union{MultiHandle,Nothing}     # model sharded over several GPUs (sub-tree ownership)
     ÏƒÂ²_set::Vector{T}
     fitted::Bool
+    Î¸                                     # the kernel of the last fit (queries must use the same one)
+    treekey::UInt                         # hash of (levels, hyperplanes) last uploaded
 end
 
-"MixtureGPType(X_set, hps)  (src/RKHS/mixtureGP.jl:54-66)"
-MixtureGPType(X_parts::Vector{Vector{Vector{T}}}, hps::Vector{PMK.HyperplaneType{T}}; device = 0) where T =
-    MixtureGPType{T}(X_parts, hps, Handle(device), T[], false)
+"MixtureGPType(X_set, hps)  (src/RKHS/mixtureGP.jl:54-66); `devices = 0:7` shards the model over those GPUs"
+function MixtureGPType(X_parts::Vector{Vector{Vector{T}}}, hps::Vector{PMK.HyperplaneType{T}}; device = 0, devices = nothing) where T
+    devices === nothing ? MixtureGPType{T}(X_parts, hps, Handle(device), nothing, T[], false, nothing, UInt(0)) :
+                          MixtureGPType{T}(X_parts, hps, nothing, MultiHandle(devices), T[], false, nothing, UInt(0))
+end
+leafhandle(Î·::MixtureGPType, n::Integer) = Î·.multi === nothing ? Î·.h.ptr : ownerhandle(Î·.multi, n, length(Î·.X_parts))
+checkleaf(Î·::MixtureGPType, rc::Cint) = Î·.multi === nothing ? check(Î·.h, rc) : (rc == PMK_OK || error("libpmk_b200 error $(rc) on the leaf's owner"))
 
 "c_set[n], L_set[n], U_set[n] of the reference's struct (mixtureGP.jl:40-46), fetched on demand (1-based leaf)"
 function c_set(Î·::MixtureGPType, n::Integer)
     out = Vector{Float64}(undef, length(Î·.X_parts[n]))
-    GC.@preserve out check(Î·.h, ccall((:pmk_get_alpha, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), Î·.h.ptr, n, out))
+    GC.@preserve out checkleaf(Î·, ccall((:pmk_get_alpha, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), leafhandle(Î·, n), n, out))
     return out
 end
 function L_set(Î·::MixtureGPType, n::Integer)
     m = length(Î·.X_parts[n]); out = Matrix{Float64}(undef, m, m)
-    GC.@preserve out check(Î·.h, ccall((:pmk_get_L, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), Î·.h.ptr, n, out))
+    GC.@preserve out checkleaf(Î·, ccall((:pmk_get_L, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), leafhandle(Î·, n), n, out))
     return LowerTriangular(out)
 end
 function U_set(Î·::MixtureGPType, n::Integer)      # Gram WITHOUT ÏƒÂ² (mixtureGP.jl:99)
     m = length(Î·.X_parts[n]); out = Matrix{Float64}(undef, m, m)
-    GC.@preserve out check(Î·.h, ccall((:pmk_get_K, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), Î·.h.ptr, n, out))
+    GC.@preserve out checkleaf(Î·, ccall((:pmk_get_K, libpmk), Cint, (Ptr{Cvoid}, Int64, Ptr{Float64}), leafhandle(Î·, n), n, out))
     return out
 end
 
@@ -114,20 +201,23 @@ function fitmixtureGP!(Î·::MixtureGPType{T}, y_parts::Vector{Vector{T}}, Î¸, ÏƒÂ
     length(yp) == leaf_off[end] || throw(DimensionMismatch("length(y) != length(X) in a leaf"))
     kp = kernelparams(Î¸)
     bad = Ref{Int64}(0); info = Ref{Cint}(0)
-    rc = GC.@preserve leaf_off Xp yp kp ccall((:pmk_fit, libpmk), Cint,
-        (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Float64, Ref{Int64}, Ref{Cint}),
-        Î·.h.ptr, size(Xp, 1), N_parts, leaf_off, Xp, yp, kernelid(Î¸), kp, length(kp), Float64(ÏƒÂ²), bad, info)
-    rc == PMK_ERR_NOT_POSDEF && throw(PosDefException(info[]))      # cholesky(U) at mixtureGP.jl:109
-    check(Î·.h, rc)
-    Î·.ÏƒÂ²_set = fill(T(ÏƒÂ²), N_parts); Î·.fitted = true
+    sig = (Ptr{Cvoid}, Cint, Int64, Ptr{Int64}, Ptr{Float64}, Ptr{Float64}, Cint, Ptr{Float64}, Cint, Float64, Ref{Int64}, Ref{Cint})
+    rc = GC.@preserve leaf_off Xp yp kp (Î·.multi === nothing ?
+        ccall((:pmk_fit, libpmk), Cint, sig, Î·.h.ptr, size(Xp, 1), N_parts, leaf_off, Xp, yp, kernelid(Î¸), kp, length(kp), Float64(ÏƒÂ²), bad, info) :
+        ccall((:pmk_multi_fit, libpmk), Cint, sig, Î·.multi.ptr, size(Xp, 1), N_parts, leaf_off, Xp, yp, kernelid(Î¸), kp, length(kp), Float64(ÏƒÂ²), bad, info))
+    rc == PMK_ERR_NOT_POSDEF && throw(PosDefException(info[]))      # cholesky(U) at mixtureGP.jl:109; bad[] = the failing leaf
+    Î·.multi === nothing ? check(Î·.h, rc) : check(Î·.multi, rc)
+    Î·.ÏƒÂ²_set = fill(T(ÏƒÂ²), N_parts); Î·.fitted = true; Î·.Î¸ = Î¸
     return Î·
 end
 
-"""How `L \\ kq` of `queryinner!` (mixtureGP.jl:311) is carried out: 0 = explicit inverse formed once per fit (default),
+"""How `L \\ kq` of `queryinner!` (mixtureGP.jl:311) is carried out: -1 = chosen by the fit's conditioning estimate (default:
+explicit inverse unless (max diag L / min diag L)Â² â‰¥ 1e4, then substitution), 0 = explicit inverse formed once per fit,
 1 = blocked forward substitution (closest to `dtrsv`), 2 = explicit inverse with the round-1 column-sweep kernel.
 `PMK_OPT_QUERY_SOLVER` of include/pmk.h."""
 function setsolver!(Î·::MixtureGPType, solver::Integer)
-    check(Î·.h, ccall((:pmk_set_option, libpmk), Cint, (Ptr{Cvoid}, Cint, Int64), Î·.h.ptr, 2, solver))
+    Î·.multi === nothing ? check(Î·.h, ccall((:pmk_set_option, libpmk), Cint, (Ptr{Cvoid}, Cint, Int64), Î·.h.ptr, 2, solver)) :
+                          check(Î·.multi, ccall((:pmk_multi_set_option, libpmk), Cint, (Ptr{Cvoid}, Cint, Int64), Î·.multi.ptr, 2, solver))
     return Î·
 end
 
@@ -144,8 +234,14 @@ function settree!(Î·::MixtureGPType, levels::Integer)
     for (i, hp) in enumerate(hps)
         hv[:, i] = hp.v; hc[i] = hp.c
     end
-    GC.@preserve hv hc check(Î·.h, ccall((:pmk_set_tree, libpmk), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
-                                        Î·.h.ptr, D, levels, hv, hc))
+    key = hash((levels, hv, hc))          # content, not identity: hyperplanes edited in place are uploaded again
+    key == Î·.treekey && return nothing
+    sig = (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64})
+    GC.@preserve hv hc (Î·.multi === nothing ?
+        check(Î·.h, ccall((:pmk_set_tree, libpmk), Cint, sig, Î·.h.ptr, D, levels, hv, hc)) :
+        check(Î·.multi, ccall((:pmk_multi_set_tree, libpmk), Cint, sig, Î·.multi.ptr, D, levels, hv, hc)))
+    Î·.treekey = key
+    return nothing
 end
 
 """
@@ -155,10 +251,18 @@ querymixtureGP!(Yq, Vq, Xq, Î·, root, levels, radius, Î´, Î¸, ÏƒÂ², weight_Î¸, d
 function querymixtureGP!(Yq::Vector{T}, Vq::Vector{T}, Xq::Vector{Vector{T}}, Î·::MixtureGPType{T}, root, levels,
                          radius::T, Î´::T, Î¸, ÏƒÂ², weight_Î¸, debug_vars = nothing; debug_flag = false)::Nothing where T
     Nq = length(Xq); resize!(Yq, Nq); resize!(Vq, Nq)
+    Î·.fitted || error("querymixtureGP! before fitmixtureGP!")
+    (kernelid(Î¸) == kernelid(Î·.Î¸) && kernelparams(Î¸) == kernelparams(Î·.Î¸)) || throw(ArgumentError("Î¸ differs from the kernel the model was fitted with"))
     settree!(Î·, levels)
     Xm = pack(Xq); wp = kernelparams(weight_Î¸)
-    GC.@preserve Xm wp Yq Vq check(Î·.h, ccall((:pmk_query, libpmk), Cint,
-        (Ptr{Cvoid}, Int64, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64}),
+    sig = (Ptr{Cvoid}, Int64, Ptr{Float64}, Float64, Float64, Cint, Ptr{Float64}, Cint, Cint, Ptr{Float64}, Ptr{Float64})
+    if Î·.multi !== nothing
+        debug_flag && error("debug_flag on a model sharded over several GPUs: query a single-GPU model for the debug outputs")
+        GC.@preserve Xm wp Yq Vq check(Î·.multi, ccall((:pmk_multi_query, libpmk), Cint, sig,
+            Î·.multi.ptr, Nq, Xm, radius, Î´, kernelid(weight_Î¸), wp, length(wp), 0, Yq, Vq))
+        return nothing
+    end
+    GC.@preserve Xm wp Yq Vq check(Î·.h, ccall((:pmk_query, libpmk), Cint, sig,
         Î·.h.ptr, Nq, Xm, radius, Î´, kernelid(weight_Î¸), wp, length(wp), 0, Yq, Vq))
     if debug_flag && debug_vars !== nothing
         fetchdebug!(debug_vars, Î·, Nq)
@@ -183,8 +287,26 @@ function fetchdebug!(dv::PMK.MixtureGPDebugType, Î·::MixtureGPType, Nq::Integer)
     dv.v_set = [v[rng(j)] for j in 1:Nq]
     dv.region_inds_set = [Int.(leaf[rng(j)][1:end-1]) for j in 1:Nq]
     dv.p_region_ind_set = Int.(home)
-    # hps_keep_flags_set / ts_set / zs_set are O(Nq * length(hps)) in the reference; the kept hyperplane ids
-    # and their t are in `hp` / `t` (see include/pmk.h pmk_last_query_debug) if a caller needs them.
+    # hps_keep_flags_set / zs_set / ts_set (mixtureGP.jl:17-19,256-258): dense over ALL hyperplanes, Nq * length(hps) entries --
+    # fetched in slices of at most 2^26 entries (pmk_last_query_debug_dense); the kept ids and their t are also in `hp` / `t`
+    n_hp = length(Î·.hps); D = length(Î·.X_parts[1][1])
+    if n_hp > 0
+        dv.hps_keep_flags_set = Vector{BitVector}(undef, Nq); dv.ts_set = Vector{Vector{Float64}}(undef, Nq)
+        dv.zs_set = Vector{Vector{Vector{Float64}}}(undef, Nq)
+        step = max(1, (1 << 26) Ã· n_hp)
+        for j0 in 0:step:Nq-1
+            m = min(step, Nq - j0)
+            keep = Vector{UInt8}(undef, m * n_hp); ts = Vector{Float64}(undef, m * n_hp); zs = Array{Float64}(undef, D, n_hp, m)
+            GC.@preserve keep ts zs check(Î·.h, ccall((:pmk_last_query_debug_dense, libpmk), Cint,
+                (Ptr{Cvoid}, Int64, Int64, Ptr{UInt8}, Ptr{Float64}, Ptr{Float64}), Î·.h.ptr, j0, m, keep, ts, zs))
+            for j in 1:m
+                r = ((j - 1) * n_hp + 1):(j * n_hp)
+                dv.hps_keep_flags_set[j0 + j] = BitVector(keep[r] .!= 0)
+                dv.ts_set[j0 + j] = ts[r]
+                dv.zs_set[j0 + j] = [zs[:, i, j] for i in 1:n_hp]
+            end
+        end
+    end
     return dv
 end
 
@@ -271,9 +393,34 @@ function setuppartition(X::Vector{Vector{T}}, levels::Integer; h::Handle = share
     return root, [X[i] for i in X_parts_inds], X_parts_inds
 end
 
+# ---- organizetrainingsets(root, levels, X0, Îµ) on the device  (src/patchwork/partition.jl:301-357; findÎµpartitions! :269-298) ----
+# Same return values as the reference: (X_set, X_set_inds, regions_list_set, problematic_inds); the per-point DFS with the
+# two comparisons v.x < c + Îµ / v.x > c - Îµ runs on the GPU (un-fused, reference order), the index lists come back ascending.
+function organizetrainingsets(root, levels::Integer, X0::Vector{Vector{T}}, Îµ::T; h::Handle = sharedhandle()) where T
+    hps = PMK.fetchhyperplanes(root)
+    D = length(X0[1]); N = length(X0)
+    hv = Matrix{Float64}(undef, D, length(hps)); hc = Vector{Float64}(undef, length(hps))
+    for (i, hp) in enumerate(hps)
+        hv[:, i] = hp.v; hc[i] = hp.c
+    end
+    GC.@preserve hv hc check(h, ccall((:pmk_set_tree, libpmk), Cint, (Ptr{Cvoid}, Cint, Cint, Ptr{Float64}, Ptr{Float64}), h.ptr, D, levels, hv, hc))
+    n_leaves = length(hps) + 1
+    Xm = pack(X0); leaf_off = Vector{Int64}(undef, n_leaves + 1); total = Ref{Int64}(0)
+    GC.@preserve Xm leaf_off check(h, ccall((:pmk_organize_training_sets, libpmk), Cint,
+        (Ptr{Cvoid}, Int64, Ptr{Float64}, Float64, Ptr{Int64}, Ref{Int64}), h.ptr, N, Xm, Float64(Îµ), leaf_off, total))
+    inds = Vector{Int32}(undef, total[]); poff = Vector{Int64}(undef, N + 1); pleaves = Vector{Int32}(undef, total[])
+    GC.@preserve inds poff pleaves check(h, ccall((:pmk_organize_fetch, libpmk), Cint,
+        (Ptr{Cvoid}, Ptr{Int32}, Ptr{Int64}, Ptr{Int32}), h.ptr, inds, poff, pleaves))
+    X_set_inds = [Int.(inds[leaf_off[r]+1:leaf_off[r+1]]) for r in 1:n_leaves]
+    X_set = [X0[i] for i in X_set_inds]
+    regions_list_set = [Int.(pleaves[poff[n]+1:poff[n+1]]) for n in 1:N]
+    return X_set, X_set_inds, regions_list_set, Vector{Vector{Int}}(undef, 0)
+end
+
 # ---- checkpoint (no counterpart in the reference: MixtureGPType lives in memory only) -------------------------------------
 "savemixtureGP(Î·, path, levels): X_parts, c_set, L_set, kernel, ÏƒÂ² and the tree in one file (pmk_save_model)"
 function savemixtureGP(Î·::MixtureGPType, path::AbstractString, levels::Integer)
+    Î·.multi === nothing || error("savemixtureGP of a model sharded over several GPUs: a model file holds a whole model")
     settree!(Î·, levels)
     check(Î·.h, ccall((:pmk_save_model, libpmk), Cint, (Ptr{Cvoid}, Cstring), Î·.h.ptr, path))
 end
@@ -297,7 +444,10 @@ function loadmixtureGP(path::AbstractString; device = 0)
     hv = Matrix{Float64}(undef, D[], n_hp); hc = Vector{Float64}(undef, n_hp)
     n_hp > 0 && GC.@preserve hv hc check(h, ccall((:pmk_get_tree, libpmk), Cint, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h.ptr, hv, hc))
     hps = [PMK.HyperplaneType{Float64}(hv[:, i], hc[i]) for i in 1:n_hp]
-    return MixtureGPType{Float64}(X_parts, hps, h, fill(s2[], nl[]), true), Int(lv[])
+    Î¸ = (PMK.GaussianKernel1DType, PMK.Spline34KernelType, nothing, nothing, PMK.BrownianBridge1Ïµ, PMK.BrownianBridge2Ïµ,
+         PMK.Spline12KernelType, PMK.Spline32KernelType, PMK.RationalQuadraticKernelType)[kid[]+1]
+    Î¸v = kid[] == 2 ? PMK.BrownianBridge10(kp[]) : kid[] == 3 ? PMK.BrownianBridge20(kp[]) : Î¸(kp[])      # declarations.jl:25-100
+    return MixtureGPType{Float64}(X_parts, hps, h, nothing, fill(s2[], nl[]), true, Î¸v, UInt(0)), Int(lv[])
 end
 
 end # module
