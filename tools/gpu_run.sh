@@ -24,6 +24,8 @@ for step in "$@"; do
     tests_fit)  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py tests/test_gpu_multi.py -m gpu -q --timeout 600 -p no:cacheprovider -k "fit or leaf_size or positive_definite or large_leaf or golden or multi or ibb1d or checkpoint or alpha" > $out/${tag}_tests_fit.log 2>&1; echo "rc=$?"; tail -15 $out/${tag}_tests_fit.log ;;
     ref_arm)    timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err; echo "rc=$?"; head -c 800 $out/${tag}_bench_ref.json ;;
     ncu_list)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-setup > $out/${tag}_ncu_list.log 2>&1; echo "rc=$?" ;;
+    ncu_k3)     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_query_rowp' -c 2 -o $out/${tag}_k3 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-setup > $out/${tag}_ncu_k3.log 2>&1; echo "rc=$?"; tail -3 $out/${tag}_ncu_k3.log; ncu -i $out/${tag}_k3.ncu-rep --page raw --csv > $out/${tag}_k3_raw.csv 2>/dev/null; ls -la $out/${tag}_k3* ;;
+    ncu_chol)   timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_chol|k_solve_alpha|k_gram_tiles' -c 3 -o $out/${tag}_chol python tools/fit_only.py c3 1 > $out/${tag}_ncu_chol.log 2>&1; echo "rc=$?"; tail -3 $out/${tag}_ncu_chol.log; ncu -i $out/${tag}_chol.ncu-rep --page raw --csv > $out/${tag}_chol_raw.csv 2>/dev/null; ls -la $out/${tag}_chol* ;;
     ncu_fit)    timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_chol|k_gram_tiles|k_solve_alpha|k_inv_' -c 30 -o $out/${tag}_fit python tools/fit_only.py > $out/${tag}_ncu_fit.log 2>&1; echo "rc=$?"; tail -3 $out/${tag}_ncu_fit.log ;;
     *) echo "unknown step $step" ;;
   esac
