@@ -47,6 +47,9 @@ def workload(name: str, nq_override: int | None = None):
     lo, hi = [-5.0, -10.0], [5.0, 10.0]
     if name == "c3":          # BASELINE configs[2]: 2-D, N = 1M, 4096 leaves of ~512 points with overlap, 10M queries
         N, levels, eps, nq = 1_000_000, 13, 0.043, 10_000_000
+    elif name == "c3_8th":    # one GPU's share of c3 at 8 GPUs: 512 leaves, same point density
+        N, levels, eps, nq = 125_000, 10, 0.043, 1_250_000
+        lo, hi = [-1.76776695, -3.5355339], [1.76776695, 3.5355339]
     elif name == "c3_mini":   # same shape, 1/16 size (for quick runs), same point density
         N, levels, eps, nq = 62_500, 9, 0.043, 625_000
         lo, hi = [-1.25, -2.5], [1.25, 2.5]

@@ -754,7 +754,8 @@ static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_
   KCHECK(h, "k_chol");
   {
     Timer t(h, PMK_T_FIT_SOLVE);
-    launch_solve(lt, h->d_order.as<int>(), n_order, max_npad, h->stream, levels ? lt.alpha : nullptr, nullptr, levels ? 1 : 0);
+    // both factorisations leave z = L^-1 y in lt.alpha (formed panel by panel on the tiles they stream anyway): only the backward sweep is left
+    launch_solve(lt, h->d_order.as<int>(), n_order, max_npad, h->stream, lt.alpha, nullptr, 1);
   }
   KCHECK(h, "k_solve_alpha");
   // conditioning estimate (by-product of the factor) and status: first failing leaf

@@ -166,8 +166,8 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
     cslot = (cslot + 1 == kCholDepth) ? 0 : cslot + 1;
     double zl = 0.0, zh = 0.0;
     if (WITH_Z) {
-      zl = zv[8 * ct + (threadIdx.x & 3)];
-      zh = zv[8 * ct + 4 + (threadIdx.x & 3)];
+      zl = __ldcg(zv + 8 * ct + (threadIdx.x & 3));          // written earlier in this launch by another warp: read through L2
+      zh = __ldcg(zv + 8 * ct + 4 + (threadIdx.x & 3));
     }
 #pragma unroll
     for (int r = 0; r < NV; ++r) {
@@ -189,28 +189,69 @@ __device__ __forceinline__ void chol_kloop(double (&acc)[R][4][2], const double2
 // A-fragment-major).  Full-occupancy elementwise kernel: the evaluations (sqrt + exp chains) run at FP64
 // pipe throughput here instead of stalling the low-occupancy factorisation (measured: evaluating them
 // inside k_chol took 31 % of its cycles).  One warp per row tile.
+// The leaf's points are staged ONCE per CTA in shared memory by 1-D TMA bulk copies (cp.async.bulk -> UBLKCP, one per
+// coordinate, completing on an mbarrier; north star (1): "points staged in shared memory via TMA"); every evaluation then
+// reads its column point with broadcast LDS instead of going through L1.
 #ifndef PMK_GRAMT_MINB
 #define PMK_GRAMT_MINB 4      // 64 registers instead of 110: 2 -> 4 resident CTAs per SM (C3: 1.80 -> 1.19 ms; 5: 1.17 with more spills)
 #endif
+__device__ __forceinline__ uint32_t f_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void f_mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void f_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(f_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void f_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(f_smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(f_smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void f_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "F_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra F_DONE;\n"
+      "bra F_WAIT;\n"
+      "F_DONE:\n"
+      "}\n" ::"r"(f_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
 template <int D>
 __global__ void __launch_bounds__(256, PMK_GRAMT_MINB)
-k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2) {
+k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sigma2, int smem_npad) {
   __shared__ double s_exp[64];
-  if (threadIdx.x < 64) s_exp[threadIdx.x] = c_exp2_64[threadIdx.x];
-  __syncthreads();
+  __shared__ __align__(8) uint64_t s_bar;
+  extern __shared__ __align__(128) unsigned char pmk_gram_smem[];
+  double* sx = reinterpret_cast<double*>(pmk_gram_smem);          // [D][smem_npad]
   const int p = order[blockIdx.x];
-  const int n = lt.n[p], ntl = lt.npad[p] >> 3;
+  const int n = lt.n[p], npad = lt.npad[p], ntl = npad >> 3;
+  if ((int)blockIdx.y * 8 >= ntl) return;                          // whole CTA past the leaf's last row tile
+  if (threadIdx.x < 64) s_exp[threadIdx.x] = c_exp2_64[threadIdx.x];
+  if (threadIdx.x == 0) {
+    f_mbar_init(&s_bar, 1);
+    // only the columns this CTA's row tiles can meet: 0 .. 8 (8 blockIdx.y + 8) - 1
+    const int ncol = min(npad, 64 * ((int)blockIdx.y + 1));
+    f_mbar_expect_tx(&s_bar, (uint32_t)(D * ncol * 8));
+#pragma unroll
+    for (int d = 0; d < D; ++d) f_bulk_g2s(sx + d * smem_npad, lt.xs + d * lt.xstride + lt.xoff[p], (uint32_t)(ncol * 8), &s_bar);
+  }
+  __syncthreads();
+  f_mbar_wait(&s_bar, 0);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t = blockIdx.y * 8 + warp;
   if (t >= ntl) return;
   const int g = lane >> 2, l = lane & 3;
-  const double* __restrict__ xs = lt.xs + lt.xoff[p];
-  const int64_t xstride = lt.xstride;
   double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]) + tri(t) * 32 + lane;
   const int row = 8 * t + g;
   double xr[D];
 #pragma unroll
-  for (int d = 0; d < D; ++d) xr[d] = xs[d * xstride + row];
+  for (int d = 0; d < D; ++d) xr[d] = sx[d * smem_npad + row];
   // one entry, every case: lower triangle of K + sigma2*I, identity on the padding
   auto entry = [&](int col) {
     double v = 0.0;
@@ -218,7 +259,7 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
       if (row < n) {          // col <= row < n
         double xc[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) xc[d] = xs[d * xstride + col];
+        for (int d = 0; d < D; ++d) xc[d] = sx[d * smem_npad + col];
         v = eval_kernel<D>(kp, xr, xc);               // evalkernel(X[i], X[j]), i >= j  (RKHS.jl:21-25)
         if (row == col) v = __dadd_rn(v, sigma2);     // mixtureGP.jl:102-104
       } else {
@@ -240,7 +281,7 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
         double s2 = 0.0;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          const double dd = xr[d] - xs[d * xstride + col];
+          const double dd = xr[d] - sx[d * smem_npad + col];
           s2 = fma(dd, dd, s2);
         }
         arg[k] = -kp.p * s2;
@@ -258,7 +299,7 @@ k_gram_tiles(LeafTable lt, const int* __restrict__ order, KParams kp, double sig
         double s2 = 0.0;
 #pragma unroll
         for (int d = 0; d < D; ++d) {
-          const double dd = xr[d] - xs[d * xstride + col];
+          const double dd = xr[d] - sx[d * smem_npad + col];
           s2 = fma(dd, dd, s2);
         }
         arg[k] = -kp.p * s2;
@@ -299,11 +340,13 @@ __device__ __forceinline__ double2 ld_once(const double2* p) {
 #ifndef PMK_CHOL_MINB
 #define PMK_CHOL_MINB 3      // resident leaves per SM the register allocation targets (4 forces 64 registers: measured below)
 #endif
-template <int NW, int R>
-__global__ void __launch_bounds__(NW * 32, PMK_CHOL_MINB)
+template <int NW, int R, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB)
 k_chol(LeafTable lt, const int* __restrict__ order) {
   __shared__ double Dbuf[32 * LDD];
   __shared__ double Ibuf[32 * LD];
+  __shared__ double s_zp[2][32];     // forward solve of alpha: L[block, older panels] z, folded in by the lookahead warps (by block parity)
+  __shared__ double s_zn[32];        // ... and L[block, newest panel] z from phase A
   __shared__ int s_fail, s_next, s_next2[2], s_ready;
   const int p = order[blockIdx.x];
   const int npad = lt.npad[p];
@@ -319,7 +362,13 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
     s_next2[1] = 8;
     s_ready = 0;
   }
+  if (threadIdx.x < 64) s_zp[threadIdx.x >> 5][threadIdx.x & 31] = 0.0;
+  if (threadIdx.x < 32) s_zn[threadIdx.x] = 0.0;
   __syncthreads();
+  // z = L^-1 y (the forward half of the solve for alpha) is formed panel by panel on the operand tiles the factorisation streams
+  // anyway: z_J = inv(L_JJ) (y_J - L[J, 0:J] z[0:J]); it lives in lt.alpha until k_solve_alpha's backward sweep overwrites it.
+  const int64_t xo = lt.xoff[p];
+  const double* zv = lt.alpha + xo;
   extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
   const double2* ring = reinterpret_cast<const double2*>(pmk_chol_smem) + (size_t)warp * (kCholDepth * R * 32) + lane;
   const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
@@ -381,15 +430,24 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
       }
       // Only the newest panel's four column tiles are left to subtract: the contributions of panels 0 .. J-2 were folded
       // into the parked tiles during panel J-1's phase B (lookahead below), off the critical path.
+      double zacc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) zacc[r] = 0.0;
       if (!PMK_CHOL_LOOKAHEAD) {
-        chol_kloop<R, 1>(acc, Lp, bo, ao, 4 * J, ring_u32, ring);
+        chol_kloop<R, 1, true>(acc, Lp, bo, ao, 4 * J, ring_u32, ring, zv, zacc);
       } else if (J > 0) {
         int bo2[4], ao2[R];
 #pragma unroll
         for (int b = 0; b < 4; ++b) bo2[b] = bo[b] + (t0 - 4) * 32;
 #pragma unroll
         for (int r = 0; r < R; ++r) ao2[r] = ao[r] + (t0 - 4) * 32;
-        chol_kloop<R, 1>(acc, Lp, bo2, ao2, 4, ring_u32, ring);
+        chol_kloop<R, 1, true>(acc, Lp, bo2, ao2, 4, ring_u32, ring, zv + 8 * (t0 - 4), zacc);
+      }
+      {
+        double zs = zacc[0];
+        zs += __shfl_xor_sync(kFull, zs, 1);
+        zs += __shfl_xor_sync(kFull, zs, 2);
+        if (l == 0) s_zn[8 * warp + g] = zs;
       }
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
@@ -422,6 +480,14 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
         __threadfence_block();
         if (lane == 0) *(volatile int*)&s_ready = J + 1;     // inv(L_JJ) is in Ibuf (or s_fail is set): the units' epilogues may run
 #endif
+        if (info == 0) {      // z_J = inv(L_JJ) (y_J - L[J, 0:J] z): row `lane` of the lower-triangular inverse
+          const double older = PMK_CHOL_LOOKAHEAD ? s_zp[J & 1][lane] : 0.0;
+          const double rl = lt.y[xo + 32 * J + lane] - older - s_zn[lane];
+          double zz = 0.0;
+#pragma unroll 8
+          for (int k = 0; k < 32; ++k) zz = fma(Ibuf[lane * LD + k], __shfl_sync(kFull, rl, k), zz);   // the inverse's upper part is zero
+          lt.alpha[xo + 32 * J + lane] = zz;
+        }
         PMK_CYC({ long long c1 = clock64(); c_factor += c1 - c0; c0 = c1; })
       }
     }
@@ -444,7 +510,17 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
           acc[r][b][1] = -kt.y;
         }
       }
-      chol_kloop<R, R>(acc, Lp, bo2, ao, 4 * J, ring_u32, ring);
+      double zacc[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) zacc[r] = 0.0;
+      chol_kloop<R, R, true>(acc, Lp, bo2, ao, 4 * J, ring_u32, ring, zv, zacc);
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        double zs = zacc[r];
+        zs += __shfl_xor_sync(kFull, zs, 1);
+        zs += __shfl_xor_sync(kFull, zs, 2);
+        if (l == 0) s_zp[(J + 1) & 1][8 * (2 * (warp - 4) + r) + g] = zs;      // rows of block J + 1, columns of panels 0 .. J-1
+      }
 #pragma unroll
       for (int r = 0; r < R; ++r)
 #pragma unroll
@@ -975,10 +1051,18 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
                        cudaStream_t s) {
   if (n_order <= 0) return;
   dim3 grid(n_order, (max_npad / 8 + 7) / 8);
+  const size_t dyn = (size_t)D * max_npad * sizeof(double);          // the leaf's points, one row of max_npad doubles per coordinate
+  static DeviceOnce once;
+  once.run([&] {
+    const int cap = 3 * PMK_MAX_LEAF_POINTS * (int)sizeof(double);
+    cudaFuncSetAttribute(k_gram_tiles<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    cudaFuncSetAttribute(k_gram_tiles<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+    cudaFuncSetAttribute(k_gram_tiles<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, cap);
+  });
   switch (D) {
-    case 1: k_gram_tiles<1><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2); break;
-    case 2: k_gram_tiles<2><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2); break;
-    case 3: k_gram_tiles<3><<<grid, 256, 0, s>>>(lt, d_order, kp, sigma2); break;
+    case 1: k_gram_tiles<1><<<grid, 256, dyn, s>>>(lt, d_order, kp, sigma2, max_npad); break;
+    case 2: k_gram_tiles<2><<<grid, 256, dyn, s>>>(lt, d_order, kp, sigma2, max_npad); break;
+    case 3: k_gram_tiles<3><<<grid, 256, dyn, s>>>(lt, d_order, kp, sigma2, max_npad); break;
     default: break;
   }
 }
@@ -986,18 +1070,29 @@ void launch_gram_tiles(int D, const LeafTable& lt, const int* d_order, int n_ord
 #ifndef PMK_CHOL_NW
 #define PMK_CHOL_NW 8
 #endif
-void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s) {
-  constexpr int NW = PMK_CHOL_NW, R = 2;
-  if (n_order <= 0) return;
-  size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings (32 KB)
+template <int NW, int MINB>
+static void launch_chol_shape(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s) {
+  constexpr int R = 2;
+  size_t dyn = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);   // per-warp operand rings
   // tuning knob: PMK_CHOL_CTAS_PER_SM=1|2 pads the dynamic shared memory so that fewer leaves are resident per SM
-  // (fewer concurrent leaves = smaller L2 working set of the left-looking re-reads, but fewer warps to hide latency)
-  static int ctas_per_sm = [] { const char* e = getenv("PMK_CHOL_CTAS_PER_SM"); return e ? atoi(e) : 3; }();
+  static int ctas_per_sm = [] { const char* e = getenv("PMK_CHOL_CTAS_PER_SM"); return e ? atoi(e) : 0; }();
   if (ctas_per_sm == 2) dyn = 100 * 1024;
   else if (ctas_per_sm == 1) dyn = 150 * 1024;
   static DeviceOnce once;           // static + dynamic shared memory exceeds the 48 KB default
-  once.run([&] { cudaFuncSetAttribute(k_chol<NW, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); });
-  k_chol<NW, R><<<n_order, NW * 32, dyn, s>>>(lt, d_order);
+  once.run([&] { cudaFuncSetAttribute(k_chol<NW, R, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 150 * 1024); });
+  k_chol<NW, R, MINB><<<n_order, NW * 32, dyn, s>>>(lt, d_order);
+}
+
+// Two CTA shapes of the same kernel: 8 warps x 3 leaves per SM (80 registers) and 6 warps x 4 leaves per SM (64 registers).
+// Measured on C3: 4096 leaves 10.25 ms (8 x 3) vs 10.07 ms (6 x 4); 512 leaves (one GPU's share at N = 8) 1.53 vs 1.84 ms -- the
+// wider CTA wins when a wave is not full.  The second shape is taken from 12 leaves per SM on; PMK_CHOL_SHAPE=0|1 forces one.
+void launch_chol(const LeafTable& lt, const int* d_order, int n_order, cudaStream_t s) {
+  if (n_order <= 0) return;
+  static int forced = [] { const char* e = getenv("PMK_CHOL_SHAPE"); return e ? atoi(e) : -1; }();
+  const int n_sm = device_sm_count();
+  const bool six = forced >= 0 ? forced == 1 : n_order >= 12 * n_sm;       // measured: 512 leaves 1.53 (8 x 3) vs 1.84 ms, 4096 leaves 10.25 vs 10.07
+  if (six) launch_chol_shape<6, 4>(lt, d_order, n_order, s);
+  else launch_chol_shape<PMK_CHOL_NW, PMK_CHOL_MINB>(lt, d_order, n_order, s);
 }
 
 void launch_make_M(const LeafTable& lt, int first_leaf, int n_leaves, int max_npad, cudaStream_t s) {

@@ -432,7 +432,35 @@ int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkerne
   if (!m->staged_queries) return mfail(m, PMK_ERR_STATE, "pmk_multi_stage_queries has not been called");
   m->results_ready = false;
   const int n = m->n, D = m->D;
-  const bool alias = (n == 1);       // one rank: the packed pairs ARE what the owner received; nothing is copied
+  if (n == 1) {
+    // one rank owns every leaf: the plan's own leaf binning feeds the pair kernel directly (nothing is packed, copied or re-sorted)
+    const int rc1 = run_ranks(m, [&](int) -> int {
+      Rank& r = m->rk[0];
+      RC(r, cudaEventRecord(r.ev[EV_START], r.stream));
+      RK(r, pmk_query_plan_dev(r.h, r.q_count, r.dXq.as<double>(), radius, delta, wkernel_id, wparams, nw, &r.n_pairs));
+      RC(r, r.pu.ensure(sizeof(double) * (size_t)r.n_pairs));
+      RC(r, r.pv.ensure(sizeof(double) * (size_t)r.n_pairs));
+      RC(r, cudaEventRecord(r.ev[EV_PLAN], r.stream));
+      RC(r, cudaEventRecord(r.ev[EV_ROUTE], r.stream));
+      RK(r, pmk_query_pairs_dev(r.h, flags, r.pu.as<double>(), r.pv.as<double>()));
+      RC(r, cudaEventRecord(r.ev[EV_PAIRS], r.stream));
+      RK(r, pmk_query_combine_dev(r.h, r.pu.as<double>(), r.pv.as<double>(), r.dYq.as<double>(), r.dVq.as<double>()));
+      RC(r, cudaEventRecord(r.ev[EV_END], r.stream));
+      RC(r, cudaStreamSynchronize(r.stream));
+      r.ms[PMK_MT_QUERY] = elapsed(r.ev[EV_START], r.ev[EV_END]);
+      r.ms[PMK_MT_Q_PLAN] = elapsed(r.ev[EV_START], r.ev[EV_PLAN]);
+      r.ms[PMK_MT_Q_ROUTE] = 0.0;
+      r.ms[PMK_MT_Q_PAIRS] = elapsed(r.ev[EV_ROUTE], r.ev[EV_PAIRS]);
+      r.ms[PMK_MT_Q_RETURN] = elapsed(r.ev[EV_PAIRS], r.ev[EV_END]);
+      return PMK_OK;
+    });
+    if (rc1 != PMK_OK) return rc1;
+    for (int k : {PMK_MT_QUERY, PMK_MT_Q_PLAN, PMK_MT_Q_ROUTE, PMK_MT_Q_PAIRS, PMK_MT_Q_RETURN}) m->ms[k] = m->rk[0].ms[k];
+    m->last_flags = flags;
+    m->results_ready = true;
+    return PMK_OK;
+  }
+  const bool alias = false;
   std::vector<int64_t> first_leaf(n + 1);
   for (int i = 0; i < n; ++i) first_leaf[i] = m->rk[i].leaf_first;
   first_leaf[n] = m->n_leaves;
