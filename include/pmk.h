@@ -283,8 +283,13 @@ int64_t pmk_multi_launch_count(const pmk_multi* m);
 /* PMK_OPT_CHOL_VARIANT: the batched Cholesky of the fit: 0 (default) = level-synchronous -- all leaves advance panel by panel,
  * the serial 32x32 diagonal factorisations in one launch (k_chol_diag), the DMMA panel updates in the next (k_chol_panel);
  * 1 = one CTA per leaf running its panels to the end (round-1 kernel, kept for A/B timing; same L to rounding). */
+/* PMK_OPT_GRAM_FAST_EXP: pmk_gram / pmk_cross_gram with the squared exponential evaluated as exp(-eps_sq |x - z|^2) by the
+ * table-driven exp of the fit and query kernels instead of the reference's sqrt, re-square and libm exp (kernel.jl:277-287,
+ * 350-357): 0 (default) = the reference's operation order (entries within 5e-15 of the oracle), 1 = fast: the exp within
+ * 1.3 ulp, the value within (3 + 6 |log K|) ulp of the reference-order entry because the argument is rounded differently
+ * (< 1e-13 relative wherever K > 1e-30); a third of the FP64 work of a kernel that is otherwise bound by it, not by its 8 n^2 bytes. */
 enum { PMK_OPT_FULL_HYPERPLANE_SCAN = 1, PMK_OPT_QUERY_SOLVER = 2, PMK_OPT_INVERSE_BUILDER = 3, PMK_OPT_ALPHA_REFINE = 4,
-       PMK_OPT_CHOL_VARIANT = 5 };
+       PMK_OPT_CHOL_VARIANT = 5, PMK_OPT_GRAM_FAST_EXP = 6 };
 int pmk_set_option(pmk_handle* h, int option, int64_t value);
 /* lower bound of the worst leaf's cond(K + sigma2 I) from the last fit, and the query solver PMK_OPT_QUERY_SOLVER = -1 resolves to */
 int pmk_condition_estimate(pmk_handle* h, double* cond_lower_bound, int* solver_in_use);

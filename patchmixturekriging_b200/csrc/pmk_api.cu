@@ -50,7 +50,7 @@ void launch_eps_partitions(int D, bool fill, const TreeDev& tr, int64_t N, const
                            const int64_t* off, int32_t* pair_leaf, int32_t* pair_pt, int32_t* leaf_count, cudaStream_t s);
 void launch_aos_to_soa(int D, const double* dX, int64_t n, int64_t stride, double* xs, cudaStream_t s);
 void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double* xc, int64_t xc_stride, int m, KParams kp,
-                 double sigma2, int symmetric, double* dK, cudaStream_t s);
+                 double sigma2, int symmetric, double* dK, cudaStream_t s, int fast_exp = 0);
 void partition_sum_plan(int64_t n, int64_t base, std::vector<int64_t>& start, std::vector<int32_t>& len, std::vector<int32_t>& depth);
 void launch_part_iota(int32_t* perm, int64_t N, cudaStream_t s);
 void launch_part_one_based(const int32_t* perm, int64_t N, int32_t* out, cudaStream_t s);
@@ -172,6 +172,7 @@ struct pmk_handle {
   DBuf d_diag_range;
   double cond_est = 0.0;
   int alpha_refine = -1;    // PMK_OPT_ALPHA_REFINE: -1 auto (flagged models), 0 never, 1 always
+  int gram_fast_exp = 0;    // PMK_OPT_GRAM_FAST_EXP: table-driven exp in the standalone Gram kernel (squared exponential; <= 2 ulp)
   int chol_variant = 1;     // PMK_OPT_CHOL_VARIANT: 1 = one CTA per leaf (default: faster on C3 / C4), 0 = level-synchronous kernels
   // organizetrainingsets on the device (results of the last call)
   DBuf o_X, o_counts, o_off, o_pl, o_pp, o_sl, o_sp, o_lcount, o_lstart;
@@ -373,6 +374,9 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
         return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: -1 (by conditioning), 0 (explicit inverse), 1 (substitution) or 2 (explicit inverse, column sweep)");
       h->solver = (int)value;
       return PMK_OK;
+    case PMK_OPT_GRAM_FAST_EXP:
+      h->gram_fast_exp = value != 0;
+      return PMK_OK;
     case PMK_OPT_CHOL_VARIANT:
       if (value != 0 && value != 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_CHOL_VARIANT: 0 (level-synchronous) or 1 (one CTA per leaf)");
       h->chol_variant = (int)value;
@@ -446,7 +450,7 @@ static int gram_impl(pmk_handle* h, int D, int64_t n, const double* X, int64_t m
   }
   {
     Timer t(h, PMK_T_GRAM);
-    launch_gram(D, xs, sx, (int)n, sym ? xs : zs, sym ? sx : sz, (int)m, kp, sigma2, sym ? 1 : 0, dK, h->stream);
+    launch_gram(D, xs, sx, (int)n, sym ? xs : zs, sym ? sx : sz, (int)m, kp, sigma2, sym ? 1 : 0, dK, h->stream, h->gram_fast_exp);
   }
   KCHECK(h, "k_gram");
   CU(h, cudaMemcpyAsync(K_out, dK, sizeof(double) * n * m, cudaMemcpyDeviceToHost, h->stream));

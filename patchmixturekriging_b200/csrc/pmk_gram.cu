@@ -59,7 +59,8 @@ static constexpr int TMP = TM + 1;     // padded row length of the mirror tile: 
 template <int D>
 __global__ void __launch_bounds__(256, 3)
 k_gram(const double* __restrict__ xr, int64_t xr_stride, int n, const double* __restrict__ xc, int64_t xc_stride, int m,
-       KParams kp, double sigma2, int symmetric, double* __restrict__ K) {
+       KParams kp, double sigma2, int symmetric, int fast_exp, double* __restrict__ K) {
+  __shared__ double s_exp[64];
   __shared__ __align__(16) double s_r[D][TM];
   __shared__ __align__(16) double s_c[D][TN];
   __shared__ __align__(8) uint64_t bar;
@@ -69,6 +70,7 @@ k_gram(const double* __restrict__ xr, int64_t xr_stride, int n, const double* __
   if (symmetric == 2 && j0 >= i0 + TM) return;       // strictly above the diagonal: the mirrored tile writes it
   const bool mirror = symmetric == 2 && i0 >= j0 + TN;   // strictly below: evaluate once, store twice
   if (tid == 0) mbar_init(&bar, 1);
+  if (tid < 64) s_exp[tid] = c_exp2_64[tid];
   __syncthreads();
   if (tid == 0) {
     mbar_expect_tx(&bar, (uint32_t)(D * (TM + TN) * sizeof(double)));
@@ -97,13 +99,30 @@ k_gram(const double* __restrict__ xr, int64_t xr_stride, int n, const double* __
       double xz[D];
 #pragma unroll
       for (int d = 0; d < D; ++d) xz[d] = s_c[d][jj];
-      // reference evaluates the lower triangle as evalkernel(X[i], X[j]) (i >= j) and mirrors it
-      double k0 = (symmetric && i < j) ? eval_kernel<D>(kp, xz, xa) : eval_kernel<D>(kp, xa, xz);
-      if (symmetric && i == j) k0 = __dadd_rn(k0, sigma2);
-      double k1 = 0.0;
-      if (two) {
-        k1 = (symmetric && i + 1 < j) ? eval_kernel<D>(kp, xz, xb) : eval_kernel<D>(kp, xb, xz);
+      double k0, k1 = 0.0;
+      if (fast_exp) {
+        // PMK_OPT_GRAM_FAST_EXP (squared exponential only): exp(-eps_sq |x - z|^2) without the reference's sqrt / re-square
+        // round trip and with the table-driven exp of the fit and query kernels -- <= 2 ulp from kernel.jl:350-357, symmetric
+        // by construction, a third of the FP64 operations: the kernel moves from FP64-ALU-bound towards its HBM writes
+        double sa = 0.0, sb = 0.0;
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+          const double da = xa[d] - xz[d], db = xb[d] - xz[d];
+          sa = fma(da, da, sa);
+          sb = fma(db, db, sb);
+        }
+        k0 = exp_neg_tab(-kp.p * sa, s_exp);
+        k1 = exp_neg_tab(-kp.p * sb, s_exp);
+        if (symmetric && i == j) k0 = __dadd_rn(k0, sigma2);
         if (symmetric && i + 1 == j) k1 = __dadd_rn(k1, sigma2);
+      } else {
+        // reference evaluates the lower triangle as evalkernel(X[i], X[j]) (i >= j) and mirrors it
+        k0 = (symmetric && i < j) ? eval_kernel<D>(kp, xz, xa) : eval_kernel<D>(kp, xa, xz);
+        if (symmetric && i == j) k0 = __dadd_rn(k0, sigma2);
+        if (two) {
+          k1 = (symmetric && i + 1 < j) ? eval_kernel<D>(kp, xz, xb) : eval_kernel<D>(kp, xb, xz);
+          if (symmetric && i + 1 == j) k1 = __dadd_rn(k1, sigma2);
+        }
       }
       double* dst = K + (int64_t)j * n + i;
       if (vec) {
@@ -151,7 +170,8 @@ void launch_aos_to_soa(int D, const double* dX, int64_t n, int64_t stride, doubl
 
 // xr/xc must be readable up to the next multiple of TM / TN points (callers pad).
 void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double* xc, int64_t xc_stride, int m, KParams kp,
-                 double sigma2, int symmetric, double* dK, cudaStream_t s) {
+                 double sigma2, int symmetric, double* dK, cudaStream_t s, int fast_exp) {
+  fast_exp = (fast_exp && kp.kind == PMK_KERNEL_SQEXP) ? 1 : 0;
   if (n <= 0 || m <= 0) return;
   dim3 grid((n + TM - 1) / TM, (m + TN - 1) / TN);
   // Gram matrices of more than a few tiles: evaluate the lower tiles only and mirror them (mode 2); PMK_GRAM_NO_MIRROR=1
@@ -166,9 +186,9 @@ void launch_gram(int D, const double* xr, int64_t xr_stride, int n, const double
     cudaFuncSetAttribute(k_gram<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(TN * TMP * sizeof(double)));
   });
   switch (D) {
-    case 1: k_gram<1><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
-    case 2: k_gram<2><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
-    case 3: k_gram<3><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, dK); break;
+    case 1: k_gram<1><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, fast_exp, dK); break;
+    case 2: k_gram<2><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, fast_exp, dK); break;
+    case 3: k_gram<3><<<grid, 256, dyn, s>>>(xr, xr_stride, n, xc, xc_stride, m, kp, sigma2, mode, fast_exp, dK); break;
     default: break;
   }
 }

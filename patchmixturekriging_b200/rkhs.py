@@ -37,11 +37,13 @@ def _as_points(X) -> np.ndarray:
     return X
 
 
-def constructkernelmatrix(X, θ, Z=None, *, σ2: float = 0.0) -> np.ndarray:
+def constructkernelmatrix(X, θ, Z=None, *, σ2: float = 0.0, fast_exp: bool = False) -> np.ndarray:
     """constructkernelmatrix(X, θ) -> n x n Gram (RKHS.jl:4-34); constructkernelmatrix(X, Z, θ) -> K_XZ
-    (RKHS.jl:95-110), here spelled constructkernelmatrix(X, θ, Z)."""
+    (RKHS.jl:95-110), here spelled constructkernelmatrix(X, θ, Z).  fast_exp (PMK_OPT_GRAM_FAST_EXP): the squared exponential
+    by the table-driven exp of the fit / query kernels, <= 2 ulp from the reference's sqrt / re-square / exp order."""
     X = _as_points(X)
     h = _handle()
+    h.check(lib().pmk_set_option(h.raw, _lib.OPT_GRAM_FAST_EXP, 1 if fast_exp else 0))
     kp = θ.params
     if Z is None:
         K = np.empty((X.shape[0], X.shape[0]), order="F")

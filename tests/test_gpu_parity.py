@@ -60,6 +60,30 @@ def test_gram_brownian_bridge(built_lib, kname, param, D, n):
     np.testing.assert_allclose(K, Kref, rtol=rtol, atol=1e-18 if rtol > 1e-14 else 0)
 
 
+@pytest.mark.parametrize("D,n", [(1, 300), (2, 1000), (3, 777)])
+def test_gram_fast_exp_option(built_lib, D, n):
+    """PMK_OPT_GRAM_FAST_EXP: exp(-eps_sq |x - z|^2) with the table-driven exp.  The exp itself is within 1.3 ulp; its argument
+    (sum of squares instead of the reference's sqrt + re-square) differs by a few ulp (measured: up to 3.3), which the exponential turns into that many |arg| ulp of
+    the value: entry by entry |fast - oracle| <= (3 + 6 |log K|) ulp, i.e. < 1e-13 relative wherever K > 1e-30.  Exactly
+    symmetric, diagonal exactly 1 (+ sigma2)."""
+    from patchmixturekriging_b200 import synth
+    X = synth.uniform_points(9 + n, n, [-1.0] * D, [1.0] * D)
+    ok, pk = helpers.kernels(("SQEXP", 37.0))
+    Kref = O.constructkernelmatrix(X, ok)
+    Kf = P.constructkernelmatrix(X, pk, fast_exp=True)
+    Ke = P.constructkernelmatrix(X, pk)
+    assert np.array_equal(Kf, Kf.T) and np.all(np.diag(Kf) == 1.0)
+    big = Kref > 1e-300
+    ulp = np.abs(Kf - Kref)[big] / np.spacing(Kref[big])
+    bound = 3.0 + 6.0 * np.abs(np.log(Kref[big]))
+    helpers.record_parity(f"gram_fast_exp/D{D}_n{n}", max_ulp_vs_oracle=float(ulp.max()), max_ulp_over_bound=float((ulp / bound).max()),
+                          exact_path_max_rel=float((np.abs(Ke - Kref)[big] / Kref[big]).max()))
+    assert np.all(ulp <= bound), float((ulp / bound).max())
+    near = Kref > 1e-30
+    np.testing.assert_allclose(Kf[near], Kref[near], rtol=1e-13)
+    assert np.array_equal(np.diag(P.constructkernelmatrix(X, pk, σ2=0.25, fast_exp=True)), np.full(n, 1.25))
+
+
 def test_cross_gram_and_evalkernel(built_lib):
     from patchmixturekriging_b200 import synth
     X = synth.uniform_points(1, 70, [-1.0, -1.0], [1.0, 1.0])
