@@ -194,7 +194,8 @@ def test_query_structure_bit_exact(built_lib, name):
     assert np.all(f["pair_w"][~nb] == 1.0)
     # device findpartition entry point
     out = np.empty(Xq.shape[0], dtype=np.int32)
-    eta.handle.check(_lib.lib().pmk_find_partition(eta.handle.raw, Xq.shape[0], _lib.ptr(np.ascontiguousarray(Xq)), _lib.ptr(out)))
+    Xqc = np.ascontiguousarray(Xq)            # bound to a name: ptr() hands out a bare address
+    eta.handle.check(_lib.lib().pmk_find_partition(eta.handle.raw, Xqc.shape[0], _lib.ptr(Xqc), _lib.ptr(out)))
     assert np.array_equal(out, home)
     assert np.array_equal(P.findpartition(Xq, root), home)
 
