@@ -265,15 +265,13 @@ int64_t pmk_multi_launch_count(const pmk_multi* m);
  *                 leaves (pmk_condition_estimate), reaches 1e4 -- then 1.  Measured against the reference's dtrsv
  *                 (profiles/parity_r02.json): the explicit inverse stays below 1e-9 of the variance up to cond ~ 1e5 and
  *                 reaches 3e-9 at cond 3e6, substitution stays at the level at which dtrsv and dtrsm differ from each other;
- *   0           = s = P kq with P = inv(L) formed once per fit by blocked substitution, as a ROW-PANEL product: the
+ *   0           = s = P kq with P = inv(L) formed once per fit (PMK_OPT_INVERSE_BUILDER), as a ROW-PANEL product: the
  *                 cross-covariance tile is evaluated once into shared memory, every warp streams its own rows of P and
  *                 keeps only ||s||^2 -- no dependency between warps, so the tensor pipe never waits.  Every kernel
- *                 function (the squared exponential with an inlined table-driven exp).  Measured vs dtrsv: <= 3e-11 at
- *                 sigma2 = 1e-3, inside 2e-8 at sigma2 = 1e-5 (Spline34, squared exponential; cond up to 4e6);
- *   1           = blocked forward substitution with 32x32 diagonal-block inverses (closest to dtrsv; use it for
- *                 very ill-conditioned leaves, cond(K) >~ 1e6);
- *   2           = s = P kq as a column sweep with the tile of s in registers (round-1 mid kernel, kept for comparison;
- *                 squared exponential only, other kernel functions fall back to 1). */
+ *                 function (the squared exponential with an inlined table-driven exp).  Measured vs dtrsv: <= 1.1e-11 at
+ *                 sigma2 = 1e-3, 2.2e-10 / 7.1e-10 at sigma2 = 1e-5 (squared exponential cond 3e6 / Spline34 cond 1.5e7);
+ *   1           = blocked forward substitution with 32x32 diagonal-block inverses (closest to dtrsv; what -1 resolves to for
+ *                 ill-conditioned models; also serves mean-only queries). */
 /* PMK_OPT_INVERSE_BUILDER: how P = inv(L) is formed (once per fit) for the explicit-inverse solvers:
  *   0 (default) = recursive doubling on the packed tiles, P21 = -inv(B) C inv(A), every flop a DMMA GEMM (pmk_invert.cu);
  *   1           = the substitution pair kernel run on identity right-hand sides (round-1 builder). */

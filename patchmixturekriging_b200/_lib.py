@@ -12,7 +12,7 @@ LIB_PATH = os.environ.get("PMK_LIB") or os.path.join(_HERE, "libpmk_b200.so")   
 
 PMK_OK, PMK_ERR_CUDA, PMK_ERR_ARG, PMK_ERR_NOT_POSDEF, PMK_ERR_STATE, PMK_ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 OPT_FULL_HYPERPLANE_SCAN, OPT_QUERY_SOLVER, OPT_INVERSE_BUILDER, OPT_ALPHA_REFINE, OPT_CHOL_VARIANT, OPT_GRAM_FAST_EXP = 1, 2, 3, 4, 5, 6
-SOLVER_AUTO, SOLVER_INVERSE, SOLVER_SUBSTITUTION, SOLVER_INVERSE_COLSWEEP = -1, 0, 1, 2
+SOLVER_AUTO, SOLVER_INVERSE, SOLVER_SUBSTITUTION = -1, 0, 1
 T_FIT_PACK, T_FIT_CHOL, T_FIT_SOLVE, T_Q_TREE, T_Q_PAIRS, T_Q_COMBINE, T_GRAM, T_COUNT = 0, 1, 2, 3, 4, 5, 6, 17
 T_Q_MAKE_M = 13
 T_Q_INVERT = 14

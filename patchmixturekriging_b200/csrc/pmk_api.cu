@@ -81,8 +81,6 @@ void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, cons
 void launch_class_tiles(const PairWork& w, int mq, int32_t* tiles, cudaStream_t s);
 bool launch_query_rowp(int D, int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags, int npmax,
                        double* pu, double* pv, cudaStream_t s);
-void launch_query_trmm(int D, int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags,
-                       double* pu, double* pv, cudaStream_t s);
 }  // namespace pmk
 
 using namespace pmk;
@@ -128,7 +126,7 @@ struct pmk_handle {
   bool m_ready = false;    // M (operand of the substitution pair kernel) built for the current factors
   bool p_ready = false;    // P = inv(L) (operand of the explicit-inverse pair kernel) built for the current factors
   int solver = -1;         // PMK_OPT_QUERY_SOLVER: -1 = by conditioning (default); 0 = explicit inverse, row-panel product;
-                           // 1 = blocked substitution (TRSM); 2 = explicit inverse, column-sweep product (round-1 kernel)
+                           // 1 = blocked substitution (TRSM)
   int class_max_npad[5] = {};
   int inverse_builder = 0; // PMK_OPT_INVERSE_BUILDER: 0 = recursive doubling (pmk_invert.cu), 1 = substitution kernel on identity columns
   InvPlanHost inv_plan;    // recursion plan of the shapes of the current model
@@ -370,8 +368,8 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
   switch (option) {
     case PMK_OPT_FULL_HYPERPLANE_SCAN: h->full_scan = value != 0; h->plan_valid = false; return PMK_OK;
     case PMK_OPT_QUERY_SOLVER:
-      if (value < -1 || value > 2)
-        return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: -1 (by conditioning), 0 (explicit inverse), 1 (substitution) or 2 (explicit inverse, column sweep)");
+      if (value < -1 || value > 1)
+        return fail(h, PMK_ERR_ARG, "PMK_OPT_QUERY_SOLVER: -1 (by conditioning), 0 (explicit inverse) or 1 (substitution)");
       h->solver = (int)value;
       return PMK_OK;
     case PMK_OPT_GRAM_FAST_EXP:
@@ -482,12 +480,8 @@ static int effective_solver(const pmk_handle* h) {
   if (h->solver >= 0) return h->solver;
   return h->cond_est >= kCondFlag ? 1 : 0;
 }
-// Does the variance query stream P = inv(L)?  Solver 0 (row-panel kernel) for every kernel function; solver 2 (column sweep,
-// squared exponential inlined) only for that one -- the others take the substitution kernel there.
-static bool uses_inverse(const pmk_handle* h) {
-  const int sv = effective_solver(h);
-  return sv == 0 || (sv == 2 && h->kp.kind == PMK_KERNEL_SQEXP);
-}
+// Does the variance query stream P = inv(L)?  Solver 0 (row-panel kernel), every kernel function.
+static bool uses_inverse(const pmk_handle* h) { return effective_solver(h) == 0; }
 
 // 0, 1, 2, ... on the device (pair / query ids for the radix sorts), grown on demand
 static int ensure_iota(pmk_handle* h, int64_t n) {
@@ -1587,9 +1581,7 @@ static int run_pair_kernels(pmk_handle* h, const QueryPlan& q, const int64_t* le
       if (!(mean_only & 1) && solver == 0) {
         if (!launch_query_rowp(h->D, c, h->lt, w, q, h->kp, mean_only, h->class_max_npad[c], pu, pv, h->stream))
           return fail(h, PMK_ERR_UNSUPPORTED, "row-panel pair kernel: no shared-memory configuration for size class %d", c);
-      } else if (!(mean_only & 1) && solver == 2 && h->kp.kind == PMK_KERNEL_SQEXP)
-        launch_query_trmm(h->D, c, h->lt, w, q, h->kp, mean_only, pu, pv, h->stream);
-      else
+      } else
         launch_query_pairs(h->D, c, (unsigned)ub, h->lt, w, q, h->kp, mean_only, pu, pv, h->stream);
     }
     KCHECK(h, "k_query_pairs");

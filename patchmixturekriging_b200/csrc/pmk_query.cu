@@ -40,21 +40,6 @@ void launch_query_pairs(int D, int cls, unsigned grid, const LeafTable& lt, cons
   }
 }
 
-void launch_trmm_d1(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, double*, double*, cudaStream_t);
-void launch_trmm_d2(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, double*, double*, cudaStream_t);
-void launch_trmm_d3(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, double*, double*, cudaStream_t);
-
-// explicit-inverse pair kernel (pmk_query_trmm.cuh); persistent, reads its tile count on the device
-void launch_query_trmm(int D, int cls, const LeafTable& lt, const PairWork& w, const QueryPlan& q, KParams kp, int flags,
-                       double* pu, double* pv, cudaStream_t s) {
-  switch (D) {
-    case 1: launch_trmm_d1(cls, lt, w, q, kp, flags, pu, pv, s); break;
-    case 2: launch_trmm_d2(cls, lt, w, q, kp, flags, pu, pv, s); break;
-    case 3: launch_trmm_d3(cls, lt, w, q, kp, flags, pu, pv, s); break;
-    default: break;
-  }
-}
-
 bool launch_rowp_d1(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, int, double*, double*, cudaStream_t);
 bool launch_rowp_d2(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, int, double*, double*, cudaStream_t);
 bool launch_rowp_d3(int, const LeafTable&, const PairWork&, const QueryPlan&, KParams, int, int, double*, double*, cudaStream_t);

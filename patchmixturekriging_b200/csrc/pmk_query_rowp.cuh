@@ -23,7 +23,7 @@
 // whichever warp produced them -> bit-reproducible; k(x*,x*) - ||s||^2, clamp, scatter to the pair arrays).
 #pragma once
 #include <type_traits>
-#include "pmk_query_trmm.cuh"
+#include "pmk_query_trsm.cuh"
 
 namespace pmk {
 

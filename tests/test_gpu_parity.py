@@ -203,16 +203,14 @@ def test_query_structure_bit_exact(built_lib, name):
 # Every solver on every configuration is held to TOL = 1e-9, the ill-conditioned ones (sigma2 = 1e-5, cond(K + sigma2 I) 3e6 ..
 # 2e7) included.  Measured (profiles/parity_r02.json, floored relative error): well-conditioned cases <= 1.1e-11; mixgp_file
 # 2.7e-10 (default = substitution) / 7.1e-10 (explicit inverse); c3_mini at sigma2 = 1e-5 6.5e-11 / 2.2e-10.
-SOLVER_NAME = {_lib.SOLVER_AUTO: "auto", _lib.SOLVER_INVERSE: "inverse", _lib.SOLVER_SUBSTITUTION: "substitution",
-               _lib.SOLVER_INVERSE_COLSWEEP: "inverse_colsweep"}
+SOLVER_NAME = {_lib.SOLVER_AUTO: "auto", _lib.SOLVER_INVERSE: "inverse", _lib.SOLVER_SUBSTITUTION: "substitution"}
 
 
-@pytest.mark.parametrize("solver", [_lib.SOLVER_AUTO, _lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION, _lib.SOLVER_INVERSE_COLSWEEP])
+@pytest.mark.parametrize("solver", [_lib.SOLVER_AUTO, _lib.SOLVER_INVERSE, _lib.SOLVER_SUBSTITUTION])
 @pytest.mark.parametrize("name", list(CASES))
 def test_query_mean_variance(built_lib, name, solver):
     """Every query solver against the oracle's dtrsv path: the default (chosen by conditioning), s = inv(L) kq with the
-    explicit inverse (row-panel kernel, every kernel function; column-sweep kernel, squared exponential only) and blocked
-    forward substitution.  Measured errors go to gpurun_out/parity_r02.json."""
+    explicit inverse (row-panel kernel) and blocked forward substitution.  Measured errors go to gpurun_out/parity_r02.json."""
     from patchmixturekriging_b200 import mixturegp
     case, m, root, eta, pk = _setup(name)
     wth, wk = helpers.kernels(case["wkernel"])

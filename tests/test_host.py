@@ -103,26 +103,6 @@ def test_kernel_descriptors():
     assert P.BrownianBridge2ϵ(2.5).params[0] == 2.5
 
 
-def test_exp_neg_arithmetic():
-    """The pair kernel's inline exp (pmk_query_trmm.cuh exp_neg: Cody-Waite reduction, degree-13 Taylor polynomial in
-    Estrin form, exponent patched in) restated in numpy: <= 2.5 ulp from libm on the argument range the squared-exponential
-    cross-covariance produces, and monotone down to the -699 clamp."""
-    import math
-    rng = np.random.default_rng(7)
-    t = -np.concatenate([rng.uniform(0, 50, 400000), rng.uniform(0, 699, 400000), [0.0, 1e-300, 1e-9, 699.0]])
-    L2E, LN2H, LN2L = 1.4426950408889634, 6.93147180369123816490e-01, 1.90821492927058770002e-10
-    nf = np.rint(t * L2E)
-    r = (t - nf * LN2H) - nf * LN2L
-    c = [1.0 / math.factorial(k) for k in range(14)]
-    r2 = r * r; r4 = r2 * r2; r8 = r4 * r4
-    p = [c[2 * k] + c[2 * k + 1] * r for k in range(7)]
-    q0, q1, q2 = p[0] + p[1] * r2, p[2] + p[3] * r2, p[4] + p[5] * r2
-    s = (q0 + q1 * r4) + r8 * (q2 + p[6] * r4)
-    got = np.ldexp(s, nf.astype(int))
-    ref = np.exp(t)
-    assert np.all(np.abs(got - ref) <= 2.5 * np.spacing(ref))
-
-
 def test_exp_neg_tab_arithmetic():
     """The row-panel pair kernel's inline exp (pmk_common.cuh exp_neg_tab: 64-entry table of 2^(j/64), the integer
     64k + j read from the low word of t*64/ln2 + 1.5*2^52, degree-5 polynomial) restated in numpy: <= 1.5 ulp from the
