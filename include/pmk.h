@@ -278,9 +278,11 @@ int64_t pmk_multi_launch_count(const pmk_multi* m);
 /* PMK_OPT_ALPHA_REFINE: one step of iterative refinement of alpha = (K + sigma2 I)^-1 y after the Cholesky solve (the reference
  * solves U\y by LU, mixtureGP.jl:106): -1 (default) = for models flagged by the same conditioning estimate, 0 = never,
  * 1 = always.  Set before pmk_fit. */
-/* PMK_OPT_CHOL_VARIANT: the batched Cholesky of the fit: 0 (default) = level-synchronous -- all leaves advance panel by panel,
- * the serial 32x32 diagonal factorisations in one launch (k_chol_diag), the DMMA panel updates in the next (k_chol_panel);
- * 1 = one CTA per leaf running its panels to the end (round-1 kernel, kept for A/B timing; same L to rounding). */
+/* PMK_OPT_CHOL_VARIANT: the batched Cholesky of the fit: -1 (default) = by leaf size -- leaves of 768 padded rows and more advance
+ * panel by panel through the level-synchronous kernels (the serial 32x32 diagonal factorisations in one launch, k_chol_factor, the
+ * DMMA panel updates with TMA-staged operands in the next, k_chol_panel_tma), smaller leaves take one CTA per leaf running its panels
+ * to the end (k_chol); 0 = level-synchronous for every leaf; 1 = one CTA per leaf for every leaf.  Same L to rounding; the default's
+ * choice depends on the leaf alone, so a leaf's factor does not depend on what else is fitted with it. */
 /* PMK_OPT_GRAM_FAST_EXP: pmk_gram / pmk_cross_gram with the squared exponential evaluated as exp(-eps_sq |x - z|^2) by the
  * table-driven exp of the fit and query kernels instead of the reference's sqrt, re-square and libm exp (kernel.jl:277-287,
  * 350-357): 0 (default) = the reference's operation order (entries within 5e-15 of the oracle), 1 = fast: the exp within

@@ -171,7 +171,7 @@ struct pmk_handle {
   double cond_est = 0.0;
   int alpha_refine = -1;    // PMK_OPT_ALPHA_REFINE: -1 auto (flagged models), 0 never, 1 always
   int gram_fast_exp = 0;    // PMK_OPT_GRAM_FAST_EXP: table-driven exp in the standalone Gram kernel (squared exponential; <= 2 ulp)
-  int chol_variant = 1;     // PMK_OPT_CHOL_VARIANT: 1 = one CTA per leaf (default: faster on C3 / C4), 0 = level-synchronous kernels
+  int chol_variant = -1;    // PMK_OPT_CHOL_VARIANT: -1 = by leaf size (default), 0 = level-synchronous kernels, 1 = one CTA per leaf
   // organizetrainingsets on the device (results of the last call)
   DBuf o_X, o_counts, o_off, o_pl, o_pp, o_sl, o_sp, o_lcount, o_lstart;
   int64_t o_N = 0, o_total = 0, o_leaves = 0;
@@ -299,7 +299,7 @@ int pmk_create(pmk_handle** out, int device) {
   pmk_handle* h = new (std::nothrow) pmk_handle();
   if (!h) return fail(nullptr, PMK_ERR_CUDA, "out of host memory");
   h->device = device;
-  if (const char* ev = getenv("PMK_CHOL_VARIANT")) h->chol_variant = atoi(ev) == 0 ? 0 : 1;      // A/B timing of the two factorisations
+  if (const char* ev = getenv("PMK_CHOL_VARIANT")) h->chol_variant = std::max(-1, std::min(1, atoi(ev)));      // A/B timing of the two factorisations
   e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (e != cudaSuccess) {
     delete h;
@@ -376,7 +376,7 @@ int pmk_set_option(pmk_handle* h, int option, int64_t value) {
       h->gram_fast_exp = value != 0;
       return PMK_OK;
     case PMK_OPT_CHOL_VARIANT:
-      if (value != 0 && value != 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_CHOL_VARIANT: 0 (level-synchronous) or 1 (one CTA per leaf)");
+      if (value < -1 || value > 1) return fail(h, PMK_ERR_ARG, "PMK_OPT_CHOL_VARIANT: -1 (by leaf size), 0 (level-synchronous) or 1 (one CTA per leaf)");
       h->chol_variant = (int)value;
       return PMK_OK;
     case PMK_OPT_ALPHA_REFINE:
@@ -736,17 +736,25 @@ static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_
     launch_gram_tiles(D, lt, h->d_order.as<int>(), n_order, max_npad, kp, sigma2, h->stream);
   }
   KCHECK(h, "k_gram_tiles");
-  const bool levels = h->chol_variant == 0;
   {
     Timer t(h, PMK_T_FIT_CHOL);
-    if (levels) {
-      // leaves of `order` (largest first) that still have a J-th 32-column panel: a prefix
+    // `order` is sorted by size: the leaves of n_pad >= kCholLevelsMinNpad are a prefix.  They advance panel by panel through the
+    // level-synchronous kernels; the smaller ones take the one-CTA-per-leaf kernel.  The choice is a property of the leaf, so a
+    // leaf's factor has the same bits whatever else is in the batch (pmk_multi: any rank count).
+    int n_levels = 0;
+    if (h->chol_variant == 0) n_levels = n_order;
+    else if (h->chol_variant < 0)
+      while (n_levels < n_order && h->h_npad[order[n_levels]] >= kCholLevelsMinNpad) ++n_levels;
+    if (n_levels > 0) {
+      // leaves of the prefix that still have a J-th 32-column panel: again a prefix
       std::vector<int> per_panel(max_npad / 32, 0);
-      for (int k = 0; k < n_order; ++k)
+      for (int k = 0; k < n_levels; ++k)
         for (int J = 0; J < h->h_npad[order[k]] / 32; ++J) ++per_panel[J];
       h->launches += launch_chol_levels(lt, h->d_order.as<int>(), per_panel, max_npad, 1, h->stream) - 1;
-    } else {
-      launch_chol(lt, h->d_order.as<int>(), n_order, h->stream);
+    }
+    if (n_levels < n_order) {
+      launch_chol(lt, h->d_order.as<int>() + n_levels, n_order - n_levels, h->stream);
+      if (n_levels > 0) ++h->launches;
     }
   }
   KCHECK(h, "k_chol");

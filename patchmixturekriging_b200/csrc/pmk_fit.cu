@@ -11,6 +11,7 @@
 //             L[J+1:, J] = C * inv(L_JJ)^T on DMMA, straight from the accumulators, stored once in packed-tile form.
 // Several CTAs are resident per SM so that one leaf's serial diagonal-block phase overlaps the
 // other leaves' DMMA phases.
+#include <algorithm>
 #include <cstdlib>
 #include <vector>
 #include "pmk_internal.cuh"
@@ -641,147 +642,165 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// K2, level-synchronous form (the default; PMK_CHOL_VARIANT=1 selects the one-CTA-per-leaf kernel above).
-//
-// What the cycle counters of k_chol showed (tools/chol_phases.py, C3): warp 0 spends 605 k of a leaf's 2.17 M cycles in
-// factor_block32 -- 38 k cycles per 32x32 block, eight times what the routine takes alone -- because its ~1500 scalar FP64
-// instructions queue behind the DMMAs of the 23 other warps of the SM on the one FP64 pipe.  The per-panel chain
-// "diagonal block -> factor -> panel solve" is serial per leaf, so every leaf carries 16 x 43 k cycles the other leaves can only
-// partly cover.  Here the two kinds of work never share an SM at the same time: all leaves advance panel by panel,
-//     k_chol_diag (J)  : D = K_JJ - L[J,0:J] L[J,0:J]^T (DMMA, four warps), then Cholesky + inverse of D by one warp -- every
-//                        CTA of the grid is in the same phase, so the scalar chain runs next to other scalar chains;
-//                        the forward solve z_J = inv(L_JJ) (y_J - L[J,0:J] z[0:J]) of alpha rides on the same operand tiles;
-//     k_chol_panel (J) : L[t, J] = (K[t,J] - L[t,0:J] L[J,0:J]^T) inv(L_JJ)^T for the row tiles below, one warp per pair of
-//                        row tiles, no flag, no barrier, no atomics: pure DMMA work at full occupancy.
-// 2 x (n_pad_max / 32) launches per fit; kernels of one panel are as long as the panel's share of the n^3/3 flops.
-template <int NW>
-__global__ void __launch_bounds__(NW * 32)
-k_chol_diag(LeafTable lt, const int* __restrict__ order, int J, int with_z) {
-  static_assert(NW == 4, "one warp per row tile of the 32x32 diagonal block");
-  __shared__ double Dbuf[32 * LDD];
-  __shared__ double Ibuf[32 * LD];
-  __shared__ double rbuf[32];
-  extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
-  const int p = order[blockIdx.x];
-  const int ntl = lt.npad[p] >> 3;
-  const int t0 = 4 * J;
-  if (t0 >= ntl || lt.info[p] != 0) return;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, l = lane & 3;
-  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
-  double2* Ip = reinterpret_cast<double2*>(lt.Linv + lt.ioff[p]);
-  const double2* ring = reinterpret_cast<const double2*>(pmk_chol_smem) + (size_t)warp * (kCholDepth * 32) + lane;
-  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
-  const int64_t xo = lt.xoff[p];
-  {
-    int bo[4], ao[1];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
-    ao[0] = (int)tri(t0 + warp) * 32 + lane;
-    double acc[1][4][2];
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const double2 kt = (b <= warp) ? ld_once(Lp + ao[0] + (t0 + b) * 32) : make_double2(0.0, 0.0);
-      acc[0][b][0] = -kt.x;
-      acc[0][b][1] = -kt.y;
-    }
-    double zacc[1] = {0.0};
-    if (with_z) chol_kloop<1, 1, true>(acc, Lp, bo, ao, t0, ring_u32, ring, lt.alpha + xo, zacc);
-    else chol_kloop<1, 1, false>(acc, Lp, bo, ao, t0, ring_u32, ring);
-#pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 0] = -acc[0][b][0];
-      Dbuf[(8 * warp + g) * LDD + 8 * b + 2 * l + 1] = -acc[0][b][1];
-    }
-    if (with_z) {
-      double zs = zacc[0];
-      zs += __shfl_xor_sync(kFull, zs, 1);
-      zs += __shfl_xor_sync(kFull, zs, 2);
-      if (l == 0) rbuf[8 * warp + g] = lt.y[xo + 32 * J + 8 * warp + g] - zs;      // y_J - L[J, 0:J] z[0:J]
-    }
-  }
-  __syncthreads();
-  if (warp != 0) return;
-  const int info = factor_block32(Dbuf, Ibuf, lane);
-  if (info != 0) {
-    if (lane == 0) lt.info[p] = 32 * J + info;
-    return;
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    for (int b = 0; b <= a; ++b) {
-      const int rd = (8 * a + g) * LDD + 8 * b + l;
-      const int ri = (8 * a + g) * LD + 8 * b + l;
-      Lp[(tri(t0 + a) + t0 + b) * 32 + lane] = make_double2(Dbuf[rd], Dbuf[rd + 4]);
-      Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane] = make_double2(Ibuf[ri], Ibuf[ri + 4]);
-    }
-  }
-  if (with_z) {          // z_J = inv(L_JJ) r  (lower triangular: row `lane` uses r[0 .. lane])
-    double zz = 0.0;
-    for (int k = 0; k <= lane; ++k) zz = fma(Ibuf[lane * LD + k], rbuf[k], zz);
-    lt.alpha[xo + 32 * J + lane] = zz;
-  }
+// K2, level-synchronous form (leaves of n_pad >= kCholLevelsMinNpad; the one-CTA-per-leaf kernel above serves the smaller ones).
+// All leaves advance panel by panel; two kinds of launches alternate, and the two kinds of work never share an SM:
+//     k_chol_factor (J)    : one warp per leaf, nothing but the serial chain -- Cholesky + explicit inverse of the 32x32 diagonal
+//                            block D_JJ, then z_J = inv(L_JJ) (y_J - S_J) (the forward half of the solve for alpha);
+//     k_chol_panel_tma (J) : L[t, J] = (K[t,J] - L[t,0:J] L[J,0:J]^T) inv(L_JJ)^T for the row tiles below, pure DMMA work, plus
+//                            the RIGHT-LOOKING extras that leave k_chol_factor nothing to accumulate: the two warps that own a
+//                            32-row block I subtract L[I,J] L[I,J]^T from the block's diagonal slots (still holding K_II minus
+//                            the earlier panels, C-fragment-major as k_gram_tiles wrote them) and add L[I,J] z_J to S_I (in lt.alpha).
+// k_chol_panel_tma runs the loop of the pair kernel -- operands in SHARED memory, moved by TMA:
+// one CTA = NW compute warps + one producer warp, all on one (leaf, panel J): warp w owns row tiles tb0 + 2w, + 1.
+//  * B operand = the panel's row block L[J, 0:4J): the producer stages it in K-chunks of KC column tiles (4 rows x KC x 512 B) with
+//    1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a two-deep ring; the compute warps walk the chunks in lock step (they all
+//    have the same loop length) and hand a buffer back through an mbarrier.  Every panel-row tile crosses L2 -> SM once per
+//    CTA instead of once per warp (and half of those through an L1 miss).
+//  * A operand = the warp's own rows, contiguous in the packed layout, streamed by its lane 0 through a private ring of bulk copies
+//    (CW column tiles x R rows per slot); the raw K block of the panel follows the finished columns in the same row, so the last
+//    chunk of the stream delivers it and C = K - sum is formed at the end: nothing is loaded in front of the loop.
+//  * inner loop per column tile: 4 + 2 LDS.128, 16 DMMA; epilogue = the panel solve with inv(L_JJ) read as packed tiles (one LDS.128
+//    per 8x8 block of the inverse).
+// Measured (profiles/chol_r02_notes.md): CTA shape 4 + 1 warps x 4 per SM beats 8 + 1 x 2 (C3 10.33 vs 11.17 ms, C4 123.6 vs 127.5 ms);
+// a persistent form of the same kernel (items dealt to resident CTAs, operand streams running across item boundaries) was slower
+// (11.0 / 133 ms) and is not kept.  One-CTA-per-leaf kernel: C3 10.33, C4 144.6 ms.
+__device__ __forceinline__ void f_mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
 }
-
-template <int NW, int R>
-__global__ void __launch_bounds__(NW * 32, PMK_CHOL_MINB)
-k_chol_panel(LeafTable lt, const int* __restrict__ order, int J) {
-  __shared__ double Ibuf[32 * LD];
-  extern __shared__ __align__(16) unsigned char pmk_chol_smem[];
+#ifndef PMK_PAN_NW
+#define PMK_PAN_NW 4        // compute warps per CTA (two row tiles each)
+#endif
+#ifndef PMK_PAN_KC
+#define PMK_PAN_KC 4
+#endif
+#ifndef PMK_PAN_MINB
+#define PMK_PAN_MINB 4      // resident CTAs per SM the register allocation targets
+#endif
+static constexpr int kPanKC = PMK_PAN_KC;      // column tiles per staged chunk of the panel rows
+static constexpr int kPanCW = 4;      // column tiles per chunk of a warp's own rows
+static constexpr int kPanDepth = 2;   // slots of a warp's own-row ring
+template <int NW>
+__global__ void __launch_bounds__((NW + 1) * 32, PMK_PAN_MINB)
+k_chol_panel_tma(LeafTable lt, const int* __restrict__ order, int J) {
+  constexpr int R = 2;
+  extern __shared__ __align__(128) unsigned char pmk_chol_smem[];
+  __shared__ __align__(8) uint64_t bfull[2], bempty[2], ifull, afull[NW * kPanDepth];
   const int p = order[blockIdx.y];
   const int ntl = lt.npad[p] >> 3;
   const int t0 = 4 * J;
-  const int tb0 = t0 + 4 + blockIdx.x * (NW * R);           // first row tile of this CTA's NW units
+  const int tb0 = t0 + 4 + blockIdx.x * (NW * R);
   if (tb0 >= ntl || lt.info[p] != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int g = lane >> 2, l = lane & 3;
-  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
-  {   // inv(L_JJ): the block's 10 packed tiles -> dense rows in shared memory (the panel solve's B operand)
-    const double* __restrict__ Ib = lt.Linv + lt.ioff[p] + (size_t)J * kInvDoublesPerBlock;
-    for (int e = threadIdx.x; e < 32 * 32; e += NW * 32) {
-      const int i = e >> 5, k = e & 31;
-      double v = 0.0;
-      if (k <= i) {
-        const int a = i >> 3, b = k >> 3;
-        v = Ib[((a * (a + 1) / 2 + b) * 32 + (i & 7) * 4 + (k & 3)) * 2 + ((k & 7) >> 2)];
-      }
-      Ibuf[i * LD + k] = v;
+  const int n_active = min(NW, (ntl - tb0 + R - 1) / R);
+  unsigned char* Bbuf = pmk_chol_smem;                                            // [2][4][kPanKC][512]
+  unsigned char* Ibuf = Bbuf + 2 * 4 * kPanKC * 512;                              // [10][512] packed inverse block
+  unsigned char* Aring = Ibuf + kInvTilesPerBlock * 512;                          // [NW][kPanDepth][R][kPanCW][512]
+  if (threadIdx.x == 0) {
+    for (int k = 0; k < 2; ++k) {
+      f_mbar_init(&bfull[k], 1);
+      f_mbar_init(&bempty[k], n_active);
     }
+    f_mbar_init(&ifull, 1);
+    for (int k = 0; k < NW * kPanDepth; ++k) f_mbar_init(&afull[k], 1);
   }
   __syncthreads();
+  const char* Lbytes = reinterpret_cast<const char*>(lt.L + lt.loff[p]);
+  const int nchunks = (t0 + kPanKC - 1) / kPanKC;
+  if (warp == NW) {
+    // ---- producer: inverse block, then the panel rows chunk by chunk
+    if (lane == 0) {
+      f_mbar_expect_tx(&ifull, kInvTilesPerBlock * 512);
+      f_bulk_g2s(Ibuf, reinterpret_cast<const char*>(lt.Linv + lt.ioff[p]) + (size_t)J * (kInvTilesPerBlock * 512), kInvTilesPerBlock * 512, &ifull);
+      for (int kc = 0; kc < nchunks; ++kc) {
+        const int buf = kc & 1;
+        if (kc >= 2) f_mbar_wait(&bempty[buf], (uint32_t)(((kc >> 1) - 1) & 1));
+        const int width = min(kPanKC, t0 - kc * kPanKC);
+        f_mbar_expect_tx(&bfull[buf], (uint32_t)(4 * width * 512));
+#pragma unroll
+        for (int b = 0; b < 4; ++b)
+          f_bulk_g2s(Bbuf + (size_t)((buf * 4 + b) * kPanKC) * 512, Lbytes + (tri(t0 + b) + (size_t)kc * kPanKC) * 512, (uint32_t)(width * 512), &bfull[buf]);
+      }
+    }
+    return;
+  }
+  if (warp >= n_active) return;
+  const int g = lane >> 2, l = lane & 3;
   const int tb = tb0 + warp * R;
-  if (tb >= ntl) return;
-  const double2* ring = reinterpret_cast<const double2*>(pmk_chol_smem) + (size_t)warp * (kCholDepth * R * 32) + lane;
-  const uint32_t ring_u32 = (uint32_t)__cvta_generic_to_shared(ring);
-  const int src_lo = (lane & ~3) | (l >> 1);
-  const int src_hi = (lane & ~3) | (2 + (l >> 1));
-  int bo[4], ao[R];
-#pragma unroll
-  for (int b = 0; b < 4; ++b) bo[b] = (int)tri(t0 + b) * 32 + lane;
+  const int nv = (tb + 1 < ntl) ? 2 : 1;
+  const int n_a = J + 1;                                  // chunks of the own-row stream: J of finished columns + the K block
+  unsigned char* myring = Aring + (size_t)warp * (kPanDepth * R * kPanCW * 512);
+  uint64_t* myfull = &afull[warp * kPanDepth];
+  auto issue_a = [&](int a) {                             // lane 0: chunk a of both rows into slot a % depth
+    const int slot = a % kPanDepth;
+    f_mbar_expect_tx(&myfull[slot], (uint32_t)(nv * kPanCW * 512));
+    for (int r = 0; r < nv; ++r)
+      f_bulk_g2s(myring + (size_t)((slot * R + r) * kPanCW) * 512, Lbytes + (tri(tb + r) + (size_t)a * kPanCW) * 512, kPanCW * 512, &myfull[slot]);
+  };
+  if (lane == 0)
+    for (int a = 0; a < kPanDepth && a < n_a; ++a) issue_a(a);
   double acc[R][4][2];
-  int nv = 0;
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-    const bool tv = tb + r < ntl;
-    nv += tv ? 1 : 0;
-    ao[r] = (int)tri(tv ? tb + r : tb) * 32 + lane;
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) {
-      const double2 kt = tv ? ld_once(Lp + ao[r] + (t0 + b) * 32) : make_double2(0.0, 0.0);
-      acc[r][b][0] = -kt.x;
-      acc[r][b][1] = -kt.y;
+    for (int b = 0; b < 4; ++b) acc[r][b][0] = acc[r][b][1] = 0.0;
+  const double2* Bl = reinterpret_cast<const double2*>(Bbuf) + lane;
+  const double2* Al = reinterpret_cast<const double2*>(myring) + lane;
+  for (int a = 0; a < J; ++a) {
+    const int kc = a / (kPanKC / kPanCW), buf = kc & 1;
+    if (a % (kPanKC / kPanCW) == 0) f_mbar_wait(&bfull[buf], (uint32_t)((kc >> 1) & 1));
+    const int slot = a % kPanDepth;
+    f_mbar_wait(&myfull[slot], (uint32_t)((a / kPanDepth) & 1));
+    const int cb0 = (a % (kPanKC / kPanCW)) * kPanCW;     // position of this chunk's first column tile inside the B chunk
+#pragma unroll
+    for (int cc = 0; cc < kPanCW; ++cc) {
+      double2 bf[4], af[R];
+#pragma unroll
+      for (int b = 0; b < 4; ++b) bf[b] = Bl[((buf * 4 + b) * kPanKC + cb0 + cc) * 32];
+#pragma unroll
+      for (int r = 0; r < R; ++r) af[r] = Al[((slot * R + r) * kPanCW + cc) * 32];
+      PMK_UNIFORM_IF(nv == 2) {
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma884(acc[1][b][0], acc[1][b][1], af[1].x, bf[b].x);
+#pragma unroll
+        for (int b = 0; b < 4; ++b) dmma884(acc[1][b][0], acc[1][b][1], af[1].y, bf[b].y);
+      }
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dmma884(acc[0][b][0], acc[0][b][1], af[0].x, bf[b].x);
+#pragma unroll
+      for (int b = 0; b < 4; ++b) dmma884(acc[0][b][0], acc[0][b][1], af[0].y, bf[b].y);
+    }
+    __syncwarp();                                         // every lane has read the slot (and this part of the B chunk)
+    if (lane == 0) {
+      if (a + kPanDepth < n_a) issue_a(a + kPanDepth);
+      if (a % (kPanKC / kPanCW) == kPanKC / kPanCW - 1 || a == J - 1) f_mbar_arrive(&bempty[buf]);
     }
   }
-  if (nv == R) chol_kloop<R, R>(acc, Lp, bo, ao, t0, ring_u32, ring);
-  else chol_kloop<R, 1>(acc, Lp, bo, ao, t0, ring_u32, ring);
-  // L[t, J] = C inv(L_JJ)^T: C-fragment -> A-fragment inside the quad, 20 DMMAs per row tile, final tiles stored once
+  // ---- the K block (last chunk of the stream): C = K - sum
+  {
+    const int slot = J % kPanDepth;
+    f_mbar_wait(&myfull[slot], (uint32_t)((J / kPanDepth) & 1));
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int b = 0; b < 4; ++b) {
+        const double2 kt = Al[((slot * R + r) * kPanCW + b) * 32];
+        acc[r][b][0] = kt.x - acc[r][b][0];
+        acc[r][b][1] = kt.y - acc[r][b][1];
+      }
+  }
+  // ---- L[t, J] = C inv(L_JJ)^T
+  f_mbar_wait(&ifull, 0);
+  const double2* Il = reinterpret_cast<const double2*>(Ibuf) + lane;
+  const int src_lo = (lane & ~3) | (l >> 1);
+  const int src_hi = (lane & ~3) | (2 + (l >> 1));
+  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
 #pragma unroll
   for (int r = 0; r < R; ++r) {
     if (r < nv) {
       double alo[4], ahi[4];
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
-        const double c0 = -acc[r][kb][0], c1 = -acc[r][kb][1];
+        const double c0 = acc[r][kb][0], c1 = acc[r][kb][1];
         const double v0 = __shfl_sync(kFull, c0, src_lo);
         const double v1 = __shfl_sync(kFull, c1, src_lo);
         const double w0 = __shfl_sync(kFull, c0, src_hi);
@@ -796,18 +815,117 @@ k_chol_panel(LeafTable lt, const int* __restrict__ order, int J) {
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
 #pragma unroll
-        for (int cb = kb; cb < 4; ++cb) dmma884(o0[cb], o1[cb], alo[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + l]);
-#pragma unroll
-        for (int cb = kb; cb < 4; ++cb) dmma884(p0[cb], p1[cb], ahi[kb], Ibuf[(8 * cb + g) * LD + 8 * kb + 4 + l]);
+        for (int cb = kb; cb < 4; ++cb) {
+          const double2 iv = Il[(cb * (cb + 1) / 2 + kb) * 32];      // {inv[8cb+g][8kb+l], inv[8cb+g][8kb+4+l]}
+          dmma884(o0[cb], o1[cb], alo[kb], iv.x);
+          dmma884(p0[cb], p1[cb], ahi[kb], iv.y);
+        }
       }
+      double zpart = 0.0;
+      double* stile_row = reinterpret_cast<double*>(myring) + (size_t)r * (kPanCW * 64);     // slot 0 of the own ring, [r][cb][64]
 #pragma unroll
       for (int cb = 0; cb < 4; ++cb) {
         double* tile = tile_row + cb * 64;
         const int q0 = 2 * l, q1 = 2 * l + 1;
-        tile[(g * 4 + (q0 & 3)) * 2 + (q0 >> 2)] = o0[cb] + p0[cb];
-        tile[(g * 4 + (q1 & 3)) * 2 + (q1 >> 2)] = o1[cb] + p1[cb];
+        const int i0 = (g * 4 + (q0 & 3)) * 2 + (q0 >> 2), i1 = (g * 4 + (q1 & 3)) * 2 + (q1 >> 2);
+        const double f0 = o0[cb] + p0[cb], f1 = o1[cb] + p1[cb];
+        tile[i0] = f0;
+        tile[i1] = f1;
+        {
+          stile_row[cb * 64 + i0] = f0;
+          stile_row[cb * 64 + i1] = f1;
+          const double2 zj = *reinterpret_cast<const double2*>(lt.alpha + lt.xoff[p] + 32 * J + 8 * cb + 2 * l);
+          zpart = fma(f1, zj.y, fma(f0, zj.x, zpart));
+        }
+      }
+      {       // S_I += L[I, J] z_J for the rows of this tile (only this warp touches them in this launch)
+        zpart += __shfl_xor_sync(kFull, zpart, 1);
+        zpart += __shfl_xor_sync(kFull, zpart, 2);
+        if (l == 0) lt.alpha[lt.xoff[p] + 8 * (tb + r) + g] += zpart;
       }
     }
+  }
+  {
+    // D_II -= L[I,J] L[I,J]^T: the pair of warps (2i, 2i+1) owns the four row tiles of block I = (tb0 >> 2) + i; n_pad is a multiple
+    // of 32, so a pair is complete or absent.  Five of the ten lower tiles each.
+    switch (warp >> 1) {                                    // literal barrier ids: a register operand makes ptxas reserve all 16
+      case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
+      case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
+      case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
+      default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+    }
+    const int I4 = tb & ~3;                                 // first row tile of the block
+    const unsigned char* pair_ring = Aring + (size_t)(warp & ~1) * (kPanDepth * R * kPanCW * 512);
+    auto xt = [&](int a, int c) {                           // final tile (row tile a of the block, column tile c of the panel), packed
+      return reinterpret_cast<const double2*>(pair_ring + (size_t)(a >> 1) * (kPanDepth * R * kPanCW * 512) + (size_t)(((a & 1) * kPanCW + c) * 512))[lane];
+    };
+    const int h = warp & 1;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+      // h = 0: (0,0) (1,0) (1,1) (2,0) (3,0);  h = 1: (2,1) (2,2) (3,1) (3,2) (3,3)
+      const int a = h ? (k < 2 ? 2 : 3) : (k == 0 ? 0 : (k < 3 ? 1 : k - 1));
+      const int b = h ? (k < 2 ? k + 1 : k - 1) : (k == 2 ? 1 : 0);
+      double o0 = 0.0, o1 = 0.0, p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const double2 af = xt(a, c), bf = xt(b, c);
+        dmma884(o0, o1, af.x, bf.x);
+        dmma884(p0, p1, af.y, bf.y);
+      }
+      double2* slot = Lp + (tri(I4 + a) + I4 + b) * 32 + lane;
+      double2 d = __ldcg(slot);
+      d.x -= o0 + p0;
+      d.y -= o1 + p1;
+      *slot = d;
+    }
+  }
+}
+
+// The diagonal block of panel J, ready to be factored: one warp per leaf, many leaves per SM, nothing but the serial
+// chain -- Cholesky + inverse of the 32x32 block, then z_J = inv(L_JJ) (y_J - S_J) with S_J the partial sums the panel kernels left
+// in lt.alpha.
+__global__ void __launch_bounds__(32)
+k_chol_factor(LeafTable lt, const int* __restrict__ order, int J, int with_z) {
+  __shared__ double Dbuf[32 * LDD];
+  __shared__ double Ibuf[32 * LD];
+  const int p = order[blockIdx.x];
+  const int ntl = lt.npad[p] >> 3;
+  const int t0 = 4 * J;
+  if (t0 >= ntl || lt.info[p] != 0) return;
+  const int lane = threadIdx.x;
+  const int g = lane >> 2, l = lane & 3;
+  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
+  double2* Ip = reinterpret_cast<double2*>(lt.Linv + lt.ioff[p]);
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      const double2 d = ld_once(Lp + (tri(t0 + a) + t0 + b) * 32 + lane);      // C-fragment-major: {M[g][2l], M[g][2l+1]}
+      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l] = d.x;
+      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l + 1] = d.y;
+    }
+  __syncwarp();
+  const int info = factor_block32(Dbuf, Ibuf, lane);
+  if (info != 0) {
+    if (lane == 0) lt.info[p] = 32 * J + info;
+    return;
+  }
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    for (int b = 0; b <= a; ++b) {
+      const int rd = (8 * a + g) * LDD + 8 * b + l;
+      const int ri = (8 * a + g) * LD + 8 * b + l;
+      Lp[(tri(t0 + a) + t0 + b) * 32 + lane] = make_double2(Dbuf[rd], Dbuf[rd + 4]);
+      Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane] = make_double2(Ibuf[ri], Ibuf[ri + 4]);
+    }
+  }
+  if (with_z) {
+    const int64_t xo = lt.xoff[p];
+    const double rl = lt.y[xo + 32 * J + lane] - lt.alpha[xo + 32 * J + lane];
+    double zz = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) zz = fma(Ibuf[lane * LD + k], __shfl_sync(kFull, rl, k), zz);      // the inverse's upper part is zero
+    lt.alpha[xo + 32 * J + lane] = zz;
   }
 }
 
@@ -1112,23 +1230,30 @@ void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_
 }
 
 // Level-synchronous factorisation: leaves sorted by size (order), leaves_per_panel[J] = how many of them have a J-th 32-column
-// panel (a prefix of `order`).  Returns the number of launches.  with_z: k_chol_diag also forms z = L^-1 y in lt.alpha.
+// panel (a prefix of `order`).  Returns the number of launches.  with_z: k_chol_factor also forms z = L^-1 y in lt.alpha.
 int launch_chol_levels(const LeafTable& lt, const int* d_order, const std::vector<int>& leaves_per_panel, int max_npad, int with_z,
                        cudaStream_t s) {
-  constexpr int NW = PMK_CHOL_NW, R = 2;
-  const size_t dyn_panel = (size_t)NW * kCholDepth * R * 32 * sizeof(double2);
-  const size_t dyn_diag = (size_t)4 * kCholDepth * 32 * sizeof(double2);
+  constexpr int PW = PMK_PAN_NW;
+  constexpr size_t dyn_tma = (size_t)2 * 4 * kPanKC * 512 + kInvTilesPerBlock * 512 + (size_t)PW * kPanDepth * 2 * kPanCW * 512;
+  static DeviceOnce once;
+  once.run([&] { cudaFuncSetAttribute(k_chol_panel_tma<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tma); });
   int launches = 0;
   const int max_ntl = max_npad / 8;
-  for (int J = 0; J < (int)leaves_per_panel.size(); ++J) {
+  const int nJ = (int)leaves_per_panel.size();
+  if (nJ == 0 || leaves_per_panel[0] <= 0) return 0;
+  k_chol_factor<<<leaves_per_panel[0], 32, 0, s>>>(lt, d_order, 0, with_z);
+  ++launches;
+  for (int J = 0; J < nJ; ++J) {
     const int cnt = leaves_per_panel[J];
     if (cnt <= 0) break;
-    k_chol_diag<4><<<cnt, 128, dyn_diag, s>>>(lt, d_order, J, with_z);
-    ++launches;
     const int rows_below = max_ntl - 4 * J - 4;
     if (rows_below > 0) {
-      dim3 grid((rows_below + NW * R - 1) / (NW * R), cnt);
-      k_chol_panel<NW, R><<<grid, NW * 32, dyn_panel, s>>>(lt, d_order, J);
+      dim3 grid((rows_below + PW * 2 - 1) / (PW * 2), cnt);
+      k_chol_panel_tma<PW><<<grid, (PW + 1) * 32, dyn_tma, s>>>(lt, d_order, J);
+      ++launches;
+    }
+    if (J + 1 < nJ && leaves_per_panel[J + 1] > 0) {
+      k_chol_factor<<<leaves_per_panel[J + 1], 32, 0, s>>>(lt, d_order, J + 1, with_z);
       ++launches;
     }
   }

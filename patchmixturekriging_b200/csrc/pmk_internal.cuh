@@ -63,6 +63,11 @@ struct PairWork {
   int64_t leaf_base;                // global id (0-based) of local leaf 0
 };
 
+// The fit's batched Cholesky: leaves of at least this many padded rows are factored by the level-synchronous kernels
+// (k_chol_factor / k_chol_panel_tma), smaller ones by the one-CTA-per-leaf kernel (k_chol).  Measured on a B200: 512-point leaves
+// (C3) 10.33 ms either way, 1.70 vs 1.53 ms for one GPU's eighth of them; 1027-point leaves (C4) 123.6 vs 144.6 ms.
+static constexpr int kCholLevelsMinNpad = 768;
+
 // Recursion plan of the explicit inverse P = inv(L) by recursive doubling (pmk_invert.cu): for every shape (number of 32-row
 // blocks) present and every height of the recursion tree, that shape's nodes of that height.
 static constexpr int kInvMaxBlocks = PMK_MAX_LEAF_POINTS / 32;      // 64

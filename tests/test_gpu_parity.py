@@ -429,6 +429,44 @@ def test_large_leaf_size_classes(built_lib, D, n, solver):
     assert_close("var", Vq, var_ref, TOL, rec)
 
 
+def test_cholesky_variants_mixed_batch(built_lib):
+    """PMK_OPT_CHOL_VARIANT: a batch with leaves on both sides of the size threshold (768 padded rows) through the default
+    (by leaf size), the level-synchronous kernels only and the one-CTA-per-leaf kernel only -- every factor against numpy's
+    dpotrf, alpha against a dense solve; and the default's choice depends on the leaf alone: a leaf fitted alone has the
+    bits it has in the batch (what makes pmk_multi independent of the rank count)."""
+    from patchmixturekriging_b200 import synth
+    sizes = [40, 300, 767, 768, 800, 1300, 96, 1025]
+    Xs, ys = [], []
+    for k, n in enumerate(sizes):
+        X = synth.uniform_points(91 + k, n, [-1.0, -1.0], [1.0, 1.0])
+        Xs.append(X)
+        ys.append(np.sin(3 * X[:, 0]) + X[:, 1])
+    spacing = (4.0 / 800) ** 0.5
+    ok, pk = helpers.kernels(("SQEXP", 1.0 / (3.0 * spacing) ** 2))
+    s2 = 1e-3
+    hps = (np.zeros((0, 2)), np.zeros(0))
+    ref = []
+    for X, y in zip(Xs, ys):
+        A = O.constructkernelmatrix(X, ok) + s2 * np.eye(len(X))
+        ref.append((np.linalg.cholesky(A), np.linalg.solve(A, y)))
+    factors = {}
+    for variant in (-1, 0, 1):
+        eta = P.MixtureGPType(Xs, hps)
+        eta.handle.check(_lib.lib().pmk_set_option(eta.handle.raw, _lib.OPT_CHOL_VARIANT, variant))
+        P.fitmixtureGP_(eta, ys, pk, s2)
+        for p, (Lr, ar) in enumerate(ref):
+            L, a = eta.L_set[p], eta.c_set[p]
+            assert np.abs(L - Lr).max() <= 3e-12 * np.abs(Lr).max(), (variant, sizes[p])
+            assert np.abs(a - ar).max() <= 1e-9 * np.abs(ar).max(), (variant, sizes[p])
+            factors[(variant, p)] = (L.copy(), a.copy())
+        eta.close()
+    for p in (2, 3, 5):          # alone, default variant: same bits as inside the batch
+        eta = P.MixtureGPType([Xs[p]], hps)
+        P.fitmixtureGP_(eta, [ys[p]], pk, s2)
+        assert np.array_equal(eta.L_set[0], factors[(-1, p)][0]) and np.array_equal(eta.c_set[0], factors[(-1, p)][1])
+        eta.close()
+
+
 @pytest.mark.parametrize("name,eps", [("mixgp_file", 1.5), ("c3_mini", 0.31), ("c4_mini", 0.35), ("c3_mini", 0.0)])
 def test_organizetrainingsets_device_bit_exact(built_lib, name, eps):
     """ε-overlap training sets on the GPU, bit-exact X_set_inds / regions_list_set."""

@@ -20,9 +20,9 @@ for step in "$@"; do
     bench_c5_n*) n=${step#bench_c5_n}; timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus $n --workload c5 --steps 2 --warmup 1 --no-setup > $out/${tag}_bench_c5_n$n.json 2> $out/${tag}_bench_c5_n$n.err; echo "rc=$?"; tail -c 1500 $out/${tag}_bench_c5_n$n.err; head -c 700 $out/${tag}_bench_c5_n$n.json ;;
     ref_n*)     n=${step#ref_n}; timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29514 bench.py --impl reference --gpus $n --steps 20 --warmup 3 > $out/${tag}_ref_n$n.json 2> $out/${tag}_ref_n$n.err; echo "rc=$?"; tail -c 600 $out/${tag}_ref_n$n.err; head -c 900 $out/${tag}_ref_n$n.json ;;
     tests_failed) timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --timeout 600 -p no:cacheprovider -k "checkpoint or gram_stationary or alpha_refinement or dense_debug" > $out/${tag}_tests_failed.log 2>&1; echo "rc=$?"; tail -15 $out/${tag}_tests_failed.log ;;
-    fit_ab)     for v in 1 0; do echo "PMK_CHOL_VARIANT=$v"; PMK_CHOL_VARIANT=$v timeout 300 python tools/fit_only.py c3 3 2>&1 | tail -2; done; for v in 1 0; do echo "c4 PMK_CHOL_VARIANT=$v"; PMK_CHOL_VARIANT=$v timeout 300 python tools/fit_only.py c4 2 2>&1 | tail -1; done ;;
-    fit_shape)  for v in 0 1; do echo "c3_8th PMK_CHOL_SHAPE=$v"; PMK_CHOL_SHAPE=$v timeout 300 python tools/fit_only.py c3_8th 3 2>&1 | tail -1; done; for v in 0 1; do echo "c3 PMK_CHOL_SHAPE=$v"; PMK_CHOL_SHAPE=$v timeout 300 python tools/fit_only.py c3 3 2>&1 | tail -1; done ;;
-    tests_fit)  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py tests/test_gpu_multi.py -m gpu -q --timeout 600 -p no:cacheprovider -k "fit or leaf_size or positive_definite or large_leaf or golden or multi or ibb1d or checkpoint or alpha" > $out/${tag}_tests_fit.log 2>&1; echo "rc=$?"; tail -15 $out/${tag}_tests_fit.log ;;
+    fit_ab)     for v in -1 0 1; do for w in c3 c4 c3_8th; do echo -n "PMK_CHOL_VARIANT=$v $w: "; PMK_CHOL_VARIANT=$v timeout 200 python tools/fit_only.py $w 3 2>&1 | tail -1; done; done ;;
+    tests_fit_levels) PMK_CHOL_VARIANT=0 timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py tests/test_gpu_multi.py -m gpu -q --timeout 600 -p no:cacheprovider -k "fit or leaf_size or positive_definite or large_leaf or golden or multi or ibb1d or checkpoint or alpha or cholesky" > $out/${tag}_tests_fit_levels.log 2>&1; echo "rc=$?"; tail -15 $out/${tag}_tests_fit_levels.log ;;
+    tests_fit)  timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_golden.py tests/test_gpu_multi.py -m gpu -q --timeout 600 -p no:cacheprovider -k "fit or leaf_size or positive_definite or large_leaf or golden or multi or ibb1d or checkpoint or alpha or cholesky" > $out/${tag}_tests_fit.log 2>&1; echo "rc=$?"; tail -15 $out/${tag}_tests_fit.log ;;
     ref_arm)    timeout 600 python bench.py --impl reference --steps 20 --warmup 3 > $out/${tag}_bench_ref.json 2> $out/${tag}_bench_ref.err; echo "rc=$?"; head -c 800 $out/${tag}_bench_ref.json ;;
     ncu_list)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $out/${tag}_launches.csv python bench.py --steps 1 --warmup 1 --no-cpu-baseline --no-e2e --no-setup > $out/${tag}_ncu_list.log 2>&1; echo "rc=$?" ;;
     ncu_k3)     timeout 1200 ncu --set full --clock-control none --import-source on -k regex:'k_query_rowp' -c 2 -o $out/${tag}_k3 python bench.py --steps 1 --warmup 0 --no-cpu-baseline --no-e2e --no-setup > $out/${tag}_ncu_k3.log 2>&1; echo "rc=$?"; tail -3 $out/${tag}_ncu_k3.log; ncu -i $out/${tag}_k3.ncu-rep --page raw --csv > $out/${tag}_k3_raw.csv 2>/dev/null; ls -la $out/${tag}_k3* ;;
