@@ -279,9 +279,9 @@ int64_t pmk_multi_launch_count(const pmk_multi* m);
  * solves U\y by LU, mixtureGP.jl:106): -1 (default) = for models flagged by the same conditioning estimate, 0 = never,
  * 1 = always.  Set before pmk_fit. */
 /* PMK_OPT_CHOL_VARIANT: the batched Cholesky of the fit: -1 (default) = by leaf size -- leaves of 768 padded rows and more advance
- * panel by panel through the level-synchronous kernels (the serial 32x32 diagonal factorisations in one launch, k_chol_factor, the
- * DMMA panel updates with TMA-staged operands in the next, k_chol_panel_tma), smaller leaves take one CTA per leaf running its panels
- * to the end (k_chol); 0 = level-synchronous for every leaf; 1 = one CTA per leaf for every leaf.  Same L to rounding; the default's
+ * 64-column panel by panel through the level-synchronous kernels (the serial factorisation of the 64x64 diagonal blocks in one
+ * launch, k_chol_factor64, the DMMA panel updates with TMA-staged operands in the next, k_chol_panel64), smaller leaves take one CTA
+ * per leaf running its panels to the end (k_chol); 0 = level-synchronous for every leaf; 1 = one CTA per leaf for every leaf.  Same L to rounding; the default's
  * choice depends on the leaf alone, so a leaf's factor does not depend on what else is fitted with it. */
 /* PMK_OPT_GRAM_FAST_EXP: pmk_gram / pmk_cross_gram with the squared exponential evaluated as exp(-eps_sq |x - z|^2) by the
  * table-driven exp of the fit and query kernels instead of the reference's sqrt, re-square and libm exp (kernel.jl:277-287,

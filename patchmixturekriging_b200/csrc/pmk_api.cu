@@ -746,10 +746,10 @@ static int fit_impl(pmk_handle* h, int D, int64_t n_leaves, const int64_t* leaf_
     else if (h->chol_variant < 0)
       while (n_levels < n_order && h->h_npad[order[n_levels]] >= kCholLevelsMinNpad) ++n_levels;
     if (n_levels > 0) {
-      // leaves of the prefix that still have a J-th 32-column panel: again a prefix
-      std::vector<int> per_panel(max_npad / 32, 0);
+      // leaves of the prefix that still have columns 64 Jp ..: again a prefix
+      std::vector<int> per_panel((max_npad + 63) / 64, 0);
       for (int k = 0; k < n_levels; ++k)
-        for (int J = 0; J < h->h_npad[order[k]] / 32; ++J) ++per_panel[J];
+        for (int Jp = 0; Jp < (h->h_npad[order[k]] + 63) / 64; ++Jp) ++per_panel[Jp];
       h->launches += launch_chol_levels(lt, h->d_order.as<int>(), per_panel, max_npad, 1, h->stream) - 1;
     }
     if (n_levels < n_order) {

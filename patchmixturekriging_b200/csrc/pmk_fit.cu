@@ -643,58 +643,186 @@ k_chol(LeafTable lt, const int* __restrict__ order) {
 
 // ---------------------------------------------------------------------------------------------
 // K2, level-synchronous form (leaves of n_pad >= kCholLevelsMinNpad; the one-CTA-per-leaf kernel above serves the smaller ones).
-// All leaves advance panel by panel; two kinds of launches alternate, and the two kinds of work never share an SM:
-//     k_chol_factor (J)    : one warp per leaf, nothing but the serial chain -- Cholesky + explicit inverse of the 32x32 diagonal
-//                            block D_JJ, then z_J = inv(L_JJ) (y_J - S_J) (the forward half of the solve for alpha);
-//     k_chol_panel_tma (J) : L[t, J] = (K[t,J] - L[t,0:J] L[J,0:J]^T) inv(L_JJ)^T for the row tiles below, pure DMMA work, plus
-//                            the RIGHT-LOOKING extras that leave k_chol_factor nothing to accumulate: the two warps that own a
-//                            32-row block I subtract L[I,J] L[I,J]^T from the block's diagonal slots (still holding K_II minus
-//                            the earlier panels, C-fragment-major as k_gram_tiles wrote them) and add L[I,J] z_J to S_I (in lt.alpha).
-// k_chol_panel_tma runs the loop of the pair kernel -- operands in SHARED memory, moved by TMA:
-// one CTA = NW compute warps + one producer warp, all on one (leaf, panel J): warp w owns row tiles tb0 + 2w, + 1.
-//  * B operand = the panel's row block L[J, 0:4J): the producer stages it in K-chunks of KC column tiles (4 rows x KC x 512 B) with
-//    1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a two-deep ring; the compute warps walk the chunks in lock step (they all
-//    have the same loop length) and hand a buffer back through an mbarrier.  Every panel-row tile crosses L2 -> SM once per
-//    CTA instead of once per warp (and half of those through an L1 miss).
+// All leaves advance panel by panel -- 64 columns at a time -- and two kinds of launches alternate, so that the serial chain of a
+// diagonal block and the DMMA work never share an SM:
+//     k_chol_factor64 (Jp)  : one warp per leaf on the 64x64 diagonal block [D00; D10 D11] the panel kernels have kept up to date:
+//                             L00 = chol(D00), L10 = D10 inv(L00)^T, L11 = chol(D11 - L10 L10^T), both 32x32 inverses, and the two
+//                             blocks of z = L^-1 y (the forward half of the solve for alpha);
+//     k_chol_panel64 (Jp)   : for the row tiles below the block: [C0 C1] = K[t, 64 columns] - L[t, 0:8Jp) L[Jp rows, 0:8Jp)^T with eight
+//                             accumulator tiles per row tile, then X0 = C0 inv(L00)^T, X1 = (C1 - X0 L10^T) inv(L11)^T, stored once as
+//                             final packed tiles; plus the RIGHT-LOOKING extras that leave k_chol_factor64 nothing to accumulate:
+//                             a CTA = one 64-row block I of the leaf, its four warps publish their final tiles in shared memory (over
+//                             the dead operand buffers) and subtract X X^T from the block's 36 diagonal tiles (still holding K_II
+//                             minus the earlier panels, C-fragment-major as k_gram_tiles wrote them), nine tiles per warp, and
+//                             S_I += X z_J goes to lt.alpha.
+// k_chol_panel64 runs the loop of the pair kernel -- operands in SHARED memory, moved by TMA: one CTA = four compute warps + one
+// producer warp, all on one (leaf, 64-row block below panel Jp); warp w owns row tiles tb0 + 2w, + 1.
+//  * B operand = the eight row tiles of the panel's own block, L[Jp rows, 0:8Jp): the producer stages them in chunks of KC column
+//    tiles with 1-D TMA bulk copies (cp.async.bulk -> UBLKCP) into a two-deep ring; the compute warps walk the chunks in lock step
+//    (they all have the same loop length) and hand a buffer back through an mbarrier.
 //  * A operand = the warp's own rows, contiguous in the packed layout, streamed by its lane 0 through a private ring of bulk copies
-//    (CW column tiles x R rows per slot); the raw K block of the panel follows the finished columns in the same row, so the last
-//    chunk of the stream delivers it and C = K - sum is formed at the end: nothing is loaded in front of the loop.
-//  * inner loop per column tile: 4 + 2 LDS.128, 16 DMMA; epilogue = the panel solve with inv(L_JJ) read as packed tiles (one LDS.128
-//    per 8x8 block of the inverse).
-// Measured (profiles/chol_r02_notes.md): CTA shape 4 + 1 warps x 4 per SM beats 8 + 1 x 2 (C3 10.33 vs 11.17 ms, C4 123.6 vs 127.5 ms);
-// a persistent form of the same kernel (items dealt to resident CTAs, operand streams running across item boundaries) was slower
-// (11.0 / 133 ms) and is not kept.  One-CTA-per-leaf kernel: C3 10.33, C4 144.6 ms.
+//    (four column tiles x two rows per slot); the two raw K blocks of the panel follow the finished columns in the same rows, so the
+//    last two chunks of the stream deliver them and C = K - sum is formed at the end: nothing is loaded in front of the loop.
+//  * inner loop per column tile: 2 + 8 LDS.128, 32 DMMA.
+// History and measurements (32-column panels, CTA shapes, a persistent form, what bounds it): profiles/chol_r02_notes.md.
 __device__ __forceinline__ void f_mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(f_smem_u32(bar)) : "memory");
 }
-#ifndef PMK_PAN_NW
-#define PMK_PAN_NW 4        // compute warps per CTA (two row tiles each)
-#endif
-#ifndef PMK_PAN_KC
-#define PMK_PAN_KC 4
-#endif
-#ifndef PMK_PAN_MINB
-#define PMK_PAN_MINB 4      // resident CTAs per SM the register allocation targets
-#endif
-static constexpr int kPanKC = PMK_PAN_KC;      // column tiles per staged chunk of the panel rows
 static constexpr int kPanCW = 4;      // column tiles per chunk of a warp's own rows
 static constexpr int kPanDepth = 2;   // slots of a warp's own-row ring
+#ifndef PMK_P64_KC
+#define PMK_P64_KC 2         // column tiles per staged chunk of the diagonal block's eight row tiles
+#endif
+#ifndef PMK_P64_MINB
+#define PMK_P64_MINB 3
+#endif
+static constexpr int kP64Tiles = 36;     // staged with the inverses: inv(L00) (10 tiles), inv(L11) (10), L10 (16)
+
+__global__ void __launch_bounds__(32)
+k_chol_factor64(LeafTable lt, const int* __restrict__ order, int Jp, int with_z) {
+  __shared__ double Dbuf[32 * LDD];
+  __shared__ double I0[32 * LD];
+  __shared__ double I1[32 * LD];
+  __shared__ double rbuf[32];
+  const int p = order[blockIdx.x];
+  const int ntl = lt.npad[p] >> 3;
+  const int t0 = 8 * Jp;
+  if (t0 >= ntl || lt.info[p] != 0) return;
+  const int lane = threadIdx.x;
+  const int g = lane >> 2, l = lane & 3;
+  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
+  double2* Ip = reinterpret_cast<double2*>(lt.Linv + lt.ioff[p]);
+  const int64_t xo = lt.xoff[p];
+  // a factored block (dense in Dbuf / Ib) -> packed tiles of L and of Linv block J
+  auto write_block = [&](const double* Ib, int tt, int J) {
+#pragma unroll
+    for (int a = 0; a < 4; ++a) {
+      for (int b = 0; b <= a; ++b) {
+        const int rd = (8 * a + g) * LDD + 8 * b + l;
+        const int ri = (8 * a + g) * LD + 8 * b + l;
+        Lp[(tri(tt + a) + tt + b) * 32 + lane] = make_double2(Dbuf[rd], Dbuf[rd + 4]);
+        Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane] = make_double2(Ib[ri], Ib[ri + 4]);
+      }
+    }
+  };
+  // ---- first 32x32 block
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      const double2 d = ld_once(Lp + (tri(t0 + a) + t0 + b) * 32 + lane);      // C-fragment-major: {M[g][2l], M[g][2l+1]}
+      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l] = d.x;
+      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l + 1] = d.y;
+    }
+  __syncwarp();
+  int info = factor_block32(Dbuf, I0, lane);
+  if (info != 0) {
+    if (lane == 0) lt.info[p] = 8 * t0 + info;
+    return;
+  }
+  write_block(I0, t0, 2 * Jp);
+  double z0 = 0.0;
+  if (with_z) {
+    const double rl = lt.y[xo + 8 * t0 + lane] - lt.alpha[xo + 8 * t0 + lane];
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) z0 = fma(I0[lane * LD + k], __shfl_sync(kFull, rl, k), z0);      // the inverse's upper part is zero
+    lt.alpha[xo + 8 * t0 + lane] = z0;
+  }
+  if (t0 + 4 >= ntl) return;
+  // ---- L10 = D10 inv(L00)^T, final tiles stored; S1 += L10 z0
+  const int src_lo = (lane & ~3) | (l >> 1);
+  const int src_hi = (lane & ~3) | (2 + (l >> 1));
+  double2 xa[4][4];
+#pragma unroll
+  for (int a = 0; a < 4; ++a) {
+    double alo[4], ahi[4];
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      const double2 cf = ld_once(Lp + (tri(t0 + 4 + a) + t0 + kb) * 32 + lane);
+      const double v0 = __shfl_sync(kFull, cf.x, src_lo);
+      const double v1 = __shfl_sync(kFull, cf.y, src_lo);
+      const double w0 = __shfl_sync(kFull, cf.x, src_hi);
+      const double w1 = __shfl_sync(kFull, cf.y, src_hi);
+      alo[kb] = (l & 1) ? v1 : v0;
+      ahi[kb] = (l & 1) ? w1 : w0;
+    }
+    double o0[4], o1[4], p0[4], p1[4];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) o0[cb] = o1[cb] = p0[cb] = p1[cb] = 0.0;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+      for (int cb = kb; cb < 4; ++cb) dmma884(o0[cb], o1[cb], alo[kb], I0[(8 * cb + g) * LD + 8 * kb + l]);
+#pragma unroll
+      for (int cb = kb; cb < 4; ++cb) dmma884(p0[cb], p1[cb], ahi[kb], I0[(8 * cb + g) * LD + 8 * kb + 4 + l]);
+    }
+    double zpart = 0.0;
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      const double f0 = o0[cb] + p0[cb], f1 = o1[cb] + p1[cb];       // row g, columns 2l, 2l + 1
+      zpart = fma(f1, __shfl_sync(kFull, z0, 8 * cb + 2 * l + 1), fma(f0, __shfl_sync(kFull, z0, 8 * cb + 2 * l), zpart));
+      const double v0 = __shfl_sync(kFull, f0, src_lo);
+      const double v1 = __shfl_sync(kFull, f1, src_lo);
+      const double w0 = __shfl_sync(kFull, f0, src_hi);
+      const double w1 = __shfl_sync(kFull, f1, src_hi);
+      xa[a][cb] = make_double2((l & 1) ? v1 : v0, (l & 1) ? w1 : w0);
+      Lp[(tri(t0 + 4 + a) + t0 + cb) * 32 + lane] = xa[a][cb];
+    }
+    zpart += __shfl_xor_sync(kFull, zpart, 1);
+    zpart += __shfl_xor_sync(kFull, zpart, 2);
+    if (l == 0) rbuf[8 * a + g] = zpart;
+  }
+  // ---- second block: D11 - L10 L10^T
+#pragma unroll
+  for (int a = 0; a < 4; ++a)
+#pragma unroll
+    for (int b = 0; b <= a; ++b) {
+      const double2 d = ld_once(Lp + (tri(t0 + 4 + a) + t0 + 4 + b) * 32 + lane);
+      double o0 = 0.0, o1 = 0.0, p0 = 0.0, p1 = 0.0;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        dmma884(o0, o1, xa[a][c].x, xa[b][c].x);
+        dmma884(p0, p1, xa[a][c].y, xa[b][c].y);
+      }
+      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l] = d.x - (o0 + p0);
+      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l + 1] = d.y - (o1 + p1);
+    }
+  __syncwarp();
+  info = factor_block32(Dbuf, I1, lane);
+  if (info != 0) {
+    if (lane == 0) lt.info[p] = 8 * t0 + 32 + info;
+    return;
+  }
+  write_block(I1, t0 + 4, 2 * Jp + 1);
+  if (with_z) {
+    const double rl = lt.y[xo + 8 * t0 + 32 + lane] - lt.alpha[xo + 8 * t0 + 32 + lane] - rbuf[lane];
+    double z1 = 0.0;
+#pragma unroll 8
+    for (int k = 0; k < 32; ++k) z1 = fma(I1[lane * LD + k], __shfl_sync(kFull, rl, k), z1);
+    lt.alpha[xo + 8 * t0 + 32 + lane] = z1;
+  }
+}
+
 template <int NW>
-__global__ void __launch_bounds__((NW + 1) * 32, PMK_PAN_MINB)
-k_chol_panel_tma(LeafTable lt, const int* __restrict__ order, int J) {
-  constexpr int R = 2;
+__global__ void __launch_bounds__((NW + 1) * 32, PMK_P64_MINB)
+k_chol_panel64(LeafTable lt, const int* __restrict__ order, int Jp) {
+  constexpr int R = 2, CW = 4, KC = PMK_P64_KC;
+  static_assert(NW == 4, "one CTA = one 64-row block = four warps of two row tiles");
+  static_assert(CW % KC == 0, "a B chunk never straddles two A chunks");
+  constexpr int kRing = kPanDepth * R * CW * 512;
+  static_assert(2 * 8 * KC * 512 + NW * kRing >= 8 * 8 * 512, "the staged final tiles reuse the operand buffers");
   extern __shared__ __align__(128) unsigned char pmk_chol_smem[];
   __shared__ __align__(8) uint64_t bfull[2], bempty[2], ifull, afull[NW * kPanDepth];
   const int p = order[blockIdx.y];
   const int ntl = lt.npad[p] >> 3;
-  const int t0 = 4 * J;
-  const int tb0 = t0 + 4 + blockIdx.x * (NW * R);
+  const int t0 = 8 * Jp;
+  const int tb0 = t0 + 8 + blockIdx.x * (NW * R);
   if (tb0 >= ntl || lt.info[p] != 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_active = min(NW, (ntl - tb0 + R - 1) / R);
-  unsigned char* Bbuf = pmk_chol_smem;                                            // [2][4][kPanKC][512]
-  unsigned char* Ibuf = Bbuf + 2 * 4 * kPanKC * 512;                              // [10][512] packed inverse block
-  unsigned char* Aring = Ibuf + kInvTilesPerBlock * 512;                          // [NW][kPanDepth][R][kPanCW][512]
+  const int n_active = min(NW, (ntl - tb0) >> 1);          // 4, or 2 for a half block at the end of the leaf
+  unsigned char* Bbuf = pmk_chol_smem;                      // [2][8][KC][512]
+  unsigned char* Aring = Bbuf + 2 * 8 * KC * 512;           // [NW][kPanDepth][R][CW][512]
+  unsigned char* Ibuf = Aring + NW * kRing;                 // [36][512]: inv(L00), inv(L11), L10
   if (threadIdx.x == 0) {
     for (int k = 0; k < 2; ++k) {
       f_mbar_init(&bfull[k], 1);
@@ -705,20 +833,30 @@ k_chol_panel_tma(LeafTable lt, const int* __restrict__ order, int J) {
   }
   __syncthreads();
   const char* Lbytes = reinterpret_cast<const char*>(lt.L + lt.loff[p]);
-  const int nchunks = (t0 + kPanKC - 1) / kPanKC;
+  const int nchunks = t0 / KC;
   if (warp == NW) {
-    // ---- producer: inverse block, then the panel rows chunk by chunk
+    if (lane != 0) {
+      // the block's diagonal tiles (last touched a launch ago) are read-modified-written at the very end: pull them into L2 now
+      const int nrt = n_active * R;
+      for (int a = 0; a < nrt; ++a) {
+        const char* row = Lbytes + (tri(tb0 + a) + (size_t)tb0) * 512;
+        for (int off = (lane - 1) * 128; off < (a + 1) * 512; off += 31 * 128)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(row + off));
+      }
+    }
     if (lane == 0) {
-      f_mbar_expect_tx(&ifull, kInvTilesPerBlock * 512);
-      f_bulk_g2s(Ibuf, reinterpret_cast<const char*>(lt.Linv + lt.ioff[p]) + (size_t)J * (kInvTilesPerBlock * 512), kInvTilesPerBlock * 512, &ifull);
+      f_mbar_expect_tx(&ifull, kP64Tiles * 512);
+      f_bulk_g2s(Ibuf, reinterpret_cast<const char*>(lt.Linv + lt.ioff[p]) + (size_t)(2 * Jp) * (kInvTilesPerBlock * 512), 2 * kInvTilesPerBlock * 512, &ifull);
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        f_bulk_g2s(Ibuf + (20 + 4 * a) * 512, Lbytes + (tri(t0 + 4 + a) + (size_t)t0) * 512, 4 * 512, &ifull);
       for (int kc = 0; kc < nchunks; ++kc) {
         const int buf = kc & 1;
         if (kc >= 2) f_mbar_wait(&bempty[buf], (uint32_t)(((kc >> 1) - 1) & 1));
-        const int width = min(kPanKC, t0 - kc * kPanKC);
-        f_mbar_expect_tx(&bfull[buf], (uint32_t)(4 * width * 512));
+        f_mbar_expect_tx(&bfull[buf], 8 * KC * 512);
 #pragma unroll
-        for (int b = 0; b < 4; ++b)
-          f_bulk_g2s(Bbuf + (size_t)((buf * 4 + b) * kPanKC) * 512, Lbytes + (tri(t0 + b) + (size_t)kc * kPanKC) * 512, (uint32_t)(width * 512), &bfull[buf]);
+        for (int b = 0; b < 8; ++b)
+          f_bulk_g2s(Bbuf + (size_t)((buf * 8 + b) * KC) * 512, Lbytes + (tri(t0 + b) + (size_t)kc * KC) * 512, KC * 512, &bfull[buf]);
       }
     }
     return;
@@ -726,207 +864,199 @@ k_chol_panel_tma(LeafTable lt, const int* __restrict__ order, int J) {
   if (warp >= n_active) return;
   const int g = lane >> 2, l = lane & 3;
   const int tb = tb0 + warp * R;
-  const int nv = (tb + 1 < ntl) ? 2 : 1;
-  const int n_a = J + 1;                                  // chunks of the own-row stream: J of finished columns + the K block
-  unsigned char* myring = Aring + (size_t)warp * (kPanDepth * R * kPanCW * 512);
+  const int n_a = 2 * Jp + 2;                             // chunks of the own-row stream: the finished columns, then K0, K1
+  unsigned char* myring = Aring + (size_t)warp * kRing;
   uint64_t* myfull = &afull[warp * kPanDepth];
-  auto issue_a = [&](int a) {                             // lane 0: chunk a of both rows into slot a % depth
+  auto issue_a = [&](int a) {
     const int slot = a % kPanDepth;
-    f_mbar_expect_tx(&myfull[slot], (uint32_t)(nv * kPanCW * 512));
-    for (int r = 0; r < nv; ++r)
-      f_bulk_g2s(myring + (size_t)((slot * R + r) * kPanCW) * 512, Lbytes + (tri(tb + r) + (size_t)a * kPanCW) * 512, kPanCW * 512, &myfull[slot]);
+    f_mbar_expect_tx(&myfull[slot], R * CW * 512);
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+      f_bulk_g2s(myring + (size_t)((slot * R + r) * CW) * 512, Lbytes + (tri(tb + r) + (size_t)a * CW) * 512, CW * 512, &myfull[slot]);
   };
   if (lane == 0)
     for (int a = 0; a < kPanDepth && a < n_a; ++a) issue_a(a);
-  double acc[R][4][2];
+  double acc[R][8][2];
 #pragma unroll
   for (int r = 0; r < R; ++r)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[r][b][0] = acc[r][b][1] = 0.0;
+    for (int b = 0; b < 8; ++b) acc[r][b][0] = acc[r][b][1] = 0.0;
   const double2* Bl = reinterpret_cast<const double2*>(Bbuf) + lane;
   const double2* Al = reinterpret_cast<const double2*>(myring) + lane;
-  for (int a = 0; a < J; ++a) {
-    const int kc = a / (kPanKC / kPanCW), buf = kc & 1;
-    if (a % (kPanKC / kPanCW) == 0) f_mbar_wait(&bfull[buf], (uint32_t)((kc >> 1) & 1));
+  for (int a = 0; a < 2 * Jp; ++a) {
     const int slot = a % kPanDepth;
     f_mbar_wait(&myfull[slot], (uint32_t)((a / kPanDepth) & 1));
-    const int cb0 = (a % (kPanKC / kPanCW)) * kPanCW;     // position of this chunk's first column tile inside the B chunk
 #pragma unroll
-    for (int cc = 0; cc < kPanCW; ++cc) {
-      double2 bf[4], af[R];
+    for (int ct = 0; ct < CW; ++ct) {
+      const int kc = (a * CW + ct) / KC, buf = kc & 1;
+      const int pos = ct % KC;
+      if (pos == 0) f_mbar_wait(&bfull[buf], (uint32_t)((kc >> 1) & 1));
+      double2 af[R];
 #pragma unroll
-      for (int b = 0; b < 4; ++b) bf[b] = Bl[((buf * 4 + b) * kPanKC + cb0 + cc) * 32];
+      for (int r = 0; r < R; ++r) af[r] = Al[((slot * R + r) * CW + ct) * 32];
 #pragma unroll
-      for (int r = 0; r < R; ++r) af[r] = Al[((slot * R + r) * kPanCW + cc) * 32];
-      PMK_UNIFORM_IF(nv == 2) {
+      for (int hb = 0; hb < 2; ++hb) {
+        double2 bf[4];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) dmma884(acc[1][b][0], acc[1][b][1], af[1].x, bf[b].x);
+        for (int b = 0; b < 4; ++b) bf[b] = Bl[((buf * 8 + 4 * hb + b) * KC + pos) * 32];
 #pragma unroll
-        for (int b = 0; b < 4; ++b) dmma884(acc[1][b][0], acc[1][b][1], af[1].y, bf[b].y);
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) dmma884(acc[r][4 * hb + b][0], acc[r][4 * hb + b][1], af[r].x, bf[b].x);
+#pragma unroll
+        for (int r = 0; r < R; ++r)
+#pragma unroll
+          for (int b = 0; b < 4; ++b) dmma884(acc[r][4 * hb + b][0], acc[r][4 * hb + b][1], af[r].y, bf[b].y);
       }
-#pragma unroll
-      for (int b = 0; b < 4; ++b) dmma884(acc[0][b][0], acc[0][b][1], af[0].x, bf[b].x);
-#pragma unroll
-      for (int b = 0; b < 4; ++b) dmma884(acc[0][b][0], acc[0][b][1], af[0].y, bf[b].y);
+      if (pos == KC - 1) {
+        __syncwarp();                                     // every lane has read the B chunk
+        if (lane == 0) f_mbar_arrive(&bempty[buf]);
+      }
     }
-    __syncwarp();                                         // every lane has read the slot (and this part of the B chunk)
-    if (lane == 0) {
-      if (a + kPanDepth < n_a) issue_a(a + kPanDepth);
-      if (a % (kPanKC / kPanCW) == kPanKC / kPanCW - 1 || a == J - 1) f_mbar_arrive(&bempty[buf]);
-    }
+    __syncwarp();                                         // every lane has read the slot
+    if (lane == 0 && a + kPanDepth < n_a) issue_a(a + kPanDepth);
   }
-  // ---- the K block (last chunk of the stream): C = K - sum
-  {
-    const int slot = J % kPanDepth;
-    f_mbar_wait(&myfull[slot], (uint32_t)((J / kPanDepth) & 1));
+  // ---- the two K blocks (last two chunks of the stream): C = K - sum
+#pragma unroll
+  for (int hb = 0; hb < 2; ++hb) {
+    const int a = 2 * Jp + hb;
+    const int slot = a % kPanDepth;
+    f_mbar_wait(&myfull[slot], (uint32_t)((a / kPanDepth) & 1));
 #pragma unroll
     for (int r = 0; r < R; ++r)
 #pragma unroll
       for (int b = 0; b < 4; ++b) {
-        const double2 kt = Al[((slot * R + r) * kPanCW + b) * 32];
-        acc[r][b][0] = kt.x - acc[r][b][0];
-        acc[r][b][1] = kt.y - acc[r][b][1];
+        const double2 kt = Al[((slot * R + r) * CW + b) * 32];
+        acc[r][4 * hb + b][0] = kt.x - acc[r][4 * hb + b][0];
+        acc[r][4 * hb + b][1] = kt.y - acc[r][4 * hb + b][1];
       }
   }
-  // ---- L[t, J] = C inv(L_JJ)^T
+  const int64_t xo = lt.xoff[p];
+  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
   f_mbar_wait(&ifull, 0);
   const double2* Il = reinterpret_cast<const double2*>(Ibuf) + lane;
   const int src_lo = (lane & ~3) | (l >> 1);
   const int src_hi = (lane & ~3) | (2 + (l >> 1));
-  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
+  double2 xs[R][8];                   // the final tiles, A-fragment form (= packed storage form)
+  // C-fragment values of a row tile's four column tiles -> X = C inv^T with the packed inverse tiles at Il + ioff tiles;
+  // out: C-fragment values f0 / f1 and the A-fragment form
+  auto solve4 = [&](const double (&c0)[4], const double (&c1)[4], int itile0, double (&f0)[4], double (&f1)[4], double2 (&xo4)[4]) {
+    double alo[4], ahi[4];
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+      const double v0 = __shfl_sync(kFull, c0[kb], src_lo);
+      const double v1 = __shfl_sync(kFull, c1[kb], src_lo);
+      const double w0 = __shfl_sync(kFull, c0[kb], src_hi);
+      const double w1 = __shfl_sync(kFull, c1[kb], src_hi);
+      alo[kb] = (l & 1) ? v1 : v0;
+      ahi[kb] = (l & 1) ? w1 : w0;
+    }
+    double o0[4], o1[4], p0[4], p1[4];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) o0[cb] = o1[cb] = p0[cb] = p1[cb] = 0.0;
+#pragma unroll
+    for (int kb = 0; kb < 4; ++kb) {
+#pragma unroll
+      for (int cb = kb; cb < 4; ++cb) {
+        const double2 iv = Il[(itile0 + cb * (cb + 1) / 2 + kb) * 32];      // {inv[8cb+g][8kb+l], inv[8cb+g][8kb+4+l]}
+        dmma884(o0[cb], o1[cb], alo[kb], iv.x);
+        dmma884(p0[cb], p1[cb], ahi[kb], iv.y);
+      }
+    }
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) {
+      f0[cb] = o0[cb] + p0[cb];
+      f1[cb] = o1[cb] + p1[cb];
+      const double v0 = __shfl_sync(kFull, f0[cb], src_lo);
+      const double v1 = __shfl_sync(kFull, f1[cb], src_lo);
+      const double w0 = __shfl_sync(kFull, f0[cb], src_hi);
+      const double w1 = __shfl_sync(kFull, f1[cb], src_hi);
+      xo4[cb] = make_double2((l & 1) ? v1 : v0, (l & 1) ? w1 : w0);
+    }
+  };
 #pragma unroll
   for (int r = 0; r < R; ++r) {
-    if (r < nv) {
-      double alo[4], ahi[4];
+    double c0[4], c1[4], f0[4], f1[4], g0[4], g1[4];
+    double2 x0[4], x1[4];
+#pragma unroll
+    for (int b = 0; b < 4; ++b) {
+      c0[b] = acc[r][b][0];
+      c1[b] = acc[r][b][1];
+    }
+    solve4(c0, c1, 0, f0, f1, x0);                       // X0 = C0 inv(L00)^T
+    // C1 -= X0 L10^T: output column tile nb, k over X0's column tiles; B[k][n] = L10[8 nb + n][8 kb + k] = the packed tile (nb, kb)
+#pragma unroll
+    for (int nb = 0; nb < 4; ++nb) {
+      double s0 = 0.0, s1 = 0.0, q0 = 0.0, q1 = 0.0;
 #pragma unroll
       for (int kb = 0; kb < 4; ++kb) {
-        const double c0 = acc[r][kb][0], c1 = acc[r][kb][1];
-        const double v0 = __shfl_sync(kFull, c0, src_lo);
-        const double v1 = __shfl_sync(kFull, c1, src_lo);
-        const double w0 = __shfl_sync(kFull, c0, src_hi);
-        const double w1 = __shfl_sync(kFull, c1, src_hi);
-        alo[kb] = (l & 1) ? v1 : v0;
-        ahi[kb] = (l & 1) ? w1 : w0;
+        const double2 lv = Il[(20 + nb * 4 + kb) * 32];
+        dmma884(s0, s1, x0[kb].x, lv.x);
+        dmma884(q0, q1, x0[kb].y, lv.y);
       }
-      double* tile_row = reinterpret_cast<double*>(Lp + (tri(tb + r) + t0) * 32);
-      double o0[4], o1[4], p0[4], p1[4];
+      c0[nb] = acc[r][4 + nb][0] - (s0 + q0);
+      c1[nb] = acc[r][4 + nb][1] - (s1 + q1);
+    }
+    solve4(c0, c1, 10, g0, g1, x1);                      // X1 = (C1 - X0 L10^T) inv(L11)^T
+    double zpart = 0.0;
 #pragma unroll
-      for (int cb = 0; cb < 4; ++cb) o0[cb] = o1[cb] = p0[cb] = p1[cb] = 0.0;
+    for (int cb = 0; cb < 4; ++cb) {
+      const double2 za = *reinterpret_cast<const double2*>(lt.alpha + xo + 8 * t0 + 8 * cb + 2 * l);
+      const double2 zb = *reinterpret_cast<const double2*>(lt.alpha + xo + 8 * t0 + 32 + 8 * cb + 2 * l);
+      zpart = fma(f1[cb], za.y, fma(f0[cb], za.x, zpart));
+      zpart = fma(g1[cb], zb.y, fma(g0[cb], zb.x, zpart));
+      xs[r][cb] = x0[cb];
+      xs[r][4 + cb] = x1[cb];
+      Lp[(tri(tb + r) + t0 + cb) * 32 + lane] = x0[cb];
+      Lp[(tri(tb + r) + t0 + 4 + cb) * 32 + lane] = x1[cb];
+    }
+    // S_I += L[I, J] z_J for the rows of this tile (only this warp touches them in this launch)
+    zpart += __shfl_xor_sync(kFull, zpart, 1);
+    zpart += __shfl_xor_sync(kFull, zpart, 2);
+    if (l == 0) lt.alpha[xo + 8 * (tb + r) + g] += zpart;
+  }
+  // ---- D -= X X^T on the block's diagonal tiles (64x64 lower, or 32x32 for a half block): the final tiles of all warps go to
+  // shared memory (over the operand buffers: every warp is past its update loop at the first barrier)
+  const int nthr = n_active * 32;
+  asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+  double2* St = reinterpret_cast<double2*>(pmk_chol_smem) + lane;        // [row tile of the block][column tile of the panel][32]
 #pragma unroll
-      for (int kb = 0; kb < 4; ++kb) {
+  for (int r = 0; r < R; ++r)
 #pragma unroll
-        for (int cb = kb; cb < 4; ++cb) {
-          const double2 iv = Il[(cb * (cb + 1) / 2 + kb) * 32];      // {inv[8cb+g][8kb+l], inv[8cb+g][8kb+4+l]}
-          dmma884(o0[cb], o1[cb], alo[kb], iv.x);
-          dmma884(p0[cb], p1[cb], ahi[kb], iv.y);
+    for (int cb = 0; cb < 8; ++cb) St[((warp * R + r) * 8 + cb) * 32] = xs[r][cb];
+  asm volatile("bar.sync 1, %0;" ::"r"(nthr) : "memory");
+  // Row a of the block's lower tile triangle has a + 1 tiles, all with the same left operand X[a]: a warp takes rows w and
+  // (rows - 1 - w) -- nine tiles each for a full block, five for a half block -- and runs a row's tiles side by side (independent
+  // accumulators), the old values of the whole row loaded first.
+  const int nrt = n_active * R;                            // row tiles of the block
+  auto syrk_row = [&](int a) {
+    double2 dold[8];
+    double o0[8], o1[8];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      o0[b] = o1[b] = 0.0;
+      dold[b] = make_double2(0.0, 0.0);
+      PMK_UNIFORM_IF(b <= a) dold[b] = __ldcg(Lp + (tri(tb0 + a) + tb0 + b) * 32 + lane);
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const double2 af = St[(a * 8 + c) * 32];
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        PMK_UNIFORM_IF(b <= a) {
+          const double2 bf = St[(b * 8 + c) * 32];
+          dmma884(o0[b], o1[b], af.x, bf.x);
+          dmma884(o0[b], o1[b], af.y, bf.y);
         }
       }
-      double zpart = 0.0;
-      double* stile_row = reinterpret_cast<double*>(myring) + (size_t)r * (kPanCW * 64);     // slot 0 of the own ring, [r][cb][64]
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) {
-        double* tile = tile_row + cb * 64;
-        const int q0 = 2 * l, q1 = 2 * l + 1;
-        const int i0 = (g * 4 + (q0 & 3)) * 2 + (q0 >> 2), i1 = (g * 4 + (q1 & 3)) * 2 + (q1 >> 2);
-        const double f0 = o0[cb] + p0[cb], f1 = o1[cb] + p1[cb];
-        tile[i0] = f0;
-        tile[i1] = f1;
-        {
-          stile_row[cb * 64 + i0] = f0;
-          stile_row[cb * 64 + i1] = f1;
-          const double2 zj = *reinterpret_cast<const double2*>(lt.alpha + lt.xoff[p] + 32 * J + 8 * cb + 2 * l);
-          zpart = fma(f1, zj.y, fma(f0, zj.x, zpart));
-        }
-      }
-      {       // S_I += L[I, J] z_J for the rows of this tile (only this warp touches them in this launch)
-        zpart += __shfl_xor_sync(kFull, zpart, 1);
-        zpart += __shfl_xor_sync(kFull, zpart, 2);
-        if (l == 0) lt.alpha[lt.xoff[p] + 8 * (tb + r) + g] += zpart;
-      }
     }
-  }
-  {
-    // D_II -= L[I,J] L[I,J]^T: the pair of warps (2i, 2i+1) owns the four row tiles of block I = (tb0 >> 2) + i; n_pad is a multiple
-    // of 32, so a pair is complete or absent.  Five of the ten lower tiles each.
-    switch (warp >> 1) {                                    // literal barrier ids: a register operand makes ptxas reserve all 16
-      case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-      case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-      case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-      default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      PMK_UNIFORM_IF(b <= a) Lp[(tri(tb0 + a) + tb0 + b) * 32 + lane] = make_double2(dold[b].x - o0[b], dold[b].y - o1[b]);
     }
-    const int I4 = tb & ~3;                                 // first row tile of the block
-    const unsigned char* pair_ring = Aring + (size_t)(warp & ~1) * (kPanDepth * R * kPanCW * 512);
-    auto xt = [&](int a, int c) {                           // final tile (row tile a of the block, column tile c of the panel), packed
-      return reinterpret_cast<const double2*>(pair_ring + (size_t)(a >> 1) * (kPanDepth * R * kPanCW * 512) + (size_t)(((a & 1) * kPanCW + c) * 512))[lane];
-    };
-    const int h = warp & 1;
-#pragma unroll
-    for (int k = 0; k < 5; ++k) {
-      // h = 0: (0,0) (1,0) (1,1) (2,0) (3,0);  h = 1: (2,1) (2,2) (3,1) (3,2) (3,3)
-      const int a = h ? (k < 2 ? 2 : 3) : (k == 0 ? 0 : (k < 3 ? 1 : k - 1));
-      const int b = h ? (k < 2 ? k + 1 : k - 1) : (k == 2 ? 1 : 0);
-      double o0 = 0.0, o1 = 0.0, p0 = 0.0, p1 = 0.0;
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const double2 af = xt(a, c), bf = xt(b, c);
-        dmma884(o0, o1, af.x, bf.x);
-        dmma884(p0, p1, af.y, bf.y);
-      }
-      double2* slot = Lp + (tri(I4 + a) + I4 + b) * 32 + lane;
-      double2 d = __ldcg(slot);
-      d.x -= o0 + p0;
-      d.y -= o1 + p1;
-      *slot = d;
-    }
-  }
-}
-
-// The diagonal block of panel J, ready to be factored: one warp per leaf, many leaves per SM, nothing but the serial
-// chain -- Cholesky + inverse of the 32x32 block, then z_J = inv(L_JJ) (y_J - S_J) with S_J the partial sums the panel kernels left
-// in lt.alpha.
-__global__ void __launch_bounds__(32)
-k_chol_factor(LeafTable lt, const int* __restrict__ order, int J, int with_z) {
-  __shared__ double Dbuf[32 * LDD];
-  __shared__ double Ibuf[32 * LD];
-  const int p = order[blockIdx.x];
-  const int ntl = lt.npad[p] >> 3;
-  const int t0 = 4 * J;
-  if (t0 >= ntl || lt.info[p] != 0) return;
-  const int lane = threadIdx.x;
-  const int g = lane >> 2, l = lane & 3;
-  double2* Lp = reinterpret_cast<double2*>(lt.L + lt.loff[p]);
-  double2* Ip = reinterpret_cast<double2*>(lt.Linv + lt.ioff[p]);
-#pragma unroll
-  for (int a = 0; a < 4; ++a)
-#pragma unroll
-    for (int b = 0; b <= a; ++b) {
-      const double2 d = ld_once(Lp + (tri(t0 + a) + t0 + b) * 32 + lane);      // C-fragment-major: {M[g][2l], M[g][2l+1]}
-      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l] = d.x;
-      Dbuf[(8 * a + g) * LDD + 8 * b + 2 * l + 1] = d.y;
-    }
-  __syncwarp();
-  const int info = factor_block32(Dbuf, Ibuf, lane);
-  if (info != 0) {
-    if (lane == 0) lt.info[p] = 32 * J + info;
-    return;
-  }
-#pragma unroll
-  for (int a = 0; a < 4; ++a) {
-    for (int b = 0; b <= a; ++b) {
-      const int rd = (8 * a + g) * LDD + 8 * b + l;
-      const int ri = (8 * a + g) * LD + 8 * b + l;
-      Lp[(tri(t0 + a) + t0 + b) * 32 + lane] = make_double2(Dbuf[rd], Dbuf[rd + 4]);
-      Ip[(size_t)J * (kInvTilesPerBlock * 32) + (a * (a + 1) / 2 + b) * 32 + lane] = make_double2(Ibuf[ri], Ibuf[ri + 4]);
-    }
-  }
-  if (with_z) {
-    const int64_t xo = lt.xoff[p];
-    const double rl = lt.y[xo + 32 * J + lane] - lt.alpha[xo + 32 * J + lane];
-    double zz = 0.0;
-#pragma unroll 8
-    for (int k = 0; k < 32; ++k) zz = fma(Ibuf[lane * LD + k], __shfl_sync(kFull, rl, k), zz);      // the inverse's upper part is zero
-    lt.alpha[xo + 32 * J + lane] = zz;
-  }
+  };
+  syrk_row(nrt - 1 - warp);
+  syrk_row(warp);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1001,7 +1131,7 @@ k_solve_alpha(LeafTable lt, const int* __restrict__ order, const double* rhs_in,
   const int64_t xo = lt.xoff[p];
   for (int i = threadIdx.x; i < npad; i += NW * 32) z[i] = rhs_in[xo + i];
   __syncthreads();
-  // ---- forward: z <- L^-1 y  (backward_only: rhs_in already holds z, computed panel by panel by k_chol_diag)
+  // ---- forward: z <- L^-1 y  (backward_only: rhs_in already holds z, computed panel by panel by the factorisation)
   for (int J = backward_only ? nblk : 0; J < nblk; ++J) {
     double part[4] = {0.0, 0.0, 0.0, 0.0};
     for (int ct = warp; ct < 4 * J; ct += NW) {
@@ -1229,31 +1359,31 @@ void launch_solve(const LeafTable& lt, const int* d_order, int n_order, int max_
   k_solve_alpha<NW><<<n_order, NW * 32, smem, s>>>(lt, d_order, rhs ? rhs : lt.y, out ? out : lt.alpha, backward_only);
 }
 
-// Level-synchronous factorisation: leaves sorted by size (order), leaves_per_panel[J] = how many of them have a J-th 32-column
-// panel (a prefix of `order`).  Returns the number of launches.  with_z: k_chol_factor also forms z = L^-1 y in lt.alpha.
+// Level-synchronous factorisation: leaves sorted by size (order), leaves_per_panel[Jp] = how many of them have columns 64 Jp ..
+// (a prefix of `order`).  Returns the number of launches.  with_z: k_chol_factor64 also forms z = L^-1 y in lt.alpha.
 int launch_chol_levels(const LeafTable& lt, const int* d_order, const std::vector<int>& leaves_per_panel, int max_npad, int with_z,
-                       cudaStream_t s) {
-  constexpr int PW = PMK_PAN_NW;
-  constexpr size_t dyn_tma = (size_t)2 * 4 * kPanKC * 512 + kInvTilesPerBlock * 512 + (size_t)PW * kPanDepth * 2 * kPanCW * 512;
+                         cudaStream_t s) {
+  constexpr int PW = 4;
+  constexpr size_t dyn = (size_t)2 * 8 * PMK_P64_KC * 512 + (size_t)PW * kPanDepth * 2 * kPanCW * 512 + kP64Tiles * 512;
   static DeviceOnce once;
-  once.run([&] { cudaFuncSetAttribute(k_chol_panel_tma<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_tma); });
+  once.run([&] { cudaFuncSetAttribute(k_chol_panel64<PW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn); });
   int launches = 0;
   const int max_ntl = max_npad / 8;
   const int nJ = (int)leaves_per_panel.size();
   if (nJ == 0 || leaves_per_panel[0] <= 0) return 0;
-  k_chol_factor<<<leaves_per_panel[0], 32, 0, s>>>(lt, d_order, 0, with_z);
+  k_chol_factor64<<<leaves_per_panel[0], 32, 0, s>>>(lt, d_order, 0, with_z);
   ++launches;
-  for (int J = 0; J < nJ; ++J) {
-    const int cnt = leaves_per_panel[J];
+  for (int Jp = 0; Jp < nJ; ++Jp) {
+    const int cnt = leaves_per_panel[Jp];
     if (cnt <= 0) break;
-    const int rows_below = max_ntl - 4 * J - 4;
+    const int rows_below = max_ntl - 8 * Jp - 8;
     if (rows_below > 0) {
       dim3 grid((rows_below + PW * 2 - 1) / (PW * 2), cnt);
-      k_chol_panel_tma<PW><<<grid, (PW + 1) * 32, dyn_tma, s>>>(lt, d_order, J);
+      k_chol_panel64<PW><<<grid, (PW + 1) * 32, dyn, s>>>(lt, d_order, Jp);
       ++launches;
     }
-    if (J + 1 < nJ && leaves_per_panel[J + 1] > 0) {
-      k_chol_factor<<<leaves_per_panel[J + 1], 32, 0, s>>>(lt, d_order, J + 1, with_z);
+    if (Jp + 1 < nJ && leaves_per_panel[Jp + 1] > 0) {
+      k_chol_factor64<<<leaves_per_panel[Jp + 1], 32, 0, s>>>(lt, d_order, Jp + 1, with_z);
       ++launches;
     }
   }

@@ -64,8 +64,8 @@ struct PairWork {
 };
 
 // The fit's batched Cholesky: leaves of at least this many padded rows are factored by the level-synchronous kernels
-// (k_chol_factor / k_chol_panel_tma), smaller ones by the one-CTA-per-leaf kernel (k_chol).  Measured on a B200: 512-point leaves
-// (C3) 10.33 ms either way, 1.70 vs 1.53 ms for one GPU's eighth of them; 1027-point leaves (C4) 123.6 vs 144.6 ms.
+// (k_chol_factor64 / k_chol_panel64), smaller ones by the one-CTA-per-leaf kernel (k_chol).  Measured on a B200 (chol phase, ms):
+// 512-point leaves (C3) 10.05 vs 10.33, one GPU's eighth of them 1.62 vs 1.56; 1027-point leaves (C4) 118.0 vs 144.6.
 static constexpr int kCholLevelsMinNpad = 768;
 
 // Recursion plan of the explicit inverse P = inv(L) by recursive doubling (pmk_invert.cu): for every shape (number of 32-row
