@@ -287,7 +287,10 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
   // (same comparisons as partition.jl:254; a point is in home iff it takes home's branch at every ancestor)
   auto exactly_one_in_home = [&](const double* x1, const double* x2) -> bool {
     bool in1 = true, in2 = true;
-    for (int d = 0; d < Lv; ++d) {
+    // deepest ancestor first: the probes are within radius + delta of a query of home, so if they are outside home it is one of the
+    // cell's own (deep) boundary planes that says so, and the walk ends after a step or two instead of ten (the conjunction does
+    // not depend on the order; ncu: this loop was 57 % of the kernel's instructions, nine lanes active on average)
+    for (int d = Lv - 1; d >= 0; --d) {
       double v[D];
 #pragma unroll
       for (int dd = 0; dd < D; ++dd) v[dd] = a_u[dd][d];
@@ -382,22 +385,32 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
       nsurv = 0;
     };
     for (int k = 0; k < nc; ++k) {
-      double tq;
+      double tq, un;
       if (k < ns) {
         double u[D];
 #pragma unroll
         for (int d = 0; d < D; ++d) u[d] = s_u[d][k];
         tq = __dadd_rn(-dot_seq<D>(u, p), s_c[k]);
+        un = s_n[k];
       } else {
         const int i = cand[ca + k];
         double u[D];
+        un = 0.0;
 #pragma unroll
-        for (int d = 0; d < D; ++d) u[d] = tr.hv[d * tr.n_hp + i];
+        for (int d = 0; d < D; ++d) {
+          u[d] = tr.hv[d * tr.n_hp + i];
+          un += u[d] * u[d];
+        }
+        un = sqrt(un);
         tq = __dadd_rn(-dot_seq<D>(u, p), tr.hc[i]);
       }
       // a full list anywhere in the warp: everybody replays what it has (ascending order is kept), then collecting goes on
       if (__any_sync(0xffffffffu, nsurv == 64)) flush();
-      if (valid && !(fabs(tq) > thr)) surv[nsurv++] = (unsigned short)k;
+      // Buffered for the exact test: within the radius (cheap form) AND not closer than the nearest boundary of the home cell
+      // (process() repeats this second rejection with the same operands -- applying it here keeps the replay, which runs at the
+      // pace of the lane with the most survivors and mostly with one or two lanes active, to the handful of planes that can pass:
+      // ncu had 622 warp instructions per QUERY, half of the lanes idle on average, nearly all of it in the replay).
+      if (valid && !(fabs(tq) > thr) && !(un * (fabs(tq) + fabs(delta)) * (1.0 + 1e-9) < mrel)) surv[nsurv++] = (unsigned short)k;
     }
     flush();
     if (valid) {
