@@ -43,19 +43,22 @@ k_inv_diag(LeafTable lt, int first_leaf) {
     for (int b = 0; b <= a; ++b) dst[(tri(4 * J + a) + 4 * J + b) * 32] = src[(a * (a + 1) / 2 + b) * 32];
 }
 
-// blockIdx.x = node * parts + part: a node's 32x32 output blocks are dealt to `parts` CTAs (8 warps each), so that the CTAs
-// working on one leaf at the same time share its tiles in L2 and fewer leaves are in flight (at 4096 leaves the top-level
-// operands of 296 resident leaves, 0.75 MB each, would not fit the 126 MB L2)
-__device__ __forceinline__ bool inv_node(const LeafTable& lt, const InvPlanDev& pl, int first_leaf, int height, int parts, int& p,
-                                         InvNode& nd, int& part) {
+// Work of one height of one leaf = the 32x32 output blocks of all its nodes of that height, numbered node-major (node j owns
+// items [j * bpn, j * bpn + its block count), bpn = the largest block count of a node of this height over all shapes).
+// One warp = one item; a CTA takes kInvWarps consecutive items, so that at the low heights (one or four blocks per node) the
+// warps of a CTA are spread over several nodes instead of idling, and at the top heights the CTAs working on one leaf at the
+// same time share its tiles in L2 / L1.
+__device__ __forceinline__ bool inv_item(const LeafTable& lt, const InvPlanDev& pl, int first_leaf, int height, int bpn, int warp, int& p,
+                                         InvNode& nd, int& b) {
   p = first_leaf + blockIdx.y;
   const int nb = lt.npad[p] >> 5;
   const int idx = nb * (kInvMaxHeight + 1) + height;
-  const int node = blockIdx.x / parts;
-  part = blockIdx.x % parts;
+  const int item = blockIdx.x * kInvWarps + warp;
+  const int node = item / bpn;
+  b = item % bpn;
   if (node >= pl.cnt[idx]) return false;
   nd = pl.nodes[pl.off[idx] + node];
-  return true;
+  return b < (nd.hi - nd.mid) * (nd.mid - nd.lo);
 }
 
 // T = C * A^-1 for the node: T tile (ti, tj) = sum_{tk >= tj} L(ti, tk) * P(tk, tj), tk inside A's range.
@@ -63,20 +66,22 @@ __device__ __forceinline__ bool inv_node(const LeafTable& lt, const InvPlanDev& 
 // two 8-byte loads per lane instead of one 16-byte load.  T goes to the scratch buffer at the tile's own packed position,
 // stored B-fragment-major so that k_inv_R loads it with one LDG.128.
 __global__ void __launch_bounds__(kInvWarps * 32, 2)
-k_inv_T(LeafTable lt, InvPlanDev pl, double* __restrict__ scratch, int first_leaf, int height, int parts) {
-  int p, part;
+k_inv_T(LeafTable lt, InvPlanDev pl, double* __restrict__ scratch, int first_leaf, int height, int bpn) {
+  int p, b;
   InvNode nd;
-  if (!inv_node(lt, pl, first_leaf, height, parts, p, nd, part)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!inv_item(lt, pl, first_leaf, height, bpn, warp, p, nd, b)) return;
   const int g = lane >> 2, l = lane & 3;
   const double2* __restrict__ Lp = reinterpret_cast<const double2*>(lt.L + lt.loff[p]) + lane;
   const double* __restrict__ Pd = lt.P + lt.loff[p];
   double* Td = scratch + lt.loff[p];
-  const int ncb = nd.mid - nd.lo, nblocks = (nd.hi - nd.mid) * ncb;
   // element (row l, column g) and (row l + 4, column g) of a packed tile = this lane's B fragments of two k-steps
   const int e0 = (l * 4 + (g & 3)) * 2 + (g >> 2), e1 = e0 + 32;
-  for (int b = part * kInvWarps + warp; b < nblocks; b += kInvWarps * parts) {
-    const int bi = nd.mid + b / ncb, bj = nd.lo + b % ncb;
+  const int nrb = nd.hi - nd.mid;
+  {
+    // column-major deal: the warps of a CTA work on consecutive ROW blocks of one column block, so they share the right operand
+    // P(tk, 4bj ..) -- and its k range -- through L1 (k_inv_R shares its left operand the same way)
+    const int bi = nd.mid + b % nrb, bj = nd.lo + b / nrb;
     double acc[4][4][2];
 #pragma unroll
     for (int r = 0; r < 4; ++r)
@@ -137,17 +142,17 @@ k_inv_T(LeafTable lt, InvPlanDev pl, double* __restrict__ scratch, int first_lea
 
 // P21 = -B^-1 * T for the node: P tile (ti, tj) = -sum_{tk <= ti} P(ti, tk) * T(tk, tj), tk inside B's range.
 __global__ void __launch_bounds__(kInvWarps * 32, 2)
-k_inv_R(LeafTable lt, InvPlanDev pl, const double* __restrict__ scratch, int first_leaf, int height, int parts) {
-  int p, part;
+k_inv_R(LeafTable lt, InvPlanDev pl, const double* __restrict__ scratch, int first_leaf, int height, int bpn) {
+  int p, b;
   InvNode nd;
-  if (!inv_node(lt, pl, first_leaf, height, parts, p, nd, part)) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (!inv_item(lt, pl, first_leaf, height, bpn, warp, p, nd, b)) return;
   const int g = lane >> 2, l = lane & 3;
   double* Pd = lt.P + lt.loff[p];
   const double2* Pp = reinterpret_cast<const double2*>(Pd) + lane;
   const double2* __restrict__ Tp = reinterpret_cast<const double2*>(scratch + lt.loff[p]) + lane;
-  const int ncb = nd.mid - nd.lo, nblocks = (nd.hi - nd.mid) * ncb;
-  for (int b = part * kInvWarps + warp; b < nblocks; b += kInvWarps * parts) {
+  const int ncb = nd.mid - nd.lo;
+  {
     const int bi = nd.mid + b / ncb, bj = nd.lo + b % ncb;
     double acc[4][4][2];
 #pragma unroll
@@ -251,10 +256,10 @@ void launch_inverse(const LeafTable& lt, const InvPlanHost& plh, const void* d_n
   ++*launches;
   for (int h = 1; h <= plh.max_height; ++h) {
     if (plh.max_cnt[h] == 0) continue;
-    const int parts = std::min(8, std::max(1, (plh.max_blocks[h] + 2 * kInvWarps - 1) / (2 * kInvWarps)));   // <= 2 blocks per warp
-    const dim3 grid(plh.max_cnt[h] * parts, n_leaves);
-    k_inv_T<<<grid, kInvWarps * 32, 0, s>>>(lt, pl, scratch, first_leaf, h, parts);
-    k_inv_R<<<grid, kInvWarps * 32, 0, s>>>(lt, pl, scratch, first_leaf, h, parts);
+    const int bpn = plh.max_blocks[h];
+    const dim3 grid((plh.max_cnt[h] * bpn + kInvWarps - 1) / kInvWarps, n_leaves);
+    k_inv_T<<<grid, kInvWarps * 32, 0, s>>>(lt, pl, scratch, first_leaf, h, bpn);
+    k_inv_R<<<grid, kInvWarps * 32, 0, s>>>(lt, pl, scratch, first_leaf, h, bpn);
     *launches += 2;
   }
 }
