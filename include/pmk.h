@@ -208,8 +208,9 @@ int pmk_query_set_flags(pmk_handle* h, int flags);
 
 /* ---- multi-GPU: one model over the GPUs of one box (north star: "patches are partitioned across the 8 GPUs ... by a
  * BSP-leaf-to-rank map") ---------------------------------------------------------------------------------------------------- */
-/* One process, one host thread and one stream set per GPU, CUDA peer copies over NVLink between them.  Rank r OWNS the
- * contiguous leaf range pmk_multi_leaf_range gives it (the top log2(n) levels of the BSP = n sub-trees) and keeps X, alpha, L and
+/* One process, one host thread and one stream set per GPU, CUDA peer copies over NVLink between them.  Rank r OWNS a
+ * contiguous leaf range (pmk_multi_owned_range: ranges of equal cost; with equal leaves the n sub-trees below the top log2(n)
+ * levels of the BSP) and keeps X, alpha, L and
  * the query operand for those leaves only; nothing is replicated but the tree.  fitmixtureGP! (mixtureGP.jl:70) = every rank
  * fits its leaves, no exchange.  querymixtureGP! (mixtureGP.jl:159) = every rank plans a contiguous slice of the queries
  * (pmk_multi_query_range), the pairs travel to the owners of their leaves (D doubles + 4 bytes each), the owners run the fused
@@ -224,9 +225,15 @@ int pmk_multi_create(pmk_multi** out, int n_devices, const int* device_ids);
 void pmk_multi_destroy(pmk_multi* m);
 const char* pmk_multi_last_error(const pmk_multi* m);     /* m may be NULL: error of a failed pmk_multi_create */
 int pmk_multi_size(const pmk_multi* m);
-/* the leaf -> rank map and the query slices (host only, no GPU needed): [first, first + count) */
+/* the equal-count split of [0, total) over n ranks (host only, no GPU needed): [first, first + count).  pmk_multi slices the
+ * QUERIES this way (pmk_multi_query_range); pmk_multi_leaf_range is the same split for a host layer that deals leaves itself
+ * (patchmixturekriging_b200/sharding.py).  pmk_multi's own leaf -> rank map is cost-balanced: see pmk_multi_owned_range. */
 int pmk_multi_leaf_range(int n_ranks, int64_t n_leaves, int rank, int64_t* first, int64_t* count);
 int pmk_multi_query_range(int n_ranks, int64_t Nq, int rank, int64_t* first, int64_t* count);
+/* the leaves rank owns, 0-based [first, first + count), valid once the training data is staged (pmk_multi_stage_training /
+ * pmk_multi_fit): contiguous ranges of nearly equal cost sum(n^3) -- a leaf's share of the factorisation, the operand build
+ * and, for queries spread like the training points, the pair kernel */
+int pmk_multi_owned_range(const pmk_multi* m, int rank, int64_t* first, int64_t* count);
 /* rank's own handle, for inspection of the leaves it owns (pmk_get_L, pmk_get_alpha, pmk_condition_estimate ...) */
 int pmk_multi_handle(pmk_multi* m, int rank, pmk_handle** h);
 int pmk_multi_set_option(pmk_multi* m, int option, int64_t value);

@@ -78,7 +78,7 @@ end
 function ownerhandle(m::MultiHandle, n::Integer, N::Integer)
     first = Ref{Int64}(0); count = Ref{Int64}(0)
     for r in 0:length(m.devices)-1
-        ccall((:pmk_multi_leaf_range, libpmk), Cint, (Cint, Int64, Cint, Ref{Int64}, Ref{Int64}), length(m.devices), N, r, first, count)
+        check(m, ccall((:pmk_multi_owned_range, libpmk), Cint, (Ptr{Cvoid}, Cint, Ref{Int64}, Ref{Int64}), m.ptr, r, first, count))
         if first[] < n <= first[] + count[]
             h = Ref{Ptr{Cvoid}}(C_NULL)
             check(m, ccall((:pmk_multi_handle, libpmk), Cint, (Ptr{Cvoid}, Cint, Ref{Ptr{Cvoid}}), m.ptr, r, h))

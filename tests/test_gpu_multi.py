@@ -63,6 +63,13 @@ def test_multi_equals_single_bit_for_bit(built_lib, name):
         for leaf in sorted({0, len(X_set) // 2 - 1, len(X_set) // 2, len(X_set) - 1}):
             assert np.array_equal(em.c_set[leaf], eta.c_set[leaf])
             assert np.array_equal(em.L_set[leaf], eta.L_set[leaf])
+        # the leaf -> rank map: contiguous ranges that cover the leaves once, every range within one leaf of its share of sum(n^3)
+        ranges = [em.multi.owned_range(r) for r in range(len(devs))]
+        assert ranges[0][0] == 0 and all(c >= 1 for _, c in ranges)
+        assert all(ranges[r][0] + ranges[r][1] == (ranges[r + 1][0] if r + 1 < len(devs) else len(X_set)) for r in range(len(devs)))
+        cost = np.array([float(x.shape[0]) ** 3 for x in X_set])
+        if len(X_set) >= 4 * len(devs):
+            assert max(cost[a:a + c].sum() for a, c in ranges) <= cost.sum() / len(devs) + cost.max() * (1 + 1e-12)
         # pairs per leaf, summed over the planners
         pl = np.empty(len(X_set), dtype=np.int64)
         em.multi.check(_lib.lib().pmk_multi_leaf_pairs(em.multi.raw, _lib.ptr(pl)))
