@@ -249,6 +249,7 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
   __shared__ double a_c[32];
   __shared__ double a_n[32];                 // |u| of home's ancestors
   __shared__ double s_n[kCandCap];           // |u| of the candidates
+  __shared__ unsigned long long s_umax;      // largest |u| among the leaf's candidates (bit pattern of a positive double)
   const int leaf = blockIdx.x;
   const int64_t qa = leaf_qstart[leaf], qb = leaf_qstart[leaf + 1];
   if (qa == qb) return;
@@ -256,17 +257,27 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
   const int nc = (int)(cand_start[leaf + 1] - ca);
   const int ns = nc < kCandCap ? nc : kCandCap;
   const int Lv = tr.levels - 1;
-  for (int k = threadIdx.x; k < ns; k += blockDim.x) {
-    const int i = cand[ca + k];
-    s_c[k] = tr.hc[i];
-    double nn = 0.0;
+  if (threadIdx.x == 0) s_umax = 0ull;
+  __syncthreads();
+  {
+    double umax = 0.0;
+    for (int k = threadIdx.x; k < nc; k += blockDim.x) {
+      const int i = cand[ca + k];
+      double nn = 0.0;
 #pragma unroll
-    for (int d = 0; d < D; ++d) {
-      const double ud = tr.hv[d * tr.n_hp + i];
-      s_u[d][k] = ud;
-      nn += ud * ud;
+      for (int d = 0; d < D; ++d) {
+        const double ud = tr.hv[d * tr.n_hp + i];
+        if (k < ns) s_u[d][k] = ud;
+        nn += ud * ud;
+      }
+      const double un = sqrt(nn);
+      if (k < ns) {
+        s_c[k] = tr.hc[i];
+        s_n[k] = un;
+      }
+      umax = fmax(umax, un);
     }
-    s_n[k] = sqrt(nn);
+    atomicMax(&s_umax, (unsigned long long)__double_as_longlong(umax));
   }
   if (threadIdx.x == 0) {        // home's ancestors: node_0 = 0, node_{d+1} = node_d + (right ? 2^(Lv-1-d) : 1)
     int node = 0;
@@ -324,19 +335,25 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
     // home cell: findpartition gives home for both, the reference's xor test fails, the hyperplane is not kept -- no need
     // to run the two descents.  (Slack 1e-9 * (1 + |p|_1): six orders above the rounding of the dot products, four below
     // delta; whatever falls inside the slack takes the exact test.)
+    // ... and which of home's ancestors are NEAR the query: a probe of a buffered candidate is p + (t +- delta) u with |t| <= thr,
+    // i.e. at most (thr + |delta|) |u| away from p, so an ancestor plane farther from p than that (plus slack) has BOTH probes of
+    // EVERY buffered candidate on home's side -- only the near ones (typically one to three of twelve) can decide the xor test.
     double mrel = 1e300;
+    const double near_r = (thr + fabs(delta)) * __longlong_as_double((long long)s_umax) * (1.0 + 1e-9) + 1e-9 * pabs;
+    unsigned long long near = 0ull;
     for (int d = 0; d < Lv; ++d) {
       double v[D];
 #pragma unroll
       for (int dd = 0; dd < D; ++dd) v[dd] = a_u[dd][d];
-      mrel = fmin(mrel, fabs(dot_seq<D>(v, p) - a_c[d]) / a_n[d]);
+      const double dist = fabs(dot_seq<D>(v, p) - a_c[d]) / a_n[d];
+      mrel = fmin(mrel, dist);
+      if (!(dist > near_r)) near |= 1ull << d;
     }
     mrel -= 1e-9 * pabs;
-    unsigned short surv[64];
-    int nsurv = 0, kept = 0;
+    unsigned short surv[64], surv2[16];
+    int nsurv = 0, nsurv2 = 0, kept = 0;
     unsigned short kl[kKeptMax];
-    auto process = [&](int k) {
-      double u[D], c, un;
+    auto load_plane = [&](int k, double (&u)[D], double& c, double& un) {
       if (k < ns) {
         c = s_c[k];
         un = s_n[k];
@@ -353,8 +370,38 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
         }
         un = sqrt(un);
       }
+    };
+    // Stage 1 (cheap, exact-safe): can candidate k's xor test come out true at all?  Directional form of the "both probes inside
+    // home" argument, ancestor by ancestor (near ones only, deepest first): with f_a(x) = u_a . x - c_a,
+    // f_a(p + (t +- delta) u) = f_a(p) + t g +- delta g, g = u_a . u.  If the midpoint value is on home's side by more than
+    // |delta g| + slack for every near ancestor, both probes are in home; if it is on the other side by more than that for one
+    // ancestor, neither is: the reference's xor (mixtureGP.jl:387) is false either way and the exact test is not needed.  Whatever
+    // falls inside a band -- a plane of home's own boundary at the projected point, above all -- goes on to stage 2.
+    auto may_keep = [&](int k) -> bool {
+      double u[D], c, un;
+      load_plane(k, u, c, un);
       const double t = __dadd_rn(-dot_seq<D>(u, p), c);            // mixtureGP.jl:361
-      if (un * (fabs(t) + fabs(delta)) * (1.0 + 1e-9) < mrel) return;   // both probes inside the home cell (see mrel)
+      bool all_in = true;
+      for (unsigned long long m = near; m != 0ull;) {
+        const int d = 63 - __clzll((long long)m);
+        m &= ~(1ull << d);
+        double v[D];
+#pragma unroll
+        for (int dd = 0; dd < D; ++dd) v[dd] = a_u[dd][d];
+        const double gd = dot_seq<D>(v, u);
+        const double fz = fma(t, gd, dot_seq<D>(v, p) - a_c[d]);
+        const double band = fabs(delta * gd) + 1e-9 * pabs * (a_n[d] + 1.0);
+        const double sm = ((leaf >> (Lv - 1 - d)) & 1) ? fz : -fz;     // > 0: home's side of ancestor d
+        if (sm < -band) return false;
+        all_in = all_in && (sm > band);
+      }
+      return !all_in;
+    };
+    // Stage 2: the reference's exact test.
+    auto exact = [&](int k) {
+      double u[D], c, un;
+      load_plane(k, u, c, un);
+      const double t = __dadd_rn(-dot_seq<D>(u, p), c);            // mixtureGP.jl:361
       double s = 0.0;
 #pragma unroll
       for (int d = 0; d < D; ++d) {
@@ -375,44 +422,49 @@ k_neighbours_scan(TreeDev tr, QueryPlan q, double radius, double delta, const in
         ++kept;
       }
     };
-    // replay the buffered survivors in order, the warp reconverged at every survivor index
+    // Both stages are replayed entry index by entry index with the warp reconverged at every step, each from its own per-lane
+    // list (ascending k throughout, so the kept list stays in the reference's order).  Stage 1 thins 25-30 radius survivors per
+    // query to the one or two planes that bound home near the query; stage 2 then runs with most of its lanes busy (with one list
+    // the exact walk ran at two active lanes of 32: ncu, profiles/ncu_r02_neighbours_scan_c3.csv).
+    auto flush2 = [&]() {
+      const int nmax = __reduce_max_sync(0xffffffffu, nsurv2);
+      for (int s_ = 0; s_ < nmax; ++s_) {
+        __syncwarp();
+        if (s_ < nsurv2) exact(surv2[s_]);
+      }
+      nsurv2 = 0;
+    };
     auto flush = [&]() {
       const int nmax = __reduce_max_sync(0xffffffffu, nsurv);
       for (int s_ = 0; s_ < nmax; ++s_) {
         __syncwarp();
-        if (s_ < nsurv) process(surv[s_]);
+        if (__any_sync(0xffffffffu, nsurv2 == 16)) flush2();
+        if (s_ < nsurv && may_keep(surv[s_])) surv2[nsurv2++] = surv[s_];
       }
       nsurv = 0;
     };
-    for (int k = 0; k < nc; ++k) {
-      double tq, un;
-      if (k < ns) {
-        double u[D];
+    // The candidate scan proper: |t| against the radius (conservative form), and the isotropic "closer than the nearest boundary of
+    // the home cell" rejection (both probes inside home) for those within it.  A list can grow by one per candidate: with the check
+    // every 16 candidates nobody passes 48 + 16 entries.
+    for (int k = 0; k < ns; ++k) {
+      double u[D];
 #pragma unroll
-        for (int d = 0; d < D; ++d) u[d] = s_u[d][k];
-        tq = __dadd_rn(-dot_seq<D>(u, p), s_c[k]);
-        un = s_n[k];
-      } else {
-        const int i = cand[ca + k];
-        double u[D];
-        un = 0.0;
-#pragma unroll
-        for (int d = 0; d < D; ++d) {
-          u[d] = tr.hv[d * tr.n_hp + i];
-          un += u[d] * u[d];
-        }
-        un = sqrt(un);
-        tq = __dadd_rn(-dot_seq<D>(u, p), tr.hc[i]);
+      for (int d = 0; d < D; ++d) u[d] = s_u[d][k];
+      const double tq = __dadd_rn(-dot_seq<D>(u, p), s_c[k]);
+      if ((k & 15) == 0 && __any_sync(0xffffffffu, nsurv > 48)) flush();
+      if (valid && !(fabs(tq) > thr)) {
+        if (!(s_n[k] * (fabs(tq) + fabs(delta)) * (1.0 + 1e-9) < mrel)) surv[nsurv++] = (unsigned short)k;
       }
-      // a full list anywhere in the warp: everybody replays what it has (ascending order is kept), then collecting goes on
+    }
+    for (int k = ns; k < nc; ++k) {          // candidates beyond the shared-memory list (very large radius only)
+      double u[D], c, un;
+      load_plane(k, u, c, un);
+      const double tq = __dadd_rn(-dot_seq<D>(u, p), c);
       if (__any_sync(0xffffffffu, nsurv == 64)) flush();
-      // Buffered for the exact test: within the radius (cheap form) AND not closer than the nearest boundary of the home cell
-      // (process() repeats this second rejection with the same operands -- applying it here keeps the replay, which runs at the
-      // pace of the lane with the most survivors and mostly with one or two lanes active, to the handful of planes that can pass:
-      // ncu had 622 warp instructions per QUERY, half of the lanes idle on average, nearly all of it in the replay).
       if (valid && !(fabs(tq) > thr) && !(un * (fabs(tq) + fabs(delta)) * (1.0 + 1e-9) < mrel)) surv[nsurv++] = (unsigned short)k;
     }
     flush();
+    flush2();
     if (valid) {
       q.npairs[j] = kept + 1;
       uint16_t* rec = kept_rec + j * 8;
