@@ -358,73 +358,92 @@ int pmk_multi_set_option(pmk_multi* m, int option, int64_t value) {
 }
 
 // ---------------------------------------------------------------------------------------------
-int pmk_multi_stage_training(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X, const double* y) {
-  if (!m) return PMK_ERR_ARG;
-  m->staged_training = false;
-  m->fitted = false;
+namespace {
+
+int check_training(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X, const double* y) {
   if (D < 1 || D > PMK_MAX_DIM) return mfail(m, PMK_ERR_UNSUPPORTED, "D=%d unsupported (1..%d)", D, PMK_MAX_DIM);
   if (!leaf_off || !X || !y) return mfail(m, PMK_ERR_ARG, "NULL pointer");
   if (n_leaves < m->n) return mfail(m, PMK_ERR_ARG, "%lld leaves cannot be dealt to %d ranks (every rank owns at least one leaf)", (long long)n_leaves, m->n);
   if (leaf_off[0] != 0) return mfail(m, PMK_ERR_ARG, "leaf_off[0] must be 0");
+  return PMK_OK;
+}
+
+// Ownership: contiguous leaf ranges of (nearly) equal COST, cost of a leaf = n^3 -- its share of the factorisation and of the
+// operand build, and with queries spread like the training points also of the pair kernel (pairs ~ n, flops per pair ~ n^2).
+// Boundary i is the leaf index whose cost prefix is nearest to i / n of the total, every rank keeping at least one leaf.
+// (Equal leaf COUNTS left the slowest of 8 owners 6 % behind the mean on C4: leaf sizes 700 .. 1400.)
+void deal_leaves(pmk_multi* m, int64_t n_leaves, const int64_t* leaf_off) {
+  std::vector<double> pre((size_t)n_leaves + 1, 0.0);
+  for (int64_t p = 0; p < n_leaves; ++p) {
+    const double np = (double)(leaf_off[p + 1] - leaf_off[p]);
+    pre[p + 1] = pre[p] + np * np * np;
+  }
+  std::vector<int64_t> bnd((size_t)m->n + 1, 0);
+  bnd[m->n] = n_leaves;
+  for (int i = 1; i < m->n; ++i) {
+    const double target = pre[n_leaves] * (double)i / (double)m->n;
+    int64_t k = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
+    if (k > 0 && target - pre[k - 1] < pre[k] - target) --k;
+    k = std::max<int64_t>(k, bnd[i - 1] + 1);
+    k = std::min<int64_t>(k, n_leaves - (m->n - i));
+    bnd[i] = k;
+  }
+  for (int i = 0; i < m->n; ++i) {
+    m->rk[i].leaf_first = bnd[i];
+    m->rk[i].leaf_count = bnd[i + 1] - bnd[i];
+  }
+}
+
+// rank i copies the inputs of its leaves to its GPU (asynchronously on its stream; `sync`: wait for the copies)
+int stage_training_rank(pmk_multi* m, int i, int D, const int64_t* leaf_off, const double* X, const double* y, bool sync) {
+  Rank& r = m->rk[i];
+  const int64_t p0 = leaf_off[r.leaf_first], p1 = leaf_off[r.leaf_first + r.leaf_count];
+  r.leaf_off.resize(r.leaf_count + 1);
+  for (int64_t k = 0; k <= r.leaf_count; ++k) r.leaf_off[k] = leaf_off[r.leaf_first + k] - p0;
+  if (p1 - p0 < 1) {
+    r.rc = PMK_ERR_ARG;
+    r.err = "no training points";
+    return r.rc;
+  }
+  RC(r, r.dX.ensure(sizeof(double) * (size_t)(p1 - p0) * D));
+  RC(r, r.dy.ensure(sizeof(double) * (size_t)(p1 - p0)));
+  RC(r, cudaMemcpyAsync(r.dX.p, X + p0 * D, sizeof(double) * (size_t)(p1 - p0) * D, cudaMemcpyHostToDevice, r.stream));
+  RC(r, cudaMemcpyAsync(r.dy.p, y + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, r.stream));
+  if (sync) RC(r, cudaStreamSynchronize(r.stream));
+  return PMK_OK;
+}
+
+}  // namespace
+
+int pmk_multi_stage_training(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X, const double* y) {
+  if (!m) return PMK_ERR_ARG;
+  m->staged_training = false;
+  m->fitted = false;
+  if (int rc = check_training(m, D, n_leaves, leaf_off, X, y)) return rc;
   m->D = D;
   m->n_leaves = n_leaves;
-  // Ownership: contiguous leaf ranges of (nearly) equal COST, cost of a leaf = n^3 -- its share of the factorisation and of the
-  // operand build, and with queries spread like the training points also of the pair kernel (pairs ~ n, flops per pair ~ n^2).
-  // Boundary i is the leaf index whose cost prefix is nearest to i / n of the total, every rank keeping at least one leaf.
-  // (Equal leaf COUNTS left the slowest of 8 owners 6 % behind the mean on C4: leaf sizes 700 .. 1400.)
-  {
-    std::vector<double> pre((size_t)n_leaves + 1, 0.0);
-    for (int64_t p = 0; p < n_leaves; ++p) {
-      const double np = (double)(leaf_off[p + 1] - leaf_off[p]);
-      pre[p + 1] = pre[p] + np * np * np;
-    }
-    std::vector<int64_t> bnd((size_t)m->n + 1, 0);
-    bnd[m->n] = n_leaves;
-    for (int i = 1; i < m->n; ++i) {
-      const double target = pre[n_leaves] * (double)i / (double)m->n;
-      int64_t k = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
-      if (k > 0 && target - pre[k - 1] < pre[k] - target) --k;
-      k = std::max<int64_t>(k, bnd[i - 1] + 1);
-      k = std::min<int64_t>(k, n_leaves - (m->n - i));
-      bnd[i] = k;
-    }
-    for (int i = 0; i < m->n; ++i) {
-      m->rk[i].leaf_first = bnd[i];
-      m->rk[i].leaf_count = bnd[i + 1] - bnd[i];
-    }
-  }
-  const int rc = run_ranks(m, [&](int i) -> int {
-    Rank& r = m->rk[i];
-    const int64_t p0 = leaf_off[r.leaf_first], p1 = leaf_off[r.leaf_first + r.leaf_count];
-    r.leaf_off.resize(r.leaf_count + 1);
-    for (int64_t k = 0; k <= r.leaf_count; ++k) r.leaf_off[k] = leaf_off[r.leaf_first + k] - p0;
-    if (p1 - p0 < 1) {
-      r.rc = PMK_ERR_ARG;
-      r.err = "no training points";
-      return r.rc;
-    }
-    RC(r, r.dX.ensure(sizeof(double) * (size_t)(p1 - p0) * D));
-    RC(r, r.dy.ensure(sizeof(double) * (size_t)(p1 - p0)));
-    RC(r, cudaMemcpyAsync(r.dX.p, X + p0 * D, sizeof(double) * (size_t)(p1 - p0) * D, cudaMemcpyHostToDevice, r.stream));
-    RC(r, cudaMemcpyAsync(r.dy.p, y + p0, sizeof(double) * (size_t)(p1 - p0), cudaMemcpyHostToDevice, r.stream));
-    RC(r, cudaStreamSynchronize(r.stream));
-    return PMK_OK;
-  });
+  deal_leaves(m, n_leaves, leaf_off);
+  const int rc = run_ranks(m, [&](int i) -> int { return stage_training_rank(m, i, D, leaf_off, X, y, true); });
   if (rc == PMK_OK) m->staged_training = true;
   return rc;
 }
 
-int pmk_multi_fit_staged(pmk_multi* m, int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
-  if (!m) return PMK_ERR_ARG;
+namespace {
+
+// every rank fits its leaves and builds its query operand; with host inputs (X != nullptr) it stages them first, in the same job
+int fit_job(pmk_multi* m, const int64_t* leaf_off, const double* X, const double* y, int kernel_id, const double* kparams, int nparams,
+            double sigma2, int64_t* bad_leaf, int* info) {
   if (bad_leaf) *bad_leaf = 0;
   if (info) *info = 0;
-  if (!m->staged_training) return mfail(m, PMK_ERR_STATE, "pmk_multi_stage_training has not been called");
   m->fitted = false;
   m->results_ready = false;
   std::vector<int64_t> bad(m->n, 0);
   std::vector<int> inf(m->n, 0);
   const int rc = run_ranks(m, [&](int i) -> int {
     Rank& r = m->rk[i];
+    if (X) {
+      if (int src = stage_training_rank(m, i, m->D, leaf_off, X, y, false)) return src;      // same stream: the fit's kernels follow the copies
+    }
     RK(r, pmk_set_leaf_base(r.h, r.leaf_first, m->n_leaves));
     RC(r, cudaEventRecord(r.ev[EV_FIT0], r.stream));
     const int frc = pmk_fit_dev(r.h, m->D, r.leaf_count, r.leaf_off.data(), r.dX.as<double>(), r.dy.as<double>(), kernel_id, kparams, nparams,
@@ -453,10 +472,35 @@ int pmk_multi_fit_staged(pmk_multi* m, int kernel_id, const double* kparams, int
   return PMK_OK;
 }
 
+}  // namespace
+
+int pmk_multi_fit_staged(pmk_multi* m, int kernel_id, const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
+  if (!m) return PMK_ERR_ARG;
+  if (!m->staged_training) {
+    if (bad_leaf) *bad_leaf = 0;
+    if (info) *info = 0;
+    return mfail(m, PMK_ERR_STATE, "pmk_multi_stage_training has not been called");
+  }
+  return fit_job(m, nullptr, nullptr, nullptr, kernel_id, kparams, nparams, sigma2, bad_leaf, info);
+}
+
+// stage + fit in ONE job per rank: the host-to-device copies and the fit's kernels are queued on the rank's stream back to back
+// (no synchronize, no second wake-up of the rank threads in between)
 int pmk_multi_fit(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_off, const double* X, const double* y, int kernel_id,
                   const double* kparams, int nparams, double sigma2, int64_t* bad_leaf, int* info) {
-  if (int rc = pmk_multi_stage_training(m, D, n_leaves, leaf_off, X, y)) return rc;
-  return pmk_multi_fit_staged(m, kernel_id, kparams, nparams, sigma2, bad_leaf, info);
+  if (!m) return PMK_ERR_ARG;
+  m->staged_training = false;
+  m->fitted = false;
+  if (bad_leaf) *bad_leaf = 0;
+  if (info) *info = 0;
+  if (int rc = check_training(m, D, n_leaves, leaf_off, X, y)) return rc;
+  m->D = D;
+  m->n_leaves = n_leaves;
+  deal_leaves(m, n_leaves, leaf_off);
+  const int rc = fit_job(m, leaf_off, X, y, kernel_id, kparams, nparams, sigma2, bad_leaf, info);
+  // the inputs are on the GPUs whenever every rank got past its copies: a not-positive-definite leaf leaves them staged
+  if (rc == PMK_OK || rc == PMK_ERR_NOT_POSDEF) m->staged_training = true;
+  return rc;
 }
 
 int pmk_multi_set_tree(pmk_multi* m, int D, int levels, const double* hp_v, const double* hp_c) {
@@ -472,24 +516,44 @@ int pmk_multi_set_tree(pmk_multi* m, int D, int levels, const double* hp_v, cons
 }
 
 // ---------------------------------------------------------------------------------------------
+namespace {
+
+int check_queries(pmk_multi* m, int64_t Nq, const double* Xq) {
+  if (m->D == 0) return mfail(m, PMK_ERR_STATE, "query before fit");
+  if (Nq < m->n) return mfail(m, PMK_ERR_ARG, "Nq=%lld: every rank plans at least one query (the reference asserts !isempty(Xq))", (long long)Nq);
+  if (!Xq) return mfail(m, PMK_ERR_ARG, "NULL pointer");
+  return PMK_OK;
+}
+
+// rank i copies its slice of the queries to its GPU (asynchronously on its stream; `sync`: wait for the copy)
+int stage_queries_rank(pmk_multi* m, int i, int64_t Nq, const double* Xq, bool sync) {
+  Rank& r = m->rk[i];
+  const int D = m->D;
+  range_of(m->n, Nq, i, &r.q_first, &r.q_count);
+  RC(r, r.dXq.ensure(sizeof(double) * (size_t)r.q_count * D));
+  RC(r, r.dYq.ensure(sizeof(double) * (size_t)r.q_count));
+  RC(r, r.dVq.ensure(sizeof(double) * (size_t)r.q_count));
+  RC(r, cudaMemcpyAsync(r.dXq.p, Xq + r.q_first * D, sizeof(double) * (size_t)r.q_count * D, cudaMemcpyHostToDevice, r.stream));
+  if (sync) RC(r, cudaStreamSynchronize(r.stream));
+  return PMK_OK;
+}
+
+// rank i copies its slice of the results into the caller's arrays (queued on its stream; the caller of this synchronises)
+int fetch_results_rank(pmk_multi* m, int i, double* Yq, double* Vq, bool mean_only) {
+  Rank& r = m->rk[i];
+  RC(r, cudaMemcpyAsync(Yq + r.q_first, r.dYq.p, sizeof(double) * (size_t)r.q_count, cudaMemcpyDeviceToHost, r.stream));
+  if (!mean_only) RC(r, cudaMemcpyAsync(Vq + r.q_first, r.dVq.p, sizeof(double) * (size_t)r.q_count, cudaMemcpyDeviceToHost, r.stream));
+  return PMK_OK;
+}
+
+}  // namespace
+
 int pmk_multi_stage_queries(pmk_multi* m, int64_t Nq, const double* Xq) {
   if (!m) return PMK_ERR_ARG;
   m->staged_queries = false;
   m->results_ready = false;
-  if (m->D == 0) return mfail(m, PMK_ERR_STATE, "query before fit");
-  if (Nq < m->n) return mfail(m, PMK_ERR_ARG, "Nq=%lld: every rank plans at least one query (the reference asserts !isempty(Xq))", (long long)Nq);
-  if (!Xq) return mfail(m, PMK_ERR_ARG, "NULL pointer");
-  const int D = m->D;
-  const int rc = run_ranks(m, [&](int i) -> int {
-    Rank& r = m->rk[i];
-    range_of(m->n, Nq, i, &r.q_first, &r.q_count);
-    RC(r, r.dXq.ensure(sizeof(double) * (size_t)r.q_count * D));
-    RC(r, r.dYq.ensure(sizeof(double) * (size_t)r.q_count));
-    RC(r, r.dVq.ensure(sizeof(double) * (size_t)r.q_count));
-    RC(r, cudaMemcpyAsync(r.dXq.p, Xq + r.q_first * D, sizeof(double) * (size_t)r.q_count * D, cudaMemcpyHostToDevice, r.stream));
-    RC(r, cudaStreamSynchronize(r.stream));
-    return PMK_OK;
-  });
+  if (int rc = check_queries(m, Nq, Xq)) return rc;
+  const int rc = run_ranks(m, [&](int i) -> int { return stage_queries_rank(m, i, Nq, Xq, true); });
   if (rc == PMK_OK) {
     m->staged_queries = true;
     m->Nq = Nq;
@@ -497,17 +561,23 @@ int pmk_multi_stage_queries(pmk_multi* m, int64_t Nq, const double* Xq) {
   return rc;
 }
 
-int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkernel_id, const double* wparams, int nw, int flags) {
-  if (!m) return PMK_ERR_ARG;
-  if (!m->fitted) return mfail(m, PMK_ERR_STATE, "query before fit");
-  if (!m->tree_set) return mfail(m, PMK_ERR_STATE, "query before pmk_multi_set_tree");
-  if (!m->staged_queries) return mfail(m, PMK_ERR_STATE, "pmk_multi_stage_queries has not been called");
+namespace {
+
+// The query of every rank as ONE job per rank thread.  With host arrays (hXq / hYq / hVq) the job also stages the rank's slice of the
+// queries in front of the plan and copies its slice of the results out behind the combine, everything queued on the rank's stream
+// back to back: no synchronize and no second wake-up of the rank threads between the copies and the stages.
+int query_job(pmk_multi* m, double radius, double delta, int wkernel_id, const double* wparams, int nw, int flags, int64_t Nq,
+              const double* hXq, double* hYq, double* hVq) {
   m->results_ready = false;
   const int n = m->n, D = m->D;
+  const bool mean_only = (flags & 1) != 0;
   if (n == 1) {
     // one rank owns every leaf: the plan's own leaf binning feeds the pair kernel directly (nothing is packed, copied or re-sorted)
     const int rc1 = run_ranks(m, [&](int) -> int {
       Rank& r = m->rk[0];
+      if (hXq) {
+        if (int src = stage_queries_rank(m, 0, Nq, hXq, false)) return src;
+      }
       RC(r, cudaEventRecord(r.ev[EV_START], r.stream));
       RK(r, pmk_query_plan_dev(r.h, r.q_count, r.dXq.as<double>(), radius, delta, wkernel_id, wparams, nw, &r.n_pairs));
       RC(r, r.pu.ensure(sizeof(double) * (size_t)r.n_pairs));
@@ -518,6 +588,9 @@ int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkerne
       RC(r, cudaEventRecord(r.ev[EV_PAIRS], r.stream));
       RK(r, pmk_query_combine_dev(r.h, r.pu.as<double>(), r.pv.as<double>(), r.dYq.as<double>(), r.dVq.as<double>()));
       RC(r, cudaEventRecord(r.ev[EV_END], r.stream));
+      if (hYq) {
+        if (int frc = fetch_results_rank(m, 0, hYq, hVq, mean_only)) return frc;
+      }
       RC(r, cudaStreamSynchronize(r.stream));
       r.ms[PMK_MT_QUERY] = elapsed(r.ev[EV_START], r.ev[EV_END]);
       r.ms[PMK_MT_Q_PLAN] = elapsed(r.ev[EV_START], r.ev[EV_PLAN]);
@@ -541,6 +614,9 @@ int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkerne
     Rank& r = m->rk[i];
     // every stage: do the work unless something failed, then meet the others (a failed rank keeps meeting)
     auto plan = [&]() -> int {
+      if (hXq) {
+        if (int src = stage_queries_rank(m, i, Nq, hXq, false)) return src;
+      }
       RC(r, cudaEventRecord(r.ev[EV_START], r.stream));
       RK(r, pmk_query_plan_dev(r.h, r.q_count, r.dXq.as<double>(), radius, delta, wkernel_id, wparams, nw, &r.n_pairs));
       r.seg.assign(n + 1, 0);
@@ -616,6 +692,9 @@ int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkerne
       RK(r, pmk_query_set_flags(r.h, flags));
       RK(r, pmk_query_combine_dev(r.h, r.pu.as<double>(), r.pv.as<double>(), r.dYq.as<double>(), r.dVq.as<double>()));
       RC(r, cudaEventRecord(r.ev[EV_END], r.stream));
+      if (hYq) {
+        if (int frc = fetch_results_rank(m, i, hYq, hVq, mean_only)) return frc;
+      }
       RC(r, cudaStreamSynchronize(r.stream));
       r.ms[PMK_MT_QUERY] = elapsed(r.ev[EV_START], r.ev[EV_END]);
       r.ms[PMK_MT_Q_PLAN] = elapsed(r.ev[EV_START], r.ev[EV_PLAN]);
@@ -638,6 +717,16 @@ int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkerne
   return PMK_OK;
 }
 
+}  // namespace
+
+int pmk_multi_query_staged(pmk_multi* m, double radius, double delta, int wkernel_id, const double* wparams, int nw, int flags) {
+  if (!m) return PMK_ERR_ARG;
+  if (!m->fitted) return mfail(m, PMK_ERR_STATE, "query before fit");
+  if (!m->tree_set) return mfail(m, PMK_ERR_STATE, "query before pmk_multi_set_tree");
+  if (!m->staged_queries) return mfail(m, PMK_ERR_STATE, "pmk_multi_stage_queries has not been called");
+  return query_job(m, radius, delta, wkernel_id, wparams, nw, flags, m->Nq, nullptr, nullptr, nullptr);
+}
+
 int pmk_multi_fetch_results(pmk_multi* m, double* Yq, double* Vq) {
   if (!m) return PMK_ERR_ARG;
   if (!m->results_ready) return mfail(m, PMK_ERR_STATE, "no query results (pmk_multi_query_staged)");
@@ -646,20 +735,28 @@ int pmk_multi_fetch_results(pmk_multi* m, double* Yq, double* Vq) {
   // every rank copies its slice straight into the caller's arrays: n concurrent device-to-host streams, no gather on a device
   return run_ranks(m, [&](int i) -> int {
     Rank& r = m->rk[i];
-    RC(r, cudaMemcpyAsync(Yq + r.q_first, r.dYq.p, sizeof(double) * (size_t)r.q_count, cudaMemcpyDeviceToHost, r.stream));
-    if (!mean_only) RC(r, cudaMemcpyAsync(Vq + r.q_first, r.dVq.p, sizeof(double) * (size_t)r.q_count, cudaMemcpyDeviceToHost, r.stream));
+    if (int rc = fetch_results_rank(m, i, Yq, Vq, mean_only)) return rc;
     RC(r, cudaStreamSynchronize(r.stream));
     return PMK_OK;
   });
 }
 
+// stage + query + fetch in ONE job per rank (see query_job)
 int pmk_multi_query(pmk_multi* m, int64_t Nq, const double* Xq, double radius, double delta, int wkernel_id, const double* wparams, int nw,
                     int flags, double* Yq, double* Vq) {
   if (!m) return PMK_ERR_ARG;
   if (!Yq || (!(flags & 1) && !Vq)) return mfail(m, PMK_ERR_ARG, "NULL pointer");
-  if (int rc = pmk_multi_stage_queries(m, Nq, Xq)) return rc;
-  if (int rc = pmk_multi_query_staged(m, radius, delta, wkernel_id, wparams, nw, flags)) return rc;
-  return pmk_multi_fetch_results(m, Yq, Vq);
+  m->staged_queries = false;
+  m->results_ready = false;
+  if (int rc = check_queries(m, Nq, Xq)) return rc;
+  if (!m->fitted) return mfail(m, PMK_ERR_STATE, "query before fit");
+  if (!m->tree_set) return mfail(m, PMK_ERR_STATE, "query before pmk_multi_set_tree");
+  const int rc = query_job(m, radius, delta, wkernel_id, wparams, nw, flags, Nq, Xq, Yq, Vq);
+  if (rc == PMK_OK) {
+    m->staged_queries = true;
+    m->Nq = Nq;
+  }
+  return rc;
 }
 
 int pmk_multi_leaf_pairs(pmk_multi* m, int64_t* pairs_per_leaf) {
