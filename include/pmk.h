@@ -234,6 +234,9 @@ int pmk_multi_query_range(int n_ranks, int64_t Nq, int rank, int64_t* first, int
  * pmk_multi_fit): contiguous ranges of nearly equal cost sum(n^3) -- a leaf's share of the factorisation, the operand build
  * and, for queries spread like the training points, the pair kernel */
 int pmk_multi_owned_range(const pmk_multi* m, int rank, int64_t* first, int64_t* count);
+/* the same deal as a host-only function (no GPU needed), for a host layer that runs one process per GPU and wants pmk_multi's map:
+ * first[0 .. n_ranks] = the boundaries of n_ranks contiguous leaf ranges of nearly equal sum(n^3); n_leaves >= n_ranks */
+int pmk_multi_balanced_ranges(int n_ranks, int64_t n_leaves, const int64_t* leaf_off, int64_t* first);
 /* rank's own handle, for inspection of the leaves it owns (pmk_get_L, pmk_get_alpha, pmk_condition_estimate ...) */
 int pmk_multi_handle(pmk_multi* m, int rank, pmk_handle** h);
 int pmk_multi_set_option(pmk_multi* m, int option, int64_t value);

@@ -29,7 +29,7 @@ SYMBOLS = [
     "pmk_query_dev", "pmk_last_query_pairs", "pmk_last_query_debug", "pmk_last_query_debug_dense", "pmk_last_query_leaf_pairs", "pmk_build_M", "pmk_query_plan_dev",
     "pmk_query_pairs_dev", "pmk_query_combine_dev", "pmk_set_leaf_base", "pmk_query_plan_segments", "pmk_query_plan_pack_dev", "pmk_query_pairs_routed_dev",
     "pmk_query_plan_unpack_dev", "pmk_query_set_flags", "pmk_set_option", "pmk_condition_estimate", "pmk_measure_fp64_peak",
-    "pmk_multi_create", "pmk_multi_destroy", "pmk_multi_last_error", "pmk_multi_size", "pmk_multi_leaf_range", "pmk_multi_query_range", "pmk_multi_owned_range", "pmk_multi_handle",
+    "pmk_multi_create", "pmk_multi_destroy", "pmk_multi_last_error", "pmk_multi_size", "pmk_multi_leaf_range", "pmk_multi_query_range", "pmk_multi_owned_range", "pmk_multi_balanced_ranges", "pmk_multi_handle",
     "pmk_multi_set_option", "pmk_multi_fit", "pmk_multi_set_tree", "pmk_multi_query", "pmk_multi_stage_training", "pmk_multi_fit_staged",
     "pmk_multi_stage_queries", "pmk_multi_query_staged", "pmk_multi_fetch_results", "pmk_multi_leaf_pairs", "pmk_multi_get_timings", "pmk_multi_launch_count", "pmk_partition_begin", "pmk_partition_level_z", "pmk_partition_level_split", "pmk_partition_fetch",
     "pmk_partition_sum_plan", "pmk_save_model", "pmk_load_model", "pmk_model_info", "pmk_get_X", "pmk_get_tree", "pmk_get_timings", "pmk_debug_counters", "pmk_launch_count", "pmk_stream", "pmk_synchronize",
@@ -109,6 +109,7 @@ def lib() -> C.CDLL:
     L.pmk_multi_size.argtypes = [vp]
     L.pmk_multi_leaf_range.argtypes = [i32, i64, i32, C.POINTER(i64), C.POINTER(i64)]
     L.pmk_multi_owned_range.argtypes = [C.c_void_p, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.pmk_multi_balanced_ranges.argtypes = [i32, i64, vp, vp]
     L.pmk_multi_query_range.argtypes = [i32, i64, i32, C.POINTER(i64), C.POINTER(i64)]
     L.pmk_multi_handle.argtypes = [vp, i32, C.POINTER(vp)]
     L.pmk_multi_set_option.argtypes = [vp, i32, i64]

@@ -233,6 +233,28 @@ void range_of(int n, int64_t total, int r, int64_t* first, int64_t* count) {
   *count = b - a;
 }
 
+// Ownership: contiguous leaf ranges of (nearly) equal COST, cost of a leaf = n^3 -- its share of the factorisation and of the
+// operand build, and with queries spread like the training points also of the pair kernel (pairs ~ n, flops per pair ~ n^2).
+// Boundary i is the leaf index whose cost prefix is nearest to i / n of the total, every rank keeping at least one leaf.
+// (Equal leaf COUNTS left the slowest of 8 owners 6 % behind the mean on C4: leaf sizes 700 .. 1400.)
+void balanced_bounds(int n, int64_t n_leaves, const int64_t* leaf_off, int64_t* bnd /* n + 1 */) {
+  std::vector<double> pre((size_t)n_leaves + 1, 0.0);
+  for (int64_t p = 0; p < n_leaves; ++p) {
+    const double np = (double)(leaf_off[p + 1] - leaf_off[p]);
+    pre[p + 1] = pre[p] + np * np * np;
+  }
+  bnd[0] = 0;
+  bnd[n] = n_leaves;
+  for (int i = 1; i < n; ++i) {
+    const double target = pre[n_leaves] * (double)i / (double)n;
+    int64_t k = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
+    if (k > 0 && target - pre[k - 1] < pre[k] - target) --k;
+    k = std::max<int64_t>(k, bnd[i - 1] + 1);
+    k = std::min<int64_t>(k, n_leaves - (n - i));
+    bnd[i] = k;
+  }
+}
+
 float elapsed(cudaEvent_t a, cudaEvent_t b) {
   float t = 0.f;
   return cudaEventElapsedTime(&t, a, b) == cudaSuccess ? t : 0.f;
@@ -250,6 +272,15 @@ int pmk_multi_leaf_range(int n_ranks, int64_t n_leaves, int rank, int64_t* first
 
 int pmk_multi_query_range(int n_ranks, int64_t Nq, int rank, int64_t* first, int64_t* count) {
   return pmk_multi_leaf_range(n_ranks, Nq, rank, first, count);
+}
+
+
+int pmk_multi_balanced_ranges(int n_ranks, int64_t n_leaves, const int64_t* leaf_off, int64_t* first) {
+  if (n_ranks < 1 || n_leaves < n_ranks || !leaf_off || !first) return PMK_ERR_ARG;
+  for (int64_t p = 0; p < n_leaves; ++p)
+    if (leaf_off[p + 1] < leaf_off[p]) return PMK_ERR_ARG;
+  balanced_bounds(n_ranks, n_leaves, leaf_off, first);
+  return PMK_OK;
 }
 
 const char* pmk_multi_last_error(const pmk_multi* m) { return m ? m->err.c_str() : g_multi_create_error.c_str(); }
@@ -368,26 +399,9 @@ int check_training(pmk_multi* m, int D, int64_t n_leaves, const int64_t* leaf_of
   return PMK_OK;
 }
 
-// Ownership: contiguous leaf ranges of (nearly) equal COST, cost of a leaf = n^3 -- its share of the factorisation and of the
-// operand build, and with queries spread like the training points also of the pair kernel (pairs ~ n, flops per pair ~ n^2).
-// Boundary i is the leaf index whose cost prefix is nearest to i / n of the total, every rank keeping at least one leaf.
-// (Equal leaf COUNTS left the slowest of 8 owners 6 % behind the mean on C4: leaf sizes 700 .. 1400.)
 void deal_leaves(pmk_multi* m, int64_t n_leaves, const int64_t* leaf_off) {
-  std::vector<double> pre((size_t)n_leaves + 1, 0.0);
-  for (int64_t p = 0; p < n_leaves; ++p) {
-    const double np = (double)(leaf_off[p + 1] - leaf_off[p]);
-    pre[p + 1] = pre[p] + np * np * np;
-  }
   std::vector<int64_t> bnd((size_t)m->n + 1, 0);
-  bnd[m->n] = n_leaves;
-  for (int i = 1; i < m->n; ++i) {
-    const double target = pre[n_leaves] * (double)i / (double)m->n;
-    int64_t k = std::lower_bound(pre.begin(), pre.end(), target) - pre.begin();
-    if (k > 0 && target - pre[k - 1] < pre[k] - target) --k;
-    k = std::max<int64_t>(k, bnd[i - 1] + 1);
-    k = std::min<int64_t>(k, n_leaves - (m->n - i));
-    bnd[i] = k;
-  }
+  balanced_bounds(m->n, n_leaves, leaf_off, bnd.data());
   for (int i = 0; i < m->n; ++i) {
     m->rk[i].leaf_first = bnd[i];
     m->rk[i].leaf_count = bnd[i + 1] - bnd[i];

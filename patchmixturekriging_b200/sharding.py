@@ -6,7 +6,7 @@ and carries the SAME flow over torch.distributed point-to-point operations (NCCL
 host layer that runs one process per GPU on top of the single-GPU building blocks (pmk_set_leaf_base,
 pmk_query_plan_segments / _pack_dev, pmk_query_pairs_routed_dev, pmk_query_plan_unpack_dev):
 
-  fit   : rank r fits leaves leaf_range(r); no exchange.
+  fit   : rank r fits leaves leaf_range(r) (equal counts; balanced_first_leaf gives pmk_multi's cost-balanced ranges); no exchange.
   query : rank r plans queries query_slice(r); its (query, leaf) pairs, sorted by leaf, form one contiguous segment per
           owner (segments); the segments travel to the owners (exchange_segments), the owners answer them in the order
           received, the answers travel back (return_segments), the planner combines in the reference's slot order.
@@ -23,6 +23,27 @@ def leaf_range(rank: int, world: int, n_leaves: int) -> Tuple[int, int]:
     a = (n_leaves * rank) // world
     b = (n_leaves * (rank + 1)) // world
     return a, b - a
+
+
+def balanced_first_leaf(world: int, leaf_sizes: Sequence[int]) -> np.ndarray:
+    """world + 1 ascending 0-based leaf ids: contiguous ranges of nearly equal cost sum(n^3) -- pmk_multi's own leaf -> rank
+    map (pmk_multi_balanced_ranges / pmk_multi_owned_range): boundary i is the leaf whose cost prefix is nearest to i / world
+    of the total, every rank keeping at least one leaf."""
+    n = np.asarray(leaf_sizes, dtype=np.float64)
+    n_leaves = len(n)
+    assert n_leaves >= world >= 1
+    pre = np.concatenate([[0.0], np.cumsum(n * n * n)])       # same left-to-right sum as the library
+    bnd = np.zeros(world + 1, dtype=np.int64)
+    bnd[world] = n_leaves
+    for i in range(1, world):
+        target = pre[n_leaves] * float(i) / float(world)
+        k = int(np.searchsorted(pre, target, side="left"))
+        if k > 0 and target - pre[k - 1] < pre[k] - target:
+            k -= 1
+        k = max(k, int(bnd[i - 1]) + 1)
+        k = min(k, n_leaves - (world - i))
+        bnd[i] = k
+    return bnd
 
 
 def query_slice(rank: int, world: int, nq: int) -> Tuple[int, int]:

@@ -67,6 +67,10 @@ def test_multi_equals_single_bit_for_bit(built_lib, name):
         ranges = [em.multi.owned_range(r) for r in range(len(devs))]
         assert ranges[0][0] == 0 and all(c >= 1 for _, c in ranges)
         assert all(ranges[r][0] + ranges[r][1] == (ranges[r + 1][0] if r + 1 < len(devs) else len(X_set)) for r in range(len(devs)))
+        first = np.zeros(len(devs) + 1, dtype=np.int64)
+        lo = np.concatenate([[0], np.cumsum([x.shape[0] for x in X_set])]).astype(np.int64)
+        assert _lib.lib().pmk_multi_balanced_ranges(len(devs), len(X_set), _lib.ptr(lo), _lib.ptr(first)) == _lib.PMK_OK
+        assert [a for a, _ in ranges] == list(first[:-1])          # the host-only export is the map pmk_multi uses
         cost = np.array([float(x.shape[0]) ** 3 for x in X_set])
         if len(X_set) >= 4 * len(devs):
             assert max(cost[a:a + c].sum() for a, c in ranges) <= cost.sum() / len(devs) + cost.max() * (1 + 1e-12)

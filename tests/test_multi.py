@@ -51,6 +51,29 @@ def test_python_mirror_equals_library_map(built_lib, world, n):
         assert np.array_equal(f, np.arange(world + 1) * (n // world))       # aligned sub-trees
 
 
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_balanced_ranges_host_only(built_lib, world):
+    """pmk_multi_balanced_ranges (host only): pmk_multi's cost-balanced leaf -> rank map -- contiguous ranges that cover the
+    leaves once, every rank at least one leaf, every range within one leaf of its share of sum(n^3); the Python mirror gives the
+    same boundaries; equal leaves give the equal-count split (the sub-trees of the BSP)."""
+    L = _lib.lib()
+    rng = np.random.default_rng(5 + world)
+    for sizes in (rng.integers(300, 1500, 4096), rng.integers(1, 2049, 37), np.full(64, 512), np.arange(1, world + 1)):
+        sizes = np.asarray(sizes, dtype=np.int64)
+        leaf_off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+        first = np.zeros(world + 1, dtype=np.int64)
+        assert L.pmk_multi_balanced_ranges(world, len(sizes), _lib.ptr(leaf_off), _lib.ptr(first)) == _lib.PMK_OK
+        assert first[0] == 0 and first[-1] == len(sizes) and np.all(np.diff(first) >= 1)
+        assert np.array_equal(first, sharding.balanced_first_leaf(world, sizes))
+        cost = sizes.astype(float) ** 3
+        worst = max(cost[a:b].sum() for a, b in zip(first[:-1], first[1:]))
+        assert worst <= cost.sum() / world + cost.max() * (1 + 1e-12)
+        if np.all(sizes == sizes[0]) and len(sizes) % world == 0:
+            assert np.array_equal(first, sharding.owner_first_leaf(world, len(sizes)))
+    bad = np.zeros(world + 1, dtype=np.int64)
+    assert L.pmk_multi_balanced_ranges(world + 1, world, _lib.ptr(np.arange(world + 1, dtype=np.int64)), _lib.ptr(bad)) == _lib.PMK_ERR_ARG
+
+
 @pytest.mark.parametrize("world", [1, 2, 3, 5])
 def test_routing_round_trip_in_numpy(world):
     """Every pair reaches the owner of its leaf and its answer comes back to its own slot: segments() / rx_offsets() with the
