@@ -286,6 +286,27 @@ __device__ __forceinline__ double exp_neg_tab(double t, const double* __restrict
   return __hiloint2double(__double2hiint(res) + ((ki >> 6) << 20), __double2loint(res));
 }
 
+// The same function for the pair kernel's phase E, which is bound by its instruction count, not by the FP64 pipe: the table comes
+// as a 32-bit shared-memory address (no generic-to-shared conversion in the loop), and the clamp at -699 is ONE unsigned integer
+// minimum on the high word of t (for t <= -0.0 the high words order like the magnitudes; 0xC085D800 is the high word of -699.0)
+// instead of a double-precision maximum (a DSETP on the FP64 pipe and three selects).  Same bits as exp_neg_tab for -699 <= t <= 0.
+__device__ __forceinline__ double exp_neg_tab_s(double t, uint32_t tab_u32) {
+  const double C = 0x1.71547652b82fep+6, HI = 0x1.62e42fee00000p-7, LO = 0x1.a39ef35793c76p-39, MAGIC = 0x1.8p52;
+  t = __hiloint2double((int)min((unsigned)__double2hiint(t), 0xC085D800u), __double2loint(t));
+  double kd = fma(t, C, MAGIC);
+  const int ki = __double2loint(kd);
+  kd -= MAGIC;
+  double r = fma(kd, -HI, t);
+  r = fma(kd, -LO, r);
+  double T;
+  asm("ld.shared.f64 %0, [%1];" : "=d"(T) : "r"(tab_u32 + (uint32_t)((ki & 63) << 3)));
+  const double r2 = r * r;
+  const double q1 = fma(1.0 / 6, r, 0.5), q2 = fma(1.0 / 120, r, 1.0 / 24);
+  const double pr = fma(fma(q2, r2, q1), r2, r);
+  const double res = fma(T, pr, T);
+  return __hiloint2double(__double2hiint(res) + ((ki >> 6) << 20), __double2loint(res));
+}
+
 // R row tiles per unit, CW column tiles per chunk, DEPTH chunks in flight per warp.
 // Dynamic shared memory: [kRW][DEPTH][R][CW][512 B] rings | K fragments: npmax * MQ doubles | per-unit ||S||^2:
 // [2][ucap][MQ] | (STAGE_X) inputs + alpha: [D+1][npmax]

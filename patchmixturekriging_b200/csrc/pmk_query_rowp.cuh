@@ -294,6 +294,7 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
       const double* __restrict__ xs = lt.xs + lt.xoff[p];
       const double* __restrict__ al = lt.alpha + lt.xoff[p];
       const bool sqexp = kp.kind == PMK_KERNEL_SQEXP;
+      const uint32_t s_exp_u32 = q_smem_u32(s_exp);
       double usum = 0.0;
       // one step = column tiles c and c + ESTRIDE.  FULL: both hold real rows only -- no row clamps, no selects.
       auto eval_step = [&](int c, auto full_tag) {
@@ -324,7 +325,7 @@ k_query_rowp(LeafTable lt, PairWork w, QueryPlan q, KParams kp, int flags, int n
             arg[e] = -kp.p * s2;
           }
 #pragma unroll
-          for (int e = 0; e < 4; ++e) kv[e] = (PMK_K3_X & 1) ? arg[e] : exp_neg_tab(arg[e], s_exp);
+          for (int e = 0; e < 4; ++e) kv[e] = (PMK_K3_X & 1) ? arg[e] : exp_neg_tab_s(arg[e], s_exp_u32);
         } else {
 #pragma unroll
           for (int e = 0; e < 4; ++e) kv[e] = eval_kernel<D>(kp, xq, xr[e]);      // evalkernel(xq, X[i]), mixtureGP.jl:304

@@ -134,6 +134,15 @@ def test_exp_neg_tab_arithmetic():
     ref = np.exp(t.astype(np.longdouble))
     err = np.abs(got.astype(np.longdouble) - ref) / np.spacing(np.exp(t)).astype(np.longdouble)
     assert err.max() <= 1.5
+    # exp_neg_tab_s (the pair kernel's phase E) clamps with one unsigned minimum on the high word instead of fmax(t, -699):
+    # the same value for every t in [-699, -0.0], within 2^-11 below -699 for anything smaller (-inf included)
+    tt = -np.concatenate([rng.uniform(0, 699, 100000), rng.uniform(699, 1e6, 1000), [0.0, 699.0, 699.0000001, 1e300, np.inf]])
+    hi = (tt.view(np.uint64) >> np.uint64(32)).astype(np.uint64)
+    lo = tt.view(np.uint64) & np.uint64(0xFFFFFFFF)
+    clamped = ((np.minimum(hi, np.uint64(0xC085D800)) << np.uint64(32)) | lo).view(np.float64)
+    inside = tt >= -699.0
+    assert np.array_equal(clamped[inside], tt[inside])
+    assert np.all(clamped[~inside] <= -699.0) and np.all(clamped[~inside] > -699.0005)      # one high-word step = 2^-11
 
 
 def test_inverse_plan_covers_every_block_once(built_lib):
