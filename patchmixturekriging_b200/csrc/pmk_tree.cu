@@ -236,7 +236,7 @@ __global__ void k_neighbours(TreeDev tr, QueryPlan q, double radius, double delt
 // The kept candidates (slot numbers in the leaf's list, at most 7, else an overflow mark) go to a
 // 16-byte record per query; the fill pass replays only those.
 static constexpr int kKeptMax = 7;
-static constexpr int kCandCap = 768;
+static constexpr int kCandCap = 1024;     // planes staged in shared memory per leaf ((D + 2) x 8 KB; C4's 3-D leaves have ~800, and the ones beyond the cap cost three global loads per query)
 
 template <int D>
 __global__ void __launch_bounds__(256)
